@@ -1,0 +1,843 @@
+// align.cu — batched read mapping on the GPU (replaces SingleAlign/PairAlign::Do_Batch).
+//
+// Kernels (all sm_100a integer / LSU work, no tensor cores):
+//   prepare_reads   warp per read: FilterReads, 2-bit planes for both chains, rolling seed hashes,
+//                   bucket-size gathers and the seed schedule (ConvertBinaySeq + ReorderSeed)
+//   classify_pairs  PE: route each pair to the pair rounds or its surviving mate to the SE rounds
+//   search_round    persistent warps, one read per warp per round (SnpAlign mode r): seed look-up,
+//                   rotated bucket walk, warp-cooperative coalesced gather of candidate windows into
+//                   shared memory, masked XOR/popcount verification, single-gap search, and the
+//                   in-order AddHit reduction (dedup, -w feedback, early stop)
+//   pair_round      thread per pair: SortHits4PE + GetPairs replay for level i
+//   finalize_reads  lowest non-empty level, -S tie-break, result records
+//
+// Discovery order inside a read is preserved exactly: candidates are numbered
+// (chain, phase, rotated bucket index) and reduced in that order by their warp.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "ctx.hpp"
+
+namespace {
+
+struct DevTables {
+    RuleTables rule;
+    u32 budget0[BSL_MAX_READLEN + 1];
+    u16 prof[16][16];
+};
+
+struct KArgs {
+    DevIndex di;
+    const DevTables *tab;
+    u32 s, I, gap, w, min_insert, max_insert, chains, report, randseed, max_ns, min_read_size, single;
+    // batch
+    u32 n_slots, n_a;              // n_a = reads in batch a (PE: slots [n_a, 2 n_a) are the mates)
+    u32 pe;                        // paired run
+    u32 readset_a, readset_b;
+    const u8 *bases; const u64 *off; const u32 *index; const u16 *rawlen; u32 first_index_a, first_index_b; u64 bases_b_shift;
+    u32 has_index, has_rawlen;
+    u32 Wb;                        // words per plane in this batch
+    u64 *planes; u8 *sched; SlotMeta *meta; SlotCounts *cnt; uint2 *stat;   // stat: executed seed look-ups / candidates per slot
+    DevHit *hits; u32 cap;         // hit pool and per-slot capacity
+    DevCounters *ctr;
+    bsl_hit *out; bsl_pair *pair_out; bsl_hit *all_a; bsl_hit *all_b; u64 all_cap;
+};
+
+__device__ __forceinline__ u64 plane_extract(const u64 *pl, u32 p) {     // 32 bases starting at base p, MSB first
+    u32 w = p >> 5, o = (p & 31u) * 2;
+    u64 x = pl[w] << o;
+    if (o) x |= pl[w + 1] >> (64 - o);
+    return x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prepare_reads
+// ------------------------------------------------------------------------------------------------
+#define PREP_WARPS 4
+struct PrepSmem {
+    u8  seq[512];
+    u64 pl[3][17];
+    u32 hash[480];
+    u32 cntp[480];
+    int cs[16][16];
+    u32 need[16];
+};
+
+__global__ void __launch_bounds__(PREP_WARPS * 32) prepare_reads(const __grid_constant__ KArgs A) {
+    __shared__ PrepSmem sm_all[PREP_WARPS];
+    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    PrepSmem &sm = sm_all[wid];
+    const DevTables *T = A.tab;
+    for (u32 slot = blockIdx.x * PREP_WARPS + wid; slot < A.n_slots; slot += gridDim.x * PREP_WARPS) {
+        const bool mate_b = A.pe && slot >= A.n_a;
+        const u32 r = mate_b ? slot - A.n_a : slot;
+        const u64 *off = mate_b ? A.off + (A.n_a + 1) : A.off;
+        const u64 b0 = off[r] + (mate_b ? A.bases_b_shift : 0), b1 = off[r + 1] + (mate_b ? A.bases_b_shift : 0);
+        const u32 Lraw = (u32)(b1 - b0);
+        const u32 L = Lraw > BSL_MAX_READLEN ? BSL_MAX_READLEN : Lraw;
+        const u32 readset = mate_b ? A.readset_b : A.readset_a;
+        const u32 index = A.has_index ? A.index[slot] : (mate_b ? A.first_index_b : A.first_index_a) + r;
+        __syncwarp();
+        u32 ns = 0;
+        for (u32 k = lane; k < 512; k += 32) { u8 c = k < L ? A.bases[b0 + k] : 0; sm.seq[k] = c; if (k < L && !T->rule.reg[c]) ns++; }
+        for (u32 o = 16; o; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
+        __syncwarp();
+        bool filtered = (L == 0) || (L < A.min_read_size) || (ns > A.max_ns) || (Lraw > BSL_MAX_READLEN);   // align.cpp:559-560
+        u32 raw = A.has_rawlen ? A.rawlen[slot] : L; if (raw == 0 || raw > BSL_MAX_READLEN) raw = L ? L : 1;
+        u32 B = 0, nseg = 0;
+        if (!filtered) {
+            B = (T->budget0[raw] + 1) * (L - 1) / raw;                                                        // align.cpp:561
+            u32 span = L + 1 - A.I;                                                                           // L >= I is implied by min_read_size
+            nseg = (L + 1 >= A.I + A.s) ? min(span / A.s, B + 1) : 0;                                         // align.cpp:450
+        }
+        u32 flags = filtered ? SF_FILTERED : 0;
+        if ((A.chains == 1) || ((A.chains <= 1) == (readset < 2))) flags |= SF_CHAIN0;                       // align.cpp:83-84
+        if ((A.chains == 1) || ((A.chains <= 1) == (readset == 2))) flags |= SF_CHAIN1;
+        const u32 W = (L + 31) >> 5;
+        const u32 ii = (L + 1 >= A.I) ? (L + 1 - A.I) % A.s : 0;
+        for (u32 c = 0; c < 2; c++) {
+            if (filtered || !(flags & (c ? SF_CHAIN1 : SF_CHAIN0))) continue;
+            // ---- planes (ConvertBinaySeq / ConvertBinarySeq, align.cpp:79-226)
+            if (lane < 17) {
+                u64 q = 0, nm = 0, cm = 0;
+                if (lane < W) {
+                    for (u32 k = 0; k < 32; k++) {
+                        u32 p = lane * 32 + k; u32 cq = 0, cn = 0, cc = 0;
+                        if (p < L) { u8 ch = c ? sm.seq[L - 1 - p] : sm.seq[p];
+                            cq = c ? T->rule.rcode[ch] : T->rule.code[ch]; cn = T->rule.reg[ch]; cc = c ? T->rule.rconv[ch] : T->rule.conv[ch]; }
+                        q = (q << 2) | cq; nm = (nm << 2) | cn; cm = (cm << 2) | cc;
+                    }
+                }
+                sm.pl[0][lane] = q; sm.pl[1][lane] = nm; sm.pl[2][lane] = cm;
+                if (lane < A.Wb) {
+                    u64 *dst = A.planes + ((u64)slot * 2 + c) * 3 * A.Wb;
+                    dst[lane] = q; dst[A.Wb + lane] = nm; dst[2 * A.Wb + lane] = cm;
+                }
+            }
+            if (lane < 16) sm.need[lane] = 0;
+            __syncwarp();
+            if (nseg == 0) continue;
+            // ---- seed hashes for every offset (xseed_array / xseedreg_array)
+            const u32 npos = L - A.s + 1; const u32 sh = 64 - 2 * A.s;
+            for (u32 p = lane; p < npos; p += 32) {
+                u32 x = (u32)(plane_extract(sm.pl[0], p) >> sh);
+                u32 m = (u32)(plane_extract(sm.pl[1], p) >> sh);
+                u32 full = (A.s == 16) ? 0xffffffffu : ((1u << (2 * A.s)) - 1);
+                sm.hash[p] = bsl_xt(x) | ((m != full) ? 0x80000000u : 0u);
+            }
+            // ---- which offsets can the schedule touch
+            const u32 nv = ii + 1, tot = nseg * A.I * nv;
+            for (u32 t = lane; t < tot; t += 32) {
+                u32 v = t % nv, i = (t / nv) % A.I, j = t / (nv * A.I);
+                u32 p = T->prof[j][i] + v - i;
+                atomicOr(&sm.need[p >> 5], 1u << (p & 31));
+            }
+            __syncwarp();
+            for (u32 p = lane; p < npos; p += 32) {
+                u32 cv = 0;
+                if (sm.need[p >> 5] >> (p & 31) & 1u) {
+                    u32 k = sm.hash[p] & 0x7fffffffu; u32 c16 = A.di.cnt16[k];
+                    cv = (c16 == 0xFFFFu) ? A.di.bucket[2 * k + 2] - A.di.bucket[2 * k] : c16;
+                }
+                sm.cntp[p] = cv;
+            }
+            __syncwarp();
+            // ---- CountSeeds(j, v) (align.cpp:526-540)
+            for (u32 t = lane; t < nseg * nv; t += 32) {
+                u32 j = t / nv, v = t % nv, total = 0, k = 0;
+                for (u32 i = 0; i < A.I; i++) {
+                    u32 p = T->prof[j][i] + v - i;
+                    if (sm.hash[p] >> 31) k = 12;
+                    total += sm.cntp[p] << k;
+                }
+                if (total == 0) total = 9999999;
+                sm.cs[j][v] = (int)total;
+            }
+            __syncwarp();
+            // ---- ReorderSeed / AdjustSeedStartArray (align.cpp:468-524)
+            if (lane == 0) {
+                u32 st[16]; u32 best = 0xffffffffu, st0 = 0;
+                for (u32 i = 0; i < ii; i++) { u32 tt = 0; for (u32 j = 0; j < nseg; j++) tt += (u32)sm.cs[j][i]; if (tt < best) { best = tt; st0 = i; } }
+                for (u32 j = 0; j < nseg; j++) st[j] = st0;
+                for (u32 t = 0; t < nseg; t++) {
+                    u32 ptr = (t & 1) ? nseg - 1 - t / 2 : t / 2;
+                    u32 lo = ptr == 0 ? 0 : st[ptr - 1], hi = ptr == nseg - 1 ? ii : st[ptr + 1];
+                    st[ptr] = lo; u32 b = 0xffffffffu;
+                    for (u32 v = lo; v <= hi; v++) { u32 tt = (u32)sm.cs[ptr][v]; if (tt < b) { b = tt; st[ptr] = v; } }
+                }
+                // rank segments by (count as int, segment) — keys are unique, any sort gives the same order
+                u8 ord[16]; for (u32 j = 0; j < nseg; j++) ord[j] = (u8)j;
+                for (u32 a = 1; a < nseg; a++) { u8 x = ord[a]; int kx = sm.cs[x][st[x]]; int b2 = (int)a - 1;
+                    while (b2 >= 0) { u8 y = ord[b2]; int ky = sm.cs[y][st[y]]; if (ky < kx || (ky == kx && y < x)) break; ord[b2 + 1] = y; b2--; }
+                    ord[b2 + 1] = x; }
+                u8 *sc = A.sched + ((u64)slot * 2 + c) * 16;
+                for (u32 t = 0; t < 16; t++) sc[t] = t < nseg ? (u8)(ord[t] | (st[ord[t]] << 4)) : 0;
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            SlotMeta m; m.rnd = bsl_rand(index, A.randseed); m.len = (u16)L; m.B = (u8)B; m.nseg = (u8)nseg; m.flags = (u8)flags; m.thr = (u8)B; m.nhit = 0; m.item = slot;
+            A.meta[slot] = m;
+        }
+        // zero the per-level counters
+        ((u16 *)&A.cnt[slot])[lane] = 0;
+        if (lane == 0) A.stat[slot] = make_uint2(0u, 0u);
+    }
+}
+
+// Builds the first active lists. SE: every passing read. PE: full pairs -> pair list, lone passing mates -> SE list.
+__global__ void build_lists(const __grid_constant__ KArgs A, u32 *se_list, u32 *pe_list) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!A.pe) {
+        if (i >= A.n_slots) return;
+        SlotMeta m = A.meta[i];
+        if (!(m.flags & SF_FILTERED) && m.nseg > 0) { u32 pos = atomicAdd(&A.ctr->active[0], 1u); se_list[pos] = i; }
+        return;
+    }
+    if (i >= A.n_a) return;
+    SlotMeta ma = A.meta[i], mb = A.meta[i + A.n_a];
+    bool oka = !(ma.flags & SF_FILTERED), okb = !(mb.flags & SF_FILTERED);
+    if (oka && okb) { u32 pos = atomicAdd(&A.ctr->active[20], 1u); pe_list[pos] = i; }
+    else {
+        if (oka && ma.nseg > 0) { u32 pos = atomicAdd(&A.ctr->active[0], 1u); se_list[pos] = i; }
+        if (okb && mb.nseg > 0) { u32 pos = atomicAdd(&A.ctr->active[0], 1u); se_list[pos] = i + A.n_a; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// search_round
+// ------------------------------------------------------------------------------------------------
+#define ROUND_WARPS 8
+#define GAP_NONE 0xffffffffu
+
+struct WarpCtx {
+    // warp-uniform running state of one read (one SingleAlign object)
+    u32 L, W, thr, nhit, chain, cap; u32 mycnt;     // mycnt: lane c*16+l holds hits[c][l]
+    DevHit *hits; bool overflow;
+};
+
+// ref word aligned to read word i for an alignment starting at window-relative base `rel`
+__device__ __forceinline__ u64 ref_word(const u64 *win, u32 NW, u32 rel, u32 i) {
+    u32 pos = rel + 32 * i, wi = pos >> 5, o = (pos & 31u) * 2;
+    u64 x = win[wi] << o;
+    if (o && wi + 1 < NW) x |= win[wi + 1] >> (64 - o);
+    return x;
+}
+
+// GapAlign (align.cpp:348-410) over MismatchPattern0/1 (align.h:133-196, 241-327). Returns GAP_NONE or
+// level | (shift+4)<<8 | gap_pos<<16
+template <bool SINGLE>
+__device__ u32 gap_search(const u64 *win, u32 NW, u32 rel, const u64 *q, const u64 *cm, u32 L, u32 W, u64 endmask,
+                          u32 thr, u32 h, u32 s, u32 G) {
+    if (thr < 2) return GAP_NONE;
+    u16 P0[16], PR[16];
+    const u32 want = thr - 1;
+    u32 n0 = 0, ret0 = L;
+    for (u32 i = 0; i < W && n0 < want; i++) {
+        u64 d = bsl_diff<SINGLE>(q[i], cm[i], ref_word(win, NW, rel, i)); if (i == W - 1) d &= endmask;
+        u64 x = bsl_pairs(d);
+        while (x && n0 < want) { u32 b = __clzll((long long)x) >> 1; u32 pos = 32 * i + b; P0[n0++] = (u16)pos; if (n0 == want) ret0 = pos; x &= ~(0x4000000000000000ULL >> (2 * b)); }
+    }
+    for (u32 k = n0; k < want; k++) P0[k] = (u16)L;
+    if (ret0 < h + s) return GAP_NONE;
+    for (u32 tt = 1; tt <= 2 * G; tt++) {
+        const u32 t = (tt + 1) >> 1; const int sh = (tt & 1) ? -(int)t : (int)t; const int sh1 = sh < 0 ? sh : 0;
+        if (thr < 1 + t) break;
+        u32 n1 = 0; const u32 rel1 = (u32)((int)rel + sh);
+        for (int i = (int)W - 1; i >= 0 && n1 < want; i--) {
+            u64 d = bsl_diff<SINGLE>(q[i], cm[i], ref_word(win, NW, rel1, (u32)i)); if (i == (int)W - 1) d &= endmask;
+            u64 x = bsl_pairs(d);
+            while (x && n1 < want) { u32 b = (u32)(__ffsll((long long)x) - 1) >> 1; u32 pos = 32 * (u32)i + 31 - b; PR[n1++] = (u16)(L - 1 - pos); x &= x - 1; }
+        }
+        for (u32 k = n1; k < want; k++) PR[k] = (u16)L;
+        const u32 rl = L - t - 1;
+        for (u32 i = 0; i < thr - t; i++) {
+            u32 gp = P0[i];
+            if (gp < 6 || gp >= rl) continue;
+            for (u32 j = 0; j < thr - t - i; j++) {
+                u32 m2 = PR[j];
+                if (m2 < 6 || m2 >= rl) continue;
+                if ((int)gp + (int)m2 - sh1 < (int)L) continue;
+                int clip = (int)gp + 6 - (int)L - sh1;
+                if (clip > 0) gp -= (u32)clip;
+                return (i + j + t) | ((u32)(sh + 4) << 8) | (gp << 16);
+            }
+        }
+    }
+    return GAP_NONE;
+}
+
+// AddHit + int2hit (align.h:329-347, align.cpp:319-346); all arguments warp-uniform.
+// returns 0 = continue, 1 = abort this SnpAlign call (level-0 list full, or storage overflow)
+__device__ int add_hit(const KArgs &A, WarpCtx &S, u32 lane, u32 level, u32 g, u32 sig, int sh, u32 gp) {
+    u32 lo = 0, hi = A.di.nseq;
+    while (lo + 1 < hi) { u32 mid = (lo + hi) >> 1; if (g >= A.di.anchor[mid]) lo = mid; else hi = mid; }
+    u32 x = g - A.di.anchor[lo];
+    if (sig) { x = A.di.rcoff[lo] - S.L - x; gp = (u32)((int)S.L + (sh < 0 ? sh : 0) - (int)gp); x -= (u32)sh; }
+    gp &= 511u;
+    if ((int)x < 0) return 0;
+    if (x + S.L > A.di.seqlen[lo]) return 0;
+    const u32 gapped = sh != 0;
+    bool dup = false;
+    for (u32 i = lane; i < S.nhit; i += 32) { DevHit hh = S.hits[i]; if (hh.loc == x && HIT_GAPPED(hh.tag) == gapped && (HIT_CHR2(hh.tag) >> 1) == lo) dup = true; }
+    if (__any_sync(0xffffffffu, dup)) return 0;
+    if (S.nhit >= S.cap) { S.overflow = true; return 1; }
+    if (lane == 0) { DevHit hh; hh.loc = x; hh.tag = (lo * 2 + sig) | (level << 20) | (S.chain << 24) | (gapped << 25); hh.gap = (u32)sh; hh.gp = gp; S.hits[S.nhit] = hh; }
+    S.nhit++;
+    __syncwarp();
+    if (lane == S.chain * 16 + level) S.mycnt++;
+    u32 tot = __shfl_sync(0xffffffffu, S.mycnt, level) + __shfl_sync(0xffffffffu, S.mycnt, 16 + level);
+    if (tot >= A.w) { if (level == 0) return 1; S.thr = level - 1; }
+    return 0;
+}
+
+template <bool SINGLE>
+__global__ void __launch_bounds__(ROUND_WARPS * 32) search_round(const __grid_constant__ KArgs A, u32 round, const u32 *list_in, u32 *list_out,
+                                                                u32 ctr_in, u32 NW, u32 NWS) {
+    extern __shared__ u64 smem[];
+    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    u64 *win_all = smem + (size_t)wid * (32 * NWS + 48);
+    u64 *pq = win_all + 32 * NWS, *pn = pq + 16, *pc = pn + 16;
+    const DevTables *T = A.tab;
+    const u32 n_items = A.ctr->active[ctr_in] * (A.pe ? 2u : 1u);
+    const u32 G = A.gap;
+    unsigned long long st_hits = 0;
+    for (;;) {
+        u32 k = 0;
+        if (lane == 0) k = atomicAdd(&A.ctr->work[ctr_in], 1u);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        if (k >= n_items) break;
+        const u32 slot = A.pe ? list_in[k >> 1] + (k & 1u) * A.n_a : list_in[k];
+        SlotMeta m = A.meta[slot];
+        if (m.flags & (SF_OVERFLOW | SF_FILTERED)) continue;
+        if (round >= m.nseg) continue;                                          // PE: this mate has no more seed segments
+        WarpCtx S; S.L = m.len; S.W = (S.L + 31) >> 5; S.thr = m.thr; S.nhit = m.nhit; S.cap = A.cap; S.overflow = false;
+        S.hits = A.hits + (u64)m.item * A.cap;
+        S.mycnt = ((const u16 *)&A.cnt[slot])[lane];
+        const u32 L = S.L, W = S.W;
+        const u32 lastb = L & 31u; const u64 endmask = lastb ? (~0ULL << (64 - 2 * lastb)) : ~0ULL;
+        const u32 hits_before = S.nhit;
+        bool stop_all = false; u32 st_lookups = 0, st_cand = 0;
+        for (u32 c = 0; c < 2 && !stop_all; c++) {
+            if (!(m.flags & (c ? SF_CHAIN1 : SF_CHAIN0))) continue;
+            S.chain = c;
+            const u8 sc = A.sched[((u64)slot * 2 + c) * 16 + round]; const u32 j = sc & 15u, stj = sc >> 4;
+            __syncwarp();
+            if (lane < 16) {
+                const u64 *src = A.planes + ((u64)slot * 2 + c) * 3 * A.Wb;
+                bool in = lane < A.Wb;
+                pq[lane] = in ? src[lane] : 0; pn[lane] = in ? src[A.Wb + lane] : 0; pc[lane] = in ? src[2 * A.Wb + lane] : 0;
+            }
+            __syncwarp();
+            // ---- seed look-ups of this mode: one phase per lane (align.cpp:279-292)
+            u32 pm = 0, pb0 = 0, ph_h = 0, prot = 0; int pmc = -1;
+            if (lane < A.I) {
+                ph_h = T->prof[j][lane] + stj - lane;
+                u32 kmer = bsl_xt((u32)(plane_extract(pq, ph_h) >> (64 - 2 * A.s)));
+                u32 e0 = A.di.bucket[2 * kmer], e1 = A.di.bucket[2 * kmer + 1], e2 = A.di.bucket[2 * kmer + 2];
+                pm = e2 - e0; pb0 = e0; pmc = (int)(e1 - e0) - 1;
+                if (pm == 0 || pm > A.di.maxk) pm = 0; else prot = m.rnd % pm;
+            }
+            u32 incl = pm;
+            for (u32 o = 1; o < 32; o <<= 1) { u32 v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const u32 poff = incl - pm; const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+            st_lookups += A.I; st_cand += total;
+            for (u32 tile = 0; tile < total && !stop_all; tile += 32) {
+                const u32 idx = tile + lane; const bool valid = idx < total;
+                u32 ph = 0;
+                for (u32 i = 1; i < A.I; i++) { u32 o = __shfl_sync(0xffffffffu, poff, i); if (idx >= o) ph = i; }
+                const u32 t = idx - __shfl_sync(0xffffffffu, poff, ph);
+                const u32 cm_ = __shfl_sync(0xffffffffu, pm, ph), crot = __shfl_sync(0xffffffffu, prot, ph), cb0 = __shfl_sync(0xffffffffu, pb0, ph);
+                const int cmc = __shfl_sync(0xffffffffu, pmc, ph); const u32 ch = __shfl_sync(0xffffffffu, ph_h, ph);
+                u32 g = 0, sig = 0, word0 = 0, rel = 0;
+                if (valid) {
+                    u32 e = crot + t; if (e >= cm_) e -= cm_;
+                    sig = ((int)e > cmc) ? 1u : 0u;
+                    g = A.di.loc[cb0 + e] - ch;                                 // _hit.loc (align.cpp:297)
+                    u32 gb = g - G; word0 = gb >> 5; rel = (gb & 31u) + G;      // window starts at word0; alignment starts `rel` bases into it
+                }
+                // ---- warp-cooperative gather: consecutive lanes fetch consecutive words of one candidate's window
+                __syncwarp();
+                for (u32 kk = 0; kk < NW; kk++) {
+                    u32 f = kk * 32 + lane; u32 cand = f / NW, w = f - cand * NW;
+                    u32 cw0 = __shfl_sync(0xffffffffu, word0, cand); u32 cs = __shfl_sync(0xffffffffu, sig, cand); bool cv = __shfl_sync(0xffffffffu, (u32)valid, cand);
+                    u64 val = cv ? __ldg(A.di.plane[cs] + cw0 + w) : 0ULL;
+                    win_all[cand * NWS + w] = val;
+                }
+                __syncwarp();
+                const u64 *win = win_all + lane * NWS;
+                u32 snp = 0xffffu, gres = GAP_NONE;
+                if (valid) {
+                    snp = 0;
+                    for (u32 i = 0; i < W; i++) {                              // CountMismatch / CountMismatch_new
+                        u64 d = bsl_diff<SINGLE>(pq[i], pc[i], ref_word(win, NW, rel, i)) & pn[i];
+                        snp += __popcll(bsl_pairs(d));
+                    }
+                    if (G) gres = gap_search<SINGLE>(win, NW, rel, pq, pc, L, W, endmask, S.thr, ch, A.s, G);
+                }
+                // ---- in-order reduction (AddHit semantics need the discovery order)
+                const u32 thr0 = S.thr;
+                u32 pending = __ballot_sync(0xffffffffu, valid && (snp <= thr0 || gres != GAP_NONE));
+                while (pending) {
+                    const u32 l = __ffs(pending) - 1; pending &= pending - 1;
+                    const u32 cg = __shfl_sync(0xffffffffu, g, l), csig = __shfl_sync(0xffffffffu, sig, l), csnp = __shfl_sync(0xffffffffu, snp, l);
+                    bool ab = false;
+                    if (csnp <= S.thr) ab = add_hit(A, S, lane, csnp, cg, csig, 0, 0);
+                    if (G && !ab) {
+                        if (S.thr != thr0 && lane == l) gres = gap_search<SINGLE>(win, NW, rel, pq, pc, L, W, endmask, S.thr, ch, A.s, G);
+                        const u32 cres = __shfl_sync(0xffffffffu, gres, l);
+                        if (cres != GAP_NONE) ab = add_hit(A, S, lane, cres & 255u, cg, csig, (int)((cres >> 8) & 255u) - 4, cres >> 16);
+                    }
+                    if (ab) {                    // SnpAlign returns here: later phases / the other chain are never looked up
+                        const u32 aph = __shfl_sync(0xffffffffu, ph, l);
+                        st_lookups -= A.I - 1 - aph;
+                        st_cand -= total - (__shfl_sync(0xffffffffu, poff, aph) + __shfl_sync(0xffffffffu, pm, aph));
+                        stop_all = true; break;
+                    }
+                }
+            }
+        }
+        st_hits += S.nhit - hits_before;
+        // ---- write back, stop rule (align.cpp:459-463)
+        ((u16 *)&A.cnt[slot])[lane] = (u16)S.mycnt;
+        u32 low = __ballot_sync(0xffffffffu, S.mycnt > 0 && (lane & 15u) <= round);
+        if (lane == 0) {
+            u32 fl = m.flags;
+            if (S.overflow) { fl |= SF_OVERFLOW; atomicAdd(&A.ctr->overflow_n, 1u); }
+            A.meta[slot].thr = (u8)S.thr; A.meta[slot].nhit = (u16)S.nhit; A.meta[slot].flags = (u8)fl;
+            uint2 ss = A.stat[slot]; ss.x += st_lookups; ss.y += st_cand; A.stat[slot] = ss;
+            if (!A.pe && !S.overflow && !low && round + 1 < m.nseg) { u32 pos = atomicAdd(&A.ctr->active[ctr_in + 1], 1u); list_out[pos] = slot; }
+        }
+    }
+    if (lane == 0) atomicAdd(&A.ctr->hits_added, st_hits);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pair_round : SortHits4PE + GetPairs (align.cpp:412-416, pairs.cpp:29-177), one thread per pair
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool hit_less(const DevHit &a, const DevHit &b) {             // HitComp, utilities.cpp:51
+    u32 ca = HIT_CHR2(a.tag), cb = HIT_CHR2(b.tag); return ca < cb || (ca == cb && a.loc < b.loc);
+}
+__device__ __forceinline__ bool tag_is(u32 tag, u32 chain, u32 level) { return HIT_CHAIN(tag) == chain && HIT_LEVEL(tag) == level; }
+
+// stable insertion sort of the sub-sequence of `h[0..n)` with (chain, level), in place
+__device__ void sort_level(DevHit *h, u32 n, u32 chain, u32 level) {
+    for (u32 i = 0; i < n; i++) {
+        if (!tag_is(h[i].tag, chain, level)) continue;
+        u32 cur = i;
+        for (;;) {
+            int p = (int)cur - 1; while (p >= 0 && !tag_is(h[p].tag, chain, level)) p--;
+            if (p < 0) break;
+            DevHit a = h[p], b = h[cur];
+            if (!hit_less(b, a)) break;
+            h[p] = b; h[cur] = a; cur = (u32)p;
+        }
+    }
+}
+
+struct PairPick { u32 found; u32 chain, na, nb, insert; DevHit a, b; };
+
+// One GetPairs(na, nb) call. mode 0: count into cnt_level (with the -w return). mode 1: same walk, but
+// additionally captures the `target`-th pair (0-based position in the level list) or emits all (-r 2).
+__device__ u32 get_pairs(const KArgs &A, const DevHit *ha, u32 nA, u32 Ba, u32 La, const DevHit *hb, u32 nB, u32 Bb, u32 Lb,
+                         u32 na, u32 nb, u32 &cnt_level, int mode, u32 target, PairPick *pick, u64 all_base) {
+    if (na > Ba || nb > Bb) return 0;
+    u32 npair = 0;
+    for (u32 chain = 0; chain < 2; chain++) {
+        u32 chra = ~0u, bs = 0, be = 0;                     // raw positions in hb delimiting the candidates of the current chr
+        for (u32 i = 0; i < nA; i++) {
+            if (!tag_is(ha[i].tag, chain, na)) continue;
+            const u32 ca = HIT_CHR2(ha[i].tag);
+            if (chra != ca) {
+                chra = ca;
+                for (bs = be; bs < nB; bs++) if (tag_is(hb[bs].tag, 1 - chain, nb) && HIT_CHR2(hb[bs].tag) >= chra) break;
+                for (be = bs; be < nB; be++) if (tag_is(hb[be].tag, 1 - chain, nb) && HIT_CHR2(hb[be].tag) > chra) break;
+            }
+            for (u32 j = bs; j < be; j++) {
+                if (!tag_is(hb[j].tag, 1 - chain, nb)) continue;
+                const bool a_first = chain == 0 ? !(chra & 1u) : (chra & 1u);
+                u32 s0, e0;
+                if (a_first) { s0 = ha[i].loc; e0 = hb[j].loc + Lb; } else { s0 = hb[j].loc; e0 = ha[i].loc + La; }
+                const u32 ins = e0 - s0;
+                if (ins >= A.min_insert && ins <= A.max_insert) {
+                    if (mode == 1 && pick) {
+                        if (A.report == 2 && A.all_a && all_base + cnt_level < A.all_cap) {
+                            bsl_hit ra, rb; memset(&ra, 0, sizeof ra); memset(&rb, 0, sizeof rb);
+                            ra.loc = ha[i].loc; ra.chr = HIT_CHR2(ha[i].tag); ra.gap_size = (int)ha[i].gap; ra.gap_pos = (u16)ha[i].gp; ra.nm = (u8)na; ra.read_chain = (u8)chain; ra.read_len = (u16)La; ra.status = BSL_ST_PAIRED; ra.all_first = ins;
+                            rb.loc = hb[j].loc; rb.chr = HIT_CHR2(hb[j].tag); rb.gap_size = (int)hb[j].gap; rb.gap_pos = (u16)hb[j].gp; rb.nm = (u8)nb; rb.read_chain = (u8)(1 - chain); rb.read_len = (u16)Lb; rb.status = BSL_ST_PAIRED; rb.all_first = ins;
+                            A.all_a[all_base + cnt_level] = ra; A.all_b[all_base + cnt_level] = rb;
+                        }
+                        if (cnt_level == target) { pick->found = 1; pick->chain = chain; pick->na = na; pick->nb = nb; pick->insert = ins; pick->a = ha[i]; pick->b = hb[j]; }
+                    }
+                    cnt_level++; npair++;
+                    if (cnt_level >= A.w) return npair;
+                }
+            }
+        }
+    }
+    return npair;
+}
+
+__device__ void fill_record(bsl_hit &o, const DevHit &h, u32 chain, u32 level) {
+    o.loc = h.loc; o.chr = HIT_CHR2(h.tag); o.gap_size = (int)h.gap; o.gap_pos = (u16)h.gp; o.nm = (u8)level; o.read_chain = (u8)chain;
+}
+
+__global__ void pair_round(const __grid_constant__ KArgs A, u32 round, const u32 *list_in, u32 *list_out, u32 ctr_in) {
+    const u32 n_items = A.ctr->active[ctr_in];
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n_items; k += gridDim.x * blockDim.x) {
+        const u32 p = list_in[k]; const u32 sa = p, sb = p + A.n_a;
+        SlotMeta ma = A.meta[sa], mb = A.meta[sb];
+        if ((ma.flags | mb.flags) & SF_OVERFLOW) {                 // re-run the whole pair on the large-capacity path
+            if (!(ma.flags & SF_OVERFLOW)) { A.meta[sa].flags = ma.flags | SF_OVERFLOW; }
+            if (!(mb.flags & SF_OVERFLOW)) { A.meta[sb].flags = mb.flags | SF_OVERFLOW; }
+            continue;
+        }
+        DevHit *ha = A.hits + (u64)ma.item * A.cap, *hb = A.hits + (u64)mb.item * A.cap;
+        const u32 nA = ma.nhit, nB = mb.nhit, Ba = ma.B, Bb = mb.B, La = ma.len, Lb = mb.len;
+        const u32 i = round;
+        if (i <= Ba) { sort_level(ha, nA, 0, i); sort_level(ha, nA, 1, i); }
+        if (i <= Bb) { sort_level(hb, nB, 0, i); sort_level(hb, nB, 1, i); }
+        // pass 1: count per level sum in the reference's call order
+        u32 total = 0, best = 0xffffffffu, best_cnt = 0;
+        {
+            u32 c = 0; total += get_pairs(A, ha, nA, Ba, La, hb, nB, Bb, Lb, i, i, c, 0, 0, nullptr, 0);
+            if (c) { best = 2 * i; best_cnt = c; }
+            for (u32 j = 0; j < i; j++) {
+                u32 cj = 0;
+                total += get_pairs(A, ha, nA, Ba, La, hb, nB, Bb, Lb, i, j, cj, 0, 0, nullptr, 0);
+                total += get_pairs(A, ha, nA, Ba, La, hb, nB, Bb, Lb, j, i, cj, 0, 0, nullptr, 0);
+                if (cj && i + j < best) { best = i + j; best_cnt = cj; }
+            }
+        }
+        if (total == 0) {
+            const u32 maxi = max(Ba, Bb);
+            if (round < maxi) { u32 pos = atomicAdd(&A.ctr->active[ctr_in + 1], 1u); list_out[pos] = p; }
+            continue;
+        }
+        // a pair exists: the search ends here (pairs.cpp:173)
+        bsl_pair pr; memset(&pr, 0, sizeof pr); pr.n_pairs = best_cnt;
+        if (best_cnt > 1 && A.report == 0) { A.pair_out[p] = pr; continue; }       // suppressed; mates get reported unpaired by finalize
+        const u32 target = best_cnt == 1 ? 0 : ma.rnd % best_cnt;
+        PairPick pk; pk.found = 0;
+        u64 all_base = 0;
+        if (A.report == 2 && A.all_a) { all_base = atomicAdd(&A.ctr->all_n, (unsigned long long)best_cnt); pr.all_first = (u32)all_base; }
+        {
+            u32 c = 0;
+            if (best == 2 * i) get_pairs(A, ha, nA, Ba, La, hb, nB, Bb, Lb, i, i, c, 1, target, &pk, all_base);
+            else { u32 j = best - i;
+                get_pairs(A, ha, nA, Ba, La, hb, nB, Bb, Lb, i, j, c, 1, target, &pk, all_base);
+                get_pairs(A, ha, nA, Ba, La, hb, nB, Bb, Lb, j, i, c, 1, target, &pk, all_base); }
+        }
+        pr.insert = pk.insert; pr.chain = (u8)pk.chain; pr.na = (u8)pk.na; pr.nb = (u8)pk.nb;
+        A.pair_out[p] = pr;
+        bsl_hit oa, ob; memset(&oa, 0, sizeof oa); memset(&ob, 0, sizeof ob);
+        fill_record(oa, pk.a, pk.chain, pk.na); fill_record(ob, pk.b, 1 - pk.chain, pk.nb);
+        oa.status = ob.status = BSL_ST_PAIRED; oa.n_hits = ob.n_hits = best_cnt; oa.read_len = (u16)La; ob.read_len = (u16)Lb; oa.max_snp = (u8)Ba; ob.max_snp = (u8)Bb;
+        A.out[sa] = oa; A.out[sb] = ob;
+        A.meta[sa].flags = ma.flags | SF_DONE; A.meta[sb].flags = mb.flags | SF_DONE;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize_reads : StringAlign / StringAlignUnpair selection (align.cpp:583-612, pairs.cpp:232-259)
+// ------------------------------------------------------------------------------------------------
+__global__ void finalize_reads(const __grid_constant__ KArgs A, const u32 *only_list, u32 only_n) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 slot;
+    if (only_list) { if (t >= only_n) return; slot = only_list[t]; } else { if (t >= A.n_slots) return; slot = t; }
+    SlotMeta m = A.meta[slot];
+    if (m.flags & SF_OVERFLOW) return;                           // will be written by the heavy pass
+    { uint2 ss = A.stat[slot]; if (ss.x) atomicAdd(&A.ctr->seed_lookups, (unsigned long long)ss.x); if (ss.y) atomicAdd(&A.ctr->candidates, (unsigned long long)ss.y); }
+    if (m.flags & SF_DONE) return;                               // already written by pair_round
+    bsl_hit o; memset(&o, 0, sizeof o); o.read_len = m.len; o.max_snp = m.B;
+    if (m.flags & SF_FILTERED) { o.status = BSL_ST_FILTERED; A.out[slot] = o; return; }
+    const SlotCounts cn = A.cnt[slot];
+    const DevHit *h = A.hits + (u64)m.item * A.cap;
+    o.status = BSL_ST_UNMAPPED;
+    for (u32 l = 0; l <= m.B; l++) {
+        u32 n0 = cn.c[0][l], n = n0 + cn.c[1][l];
+        if (!n) continue;
+        u32 pick = n == 1 ? 0 : m.rnd % n; u32 chain = pick < n0 ? 0 : 1; u32 want = pick - (chain ? n0 : 0);
+        u32 seen = 0;
+        for (u32 i = 0; i < m.nhit; i++) if (tag_is(h[i].tag, chain, l)) { if (seen == want) { fill_record(o, h[i], chain, l); break; } seen++; }
+        o.n_hits = n; o.n_chain0 = n0; o.status = n == 1 ? BSL_ST_UNIQUE : BSL_ST_MULTI;
+        if (A.report == 2 && !A.pe && A.all_a && n > 1) {
+            u64 base = atomicAdd(&A.ctr->all_n, (unsigned long long)n); o.all_first = (u32)base; u64 w = base;
+            for (u32 c = 0; c < 2; c++) for (u32 i = 0; i < m.nhit; i++) if (tag_is(h[i].tag, c, l)) {
+                if (w < A.all_cap) { bsl_hit r = o; fill_record(r, h[i], c, l); A.all_a[w] = r; } w++; }
+        }
+        break;
+    }
+    A.out[slot] = o;
+}
+
+// heavy pass: reset the state of the overflowed items and point them at the large pool
+__global__ void collect_overflow(const __grid_constant__ KArgs A, u32 *heavy_list, u32 *n_heavy) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 n = A.pe ? A.n_a : A.n_slots;
+    if (i >= n) return;
+    bool ov = A.meta[i].flags & SF_OVERFLOW;
+    if (A.pe) ov = ov || (A.meta[i + A.n_a].flags & SF_OVERFLOW);
+    if (ov) { u32 pos = atomicAdd(n_heavy, 1u); heavy_list[pos] = i; }
+}
+
+__global__ void reset_heavy(const __grid_constant__ KArgs A, const u32 *heavy_list, u32 first, u32 count, u32 *se_list, u32 *pe_list) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    u32 i = heavy_list[first + t];
+    for (u32 mate = 0; mate < (A.pe ? 2u : 1u); mate++) {
+        u32 slot = i + mate * A.n_a;
+        SlotMeta m = A.meta[slot];
+        m.flags &= ~(SF_OVERFLOW | SF_DONE); m.thr = m.B; m.nhit = 0; m.item = A.pe ? 2 * t + mate : t;
+        A.meta[slot] = m;
+        for (u32 k = 0; k < 32; k++) ((u16 *)&A.cnt[slot])[k] = 0;
+        A.stat[slot] = make_uint2(0u, 0u);
+    }
+    if (!A.pe) { u32 pos = atomicAdd(&A.ctr->active[0], 1u); se_list[pos] = i; return; }
+    SlotMeta ma = A.meta[i], mb = A.meta[i + A.n_a];
+    bool oka = !(ma.flags & SF_FILTERED), okb = !(mb.flags & SF_FILTERED);
+    if (oka && okb) { u32 pos = atomicAdd(&A.ctr->active[20], 1u); pe_list[pos] = i; }
+    else {
+        if (oka && ma.nseg > 0) { u32 pos = atomicAdd(&A.ctr->active[0], 1u); se_list[pos] = i; }
+        if (okb && mb.nseg > 0) { u32 pos = atomicAdd(&A.ctr->active[0], 1u); se_list[pos] = i + A.n_a; }
+    }
+}
+
+__global__ void expand_pairs_to_slots(const u32 *heavy_list, u32 first, u32 count, u32 n_a, u32 pe, u32 *slots) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    u32 i = heavy_list[first + t];
+    if (pe) { slots[2 * t] = i; slots[2 * t + 1] = i + n_a; } else slots[t] = i;
+}
+
+template <typename T> int grow(bsl_ctx *ctx, T **p, size_t *cap, size_t need, bool pinned = false) {
+    if (need <= *cap && *p) return 0;
+    size_t ncap = std::max(need, *cap + *cap / 2);
+    if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; }
+    cudaError_t e = pinned ? cudaMallocHost((void **)p, ncap * sizeof(T)) : cudaMalloc((void **)p, ncap * sizeof(T));
+    if (e != cudaSuccess) { set_error(ctx, "allocation of %zu bytes failed: %s", ncap * sizeof(T), cudaGetErrorString(e)); *cap = 0; return BSL_ENOMEM; }
+    *cap = ncap; return 0;
+}
+
+} // namespace
+
+void bsl_lane_free(Lane &ln) {
+    cudaFree(ln.d_bases); cudaFree(ln.d_off); cudaFree(ln.d_index); cudaFree(ln.d_rawlen); cudaFree(ln.d_meta); cudaFree(ln.d_cnt); cudaFree(ln.d_sched); cudaFree(ln.d_stat);
+    cudaFree(ln.d_planes); cudaFree(ln.d_hits); cudaFree(ln.d_heavy_hits); cudaFree(ln.d_list[0]); cudaFree(ln.d_list[1]); cudaFree(ln.d_heavy_list);
+    cudaFree(ln.d_pe_list[0]); cudaFree(ln.d_pe_list[1]); cudaFree(ln.d_out); cudaFree(ln.d_pair); cudaFree(ln.d_all[0]); cudaFree(ln.d_all[1]); cudaFree(ln.d_ctr);
+    if (ln.h_ctr) cudaFreeHost(ln.h_ctr);
+    for (auto &e : ln.ev) if (e) cudaEventDestroy(e);
+    if (ln.stream) cudaStreamDestroy(ln.stream);
+    ln.stream = nullptr;
+}
+
+int bsl_upload_params(bsl_ctx *ctx) {
+    // device copy of the rule / budget / profile tables (one per context)
+    DevTables h; memset(&h, 0, sizeof h);
+    h.rule = ctx->rule;
+    const bsl_params &P = ctx->P;
+    for (u32 raw = 0; raw <= BSL_MAX_READLEN; raw++) {                       // FilterReads, align.cpp:550-556
+        u32 B = P.max_snp_num < 100 ? P.max_snp_num : (u32)((P.max_snp_num - 100) / 100.0 * raw + 0.5);
+        if (P.gap > 0) B = B + 1 + P.gap;
+        if (B > BSL_MAXSNPS) B = BSL_MAXSNPS;
+        h.budget0[raw] = B;
+    }
+    for (u32 i = 0; i < P.index_interval && i < 16; i++) for (u32 j = 0; j <= BSL_MAXSNPS; j++)
+        h.prof[j][i] = (u16)(((j * P.seed_size + i + P.index_interval - 1) / P.index_interval) * P.index_interval);   // param.cpp:70-74
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    if (!ctx->d_tables) CUDA_TRY(cudaMalloc(&ctx->d_tables, sizeof(DevTables)));
+    CUDA_TRY(cudaMemcpy(ctx->d_tables, &h, sizeof h, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int ensure_lane(bsl_ctx *ctx, Lane &ln) {
+    if (ln.stream) return 0;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+    for (auto &e : ln.ev) CUDA_TRY(cudaEventCreate(&e));
+    CUDA_TRY(cudaMalloc(&ln.d_ctr, sizeof(DevCounters)));
+    CUDA_TRY(cudaMallocHost(&ln.h_ctr, sizeof(DevCounters)));
+    return 0;
+}
+
+static u32 max_len_of(const bsl_batch *b) {
+    u32 mx = 0; for (u32 i = 0; i < b->n; i++) { u64 l = b->offsets[i + 1] - b->offsets[i]; if (l > mx) mx = (u32)std::min<u64>(l, 0xffffffffu); } return mx;
+}
+
+int bsl_align_impl(bsl_ctx *ctx, const bsl_batch *a, const bsl_batch *b, bsl_hit *out_a, bsl_hit *out_b, bsl_pair *out_pair,
+                   bsl_hit *all_a, bsl_hit *all_b, u64 all_cap, u64 *n_all) {
+    if (!ctx->has_index) { set_error(ctx, "bsl_align: no index (call bsl_index_build first)"); return BSL_ESTATE; }
+    if (!a || !out_a || (b && (!out_b || !out_pair))) { set_error(ctx, "bsl_align: null argument"); return BSL_EINVAL; }
+    if (b && a->n != b->n) { set_error(ctx, "bsl_align_pe: batches differ in size (%u vs %u)", a->n, b->n); return BSL_EINVAL; }
+    if (n_all) *n_all = 0;
+    const u32 n_a = a->n; const bool pe = b != nullptr; const u32 n_slots = pe ? 2 * n_a : n_a;
+    if (n_a == 0) return 0;
+    if (n_slots >= 0x7fffffffu) { set_error(ctx, "batch too large"); return BSL_ELIMIT; }
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    // pick a lane
+    Lane *lnp = nullptr; std::unique_lock<std::mutex> lk;
+    for (int t = 0; t < 2 && !lnp; t++) { std::unique_lock<std::mutex> l(ctx->lanes[t].mu, std::try_to_lock); if (l.owns_lock()) { lk = std::move(l); lnp = &ctx->lanes[t]; } }
+    if (!lnp) { lk = std::unique_lock<std::mutex>(ctx->lanes[0].mu); lnp = &ctx->lanes[0]; }
+    Lane &ln = *lnp;
+    int rc = ensure_lane(ctx, ln); if (rc) return rc;
+    cudaStream_t st = ln.stream;
+
+    const u64 bases_a = a->offsets[n_a], bases_b = pe ? b->offsets[n_a] : 0;
+    u32 Lmax = max_len_of(a); if (pe) Lmax = std::max(Lmax, max_len_of(b));
+    if (Lmax > BSL_MAX_READLEN) Lmax = BSL_MAX_READLEN;       // longer reads are flagged filtered by prepare_reads; the CLI truncates like the reference
+    const u32 Wb = std::max(1u, (Lmax + 31) / 32);
+    const u32 cap = 32;
+    const char *env_cap = getenv("BSL_HIT_CAP"); const u32 cap_main = env_cap ? std::max(2, atoi(env_cap)) : cap;
+
+    // ---- buffers
+    size_t c0;
+    c0 = ln.cap_bases; if ((rc = grow(ctx, &ln.d_bases, &c0, (size_t)(bases_a + bases_b + 16)))) return rc; ln.cap_bases = c0;
+    {
+        size_t need = n_slots + 2;
+        if (need > ln.cap_slots) {
+            size_t ncap = std::max(need, ln.cap_slots + ln.cap_slots / 2);
+            cudaFree(ln.d_off); cudaFree(ln.d_index); cudaFree(ln.d_rawlen); cudaFree(ln.d_meta); cudaFree(ln.d_cnt); cudaFree(ln.d_sched); cudaFree(ln.d_stat);
+            cudaFree(ln.d_list[0]); cudaFree(ln.d_list[1]); cudaFree(ln.d_pe_list[0]); cudaFree(ln.d_pe_list[1]); cudaFree(ln.d_heavy_list); cudaFree(ln.d_out); cudaFree(ln.d_pair);
+            ln.cap_slots = 0;
+            CUDA_TRY(cudaMalloc(&ln.d_off, (ncap + 4) * 8)); CUDA_TRY(cudaMalloc(&ln.d_index, ncap * 4)); CUDA_TRY(cudaMalloc(&ln.d_rawlen, ncap * 2));
+            CUDA_TRY(cudaMalloc(&ln.d_meta, ncap * sizeof(SlotMeta))); CUDA_TRY(cudaMalloc(&ln.d_cnt, ncap * sizeof(SlotCounts))); CUDA_TRY(cudaMalloc(&ln.d_sched, ncap * 32)); CUDA_TRY(cudaMalloc(&ln.d_stat, ncap * sizeof(uint2)));
+            for (int k = 0; k < 2; k++) { CUDA_TRY(cudaMalloc(&ln.d_list[k], ncap * 4)); CUDA_TRY(cudaMalloc(&ln.d_pe_list[k], ncap * 4)); }
+            CUDA_TRY(cudaMalloc(&ln.d_heavy_list, ncap * 4)); CUDA_TRY(cudaMalloc(&ln.d_out, ncap * sizeof(bsl_hit))); CUDA_TRY(cudaMalloc(&ln.d_pair, ncap * sizeof(bsl_pair)));
+            ln.cap_slots = ncap;
+        }
+    }
+    c0 = ln.cap_words; if ((rc = grow(ctx, &ln.d_planes, &c0, (size_t)n_slots * 6 * Wb))) return rc; ln.cap_words = c0;
+    c0 = ln.cap_hits; if ((rc = grow(ctx, &ln.d_hits, &c0, (size_t)n_slots * cap_main))) return rc; ln.cap_hits = c0;
+    const bool want_all = ctx->P.report_repeat_hits == 2 && all_a && (!pe || all_b) && all_cap > 0;
+    if (want_all) {
+        if (all_cap > ln.cap_all) { cudaFree(ln.d_all[0]); cudaFree(ln.d_all[1]); ln.cap_all = 0;
+            CUDA_TRY(cudaMalloc(&ln.d_all[0], all_cap * sizeof(bsl_hit))); CUDA_TRY(cudaMalloc(&ln.d_all[1], all_cap * sizeof(bsl_hit))); ln.cap_all = all_cap; }
+    }
+
+    // ---- kernel arguments
+    KArgs A; memset(&A, 0, sizeof A);
+    A.di = ctx->di; A.tab = (const DevTables *)ctx->d_tables;
+    const bsl_params &P = ctx->P;
+    A.s = P.seed_size; A.I = P.index_interval; A.gap = P.gap; A.w = P.max_num_hits; A.min_insert = P.min_insert; A.max_insert = P.max_insert;
+    A.chains = P.chains; A.report = P.report_repeat_hits; A.randseed = P.randseed; A.max_ns = P.max_ns; A.min_read_size = P.min_read_size; A.single = ctx->rule.single;
+    A.n_slots = n_slots; A.n_a = n_a; A.pe = pe; A.readset_a = a->readset; A.readset_b = pe ? b->readset : 0;
+    A.bases = ln.d_bases; A.off = ln.d_off; A.index = ln.d_index; A.rawlen = ln.d_rawlen; A.first_index_a = a->first_index; A.first_index_b = pe ? b->first_index : 0;
+    A.bases_b_shift = bases_a; A.has_index = (a->index != nullptr) && (!pe || b->index != nullptr); A.has_rawlen = (a->raw_len != nullptr) && (!pe || b->raw_len != nullptr);
+    A.Wb = Wb; A.planes = ln.d_planes; A.sched = ln.d_sched; A.meta = ln.d_meta; A.cnt = ln.d_cnt; A.stat = ln.d_stat; A.hits = ln.d_hits; A.cap = cap_main; A.ctr = ln.d_ctr;
+    A.out = ln.d_out; A.pair_out = ln.d_pair; A.all_a = want_all ? ln.d_all[0] : nullptr; A.all_b = want_all ? ln.d_all[1] : nullptr; A.all_cap = want_all ? all_cap : 0;
+
+    // ---- H2D
+    CUDA_TRY(cudaEventRecord(ln.ev[0], st));
+    CUDA_TRY(cudaMemsetAsync(ln.d_ctr, 0, sizeof(DevCounters), st));
+    CUDA_TRY(cudaMemcpyAsync(ln.d_bases, a->bases, bases_a, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ln.d_off, a->offsets, (size_t)(n_a + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (pe) {
+        CUDA_TRY(cudaMemcpyAsync(ln.d_bases + bases_a, b->bases, bases_b, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ln.d_off + (n_a + 1), b->offsets, (size_t)(n_a + 1) * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemsetAsync(ln.d_pair, 0, (size_t)n_a * sizeof(bsl_pair), st));
+    }
+    if (A.has_index) { CUDA_TRY(cudaMemcpyAsync(ln.d_index, a->index, (size_t)n_a * 4, cudaMemcpyHostToDevice, st));
+        if (pe) CUDA_TRY(cudaMemcpyAsync(ln.d_index + n_a, b->index, (size_t)n_a * 4, cudaMemcpyHostToDevice, st)); }
+    if (A.has_rawlen) { CUDA_TRY(cudaMemcpyAsync(ln.d_rawlen, a->raw_len, (size_t)n_a * 2, cudaMemcpyHostToDevice, st));
+        if (pe) CUDA_TRY(cudaMemcpyAsync(ln.d_rawlen + n_a, b->raw_len, (size_t)n_a * 2, cudaMemcpyHostToDevice, st)); }
+
+    u64 launches = 0;
+    const int grid_p = ctx->sm_count * 8;
+    CUDA_TRY(cudaEventRecord(ln.ev[1], st));
+    prepare_reads<<<std::min<u32>((n_slots + PREP_WARPS - 1) / PREP_WARPS, (u32)grid_p * 4), PREP_WARPS * 32, 0, st>>>(A); launches++;
+    build_lists<<<(std::max(n_slots, n_a) + 255) / 256, 256, 0, st>>>(A, ln.d_list[0], ln.d_pe_list[0]); launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(ln.ev[2], st));
+
+    const u32 G = P.gap;
+    const u32 NW = (31 + 2 * G + Lmax + 31) / 32; const u32 NWS = NW | 1u;
+    const size_t smem = (size_t)ROUND_WARPS * (32 * NWS + 48) * 8;
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(search_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(search_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr_set = true; }
+    const u32 rounds_se = std::min<u32>((Lmax + 1 >= P.index_interval + P.seed_size) ? (Lmax + 1 - P.index_interval) / P.seed_size : 0, 16);
+    const int grid_r = ctx->sm_count * 4;
+
+    auto run_passes = [&](KArgs &K) -> int {
+        // SE rounds (stop rule inside the kernel)
+        KArgs Kse = K; Kse.pe = 0;
+        for (u32 r = 0; r < rounds_se; r++) {
+            if (ctx->rule.single) search_round<true><<<grid_r, ROUND_WARPS * 32, smem, st>>>(Kse, r, ln.d_list[r & 1], ln.d_list[(r + 1) & 1], r, NW, NWS);
+            else search_round<false><<<grid_r, ROUND_WARPS * 32, smem, st>>>(Kse, r, ln.d_list[r & 1], ln.d_list[(r + 1) & 1], r, NW, NWS);
+            launches++;
+        }
+        if (K.pe) {
+            for (u32 r = 0; r <= BSL_MAXSNPS; r++) {
+                if (r < rounds_se) {
+                    if (ctx->rule.single) search_round<true><<<grid_r, ROUND_WARPS * 32, smem, st>>>(K, r, ln.d_pe_list[r & 1], nullptr, 20 + r, NW, NWS);
+                    else search_round<false><<<grid_r, ROUND_WARPS * 32, smem, st>>>(K, r, ln.d_pe_list[r & 1], nullptr, 20 + r, NW, NWS);
+                    launches++;
+                }
+                pair_round<<<ctx->sm_count * 4, 128, 0, st>>>(K, r, ln.d_pe_list[r & 1], ln.d_pe_list[(r + 1) & 1], 20 + r); launches++;
+            }
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { set_error(ctx, "kernel launch failed: %s", cudaGetErrorString(e)); return BSL_ECUDA; }
+        return 0;
+    };
+    if ((rc = run_passes(A))) return rc;
+    CUDA_TRY(cudaEventRecord(ln.ev[3], st));
+    finalize_reads<<<(n_slots + 255) / 256, 256, 0, st>>>(A, nullptr, 0); launches++;
+    CUDA_TRY(cudaMemcpyAsync(ln.h_ctr, ln.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    DevCounters c1 = *ln.h_ctr;
+    u64 heavy_total = 0;
+    if (c1.overflow_n > 0) {
+        // ---- heavy pass: re-run the overflowed reads / pairs from scratch with room for every list (16 levels x -w)
+        u32 *d_nheavy = &ln.d_ctr->overflow_n;
+        CUDA_TRY(cudaMemsetAsync(d_nheavy, 0, 4, st));
+        const u32 n_items = pe ? n_a : n_slots;
+        collect_overflow<<<(n_items + 255) / 256, 256, 0, st>>>(A, ln.d_heavy_list, d_nheavy); launches++;
+        u32 n_heavy = 0; CUDA_TRY(cudaMemcpyAsync(&n_heavy, d_nheavy, 4, cudaMemcpyDeviceToHost, st)); CUDA_TRY(cudaStreamSynchronize(st));
+        heavy_total = n_heavy;
+        const u32 hcap = std::min<u32>(16 * P.max_num_hits + 32, 65535u);
+        const u32 per_item = pe ? 2 : 1;
+        u32 chunk = (u32)std::max<u64>(1, (1ull << 30) / ((u64)hcap * 16 * per_item));
+        chunk = std::min(chunk, n_heavy);
+        c0 = ln.cap_heavy_hits; if ((rc = grow(ctx, &ln.d_heavy_hits, &c0, (size_t)chunk * per_item * hcap))) return rc; ln.cap_heavy_hits = c0;
+        KArgs H = A; H.hits = ln.d_heavy_hits; H.cap = hcap;
+        u32 *d_slots = ln.d_list[0];     // reused after the rounds as scratch for finalize's slot list (rounds use it first, so take pe_list[1]... see below)
+        for (u32 first = 0; first < n_heavy; first += chunk) {
+            const u32 count = std::min(chunk, n_heavy - first);
+            CUDA_TRY(cudaMemsetAsync(ln.d_ctr->active, 0, sizeof(u32) * 80, st));
+            reset_heavy<<<(count + 127) / 128, 128, 0, st>>>(H, ln.d_heavy_list, first, count, ln.d_list[0], ln.d_pe_list[0]); launches++;
+            if ((rc = run_passes(H))) return rc;
+            d_slots = ln.d_list[0];
+            expand_pairs_to_slots<<<(count + 127) / 128, 128, 0, st>>>(ln.d_heavy_list, first, count, n_a, pe, d_slots); launches++;
+            finalize_reads<<<(count * per_item + 255) / 256, 256, 0, st>>>(H, d_slots, count * per_item); launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaMemcpyAsync(ln.h_ctr, ln.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+    }
+    CUDA_TRY(cudaEventRecord(ln.ev[4], st));
+    // ---- D2H
+    CUDA_TRY(cudaMemcpyAsync(out_a, ln.d_out, (size_t)n_a * sizeof(bsl_hit), cudaMemcpyDeviceToHost, st));
+    if (pe) { CUDA_TRY(cudaMemcpyAsync(out_b, ln.d_out + n_a, (size_t)n_a * sizeof(bsl_hit), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(out_pair, ln.d_pair, (size_t)n_a * sizeof(bsl_pair), cudaMemcpyDeviceToHost, st)); }
+    CUDA_TRY(cudaEventRecord(ln.ev[5], st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    DevCounters c2 = *ln.h_ctr;
+    if (want_all) {
+        u64 na_ = std::min<u64>(c2.all_n, all_cap);
+        if (na_) { CUDA_TRY(cudaMemcpy(all_a, ln.d_all[0], na_ * sizeof(bsl_hit), cudaMemcpyDeviceToHost));
+            if (pe) CUDA_TRY(cudaMemcpy(all_b, ln.d_all[1], na_ * sizeof(bsl_hit), cudaMemcpyDeviceToHost)); }
+        if (n_all) *n_all = c2.all_n;
+    }
+    float ms_pack = 0, ms_search = 0, ms_total = 0, ms_h2d = 0;
+    cudaEventElapsedTime(&ms_h2d, ln.ev[0], ln.ev[1]); cudaEventElapsedTime(&ms_pack, ln.ev[1], ln.ev[2]);
+    cudaEventElapsedTime(&ms_search, ln.ev[2], ln.ev[3]); cudaEventElapsedTime(&ms_total, ln.ev[0], ln.ev[5]);
+    {
+        std::lock_guard<std::mutex> g(ctx->stats_mu);
+        bsl_stats &S = ctx->stats; memset(&S, 0, sizeof S);
+        S.reads = n_slots; S.seed_lookups = c2.seed_lookups; S.candidates = c2.candidates; S.hits_added = c2.hits_added; S.heavy_reads = heavy_total;
+        S.ms_pack = ms_pack; S.ms_search = ms_search; S.ms_pair = 0; S.ms_total = ms_total; S.kernel_launches = launches;
+        const u32 Wd = (Lmax + 31) / 32 + 1 + (G ? 1 : 0);
+        S.verify_bytes = c2.candidates * (4 + 8ull * Wd);
+    }
+    return 0;
+}

@@ -496,7 +496,8 @@ int orc_align_pe(orc_ctx *c, const bsl_batch *a, const bsl_batch *b, bsl_hit *oa
             u32 k = (u32)ph[l].size(); op[i].n_pairs = k;
             if (k > 1 && C.P.report_repeat_hits == 0) break;                             // suppressed: mates reported unpaired
             u32 pick = k == 1 ? 0 : A.S.Rnd % k; const PairRec &pr = ph[l][pick];
-            report_single(A, oa[i], nullptr); report_single(B, ob[i], nullptr);          // fills len/budget
+            memset(&oa[i], 0, sizeof oa[i]); memset(&ob[i], 0, sizeof ob[i]);
+            oa[i].read_len = (uint16_t)A.S.L; ob[i].read_len = (uint16_t)B.S.L; oa[i].max_snp = (u8)A.S.B; ob[i].max_snp = (u8)B.S.B;
             fill_hit(oa[i], pr.a, pr.chain, pr.na); fill_hit(ob[i], pr.b, 1 - pr.chain, pr.nb);
             oa[i].status = ob[i].status = BSL_ST_PAIRED; oa[i].n_hits = ob[i].n_hits = k;
             op[i].insert = pr.insert; op[i].chain = (u8)pr.chain; op[i].na = (u8)pr.na; op[i].nb = (u8)pr.nb;
