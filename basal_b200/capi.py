@@ -48,7 +48,8 @@ class IndexInfo(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("reads", C.c_uint64), ("seed_lookups", C.c_uint64), ("candidates", C.c_uint64), ("hits_added", C.c_uint64),
                 ("heavy_reads", C.c_uint64), ("ms_pack", C.c_double), ("ms_search", C.c_double), ("ms_pair", C.c_double),
-                ("ms_total", C.c_double), ("kernel_launches", C.c_uint64), ("verify_bytes", C.c_uint64)]
+                ("ms_total", C.c_double), ("kernel_launches", C.c_uint64), ("verify_bytes", C.c_uint64),
+                ("ms_device", C.c_double), ("search_launches", C.c_uint64)]
 
 
 def parse_v(text: str) -> int:
@@ -105,6 +106,8 @@ class _Api:
             self.host_alloc = f("host_alloc"); self.host_alloc.restype = vp; self.host_alloc.argtypes = [C.c_size_t]
             self.host_free = f("host_free"); self.host_free.argtypes = [vp]; self.host_free.restype = None
             self.abi_version = f("abi_version"); self.abi_version.restype = C.c_int
+            self.align_rerun = f("align_rerun"); self.align_rerun.restype = C.c_int
+            self.align_rerun.argtypes = [vp, C.POINTER(Batch), C.POINTER(Batch)]
 
 
 _gpu_api: Optional[_Api] = None
@@ -234,6 +237,11 @@ class Context:
             k = min(n_all.value, all_cap)
             return oa, ob, op, alla[:k], allb[:k]
         return oa, ob, op
+
+    def align_rerun(self, a: ReadBatch, b: Optional[ReadBatch] = None):
+        """Kernels only, on the batch the previous align call left resident on the device (bench hook)."""
+        sa = a.struct(); sb = b.struct() if b is not None else None
+        self._check(self.api.align_rerun(self._h, C.byref(sa), C.byref(sb) if b is not None else None), "align_rerun")
 
     def stats(self) -> Stats:
         s = Stats(); self.api.stats_get(self._h, C.byref(s)); return s

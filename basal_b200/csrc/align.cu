@@ -628,6 +628,7 @@ void bsl_lane_free(Lane &ln) {
     cudaFree(ln.d_pe_list[0]); cudaFree(ln.d_pe_list[1]); cudaFree(ln.d_out); cudaFree(ln.d_pair); cudaFree(ln.d_all[0]); cudaFree(ln.d_all[1]); cudaFree(ln.d_ctr);
     if (ln.h_ctr) cudaFreeHost(ln.h_ctr);
     for (auto &e : ln.ev) if (e) cudaEventDestroy(e);
+    for (auto &e : ln.evk) if (e) cudaEventDestroy(e);
     if (ln.stream) cudaStreamDestroy(ln.stream);
     ln.stream = nullptr;
 }
@@ -655,6 +656,7 @@ static int ensure_lane(bsl_ctx *ctx, Lane &ln) {
     if (ln.stream) return 0;
     CUDA_TRY(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
     for (auto &e : ln.ev) CUDA_TRY(cudaEventCreate(&e));
+    for (auto &e : ln.evk) CUDA_TRY(cudaEventCreate(&e));
     CUDA_TRY(cudaMalloc(&ln.d_ctr, sizeof(DevCounters)));
     CUDA_TRY(cudaMallocHost(&ln.h_ctr, sizeof(DevCounters)));
     return 0;
@@ -665,9 +667,9 @@ static u32 max_len_of(const bsl_batch *b) {
 }
 
 int bsl_align_impl(bsl_ctx *ctx, const bsl_batch *a, const bsl_batch *b, bsl_hit *out_a, bsl_hit *out_b, bsl_pair *out_pair,
-                   bsl_hit *all_a, bsl_hit *all_b, u64 all_cap, u64 *n_all) {
+                   bsl_hit *all_a, bsl_hit *all_b, u64 all_cap, u64 *n_all, int resident) {
     if (!ctx->has_index) { set_error(ctx, "bsl_align: no index (call bsl_index_build first)"); return BSL_ESTATE; }
-    if (!a || !out_a || (b && (!out_b || !out_pair))) { set_error(ctx, "bsl_align: null argument"); return BSL_EINVAL; }
+    if (!a || (!resident && (!out_a || (b && (!out_b || !out_pair))))) { set_error(ctx, "bsl_align: null argument"); return BSL_EINVAL; }
     if (b && a->n != b->n) { set_error(ctx, "bsl_align_pe: batches differ in size (%u vs %u)", a->n, b->n); return BSL_EINVAL; }
     if (n_all) *n_all = 0;
     const u32 n_a = a->n; const bool pe = b != nullptr; const u32 n_slots = pe ? 2 * n_a : n_a;
@@ -729,16 +731,18 @@ int bsl_align_impl(bsl_ctx *ctx, const bsl_batch *a, const bsl_batch *b, bsl_hit
     // ---- H2D
     CUDA_TRY(cudaEventRecord(ln.ev[0], st));
     CUDA_TRY(cudaMemsetAsync(ln.d_ctr, 0, sizeof(DevCounters), st));
+    if (!resident) {
     CUDA_TRY(cudaMemcpyAsync(ln.d_bases, a->bases, bases_a, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(ln.d_off, a->offsets, (size_t)(n_a + 1) * 8, cudaMemcpyHostToDevice, st));
     if (pe) {
         CUDA_TRY(cudaMemcpyAsync(ln.d_bases + bases_a, b->bases, bases_b, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(ln.d_off + (n_a + 1), b->offsets, (size_t)(n_a + 1) * 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemsetAsync(ln.d_pair, 0, (size_t)n_a * sizeof(bsl_pair), st));
     }
-    if (A.has_index) { CUDA_TRY(cudaMemcpyAsync(ln.d_index, a->index, (size_t)n_a * 4, cudaMemcpyHostToDevice, st));
+    }
+    if (pe) CUDA_TRY(cudaMemsetAsync(ln.d_pair, 0, (size_t)n_a * sizeof(bsl_pair), st));
+    if (A.has_index && !resident) { CUDA_TRY(cudaMemcpyAsync(ln.d_index, a->index, (size_t)n_a * 4, cudaMemcpyHostToDevice, st));
         if (pe) CUDA_TRY(cudaMemcpyAsync(ln.d_index + n_a, b->index, (size_t)n_a * 4, cudaMemcpyHostToDevice, st)); }
-    if (A.has_rawlen) { CUDA_TRY(cudaMemcpyAsync(ln.d_rawlen, a->raw_len, (size_t)n_a * 2, cudaMemcpyHostToDevice, st));
+    if (A.has_rawlen && !resident) { CUDA_TRY(cudaMemcpyAsync(ln.d_rawlen, a->raw_len, (size_t)n_a * 2, cudaMemcpyHostToDevice, st));
         if (pe) CUDA_TRY(cudaMemcpyAsync(ln.d_rawlen + n_a, b->raw_len, (size_t)n_a * 2, cudaMemcpyHostToDevice, st)); }
 
     u64 launches = 0;
@@ -758,22 +762,29 @@ int bsl_align_impl(bsl_ctx *ctx, const bsl_batch *a, const bsl_batch *b, bsl_hit
     const u32 rounds_se = std::min<u32>((Lmax + 1 >= P.index_interval + P.seed_size) ? (Lmax + 1 - P.index_interval) / P.seed_size : 0, 16);
     const int grid_r = ctx->sm_count * 4;
 
+    int nev = 0; std::vector<char> ev_kind;           // per-launch CUDA-event pairs: 's' search_round, 'p' pair_round
+    auto ev_begin = [&](char kind) { if (nev + 2 <= (int)(sizeof ln.evk / sizeof ln.evk[0])) { cudaEventRecord(ln.evk[nev], st); ev_kind.push_back(kind); } };
+    auto ev_end = [&]() { if (nev + 2 <= (int)(sizeof ln.evk / sizeof ln.evk[0])) { cudaEventRecord(ln.evk[nev + 1], st); nev += 2; } };
     auto run_passes = [&](KArgs &K) -> int {
         // SE rounds (stop rule inside the kernel)
         KArgs Kse = K; Kse.pe = 0;
         for (u32 r = 0; r < rounds_se; r++) {
+            ev_begin('s');
             if (ctx->rule.single) search_round<true><<<grid_r, ROUND_WARPS * 32, smem, st>>>(Kse, r, ln.d_list[r & 1], ln.d_list[(r + 1) & 1], r, NW, NWS);
             else search_round<false><<<grid_r, ROUND_WARPS * 32, smem, st>>>(Kse, r, ln.d_list[r & 1], ln.d_list[(r + 1) & 1], r, NW, NWS);
-            launches++;
+            ev_end(); launches++;
         }
         if (K.pe) {
             for (u32 r = 0; r <= BSL_MAXSNPS; r++) {
                 if (r < rounds_se) {
+                    ev_begin('s');
                     if (ctx->rule.single) search_round<true><<<grid_r, ROUND_WARPS * 32, smem, st>>>(K, r, ln.d_pe_list[r & 1], nullptr, 20 + r, NW, NWS);
                     else search_round<false><<<grid_r, ROUND_WARPS * 32, smem, st>>>(K, r, ln.d_pe_list[r & 1], nullptr, 20 + r, NW, NWS);
-                    launches++;
+                    ev_end(); launches++;
                 }
-                pair_round<<<ctx->sm_count * 4, 128, 0, st>>>(K, r, ln.d_pe_list[r & 1], ln.d_pe_list[(r + 1) & 1], 20 + r); launches++;
+                ev_begin('p');
+                pair_round<<<ctx->sm_count * 4, 128, 0, st>>>(K, r, ln.d_pe_list[r & 1], ln.d_pe_list[(r + 1) & 1], 20 + r);
+                ev_end(); launches++;
             }
         }
         cudaError_t e = cudaGetLastError();
@@ -816,26 +827,28 @@ int bsl_align_impl(bsl_ctx *ctx, const bsl_batch *a, const bsl_batch *b, bsl_hit
     }
     CUDA_TRY(cudaEventRecord(ln.ev[4], st));
     // ---- D2H
+    if (!resident) {
     CUDA_TRY(cudaMemcpyAsync(out_a, ln.d_out, (size_t)n_a * sizeof(bsl_hit), cudaMemcpyDeviceToHost, st));
     if (pe) { CUDA_TRY(cudaMemcpyAsync(out_b, ln.d_out + n_a, (size_t)n_a * sizeof(bsl_hit), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(out_pair, ln.d_pair, (size_t)n_a * sizeof(bsl_pair), cudaMemcpyDeviceToHost, st)); }
+    }
     CUDA_TRY(cudaEventRecord(ln.ev[5], st));
     CUDA_TRY(cudaStreamSynchronize(st));
     DevCounters c2 = *ln.h_ctr;
-    if (want_all) {
+    if (want_all && !resident) {
         u64 na_ = std::min<u64>(c2.all_n, all_cap);
         if (na_) { CUDA_TRY(cudaMemcpy(all_a, ln.d_all[0], na_ * sizeof(bsl_hit), cudaMemcpyDeviceToHost));
             if (pe) CUDA_TRY(cudaMemcpy(all_b, ln.d_all[1], na_ * sizeof(bsl_hit), cudaMemcpyDeviceToHost)); }
         if (n_all) *n_all = c2.all_n;
     }
-    float ms_pack = 0, ms_search = 0, ms_total = 0, ms_h2d = 0;
-    cudaEventElapsedTime(&ms_h2d, ln.ev[0], ln.ev[1]); cudaEventElapsedTime(&ms_pack, ln.ev[1], ln.ev[2]);
-    cudaEventElapsedTime(&ms_search, ln.ev[2], ln.ev[3]); cudaEventElapsedTime(&ms_total, ln.ev[0], ln.ev[5]);
+    float ms_pack = 0, ms_search = 0, ms_pair = 0, ms_total = 0, ms_dev = 0; u64 n_search = 0;
+    cudaEventElapsedTime(&ms_pack, ln.ev[1], ln.ev[2]); cudaEventElapsedTime(&ms_total, ln.ev[0], ln.ev[5]); cudaEventElapsedTime(&ms_dev, ln.ev[1], ln.ev[4]);
+    for (int k = 0; k + 1 < nev; k += 2) { float t = 0; cudaEventElapsedTime(&t, ln.evk[k], ln.evk[k + 1]); if (ev_kind[k / 2] == 's') { ms_search += t; n_search++; } else ms_pair += t; }
     {
         std::lock_guard<std::mutex> g(ctx->stats_mu);
         bsl_stats &S = ctx->stats; memset(&S, 0, sizeof S);
         S.reads = n_slots; S.seed_lookups = c2.seed_lookups; S.candidates = c2.candidates; S.hits_added = c2.hits_added; S.heavy_reads = heavy_total;
-        S.ms_pack = ms_pack; S.ms_search = ms_search; S.ms_pair = 0; S.ms_total = ms_total; S.kernel_launches = launches;
+        S.ms_pack = ms_pack; S.ms_search = ms_search; S.ms_pair = ms_pair; S.ms_total = ms_total; S.ms_device = ms_dev; S.kernel_launches = launches; S.search_launches = n_search;
         const u32 Wd = (Lmax + 31) / 32 + 1 + (G ? 1 : 0);
         S.verify_bytes = c2.candidates * (4 + 8ull * Wd);
     }

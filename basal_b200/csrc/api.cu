@@ -82,14 +82,19 @@ void bsl_index_free(bsl_ctx *ctx) { bsl_index_free_impl(ctx); }
 
 int bsl_align_se(bsl_ctx *ctx, const bsl_batch *reads, bsl_hit *out, bsl_hit *all_hits, uint64_t all_cap, uint64_t *n_all) {
     if (!ctx) return BSL_EINVAL;
-    return bsl_align_impl(ctx, reads, nullptr, out, nullptr, nullptr, all_hits, nullptr, all_cap, n_all);
+    return bsl_align_impl(ctx, reads, nullptr, out, nullptr, nullptr, all_hits, nullptr, all_cap, n_all, 0);
 }
 
 int bsl_align_pe(bsl_ctx *ctx, const bsl_batch *a, const bsl_batch *b, bsl_hit *out_a, bsl_hit *out_b, bsl_pair *out_pair,
                  bsl_hit *all_a, bsl_hit *all_b, uint64_t all_cap, uint64_t *n_all) {
     if (!ctx) return BSL_EINVAL;
     if (!b) { set_error(ctx, "bsl_align_pe: second batch is null"); return BSL_EINVAL; }
-    return bsl_align_impl(ctx, a, b, out_a, out_b, out_pair, all_a, all_b, all_cap, n_all);
+    return bsl_align_impl(ctx, a, b, out_a, out_b, out_pair, all_a, all_b, all_cap, n_all, 0);
+}
+
+int bsl_align_rerun(bsl_ctx *ctx, const bsl_batch *a, const bsl_batch *b) {
+    if (!ctx) return BSL_EINVAL;
+    return bsl_align_impl(ctx, a, b, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, 1);
 }
 
 int bsl_stats_get(const bsl_ctx *ctx, bsl_stats *st) {

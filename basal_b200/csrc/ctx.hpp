@@ -13,6 +13,7 @@
 struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
+    cudaEvent_t evk[160] = {};   // per-launch timing of search_round / pair_round
     std::mutex mu;
     // capacities
     size_t cap_slots = 0, cap_bases = 0, cap_words = 0, cap_hits = 0, cap_heavy_hits = 0, cap_pairs = 0;
@@ -63,6 +64,6 @@ void bsl_index_free_impl(bsl_ctx *ctx);
 int  bsl_index_download_impl(const bsl_ctx *ctx, u32 *bucket_start, u32 *n_fwd, u32 *loc, u64 *fwd, u64 *rc);
 // align.cu
 int  bsl_align_impl(bsl_ctx *ctx, const bsl_batch *a, const bsl_batch *b, bsl_hit *out_a, bsl_hit *out_b, bsl_pair *out_pair,
-                    bsl_hit *all_a, bsl_hit *all_b, u64 all_cap, u64 *n_all);
+                    bsl_hit *all_a, bsl_hit *all_b, u64 all_cap, u64 *n_all, int resident);
 void bsl_lane_free(Lane &ln);
 int  bsl_upload_params(bsl_ctx *ctx);

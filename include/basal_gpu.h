@@ -128,6 +128,8 @@ typedef struct bsl_stats {
     double   ms_total;       /* first H2D to last D2H                                               */
     uint64_t kernel_launches;
     uint64_t verify_bytes;   /* candidates x (4 + 8 W) algorithmic bytes               */
+    double   ms_device;      /* first kernel to last kernel (inputs resident, records still on device) */
+    uint64_t search_launches;/* search_round launches inside ms_search                               */
 } bsl_stats;
 
 /* -- context ---------------------------------------------------------------------------- */
@@ -169,6 +171,10 @@ int  bsl_align_pe(bsl_ctx *ctx, const bsl_batch *a, const bsl_batch *b,
                   bsl_hit *out_a, bsl_hit *out_b, bsl_pair *out_pair,
                   bsl_hit *all_a, bsl_hit *all_b, uint64_t all_cap, uint64_t *n_all);
 int  bsl_stats_get(const bsl_ctx *ctx, bsl_stats *st);
+/* Measurement hook: run the kernels again on the batch the previous bsl_align_se/pe call of this
+ * thread left resident in device memory (same descriptors; no H2D, no D2H of records).  Used by
+ * bench.py for the inputs-resident throughput; results stay on the device.                        */
+int  bsl_align_rerun(bsl_ctx *ctx, const bsl_batch *a, const bsl_batch *b);
 
 /* Pinned host memory for callers that want zero-copy staging (optional). */
 void *bsl_host_alloc(size_t bytes);

@@ -1,0 +1,103 @@
+"""GPU parity tests at the process boundary: our `basal` CLI against the UNMODIFIED reference binary.
+
+Both programs get the same files and flags (fixed -S); SAM output must be byte-identical except the @PG CL line.
+The reference binary is oracle/_ref/basal (built by oracle/Makefile.ref; it travels to the GPU box).
+"""
+import os
+
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def data(tmp_path_factory):
+    root = tmp_path_factory.mktemp("synth")
+    out = {}
+    for cid, scale in ((1, 0.01), (2, 0.002), (3, 0.002), (4, 0.002), (5, 0.0003)):
+        cfg = helpers.synth.baseline_config(cid, scale)
+        d = str(root / f"c{cid}")
+        paths = helpers.synth.materialise(cfg, d, limit=20000)
+        out[cid] = (cfg, d, paths)
+    return out
+
+
+def _inputs(cfg, paths):
+    a = ["-a", os.path.basename(paths["a"])]
+    if paths["b"]:
+        a += ["-b", os.path.basename(paths["b"])]
+    return a + ["-d", "ref.fa", "-M", cfg.rule] + list(cfg.flags)
+
+
+CASES = [
+    (1, ["-S", "7"]),
+    (1, ["-S", "7", "-u", "-R"]),
+    (1, ["-S", "4321", "-n", "1", "-g", "2", "-u"]),
+    (1, ["-S", "7", "-H", "-B", "101", "-E", "5000"]),
+    (1, ["-S", "7", "-r", "0", "-u", "-w", "2"]),
+    (1, ["-S", "7", "-r", "2", "-w", "5"]),
+    (1, ["-S=9", "-s=12", "-I=2", "-v=4", "-f", "0", "-u"]),
+    (1, ["-S", "7", "-L", "60", "-q", "20", "-A", "AGATCGGAAGAGC", "-u"]),
+    (2, ["-S", "7"]),
+    (2, ["-S", "7", "-u", "-R"]),
+    (2, ["-S", "7", "-m", "250", "-x", "320", "-u"]),
+    (2, ["-S", "7", "-n", "1", "-g", "1", "-u", "-w", "3"]),
+    (2, ["-S", "7", "-r", "0", "-u"]),
+    (3, ["-S", "7"]),
+    (3, ["-S", "7", "-n", "1", "-R", "-u"]),
+    (4, ["-S", "7"]),
+    (4, ["-S", "7", "-n", "1", "-R", "-u"]),
+    (5, ["-S", "7", "-u"]),
+]
+
+
+@pytest.mark.parametrize("cid,extra", CASES)
+def test_cli_matches_reference_binary(data, cid, extra):
+    assert helpers.have_ref(), "oracle/_ref/basal missing: run make -f oracle/Makefile.ref"
+    cfg, d, paths = data[cid]
+    args = _inputs(cfg, paths) + extra
+    want = helpers.run_cli(helpers.REF_BIN, args + ["-p", "1"], d, "ref.sam")
+    got = helpers.run_cli(helpers.GPU_BIN, args, d, "gpu.sam")
+    if got != want:
+        g, w = got.splitlines(), want.splitlines()
+        assert len(g) == len(w), f"{len(g)} lines vs {len(w)} expected"
+        for i, (x, y) in enumerate(zip(g, w)):
+            assert x == y, f"line {i}:\n got {x}\nwant {y}"
+
+
+def test_cli_fasta_reads_and_stdout(data, tmp_path):
+    """FASTA read input (qualities synthesised as 'I') and SAM on stdout."""
+    import subprocess
+    cfg, d, paths = data[1]
+    fa = os.path.join(d, "reads.fa")
+    with open(paths["a"]) as fq, open(fa, "w") as out:
+        for i, line in enumerate(fq):
+            if i >= 4000:
+                break
+            if i % 4 == 0:
+                out.write(">" + line[1:])
+            elif i % 4 == 1:
+                out.write(line)
+    args = ["-a", "reads.fa", "-d", "ref.fa", "-M", "C:T", "-S", "7", "-u"]
+    want = helpers.run_cli(helpers.REF_BIN, args + ["-p", "1"], d, "ref_fa.sam")
+    p = subprocess.run([helpers.GPU_BIN] + args, cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True)
+    lines = p.stdout.decode().splitlines(keepends=True)
+    assert lines[0].startswith("[BASAL @") and "convert-from base: C" in lines[0]      # SetAlign prints to stdout (param.cpp:175,200)
+    assert "convert-to base(s):T" in lines[1]
+    got = "".join(l for l in lines[2:] if not l.startswith("@PG"))
+    assert got == want
+
+
+def test_cli_error_contract(data):
+    import subprocess
+    cfg, d, paths = data[1]
+    r = subprocess.run([helpers.GPU_BIN, "-a", "reads.fq", "-d", "ref.fa", "-Q"], cwd=d, capture_output=True)
+    assert r.returncode == 5 and b"unknown option: -Q" in r.stderr                       # exit(argv index), main.cpp:621-624
+    r = subprocess.run([helpers.GPU_BIN, "-a", "reads.fq", "-d", "ref.fa"], cwd=d, capture_output=True)
+    assert r.returncode == 1 and b"-M option is required" in r.stderr
+    r = subprocess.run([helpers.GPU_BIN, "-a", "reads.fq", "-d", "ref.fa", "-M", "C:C"], cwd=d, capture_output=True)
+    assert r.returncode == 1 and b"should not be equal to ref base" in r.stderr
+    r = subprocess.run([helpers.GPU_BIN, "-a", "nope.fq", "-d", "ref.fa", "-M", "C:T", "-S", "3"], cwd=d, capture_output=True)
+    assert r.returncode == 1 and b"failed to open read file" in r.stderr
