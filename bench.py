@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py — reads aligned per second of the BASAL hot path on B200 (BASELINE.json metric).
+
+Workload at every N: BASELINE.json configs[1] — `-M A:G` paired-end 2x150 bp GLORI-style reads against a
+synthetic 500 Mb reference (24 chromosomes, repeat families, N runs; tools/synth.py, seeds 1002 / 2002).
+One "step" = one pass of the whole hot path (read packing + seed scheduling, seed look-up, candidate
+verification, pairing, best-hit selection) over one batch of STEP_PAIRS synthetic pairs per GPU.
+Reads shard across GPUs (weak scaling: every rank maps its own STEP_PAIRS pairs per step against its own
+replica of the index); there is no collective on the data path.
+
+  value      reads/s with the batch already resident in HBM (kernels only, CUDA events on the launching stream)
+  e2e        reads/s through the C-ABI call a user makes (bsl_align_pe) with pinned HOST buffers: H2D of the
+             bases/offsets and D2H of the result records are inside the timed region
+  roofline   search_round (seed look-up + candidate verification + reduce): algorithmic bytes
+             candidates x (4 + 8 (ceil(L/32)+1)) / kernel time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the unmodified reference binary (oracle/_ref/basal -p <all cores>) on a bounded sample
+
+`--impl reference` times the reference binary itself (CPU) on the same config and prints the same line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+import synth  # noqa: E402
+
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "basal")
+CONFIG_ID = int(os.environ.get("BENCH_CONFIG", "2"))
+SCALE = float(os.environ.get("BENCH_SCALE", "1.0"))            # <1 only for smoke-testing the script itself
+STEP_PAIRS = int(os.environ.get("BENCH_STEP_PAIRS", "1000000"))
+METRIC = "reads_aligned_per_sec"
+UNIT = "reads/s"
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def workload_name(cfg):
+    return (f"configs[{cfg.cid - 1}]: -M {cfg.rule} {'paired-end 2x' if cfg.paired else 'single-end '}{cfg.read_len}bp, "
+            f"synthetic {cfg.ref_len / 1e6:.0f} Mb reference, flags {' '.join(cfg.flags) or '(defaults)'} -S 7")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        self.proc = None
+        self.gpu = gpu
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm / cpu baseline
+
+def run_reference_sample(cfg, chrs, pairs: int, workdir: str, threads: int, index_time: float | None = None):
+    """Run the reference binary on `pairs` simulated pairs. Returns (reads, align_seconds, index_seconds)."""
+    os.makedirs(workdir, exist_ok=True)
+    ref = os.path.join(workdir, "ref.fa")
+    if not os.path.exists(ref):
+        synth.write_fasta(chrs, ref)
+    sim = synth.ReadSimulator(cfg, chrs)
+    fa, fb = os.path.join(workdir, "s_1.fq"), os.path.join(workdir, "s_2.fq")
+    idx = 0
+    first = True
+    for m1, m2 in sim.chunks(chunk=500_000, limit=pairs):
+        synth.write_fastq(fa, m1, idx, "/1" if cfg.paired else "", append=not first)
+        if m2 is not None:
+            synth.write_fastq(fb, m2, idx, "/2", append=not first)
+        idx += len(m1); first = False
+    base = [REF_BIN, "-a", fa] + (["-b", fb] if cfg.paired else []) + ["-d", ref, "-M", cfg.rule] + list(cfg.flags) + ["-S", "7", "-p", str(threads)]
+
+    def timed(extra):
+        t0 = time.perf_counter()
+        subprocess.run(base + extra + ["-o", os.path.join(workdir, "ref_out.sam")], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        return time.perf_counter() - t0
+    if index_time is None:
+        index_time = timed(["-E", "1"])          # load + pack + seed table only
+    total = timed([])
+    reads = idx * (2 if cfg.paired else 1)
+    return reads, max(total - index_time, 1e-3), index_time
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = synth.baseline_config(CONFIG_ID, SCALE)
+    if not os.path.exists(REF_BIN):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/basal not built (run make -f oracle/Makefile.ref)"}))
+        return
+    threads = os.cpu_count() or 1
+    log(f"reference arm: generating {workload_name(cfg)}")
+    chrs = synth.make_reference(cfg)
+    work = tempfile.mkdtemp(prefix="bench_ref_")
+    try:
+        sample = int(os.environ.get("BENCH_REF_PAIRS", str(min(max(200_000, threads * 50_000), 2_000_000))))
+        sample = max(1000, int(sample * min(SCALE * 10, 1.0))) if SCALE < 0.1 else sample
+        budget_s = float(os.environ.get("BENCH_REF_BUDGET", "300"))
+        t_start = time.perf_counter()
+        reads, t_al, t_idx = run_reference_sample(cfg, chrs, sample, work, threads)       # warm-up run, also yields T_index
+        per_run = t_al + t_idx
+        steps = max(1, min(args.steps, int((budget_s - (time.perf_counter() - t_start)) / max(per_run, 1e-3))))
+        times = []
+        for _ in range(steps):
+            r, t, _ = run_reference_sample(cfg, chrs, sample, work, threads, index_time=t_idx)
+            times.append(t)
+        tot_t = sum(times)
+        value = reads * steps / tot_t
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+                "ms_per_step": 1000 * tot_t / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+                "data": "synthetic", "config": {"workload": workload_name(cfg), "sample_pairs_per_step": sample,
+                                                "timing": "wall-clock of the process minus an index-only (-E 1) run"},
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
+                                 "sample": f"{sample} pairs/step, {steps} timed process runs, index time {t_idx:.1f}s subtracted"},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+
+def gpu_arm(args):
+    from basal_b200 import capi
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cfg = synth.baseline_config(CONFIG_ID, SCALE)
+    step_pairs = max(1000, int(STEP_PAIRS * min(1.0, SCALE * 10))) if SCALE < 0.1 else STEP_PAIRS
+    t0 = time.perf_counter()
+    chrs = synth.make_reference(cfg)
+    cat, offs, lens = synth.reference_ascii(chrs)
+    log(f"rank {rank}: reference generated in {time.perf_counter() - t0:.1f}s")
+    params = capi.make_params(rule=cfg.rule, S=7, **_flag_kwargs(cfg))
+    ctx = capi.Context(params, device=local)
+    t0 = time.perf_counter()
+    ctx.index_build(cat, offs, lens)
+    t_index = time.perf_counter() - t0
+    info = ctx.index_info()
+    log(f"rank {rank}: GPU index built in {t_index:.2f}s ({info.n_entries} entries, max_kmer_num {info.max_kmer_num})")
+    # per-rank read shards: each rank simulates its own pairs (weak scaling)
+    sim = synth.ReadSimulator(cfg, chrs)
+    sim.rng = np.random.default_rng(2000 + cfg.cid + 7919 * rank)
+    n_host_batches = 2
+    host = []
+    L = cfg.read_len
+    for m1, m2 in sim.chunks(chunk=step_pairs, limit=step_pairs * n_host_batches):
+        # pinned staging buffers, as a caller that cares about transfer speed would use
+        pa = capi.pinned_array(m1.size); pa[:] = m1.reshape(-1)
+        off = np.arange(len(m1) + 1, dtype=np.uint64) * L
+        a = capi.ReadBatch(pa, off, readset=1 if cfg.paired else 0, first_index=len(host) * step_pairs)
+        b = None
+        if m2 is not None:
+            pb = capi.pinned_array(m2.size); pb[:] = m2.reshape(-1)
+            b = capi.ReadBatch(pb, off.copy(), readset=2, first_index=len(host) * step_pairs)
+        host.append((a, b))
+    n = host[0][0].n
+    reads_per_step = n * (2 if cfg.paired else 1)
+    oa = capi.pinned_array(n * capi.HIT_DTYPE.itemsize).view(capi.HIT_DTYPE)
+    ob = capi.pinned_array(n * capi.HIT_DTYPE.itemsize).view(capi.HIT_DTYPE)
+    op = capi.pinned_array(n * capi.PAIR_DTYPE.itemsize).view(capi.PAIR_DTYPE)
+
+    def call(i):
+        a, b = host[i % len(host)]
+        if b is not None:
+            ctx.align_pe(a, b, out=(oa, ob, op))
+        else:
+            ctx.align_se(a, out=oa)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    W = max(args.warmup, 3)
+    for i in range(W):
+        call(i)
+    # ---- e2e: K calls through the C-ABI with host buffers (H2D + kernels + D2H inside the timed region)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        call(i)
+    t_e2e = time.perf_counter() - t0
+    h2d = sum(x.bases.nbytes + x.offsets.nbytes for x in host[0] if x is not None)
+    d2h = oa.nbytes + (ob.nbytes + op.nbytes if cfg.paired else 0)
+    # ---- value: the same step with the batch resident in HBM (kernels only)
+    call(0)
+    a0, b0 = host[0]
+    for _ in range(2):
+        ctx.align_rerun(a0, b0)
+    barrier()
+    clocks = ClockSampler(local); clocks.start()
+    dev_ms = search_ms = pack_ms = pair_ms = 0.0
+    vbytes = cands = lookups = launches = s_launch = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.align_rerun(a0, b0)
+        st = ctx.stats()
+        dev_ms += st.ms_device; search_ms += st.ms_search; pack_ms += st.ms_pack; pair_ms += st.ms_pair
+        vbytes += st.verify_bytes; cands += st.candidates; lookups += st.seed_lookups; launches += st.kernel_launches; s_launch += st.search_launches
+    t_wall = time.perf_counter() - t0
+    clk = clocks.stop()
+    barrier()
+    # ---- reduce over ranks: max time, summed work
+    t_dev = dev_ms / 1000.0
+    if dist is not None:
+        import torch
+        tt = torch.tensor([t_dev, t_e2e, t_wall], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e, t_wall = [float(x) for x in tt.tolist()]
+    total_reads = reads_per_step * args.steps * world
+    value = total_reads / t_dev
+    e2e = total_reads / t_e2e
+    peak, peak_src = peaks()
+    achieved = (vbytes / 1e9) / (search_ms / 1000.0) if search_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+        "ms_per_step": 1000.0 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(cfg), "pairs_per_step_per_gpu": n, "reads_per_step": reads_per_step * world,
+                   "l2": "inputs larger than L2 (index 1.9 GB + 300 MB batch per step); no flush needed",
+                   "timing": "CUDA events on the launching stream (first kernel to last kernel), max over ranks",
+                   "index_build_s": round(t_index, 2), "parallelism": f"read-sharded x{world}, index replicated, no collective"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1000.0 * t_e2e / args.steps, "note": "bsl_align_pe from pinned host buffers, one in-flight call"},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": {"bound": "hbm", "kernel": "search_round (seed look-up + candidate verification + reduce)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
+                     "candidates_per_step": cands // max(args.steps, 1), "seed_lookups_per_step": lookups // max(args.steps, 1),
+                     "bytes_per_candidate": (vbytes // cands) if cands else None, "launches_per_step": s_launch // max(args.steps, 1),
+                     "ms_search_per_step": search_ms / args.steps, "ms_pack_per_step": pack_ms / args.steps, "ms_pair_per_step": pair_ms / args.steps,
+                     "wall_ms_per_step": 1000.0 * t_wall / args.steps},
+    }
+    if rank == 0:
+        if world == 1 and os.environ.get("BENCH_SKIP_CPU", "0") != "1" and os.path.exists(REF_BIN):
+            threads = os.cpu_count() or 1
+            work = tempfile.mkdtemp(prefix="bench_cpu_")
+            try:
+                sample = int(os.environ.get("BENCH_CPU_PAIRS", str(min(max(100_000, threads * 25_000), 1_000_000))))
+                if SCALE < 0.1:
+                    sample = max(1000, int(sample * SCALE * 10))
+                log(f"cpu_baseline: reference binary, {sample} pairs, -p {threads}")
+                r, t, ti = run_reference_sample(cfg, chrs, sample, work, threads)
+                line["cpu_baseline"] = {"value": r / t, "unit": UNIT, "cores": threads, "kind": "reference",
+                                        "sample": f"{sample} pairs of the same workload, wall-clock minus index-only run ({ti:.1f}s index, {t:.1f}s align)"}
+            except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": f"failed: {e}"}
+            finally:
+                shutil.rmtree(work, ignore_errors=True)
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def _flag_kwargs(cfg):
+    kw = {}
+    f = list(cfg.flags)
+    for i in range(0, len(f), 2):
+        k, v = f[i], f[i + 1]
+        if k == "-v": kw["v"] = v
+        elif k == "-g": kw["g"] = int(v)
+        elif k == "-s": kw["s"] = int(v); kw["s_given"] = True
+        elif k == "-I": kw["I"] = int(v)
+        elif k == "-w": kw["w"] = int(v)
+    return kw
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -17,7 +17,6 @@ Shapes follow SURVEY.md §8(d):
 from __future__ import annotations
 
 import dataclasses
-import io
 import os
 from typing import Iterator
 
@@ -263,20 +262,41 @@ class ReadSimulator:
             done += n
 
 
-def write_fastq(path: str, reads: np.ndarray, first_index: int, suffix: str = "", append: bool = False) -> None:
-    """reads: (n, L) uint8 ASCII. names r<i><suffix>, qualities 'I'."""
+def fastq_bytes(reads: np.ndarray, first_index: int, suffix: str = "") -> bytes:
+    """FASTQ text of (n, L) uint8 ASCII reads; names r<i><suffix>, qualities 'I' (vectorised per digit count)."""
     n, L = reads.shape
-    qual = b"I" * L
-    buf = io.BytesIO()
-    rows = reads.tobytes()
-    for i in range(n):
-        buf.write(b"@r%d%s\n" % (first_index + i, suffix.encode()))
-        buf.write(rows[i * L:(i + 1) * L])
-        buf.write(b"\n+\n")
-        buf.write(qual)
-        buf.write(b"\n")
+    idx = np.arange(first_index, first_index + n, dtype=np.int64)
+    suf = np.frombuffer(suffix.encode(), dtype=np.uint8)
+    parts = []
+    lo = 0
+    while lo < n:
+        d = len(str(int(idx[lo])))
+        hi = int(np.searchsorted(idx, 10 ** d, side="left"))
+        hi = max(hi, lo + 1)
+        k = hi - lo
+        width = 2 + d + len(suf) + 1 + L + 3 + L + 1
+        rec = np.empty((k, width), dtype=np.uint8)
+        rec[:, 0] = ord("@"); rec[:, 1] = ord("r")
+        sub = idx[lo:hi]
+        for j in range(d):
+            rec[:, 2 + j] = 48 + (sub // 10 ** (d - 1 - j)) % 10
+        p = 2 + d
+        if len(suf):
+            rec[:, p:p + len(suf)] = suf
+            p += len(suf)
+        rec[:, p] = 10; p += 1
+        rec[:, p:p + L] = reads[lo:hi]; p += L
+        rec[:, p] = 10; rec[:, p + 1] = ord("+"); rec[:, p + 2] = 10; p += 3
+        rec[:, p:p + L] = ord("I"); p += L
+        rec[:, p] = 10
+        parts.append(rec.tobytes())
+        lo = hi
+    return b"".join(parts)
+
+
+def write_fastq(path: str, reads: np.ndarray, first_index: int, suffix: str = "", append: bool = False) -> None:
     with open(path, "ab" if append else "wb") as fh:
-        fh.write(buf.getvalue())
+        fh.write(fastq_bytes(reads, first_index, suffix))
 
 
 def materialise(cfg: Config, outdir: str, limit: int | None = None, chunk: int = 500_000) -> dict:
