@@ -49,7 +49,8 @@ class Stats(C.Structure):
     _fields_ = [("reads", C.c_uint64), ("seed_lookups", C.c_uint64), ("candidates", C.c_uint64), ("hits_added", C.c_uint64),
                 ("heavy_reads", C.c_uint64), ("ms_pack", C.c_double), ("ms_search", C.c_double), ("ms_pair", C.c_double),
                 ("ms_total", C.c_double), ("kernel_launches", C.c_uint64), ("verify_bytes", C.c_uint64),
-                ("ms_device", C.c_double), ("search_launches", C.c_uint64)]
+                ("ms_device", C.c_double), ("search_launches", C.c_uint64),
+                ("ms_lookup", C.c_double), ("ms_verify", C.c_double), ("ms_reduce", C.c_double)]
 
 
 def parse_v(text: str) -> int:

@@ -1,18 +1,25 @@
 // align.cu — batched read mapping on the GPU (replaces SingleAlign/PairAlign::Do_Batch).
 //
 // Kernels (all sm_100a integer / LSU work, no tensor cores):
-//   prepare_reads   warp per read: FilterReads, 2-bit planes for both chains, rolling seed hashes,
-//                   bucket-size gathers and the seed schedule (ConvertBinaySeq + ReorderSeed)
-//   classify_pairs  PE: route each pair to the pair rounds or its surviving mate to the SE rounds
-//   search_round    persistent warps, one read per warp per round (SnpAlign mode r): seed look-up,
-//                   rotated bucket walk, warp-cooperative coalesced gather of candidate windows into
-//                   shared memory, masked XOR/popcount verification, single-gap search, and the
-//                   in-order AddHit reduction (dedup, -w feedback, early stop)
-//   pair_round      thread per pair: SortHits4PE + GetPairs replay for level i
-//   finalize_reads  lowest non-empty level, -S tie-break, result records
+//   prepare_reads      warp per read: FilterReads, 2-bit planes for both chains (ballot transpose), rolling
+//                      seed hashes, bucket-size gathers and the seed schedule (ConvertBinaySeq + ReorderSeed)
+//   build_lists        first active lists (SE reads / full pairs / lone mates)
+//   per search round r (= SnpAlign mode r of every still-active read, align.cpp:274-316):
+//     seed_lookup      thread per (read, chain): the I bucket look-ups of mode r; every non-empty bucket becomes
+//                      an "item" that owns a contiguous range of a flat candidate index space
+//     verify_candidates  THE roofline kernel: flat over candidates, 4 lanes per candidate, one 16-byte gather
+//                      per lane covering only the reference words the window needs, read bit planes staged in
+//                      shared memory, masked XOR/popcount (CountMismatch / CountMismatch_new), output = 1 bit
+//                      per candidate (could this candidate produce a hit?) + list of reads with a marked bit
+//     reduce_round     warp per read that has marked candidates: replays them in discovery order with the
+//                      reference's AddHit semantics (dedup, -w feedback on the threshold, abort) and runs the
+//                      single-gap search (GapAlign) on the marked candidates
+//     pair_round       PE: SortHits4PE + GetPairs replay for level r (thread per pair; block per pair on the
+//                      large-capacity path)
+//   finalize_reads     lowest non-empty level, -S tie-break, result records
 //
-// Discovery order inside a read is preserved exactly: candidates are numbered
-// (chain, phase, rotated bucket index) and reduced in that order by their warp.
+// Discovery order inside a read is preserved exactly: the flat candidate index of a read's candidates grows in
+// (chain, phase, rotated bucket index) order and reduce_round walks the marked bits in that order.
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -25,6 +32,8 @@ struct DevTables {
     RuleTables rule;
     u32 budget0[BSL_MAX_READLEN + 1];
     u16 prof[16][16];
+    u32 tab_code[2];      // 4 x 2-bit codes indexed by (ascii>>1)&3 for chain 0 / chain 1 (alphabet / rev_alphabet)
+    u32 tab_conv[2];      // same for alphabet_Mread / rev_alphabet_Mread
 };
 
 struct KArgs {
@@ -37,10 +46,19 @@ struct KArgs {
     u32 readset_a, readset_b;
     const u8 *bases; const u64 *off; const u32 *index; const u16 *rawlen; u32 first_index_a, first_index_b; u64 bases_b_shift;
     u32 has_index, has_rawlen;
+    u64 off_base_a, off_base_b;    // value of offsets[first] of the sub-range (offsets are passed as given)
+    u64 all_off;                   // all-hits records already produced by earlier sub-ranges of this call
     u32 Wb;                        // words per plane in this batch
-    u64 *planes; u8 *sched; SlotMeta *meta; SlotCounts *cnt; uint2 *stat;   // stat: executed seed look-ups / candidates per slot
+    u64 *planes; u8 *sched; SlotMeta *meta; SlotCounts *cnt; uint2 *stat; u8 *minlvl;   // stat: executed seed look-ups / candidates per slot
     DevHit *hits; u32 cap;         // hit pool and per-slot capacity
     DevCounters *ctr;
+    // per-round scratch
+    ItemHdr *hdr; u32 cap_items; u32 cap_cands;
+    uint2 *slot_item;              // [slot*2+chain] = {first item, number of items} of this round
+    u32 *slot_flag;                // set by verify when a slot has a marked candidate
+    u32 *flag_list;                // slots with marked candidates
+    u32 *chunk_first;              // first item overlapping each chunk of the flat candidate space
+    u32 *bitmap;                   // 1 bit per flat candidate
     bsl_hit *out; bsl_pair *pair_out; bsl_hit *all_a; bsl_hit *all_b; u64 all_cap;
 };
 
@@ -51,12 +69,25 @@ __device__ __forceinline__ u64 plane_extract(const u64 *pl, u32 p) {     // 32 b
     return x;
 }
 
+// spread bit k of x to bit 2k
+__device__ __forceinline__ u64 spread32(u32 v) {
+    u64 x = v;
+    x = (x | (x << 16)) & 0x0000FFFF0000FFFFULL;
+    x = (x | (x << 8)) & 0x00FF00FF00FF00FFULL;
+    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0FULL;
+    x = (x | (x << 2)) & 0x3333333333333333ULL;
+    x = (x | (x << 1)) & 0x5555555555555555ULL;
+    return x;
+}
+// ballot masks (bit l = base 32w+l) of the high and low code bits -> packed word (base k at bits 63-2k, 62-2k)
+__device__ __forceinline__ u64 weave(u32 hi, u32 lo) { return (spread32(__brev(hi)) << 1) | spread32(__brev(lo)); }
+
 // ------------------------------------------------------------------------------------------------
 // prepare_reads
 // ------------------------------------------------------------------------------------------------
-#define PREP_WARPS 4
+#define PREP_WARPS 8
 struct PrepSmem {
-    u8  seq[512];
+    u32 bal[5][16];       // raw ballots per word: code hi, code lo, regular, conv hi, conv lo
     u64 pl[3][17];
     u32 hash[480];
     u32 cntp[480];
@@ -69,45 +100,66 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prepare_reads(const __grid_co
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     PrepSmem &sm = sm_all[wid];
     const DevTables *T = A.tab;
+    const u32 tabq0 = T->tab_code[0], tabq1 = T->tab_code[1], tabc0 = T->tab_conv[0], tabc1 = T->tab_conv[1];
     for (u32 slot = blockIdx.x * PREP_WARPS + wid; slot < A.n_slots; slot += gridDim.x * PREP_WARPS) {
         const bool mate_b = A.pe && slot >= A.n_a;
         const u32 r = mate_b ? slot - A.n_a : slot;
         const u64 *off = mate_b ? A.off + (A.n_a + 1) : A.off;
-        const u64 b0 = off[r] + (mate_b ? A.bases_b_shift : 0), b1 = off[r + 1] + (mate_b ? A.bases_b_shift : 0);
+        const u64 ob = mate_b ? A.off_base_b : A.off_base_a;
+        const u64 b0 = off[r] - ob + (mate_b ? A.bases_b_shift : 0), b1 = off[r + 1] - ob + (mate_b ? A.bases_b_shift : 0);
         const u32 Lraw = (u32)(b1 - b0);
         const u32 L = Lraw > BSL_MAX_READLEN ? BSL_MAX_READLEN : Lraw;
         const u32 readset = mate_b ? A.readset_b : A.readset_a;
         const u32 index = A.has_index ? A.index[slot] : (mate_b ? A.first_index_b : A.first_index_a) + r;
-        __syncwarp();
-        u32 ns = 0;
-        for (u32 k = lane; k < 512; k += 32) { u8 c = k < L ? A.bases[b0 + k] : 0; sm.seq[k] = c; if (k < L && !T->rule.reg[c]) ns++; }
-        for (u32 o = 16; o; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
-        __syncwarp();
-        bool filtered = (L == 0) || (L < A.min_read_size) || (ns > A.max_ns) || (Lraw > BSL_MAX_READLEN);   // align.cpp:559-560
-        u32 raw = A.has_rawlen ? A.rawlen[slot] : L; if (raw == 0 || raw > BSL_MAX_READLEN) raw = L ? L : 1;
-        u32 B = 0, nseg = 0;
-        if (!filtered) {
-            B = (T->budget0[raw] + 1) * (L - 1) / raw;                                                        // align.cpp:561
-            u32 span = L + 1 - A.I;                                                                           // L >= I is implied by min_read_size
-            nseg = (L + 1 >= A.I + A.s) ? min(span / A.s, B + 1) : 0;                                         // align.cpp:450
-        }
-        u32 flags = filtered ? SF_FILTERED : 0;
+        const u32 W = (L + 31) >> 5;
+        u32 flags = 0;
         if ((A.chains == 1) || ((A.chains <= 1) == (readset < 2))) flags |= SF_CHAIN0;                       // align.cpp:83-84
         if ((A.chains == 1) || ((A.chains <= 1) == (readset == 2))) flags |= SF_CHAIN1;
-        const u32 W = (L + 31) >> 5;
+        // zero the per-level counters, stats
+        ((u16 *)&A.cnt[slot])[lane] = 0;
+        if (lane == 0) { A.stat[slot] = make_uint2(0u, 0u); A.minlvl[slot] = 255; }
+        u32 B = 0, nseg = 0; bool filtered = false; u32 ns_known = 0xffffffffu;
         const u32 ii = (L + 1 >= A.I) ? (L + 1 - A.I) % A.s : 0;
-        for (u32 c = 0; c < 2; c++) {
-            if (filtered || !(flags & (c ? SF_CHAIN1 : SF_CHAIN0))) continue;
-            // ---- planes (ConvertBinaySeq / ConvertBinarySeq, align.cpp:79-226)
+        for (u32 c = 0; c < 2 && !filtered; c++) {
+            if (!(flags & (c ? SF_CHAIN1 : SF_CHAIN0))) continue;
+            __syncwarp();
+            // ---- planes (ConvertBinaySeq / ConvertBinarySeq, align.cpp:79-226) by ballot transpose
+            const u32 tq = c ? tabq1 : tabq0, tc = c ? tabc1 : tabc0;
+            u32 ns = 0;
+            for (u32 wv = 0; wv < W; wv++) {
+                const u32 p = wv * 32 + lane;
+                u32 cq = 0, cc = 0; bool reg = false;
+                if (p < L) {
+                    const u8 ch = A.bases[b0 + (c ? L - 1 - p : p)];
+                    const u8 up = ch & 0xDFu;
+                    reg = (up == 'A') | (up == 'C') | (up == 'G') | (up == 'T');
+                    const u32 ix = (ch >> 1) & 3u;
+                    if (reg) { cq = (tq >> (2 * ix)) & 3u; cc = (tc >> (2 * ix)) & 3u; }
+                }
+                const u32 bh = __ballot_sync(0xffffffffu, cq & 2u), bl = __ballot_sync(0xffffffffu, cq & 1u), br = __ballot_sync(0xffffffffu, reg);
+                const u32 ch_ = __ballot_sync(0xffffffffu, cc & 2u), cl_ = __ballot_sync(0xffffffffu, cc & 1u);
+                const u32 inr = (L - wv * 32 >= 32) ? 0xffffffffu : ((1u << (L - wv * 32)) - 1u);
+                ns += __popc(~br & inr);
+                if (lane == 0) { sm.bal[0][wv] = bh; sm.bal[1][wv] = bl; sm.bal[2][wv] = br; sm.bal[3][wv] = ch_; sm.bal[4][wv] = cl_; }
+            }
+            if (ns_known == 0xffffffffu) {
+                ns_known = ns;
+                filtered = (L == 0) || (L < A.min_read_size) || (ns > A.max_ns) || (Lraw > BSL_MAX_READLEN);   // align.cpp:559-560
+                if (!filtered) {
+                    u32 raw = A.has_rawlen ? A.rawlen[slot] : L; if (raw == 0 || raw > BSL_MAX_READLEN) raw = L ? L : 1;
+                    B = (T->budget0[raw] + 1) * (L - 1) / raw;                                                    // align.cpp:561
+                    const u32 span = L + 1 - A.I;                                                                 // L >= I is implied by min_read_size
+                    nseg = (L + 1 >= A.I + A.s) ? min(span / A.s, B + 1) : 0;                                     // align.cpp:450
+                }
+            }
+            if (filtered) break;
+            __syncwarp();
             if (lane < 17) {
                 u64 q = 0, nm = 0, cm = 0;
                 if (lane < W) {
-                    for (u32 k = 0; k < 32; k++) {
-                        u32 p = lane * 32 + k; u32 cq = 0, cn = 0, cc = 0;
-                        if (p < L) { u8 ch = c ? sm.seq[L - 1 - p] : sm.seq[p];
-                            cq = c ? T->rule.rcode[ch] : T->rule.code[ch]; cn = T->rule.reg[ch]; cc = c ? T->rule.rconv[ch] : T->rule.conv[ch]; }
-                        q = (q << 2) | cq; nm = (nm << 2) | cn; cm = (cm << 2) | cc;
-                    }
+                    q = weave(sm.bal[0][lane], sm.bal[1][lane]);
+                    const u64 rg = spread32(__brev(sm.bal[2][lane])); nm = rg | (rg << 1);
+                    cm = weave(sm.bal[3][lane], sm.bal[4][lane]);
                 }
                 sm.pl[0][lane] = q; sm.pl[1][lane] = nm; sm.pl[2][lane] = cm;
                 if (lane < A.Wb) {
@@ -120,10 +172,10 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prepare_reads(const __grid_co
             if (nseg == 0) continue;
             // ---- seed hashes for every offset (xseed_array / xseedreg_array)
             const u32 npos = L - A.s + 1; const u32 sh = 64 - 2 * A.s;
+            const u32 full = (A.s == 16) ? 0xffffffffu : ((1u << (2 * A.s)) - 1);
             for (u32 p = lane; p < npos; p += 32) {
                 u32 x = (u32)(plane_extract(sm.pl[0], p) >> sh);
                 u32 m = (u32)(plane_extract(sm.pl[1], p) >> sh);
-                u32 full = (A.s == 16) ? 0xffffffffu : ((1u << (2 * A.s)) - 1);
                 sm.hash[p] = bsl_xt(x) | ((m != full) ? 0x80000000u : 0u);
             }
             // ---- which offsets can the schedule touch
@@ -155,10 +207,19 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prepare_reads(const __grid_co
                 sm.cs[j][v] = (int)total;
             }
             __syncwarp();
-            // ---- ReorderSeed / AdjustSeedStartArray (align.cpp:468-524)
+            // ---- ReorderSeed (align.cpp:468-498): global start = first minimum of the column sums
+            u32 st0 = 0;
+            {
+                u32 colsum = 0xffffffffu;
+                if (lane < ii) { colsum = 0; for (u32 j = 0; j < nseg; j++) colsum += (u32)sm.cs[j][lane]; }
+                unsigned long long key = ((unsigned long long)colsum << 32) | lane;
+                for (u32 o = 16; o; o >>= 1) { unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o); if (k2 < key) key = k2; }
+                st0 = ii ? (u32)key & 31u : 0;
+                if (ii && (u32)(key >> 32) == 0xffffffffu) st0 = 0;     // every sum is 2^32-1: `<` never fires, start stays 0
+            }
+            // ---- AdjustSeedStartArray (align.cpp:500-524) + ranking: sequential by construction, lane 0
             if (lane == 0) {
-                u32 st[16]; u32 best = 0xffffffffu, st0 = 0;
-                for (u32 i = 0; i < ii; i++) { u32 tt = 0; for (u32 j = 0; j < nseg; j++) tt += (u32)sm.cs[j][i]; if (tt < best) { best = tt; st0 = i; } }
+                u32 st[16];
                 for (u32 j = 0; j < nseg; j++) st[j] = st0;
                 for (u32 t = 0; t < nseg; t++) {
                     u32 ptr = (t & 1) ? nseg - 1 - t / 2 : t / 2;
@@ -172,17 +233,18 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prepare_reads(const __grid_co
                     while (b2 >= 0) { u8 y = ord[b2]; int ky = sm.cs[y][st[y]]; if (ky < kx || (ky == kx && y < x)) break; ord[b2 + 1] = y; b2--; }
                     ord[b2 + 1] = x; }
                 u8 *sc = A.sched + ((u64)slot * 2 + c) * 16;
-                for (u32 t = 0; t < 16; t++) sc[t] = t < nseg ? (u8)(ord[t] | (st[ord[t]] << 4)) : 0;
+                uint4 pk; u32 wv[4] = {0, 0, 0, 0};
+                for (u32 t = 0; t < 16; t++) { u32 v = t < nseg ? (u32)(ord[t] | (st[ord[t]] << 4)) : 0u; wv[t >> 2] |= v << (8 * (t & 3)); }
+                pk.x = wv[0]; pk.y = wv[1]; pk.z = wv[2]; pk.w = wv[3];
+                *(uint4 *)sc = pk;
             }
             __syncwarp();
         }
+        if (filtered) flags |= SF_FILTERED;
         if (lane == 0) {
             SlotMeta m; m.rnd = bsl_rand(index, A.randseed); m.len = (u16)L; m.B = (u8)B; m.nseg = (u8)nseg; m.flags = (u8)flags; m.thr = (u8)B; m.nhit = 0; m.item = slot;
             A.meta[slot] = m;
         }
-        // zero the per-level counters
-        ((u16 *)&A.cnt[slot])[lane] = 0;
-        if (lane == 0) A.stat[slot] = make_uint2(0u, 0u);
     }
 }
 
@@ -192,21 +254,245 @@ __global__ void build_lists(const __grid_constant__ KArgs A, u32 *se_list, u32 *
     if (!A.pe) {
         if (i >= A.n_slots) return;
         SlotMeta m = A.meta[i];
-        if (!(m.flags & SF_FILTERED) && m.nseg > 0) { u32 pos = atomicAdd(&A.ctr->active[0], 1u); se_list[pos] = i; }
+        if (!(m.flags & SF_FILTERED) && m.nseg > 0) { u32 pos = atomicAdd(&A.ctr->rc[0].active, 1u); se_list[pos] = i; }
         return;
     }
     if (i >= A.n_a) return;
     SlotMeta ma = A.meta[i], mb = A.meta[i + A.n_a];
     bool oka = !(ma.flags & SF_FILTERED), okb = !(mb.flags & SF_FILTERED);
-    if (oka && okb) { u32 pos = atomicAdd(&A.ctr->active[20], 1u); pe_list[pos] = i; }
+    if (oka && okb) { u32 pos = atomicAdd(&A.ctr->rc[20].active, 1u); pe_list[pos] = i; }
     else {
-        if (oka && ma.nseg > 0) { u32 pos = atomicAdd(&A.ctr->active[0], 1u); se_list[pos] = i; }
-        if (okb && mb.nseg > 0) { u32 pos = atomicAdd(&A.ctr->active[0], 1u); se_list[pos] = i + A.n_a; }
+        if (oka && ma.nseg > 0) { u32 pos = atomicAdd(&A.ctr->rc[0].active, 1u); se_list[pos] = i; }
+        if (okb && mb.nseg > 0) { u32 pos = atomicAdd(&A.ctr->rc[0].active, 1u); se_list[pos] = i + A.n_a; }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// search_round
+// seed_lookup : the bucket look-ups of mode `round` (align.cpp:279-292) for every active (read, chain)
+// ------------------------------------------------------------------------------------------------
+#define LK_THREADS 256
+#define CHUNK 256            // candidates per verify chunk
+#define ALLOC_SHIFT 40       // RoundCtr::alloc = items << 40 | candidates
+#define ALLOC_MASK ((1ULL << ALLOC_SHIFT) - 1)
+#define MAX_ITEMS_PER_ROUND ((1u << 24) - (1u << 16))
+
+template <bool PE>
+__global__ void __launch_bounds__(LK_THREADS) seed_lookup(const __grid_constant__ KArgs A, u32 round, const u32 *list_in, u32 *list_out, u32 ci) {
+    __shared__ u32 s_wi[LK_THREADS / 32], s_wc[LK_THREADS / 32];
+    __shared__ u32 s_ibase, s_cbase, s_ok;
+    const DevTables *T = A.tab;
+    RoundCtr *rc = A.ctr->rc + ci;
+    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr u32 SH = PE ? 2 : 1;
+    const u32 n_in = rc->active;
+    const u32 n_thr = n_in << SH;
+    const u32 shs = 64 - 2 * A.s;
+    for (u32 k0 = blockIdx.x * LK_THREADS; k0 < n_thr; k0 += gridDim.x * LK_THREADS) {
+        const u32 k = k0 + threadIdx.x;
+        const bool act = k < n_thr;
+        const u32 entry = k >> SH, c = k & 1u, mate = PE ? (k >> 1) & 1u : 0u;
+        u32 slot = 0; SlotMeta m; m.flags = 0; m.nseg = 0; m.rnd = 0; m.len = 0; m.thr = 0;
+        bool search = false, keep = false;
+        if (act) {
+            slot = list_in[entry] + mate * A.n_a;
+            m = A.meta[slot];
+            bool cont = !(m.flags & (SF_OVERFLOW | SF_FILTERED));
+            if (!PE) cont = cont && round < m.nseg && A.minlvl[slot] >= round;          // stop rule of RunAlign (align.cpp:459-463)
+            search = cont && round < m.nseg && (m.flags & (c ? SF_CHAIN1 : SF_CHAIN0));
+            keep = !PE && c == 0 && cont;
+        }
+        if (!PE) {                                                                      // compact the list of reads searched in this round
+            const u32 bal = __ballot_sync(0xffffffffu, keep);
+            if (bal) {
+                u32 base = 0; const u32 leader = __ffs(bal) - 1;
+                if (lane == leader) base = atomicAdd(&rc[1].active, (u32)__popc(bal));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (keep) list_out[base + __popc(bal & ((1u << lane) - 1u))] = slot;
+            }
+        }
+        // ---- pass 1: bucket sizes
+        u32 tot = 0, nne = 0, j = 0, stj = 0; const u64 *pq = nullptr;
+        if (search) {
+            const u8 sc = A.sched[((u64)slot * 2 + c) * 16 + round]; j = sc & 15u; stj = sc >> 4;
+            pq = A.planes + ((u64)slot * 2 + c) * 3 * A.Wb;
+            for (u32 i = 0; i < A.I; i++) {
+                const u32 h = T->prof[j][i] + stj - i;
+                const u32 kmer = bsl_xt((u32)(plane_extract(pq, h) >> shs));
+                const u32 pm = A.di.bucket[2 * kmer + 2] - A.di.bucket[2 * kmer];
+                if (pm != 0 && pm <= A.di.maxk) { tot += pm; nne++; }
+            }
+        }
+        // ---- block-wide exclusive scan of (items, candidates)
+        u32 xi = nne, xc = tot;
+        for (u32 o = 1; o < 32; o <<= 1) { u32 a = __shfl_up_sync(0xffffffffu, xi, o), b = __shfl_up_sync(0xffffffffu, xc, o); if (lane >= o) { xi += a; xc += b; } }
+        if (lane == 31) { s_wi[wid] = xi; s_wc[wid] = xc; }
+        __syncthreads();
+        u32 wi0 = 0, wc0 = 0, bi = 0, bc = 0;
+        for (u32 w = 0; w < LK_THREADS / 32; w++) { if (w < wid) { wi0 += s_wi[w]; wc0 += s_wc[w]; } bi += s_wi[w]; bc += s_wc[w]; }
+        if (threadIdx.x == 0) {
+            u32 ok = 1; unsigned long long old = 0;
+            if (bi) {
+                // one atomicAdd per block (a CAS loop serialises: one winner per round trip). A block whose range does not
+                // fit records its start in rc->limit_inv (as the complement, so that 0 = none): every earlier range fits, every later one fails too, so
+                // [0, limit) is exactly the part of the flat space that exists. Sticky check keeps the packed counter from wrapping.
+                if (*(volatile unsigned long long *)&rc->limit_inv != 0ULL) ok = 0;
+                else {
+                    old = atomicAdd(&rc->alloc, ((unsigned long long)bi << ALLOC_SHIFT) | bc);
+                    if ((old & ALLOC_MASK) + bc > A.cap_cands || (old >> ALLOC_SHIFT) + bi > A.cap_items) { ok = 0; atomicMax(&rc->limit_inv, ~old); }
+                }
+            }
+            s_ok = ok; s_ibase = (u32)(old >> ALLOC_SHIFT); s_cbase = (u32)(old & ALLOC_MASK);
+        }
+        __syncthreads();
+        const bool ok = s_ok != 0;
+        u32 it = s_ibase + wi0 + xi - nne, cb = s_cbase + wc0 + xc - tot;
+        // ---- per-slot bookkeeping (the two chain threads of a slot are neighbouring lanes)
+        const u32 tot_o = __shfl_xor_sync(0xffffffffu, tot, 1), se_o = __shfl_xor_sync(0xffffffffu, (u32)search, 1);
+        if (c == 0 && (search || se_o)) {
+            if (ok) {
+                uint2 ss = A.stat[slot]; ss.x += A.I * ((u32)search + se_o); ss.y += tot + tot_o; A.stat[slot] = ss;
+                A.slot_flag[slot] = 0;
+            } else { A.meta[slot].flags = m.flags | SF_OVERFLOW; atomicAdd(&A.ctr->overflow_n, 1u); }
+        }
+        // ---- pass 2: item headers
+        if (search && ok) {
+            A.slot_item[(u64)slot * 2 + c] = make_uint2(it, nne);
+            for (u32 i = 0; i < A.I && nne; i++) {
+                const u32 h = T->prof[j][i] + stj - i;
+                const u32 kmer = bsl_xt((u32)(plane_extract(pq, h) >> shs));
+                const u32 e0 = A.di.bucket[2 * kmer], e1 = A.di.bucket[2 * kmer + 1], e2 = A.di.bucket[2 * kmer + 2];
+                const u32 pm = e2 - e0;
+                if (pm == 0 || pm > A.di.maxk) continue;
+                uint4 a, b;
+                a.x = cb; a.y = pm; a.z = e0; a.w = e1 - e0;
+                b.x = m.rnd % pm; b.y = h | ((u32)m.len << 9) | ((u32)m.thr << 18) | (i << 22) | (c << 26); b.z = slot; b.w = 0;
+                uint4 *dst = (uint4 *)(A.hdr + it); dst[0] = a; dst[1] = b;
+                for (u32 cc = (cb + CHUNK - 1) / CHUNK; (u64)cc * CHUNK < (u64)cb + pm; cc++) A.chunk_first[cc] = it;
+                cb += pm; it++;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// verify_candidates : CountMismatch / CountMismatch_new over the flat candidate space
+// ------------------------------------------------------------------------------------------------
+#define VF_THREADS 256
+
+// 32 bases of a zero-extended read plane starting at SIGNED base position p0
+__device__ __forceinline__ u64 rextract(const u64 *pl, int p0, int Wb) {
+    const int w = p0 >> 5; const u32 o = ((u32)p0 & 31u) * 2;
+    const u64 a = (w >= 0 && w < Wb) ? pl[w] : 0ULL;
+    const u64 b = (w + 1 >= 0 && w + 1 < Wb) ? pl[w + 1] : 0ULL;
+    return o ? ((a << o) | (b >> (64 - o))) : a;
+}
+// digit mask (01 per base) of the bases k of a word whose read position p0+k lies in [0, hs)
+__device__ __forceinline__ u64 posmask(int p0, int hs) {
+    const int lo = p0 < 0 ? -p0 : 0, hi = (hs - p0) < 32 ? (hs - p0) : 32;
+    if (hi <= lo) return 0ULL;
+    u64 mk = 0x5555555555555555ULL >> (2 * lo);
+    if (hi < 32) mk &= ~(0x5555555555555555ULL >> (2 * hi));
+    return mk;
+}
+
+template <bool SINGLE, bool GAP>
+__global__ void __launch_bounds__(VF_THREADS) verify_candidates(const __grid_constant__ KArgs A, u32 ci, u32 KIT) {
+    extern __shared__ u64 vsm[];                          // staged read planes: item x plane x word
+    __shared__ u32 s_base[CHUNK + 1], s_m[CHUNK], s_b0[CHUNK], s_nfwd[CHUNK], s_rot[CHUNK], s_pack[CHUNK], s_slot[CHUNK];
+    __shared__ u32 s_bits[CHUNK / 32], s_push[CHUNK], s_npush, s_pbase;
+    constexpr u32 NP = SINGLE ? 2 : 3;
+    RoundCtr *rc = A.ctr->rc + ci;
+    const unsigned long long al = min(rc->alloc, ~rc->limit_inv);
+    const u32 n_cands = (u32)(al & ALLOC_MASK), n_items = (u32)(al >> ALLOC_SHIFT);
+    const u32 n_chunks = (n_cands + CHUNK - 1) / CHUNK;
+    const u32 t = threadIdx.x, lane = t & 31u, q = t & 3u;
+    const int Wb = (int)A.Wb;
+    const u32 PW = NP * A.Wb;
+    for (u32 chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        const u32 cbeg = chunk * CHUNK, cend = min(cbeg + CHUNK, n_cands);
+        const u32 first = A.chunk_first[chunk];
+        // ---- stage the headers of the items that overlap this chunk (their bases are increasing)
+        bool mine = false; uint4 ha, hb;
+        if (first + t < n_items) { const uint4 *src = (const uint4 *)(A.hdr + first + t); ha = src[0]; mine = (t == 0) || ha.x < cend; if (mine) hb = src[1]; }
+        const u32 n_it = (u32)__syncthreads_count(mine);
+        if (mine) { s_base[t] = ha.x; s_m[t] = ha.y; s_b0[t] = ha.z; s_nfwd[t] = ha.w; s_rot[t] = hb.x; s_pack[t] = hb.y; s_slot[t] = hb.z; }
+        if (t == 0) { s_base[n_it] = 0xffffffffu; s_npush = 0; }
+        if (t < CHUNK / 32) s_bits[t] = 0;
+        __syncthreads();
+        // ---- stage their read planes
+        for (u32 x = t; x < n_it * PW; x += VF_THREADS) {
+            const u32 it = x / PW, r = x - it * PW;
+            vsm[x] = A.planes[((u64)s_slot[it] * 2 + IH_CHAIN(s_pack[it])) * 3 * A.Wb + r];
+        }
+        __syncthreads();
+        // ---- 4 lanes per candidate, 64 candidates per pass
+#pragma unroll 2
+        for (u32 pass = 0; pass < CHUNK / 64; pass++) {
+            const u32 cidx = pass * 64 + (t >> 2), idx = cbeg + cidx;
+            const bool valid = idx < cend;
+            u32 snp = 0, pre = 0, thr = 0, it = 0;
+            if (valid) {
+                u32 lo = 0, hi = n_it;
+                while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (s_base[mid] <= idx) lo = mid; else hi = mid; }
+                it = lo;
+                const u32 m_ = s_m[it]; u32 e = s_rot[it] + (idx - s_base[it]); if (e >= m_) e -= m_;
+                const u32 sig = e >= s_nfwd[it] ? 1u : 0u;
+                const u32 pack = s_pack[it]; const u32 h = IH_H(pack), L = IH_L(pack); thr = IH_THR(pack);
+                const u32 g = __ldg(A.di.loc + s_b0[it] + e) - h;                      // _hit.loc (align.cpp:297)
+                const u32 word0 = g >> 5, wb = word0 & ~1u, nwc = ((g & 31u) + L + 31u) >> 5;
+                const int rel = (int)(g - 32u * wb);
+                const u64 *P = A.di.plane[sig];
+                const u64 *rp = vsm + (size_t)it * PW;
+                const int hs = (int)(h + A.s);
+                for (u32 kk = 0; kk < KIT; kk++) {
+                    const u32 wq = wb + 8 * kk + 2 * q;
+                    if (wq + 1 >= word0 && wq < word0 + nwc) {
+                        const ulonglong2 r2 = __ldg((const ulonglong2 *)(P + wq));
+#pragma unroll
+                        for (u32 z = 0; z < 2; z++) {
+                            const u64 r = z ? r2.y : r2.x;
+                            const int p0 = 32 * (int)(8 * kk + 2 * q + z) - rel;
+                            const u64 qv = rextract(rp, p0, Wb), nv = rextract(rp + Wb, p0, Wb);
+                            const u64 cv = SINGLE ? 0ULL : rextract(rp + 2 * Wb, p0, Wb);
+                            const u64 d = bsl_pairs(bsl_diff<SINGLE>(qv, cv, r));
+                            snp += __popcll(d & nv);
+                            if (GAP) pre += __popcll(d & posmask(p0, hs));
+                        }
+                    }
+                }
+            }
+            u32 v = snp | (pre << 16);
+            v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+            snp = v & 0xffffu; pre = v >> 16;
+            // could this candidate add a hit?  ungapped: snp <= thr.  gapped: GapAlign's first test (align.cpp:353-360)
+            const bool mark = valid && q == 0 && (snp <= thr || (GAP && thr >= 2 && pre < thr - 1));
+            const u32 bal = __ballot_sync(0xffffffffu, mark);
+            if (bal) {
+                if (lane == 0) {
+                    u32 byte = 0;
+#pragma unroll
+                    for (u32 b = 0; b < 8; b++) byte |= ((bal >> (4 * b)) & 1u) << b;
+                    const u32 c0 = pass * 64 + (t >> 5) * 8;
+                    atomicOr(&s_bits[c0 >> 5], byte << (c0 & 31u));
+                }
+                if (mark) { const u32 slot = s_slot[it]; if (atomicExch(&A.slot_flag[slot], 1u) == 0u) { const u32 p = atomicAdd(&s_npush, 1u); s_push[p] = slot; } }
+            }
+        }
+        __syncthreads();
+        if (t < CHUNK / 32) A.bitmap[(cbeg >> 5) + t] = s_bits[t];
+        const u32 np = s_npush;
+        if (np) {
+            if (t == 0) s_pbase = atomicAdd(&rc->flagged, np);
+            __syncthreads();
+            if (t < np) A.flag_list[s_pbase + t] = s_push[t];
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reduce_round
 // ------------------------------------------------------------------------------------------------
 #define ROUND_WARPS 8
 #define GAP_NONE 0xffffffffu
@@ -293,36 +579,46 @@ __device__ int add_hit(const KArgs &A, WarpCtx &S, u32 lane, u32 level, u32 g, u
 }
 
 template <bool SINGLE>
-__global__ void __launch_bounds__(ROUND_WARPS * 32) search_round(const __grid_constant__ KArgs A, u32 round, const u32 *list_in, u32 *list_out,
-                                                                u32 ctr_in, u32 NW, u32 NWS) {
+__global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_constant__ KArgs A, u32 round, u32 ci, u32 NW, u32 NWS) {
     extern __shared__ u64 smem[];
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     u64 *win_all = smem + (size_t)wid * (32 * NWS + 48);
     u64 *pq = win_all + 32 * NWS, *pn = pq + 16, *pc = pn + 16;
-    const DevTables *T = A.tab;
-    const u32 n_items = A.ctr->active[ctr_in] * (A.pe ? 2u : 1u);
+    RoundCtr *rc = A.ctr->rc + ci;
+    const u32 n_items = rc->flagged;
     const u32 G = A.gap;
     unsigned long long st_hits = 0;
     for (;;) {
         u32 k = 0;
-        if (lane == 0) k = atomicAdd(&A.ctr->work[ctr_in], 1u);
+        if (lane == 0) k = atomicAdd(&rc->work, 1u);
         k = __shfl_sync(0xffffffffu, k, 0);
         if (k >= n_items) break;
-        const u32 slot = A.pe ? list_in[k >> 1] + (k & 1u) * A.n_a : list_in[k];
+        const u32 slot = A.flag_list[k];
         SlotMeta m = A.meta[slot];
-        if (m.flags & (SF_OVERFLOW | SF_FILTERED)) continue;
-        if (round >= m.nseg) continue;                                          // PE: this mate has no more seed segments
         WarpCtx S; S.L = m.len; S.W = (S.L + 31) >> 5; S.thr = m.thr; S.nhit = m.nhit; S.cap = A.cap; S.overflow = false;
         S.hits = A.hits + (u64)m.item * A.cap;
         S.mycnt = ((const u16 *)&A.cnt[slot])[lane];
         const u32 L = S.L, W = S.W;
         const u32 lastb = L & 31u; const u64 endmask = lastb ? (~0ULL << (64 - 2 * lastb)) : ~0ULL;
         const u32 hits_before = S.nhit;
-        bool stop_all = false; u32 st_lookups = 0, st_cand = 0;
-        for (u32 c = 0; c < 2 && !stop_all; c++) {
+        bool stop_all = false; u32 un_lookups = 0, un_cand = 0;     // work the reference never did because SnpAlign returned early
+        for (u32 c = 0; c < 2; c++) {
             if (!(m.flags & (c ? SF_CHAIN1 : SF_CHAIN0))) continue;
+            const uint2 si = A.slot_item[(u64)slot * 2 + c];
+            const u32 ni = si.y;
+            // ---- the items (non-empty buckets) of this chain, one per lane
+            u32 pm = 0, pb0 = 0, pnf = 0, ph_h = 0, prot = 0, pphase = 0, pbase = 0;
+            if (lane < ni) {
+                const uint4 *src = (const uint4 *)(A.hdr + si.x + lane); const uint4 a = src[0], b = src[1];
+                pbase = a.x; pm = a.y; pb0 = a.z; pnf = a.w; prot = b.x; ph_h = IH_H(b.y); pphase = IH_PHASE(b.y);
+            }
+            u32 incl = pm;
+            for (u32 o = 1; o < 32; o <<= 1) { u32 v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const u32 poff = incl - pm; const u32 total = __shfl_sync(0xffffffffu, incl, 31);
+            if (stop_all) { un_lookups += A.I; un_cand += total; continue; }            // an abort in chain 0 ends the read's SnpAlign calls of this mode
+            if (total == 0) continue;
+            const u32 cbase = __shfl_sync(0xffffffffu, pbase, 0);
             S.chain = c;
-            const u8 sc = A.sched[((u64)slot * 2 + c) * 16 + round]; const u32 j = sc & 15u, stj = sc >> 4;
             __syncwarp();
             if (lane < 16) {
                 const u64 *src = A.planes + ((u64)slot * 2 + c) * 3 * A.Wb;
@@ -330,43 +626,25 @@ __global__ void __launch_bounds__(ROUND_WARPS * 32) search_round(const __grid_co
                 pq[lane] = in ? src[lane] : 0; pn[lane] = in ? src[A.Wb + lane] : 0; pc[lane] = in ? src[2 * A.Wb + lane] : 0;
             }
             __syncwarp();
-            // ---- seed look-ups of this mode: one phase per lane (align.cpp:279-292)
-            u32 pm = 0, pb0 = 0, ph_h = 0, prot = 0; int pmc = -1;
-            if (lane < A.I) {
-                ph_h = T->prof[j][lane] + stj - lane;
-                u32 kmer = bsl_xt((u32)(plane_extract(pq, ph_h) >> (64 - 2 * A.s)));
-                u32 e0 = A.di.bucket[2 * kmer], e1 = A.di.bucket[2 * kmer + 1], e2 = A.di.bucket[2 * kmer + 2];
-                pm = e2 - e0; pb0 = e0; pmc = (int)(e1 - e0) - 1;
-                if (pm == 0 || pm > A.di.maxk) pm = 0; else prot = m.rnd % pm;
-            }
-            u32 incl = pm;
-            for (u32 o = 1; o < 32; o <<= 1) { u32 v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-            const u32 poff = incl - pm; const u32 total = __shfl_sync(0xffffffffu, incl, 31);
-            st_lookups += A.I; st_cand += total;
             for (u32 tile = 0; tile < total && !stop_all; tile += 32) {
-                const u32 idx = tile + lane; const bool valid = idx < total;
+                const u32 idx = tile + lane; const u32 flat = cbase + idx;
+                const bool valid = idx < total && ((A.bitmap[flat >> 5] >> (flat & 31u)) & 1u);
+                if (!__any_sync(0xffffffffu, valid)) continue;
                 u32 ph = 0;
-                for (u32 i = 1; i < A.I; i++) { u32 o = __shfl_sync(0xffffffffu, poff, i); if (idx >= o) ph = i; }
+                for (u32 i = 1; i < ni; i++) { u32 o = __shfl_sync(0xffffffffu, poff, i); if (idx >= o) ph = i; }
                 const u32 t = idx - __shfl_sync(0xffffffffu, poff, ph);
                 const u32 cm_ = __shfl_sync(0xffffffffu, pm, ph), crot = __shfl_sync(0xffffffffu, prot, ph), cb0 = __shfl_sync(0xffffffffu, pb0, ph);
-                const int cmc = __shfl_sync(0xffffffffu, pmc, ph); const u32 ch = __shfl_sync(0xffffffffu, ph_h, ph);
-                u32 g = 0, sig = 0, word0 = 0, rel = 0;
+                const u32 cnf = __shfl_sync(0xffffffffu, pnf, ph); const u32 ch = __shfl_sync(0xffffffffu, ph_h, ph);
+                u32 g = 0, sig = 0, rel = 0;
+                u64 *win = win_all + lane * NWS;
                 if (valid) {
                     u32 e = crot + t; if (e >= cm_) e -= cm_;
-                    sig = ((int)e > cmc) ? 1u : 0u;
+                    sig = e >= cnf ? 1u : 0u;
                     g = A.di.loc[cb0 + e] - ch;                                 // _hit.loc (align.cpp:297)
-                    u32 gb = g - G; word0 = gb >> 5; rel = (gb & 31u) + G;      // window starts at word0; alignment starts `rel` bases into it
+                    const u32 gb = g - G; const u32 word0 = gb >> 5; rel = (gb & 31u) + G;      // window starts at word0; alignment starts `rel` bases into it
+                    const u64 *P = A.di.plane[sig] + word0;
+                    for (u32 w = 0; w < NW; w++) win[w] = __ldg(P + w);
                 }
-                // ---- warp-cooperative gather: consecutive lanes fetch consecutive words of one candidate's window
-                __syncwarp();
-                for (u32 kk = 0; kk < NW; kk++) {
-                    u32 f = kk * 32 + lane; u32 cand = f / NW, w = f - cand * NW;
-                    u32 cw0 = __shfl_sync(0xffffffffu, word0, cand); u32 cs = __shfl_sync(0xffffffffu, sig, cand); bool cv = __shfl_sync(0xffffffffu, (u32)valid, cand);
-                    u64 val = cv ? __ldg(A.di.plane[cs] + cw0 + w) : 0ULL;
-                    win_all[cand * NWS + w] = val;
-                }
-                __syncwarp();
-                const u64 *win = win_all + lane * NWS;
                 u32 snp = 0xffffu, gres = GAP_NONE;
                 if (valid) {
                     snp = 0;
@@ -390,27 +668,29 @@ __global__ void __launch_bounds__(ROUND_WARPS * 32) search_round(const __grid_co
                         if (cres != GAP_NONE) ab = add_hit(A, S, lane, cres & 255u, cg, csig, (int)((cres >> 8) & 255u) - 4, cres >> 16);
                     }
                     if (ab) {                    // SnpAlign returns here: later phases / the other chain are never looked up
-                        const u32 aph = __shfl_sync(0xffffffffu, ph, l);
-                        st_lookups -= A.I - 1 - aph;
-                        st_cand -= total - (__shfl_sync(0xffffffffu, poff, aph) + __shfl_sync(0xffffffffu, pm, aph));
+                        const u32 aitem = __shfl_sync(0xffffffffu, ph, l);
+                        const u32 aph = __shfl_sync(0xffffffffu, pphase, aitem);
+                        un_lookups += A.I - 1 - aph;
+                        un_cand += total - (__shfl_sync(0xffffffffu, poff, aitem) + __shfl_sync(0xffffffffu, pm, aitem));
                         stop_all = true; break;
                     }
                 }
             }
         }
         st_hits += S.nhit - hits_before;
-        // ---- write back, stop rule (align.cpp:459-463)
+        // ---- write back
         ((u16 *)&A.cnt[slot])[lane] = (u16)S.mycnt;
-        u32 low = __ballot_sync(0xffffffffu, S.mycnt > 0 && (lane & 15u) <= round);
+        const u32 nz = __ballot_sync(0xffffffffu, S.mycnt > 0);
         if (lane == 0) {
             u32 fl = m.flags;
             if (S.overflow) { fl |= SF_OVERFLOW; atomicAdd(&A.ctr->overflow_n, 1u); }
-            A.meta[slot].thr = (u8)S.thr; A.meta[slot].nhit = (u16)S.nhit; A.meta[slot].flags = (u8)fl;
-            uint2 ss = A.stat[slot]; ss.x += st_lookups; ss.y += st_cand; A.stat[slot] = ss;
-            if (!A.pe && !S.overflow && !low && round + 1 < m.nseg) { u32 pos = atomicAdd(&A.ctr->active[ctr_in + 1], 1u); list_out[pos] = slot; }
+            SlotMeta *mp = A.meta + slot; mp->thr = (u8)S.thr; mp->nhit = (u16)S.nhit; mp->flags = (u8)fl;
+            if (un_lookups | un_cand) { uint2 ss = A.stat[slot]; ss.x -= un_lookups; ss.y -= un_cand; A.stat[slot] = ss; }
+            const u32 lv = (nz | (nz >> 16)) & 0xffffu;
+            A.minlvl[slot] = lv ? (u8)(__ffs(lv) - 1) : (u8)255;
         }
     }
-    if (lane == 0) atomicAdd(&A.ctr->hits_added, st_hits);
+    if (lane == 0 && st_hits) atomicAdd(&A.ctr->hits_added, st_hits);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -483,8 +763,9 @@ __device__ void fill_record(bsl_hit &o, const DevHit &h, u32 chain, u32 level) {
     o.loc = h.loc; o.chr = HIT_CHR2(h.tag); o.gap_size = (int)h.gap; o.gap_pos = (u16)h.gp; o.nm = (u8)level; o.read_chain = (u8)chain;
 }
 
-__global__ void pair_round(const __grid_constant__ KArgs A, u32 round, const u32 *list_in, u32 *list_out, u32 ctr_in) {
-    const u32 n_items = A.ctr->active[ctr_in];
+__global__ void pair_round(const __grid_constant__ KArgs A, u32 round, const u32 *list_in, u32 *list_out, u32 ci) {
+    RoundCtr *rc = A.ctr->rc + ci;
+    const u32 n_items = rc->active;
     for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n_items; k += gridDim.x * blockDim.x) {
         const u32 p = list_in[k]; const u32 sa = p, sb = p + A.n_a;
         SlotMeta ma = A.meta[sa], mb = A.meta[sb];
@@ -496,11 +777,11 @@ __global__ void pair_round(const __grid_constant__ KArgs A, u32 round, const u32
         DevHit *ha = A.hits + (u64)ma.item * A.cap, *hb = A.hits + (u64)mb.item * A.cap;
         const u32 nA = ma.nhit, nB = mb.nhit, Ba = ma.B, Bb = mb.B, La = ma.len, Lb = mb.len;
         const u32 i = round;
-        if (i <= Ba) { sort_level(ha, nA, 0, i); sort_level(ha, nA, 1, i); }
-        if (i <= Bb) { sort_level(hb, nB, 0, i); sort_level(hb, nB, 1, i); }
-        // pass 1: count per level sum in the reference's call order
         u32 total = 0, best = 0xffffffffu, best_cnt = 0;
-        {
+        if (i <= Ba) { sort_level(ha, nA, 0, i); sort_level(ha, nA, 1, i); }      // SortHits4PE happens even when the mate has no hit yet
+        if (i <= Bb) { sort_level(hb, nB, 0, i); sort_level(hb, nB, 1, i); }
+        if (nA && nB) {
+            // pass 1: count per level sum in the reference's call order
             u32 c = 0; total += get_pairs(A, ha, nA, Ba, La, hb, nB, Bb, Lb, i, i, c, 0, 0, nullptr, 0);
             if (c) { best = 2 * i; best_cnt = c; }
             for (u32 j = 0; j < i; j++) {
@@ -512,7 +793,7 @@ __global__ void pair_round(const __grid_constant__ KArgs A, u32 round, const u32
         }
         if (total == 0) {
             const u32 maxi = max(Ba, Bb);
-            if (round < maxi) { u32 pos = atomicAdd(&A.ctr->active[ctr_in + 1], 1u); list_out[pos] = p; }
+            if (round < maxi) { u32 pos = atomicAdd(&rc[1].active, 1u); list_out[pos] = p; }
             continue;
         }
         // a pair exists: the search ends here (pairs.cpp:173)
@@ -521,7 +802,7 @@ __global__ void pair_round(const __grid_constant__ KArgs A, u32 round, const u32
         const u32 target = best_cnt == 1 ? 0 : ma.rnd % best_cnt;
         PairPick pk; pk.found = 0;
         u64 all_base = 0;
-        if (A.report == 2 && A.all_a) { all_base = atomicAdd(&A.ctr->all_n, (unsigned long long)best_cnt); pr.all_first = (u32)all_base; }
+        if (A.report == 2 && A.all_a) { all_base = atomicAdd(&A.ctr->all_n, (unsigned long long)best_cnt); pr.all_first = (u32)(all_base + A.all_off); }
         {
             u32 c = 0;
             if (best == 2 * i) get_pairs(A, ha, nA, Ba, La, hb, nB, Bb, Lb, i, i, c, 1, target, &pk, all_base);
@@ -543,27 +824,35 @@ __global__ void pair_round(const __grid_constant__ KArgs A, u32 round, const u32
 // finalize_reads : StringAlign / StringAlignUnpair selection (align.cpp:583-612, pairs.cpp:232-259)
 // ------------------------------------------------------------------------------------------------
 __global__ void finalize_reads(const __grid_constant__ KArgs A, const u32 *only_list, u32 only_n) {
-    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    u32 slot;
-    if (only_list) { if (t >= only_n) return; slot = only_list[t]; } else { if (t >= A.n_slots) return; slot = t; }
-    SlotMeta m = A.meta[slot];
-    if (m.flags & SF_OVERFLOW) return;                           // will be written by the heavy pass
-    { uint2 ss = A.stat[slot]; if (ss.x) atomicAdd(&A.ctr->seed_lookups, (unsigned long long)ss.x); if (ss.y) atomicAdd(&A.ctr->candidates, (unsigned long long)ss.y); }
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 n = only_list ? only_n : A.n_slots;
+    u32 slot = 0; bool live = t < n;
+    if (live) slot = only_list ? only_list[t] : t;
+    SlotMeta m; m.flags = SF_OVERFLOW;
+    if (live) m = A.meta[slot];
+    if (m.flags & SF_OVERFLOW) live = false;                     // will be written by the heavy pass
+    // work counters: one atomic per warp
+    uint2 ss = make_uint2(0u, 0u); if (live) ss = A.stat[slot];
+    unsigned long long lx = ss.x, ly = ss.y;
+    for (u32 o = 16; o; o >>= 1) { lx += __shfl_xor_sync(0xffffffffu, lx, o); ly += __shfl_xor_sync(0xffffffffu, ly, o); }
+    if ((threadIdx.x & 31u) == 0) { if (lx) atomicAdd(&A.ctr->seed_lookups, lx); if (ly) atomicAdd(&A.ctr->candidates, ly); }
+    if (!live) return;
     if (m.flags & SF_DONE) return;                               // already written by pair_round
     bsl_hit o; memset(&o, 0, sizeof o); o.read_len = m.len; o.max_snp = m.B;
     if (m.flags & SF_FILTERED) { o.status = BSL_ST_FILTERED; A.out[slot] = o; return; }
+    o.status = BSL_ST_UNMAPPED;
+    if (m.nhit == 0) { A.out[slot] = o; return; }
     const SlotCounts cn = A.cnt[slot];
     const DevHit *h = A.hits + (u64)m.item * A.cap;
-    o.status = BSL_ST_UNMAPPED;
     for (u32 l = 0; l <= m.B; l++) {
-        u32 n0 = cn.c[0][l], n = n0 + cn.c[1][l];
-        if (!n) continue;
-        u32 pick = n == 1 ? 0 : m.rnd % n; u32 chain = pick < n0 ? 0 : 1; u32 want = pick - (chain ? n0 : 0);
+        u32 n0 = cn.c[0][l], nn = n0 + cn.c[1][l];
+        if (!nn) continue;
+        u32 pick = nn == 1 ? 0 : m.rnd % nn; u32 chain = pick < n0 ? 0 : 1; u32 want = pick - (chain ? n0 : 0);
         u32 seen = 0;
         for (u32 i = 0; i < m.nhit; i++) if (tag_is(h[i].tag, chain, l)) { if (seen == want) { fill_record(o, h[i], chain, l); break; } seen++; }
-        o.n_hits = n; o.n_chain0 = n0; o.status = n == 1 ? BSL_ST_UNIQUE : BSL_ST_MULTI;
-        if (A.report == 2 && !A.pe && A.all_a && n > 1) {
-            u64 base = atomicAdd(&A.ctr->all_n, (unsigned long long)n); o.all_first = (u32)base; u64 w = base;
+        o.n_hits = nn; o.n_chain0 = n0; o.status = nn == 1 ? BSL_ST_UNIQUE : BSL_ST_MULTI;
+        if (A.report == 2 && !A.pe && A.all_a && nn > 1) {
+            u64 base = atomicAdd(&A.ctr->all_n, (unsigned long long)nn); o.all_first = (u32)(base + A.all_off); u64 w = base;
             for (u32 c = 0; c < 2; c++) for (u32 i = 0; i < m.nhit; i++) if (tag_is(h[i].tag, c, l)) {
                 if (w < A.all_cap) { bsl_hit r = o; fill_record(r, h[i], c, l); A.all_a[w] = r; } w++; }
         }
@@ -593,14 +882,15 @@ __global__ void reset_heavy(const __grid_constant__ KArgs A, const u32 *heavy_li
         A.meta[slot] = m;
         for (u32 k = 0; k < 32; k++) ((u16 *)&A.cnt[slot])[k] = 0;
         A.stat[slot] = make_uint2(0u, 0u);
+        A.minlvl[slot] = 255;
     }
-    if (!A.pe) { u32 pos = atomicAdd(&A.ctr->active[0], 1u); se_list[pos] = i; return; }
+    if (!A.pe) { u32 pos = atomicAdd(&A.ctr->rc[0].active, 1u); se_list[pos] = i; return; }
     SlotMeta ma = A.meta[i], mb = A.meta[i + A.n_a];
     bool oka = !(ma.flags & SF_FILTERED), okb = !(mb.flags & SF_FILTERED);
-    if (oka && okb) { u32 pos = atomicAdd(&A.ctr->active[20], 1u); pe_list[pos] = i; }
+    if (oka && okb) { u32 pos = atomicAdd(&A.ctr->rc[20].active, 1u); pe_list[pos] = i; }
     else {
-        if (oka && ma.nseg > 0) { u32 pos = atomicAdd(&A.ctr->active[0], 1u); se_list[pos] = i; }
-        if (okb && mb.nseg > 0) { u32 pos = atomicAdd(&A.ctr->active[0], 1u); se_list[pos] = i + A.n_a; }
+        if (oka && ma.nseg > 0) { u32 pos = atomicAdd(&A.ctr->rc[0].active, 1u); se_list[pos] = i; }
+        if (okb && mb.nseg > 0) { u32 pos = atomicAdd(&A.ctr->rc[0].active, 1u); se_list[pos] = i + A.n_a; }
     }
 }
 
@@ -624,6 +914,8 @@ template <typename T> int grow(bsl_ctx *ctx, T **p, size_t *cap, size_t need, bo
 
 void bsl_lane_free(Lane &ln) {
     cudaFree(ln.d_bases); cudaFree(ln.d_off); cudaFree(ln.d_index); cudaFree(ln.d_rawlen); cudaFree(ln.d_meta); cudaFree(ln.d_cnt); cudaFree(ln.d_sched); cudaFree(ln.d_stat);
+    cudaFree(ln.d_minlvl); cudaFree(ln.d_slot_item); cudaFree(ln.d_slot_flag); cudaFree(ln.d_flag_list);
+    cudaFree(ln.d_hdr); cudaFree(ln.d_chunk_first); cudaFree(ln.d_bitmap);
     cudaFree(ln.d_planes); cudaFree(ln.d_hits); cudaFree(ln.d_heavy_hits); cudaFree(ln.d_list[0]); cudaFree(ln.d_list[1]); cudaFree(ln.d_heavy_list);
     cudaFree(ln.d_pe_list[0]); cudaFree(ln.d_pe_list[1]); cudaFree(ln.d_out); cudaFree(ln.d_pair); cudaFree(ln.d_all[0]); cudaFree(ln.d_all[1]); cudaFree(ln.d_ctr);
     if (ln.h_ctr) cudaFreeHost(ln.h_ctr);
@@ -646,6 +938,12 @@ int bsl_upload_params(bsl_ctx *ctx) {
     }
     for (u32 i = 0; i < P.index_interval && i < 16; i++) for (u32 j = 0; j <= BSL_MAXSNPS; j++)
         h.prof[j][i] = (u16)(((j * P.seed_size + i + P.index_interval - 1) / P.index_interval) * P.index_interval);   // param.cpp:70-74
+    static const char kNt[4] = {'A', 'C', 'G', 'T'};
+    for (int k = 0; k < 4; k++) {                                            // 2-bit tables indexed by (ascii >> 1) & 3
+        const u32 ix = ((u32)kNt[k] >> 1) & 3u;
+        h.tab_code[0] |= (u32)ctx->rule.code[(u8)kNt[k]] << (2 * ix); h.tab_code[1] |= (u32)ctx->rule.rcode[(u8)kNt[k]] << (2 * ix);
+        h.tab_conv[0] |= (u32)ctx->rule.conv[(u8)kNt[k]] << (2 * ix); h.tab_conv[1] |= (u32)ctx->rule.rconv[(u8)kNt[k]] << (2 * ix);
+    }
     CUDA_TRY(cudaSetDevice(ctx->device));
     if (!ctx->d_tables) CUDA_TRY(cudaMalloc(&ctx->d_tables, sizeof(DevTables)));
     CUDA_TRY(cudaMemcpy(ctx->d_tables, &h, sizeof h, cudaMemcpyHostToDevice));
@@ -662,30 +960,22 @@ static int ensure_lane(bsl_ctx *ctx, Lane &ln) {
     return 0;
 }
 
-static u32 max_len_of(const bsl_batch *b) {
-    u32 mx = 0; for (u32 i = 0; i < b->n; i++) { u64 l = b->offsets[i + 1] - b->offsets[i]; if (l > mx) mx = (u32)std::min<u64>(l, 0xffffffffu); } return mx;
+static u32 max_len_of(const bsl_batch *b, u32 first, u32 n) {
+    u32 mx = 0; for (u32 i = first; i < first + n; i++) { u64 l = b->offsets[i + 1] - b->offsets[i]; if (l > mx) mx = (u32)std::min<u64>(l, 0xffffffffu); } return mx;
 }
 
-int bsl_align_impl(bsl_ctx *ctx, const bsl_batch *a, const bsl_batch *b, bsl_hit *out_a, bsl_hit *out_b, bsl_pair *out_pair,
-                   bsl_hit *all_a, bsl_hit *all_b, u64 all_cap, u64 *n_all, int resident) {
-    if (!ctx->has_index) { set_error(ctx, "bsl_align: no index (call bsl_index_build first)"); return BSL_ESTATE; }
-    if (!a || (!resident && (!out_a || (b && (!out_b || !out_pair))))) { set_error(ctx, "bsl_align: null argument"); return BSL_EINVAL; }
-    if (b && a->n != b->n) { set_error(ctx, "bsl_align_pe: batches differ in size (%u vs %u)", a->n, b->n); return BSL_EINVAL; }
-    if (n_all) *n_all = 0;
-    const u32 n_a = a->n; const bool pe = b != nullptr; const u32 n_slots = pe ? 2 * n_a : n_a;
-    if (n_a == 0) return 0;
-    if (n_slots >= 0x7fffffffu) { set_error(ctx, "batch too large"); return BSL_ELIMIT; }
-    CUDA_TRY(cudaSetDevice(ctx->device));
-    // pick a lane
-    Lane *lnp = nullptr; std::unique_lock<std::mutex> lk;
-    for (int t = 0; t < 2 && !lnp; t++) { std::unique_lock<std::mutex> l(ctx->lanes[t].mu, std::try_to_lock); if (l.owns_lock()) { lk = std::move(l); lnp = &ctx->lanes[t]; } }
-    if (!lnp) { lk = std::unique_lock<std::mutex>(ctx->lanes[0].mu); lnp = &ctx->lanes[0]; }
-    Lane &ln = *lnp;
-    int rc = ensure_lane(ctx, ln); if (rc) return rc;
+// One sub-range [first, first+n_a) of the caller's batch on one lane. Sub-ranges keep the number of items a search
+// round can produce below MAX_ITEMS_PER_ROUND and bound the device memory of a call.
+static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_batch *b, u32 first, u32 n_a, bsl_hit *out_a, bsl_hit *out_b, bsl_pair *out_pair,
+                       bsl_hit *all_a, bsl_hit *all_b, u64 all_cap, u64 all_off, u64 *all_made, int resident, bsl_stats *acc) {
+    int rc = 0;
+    const bool pe = b != nullptr; const u32 n_slots = pe ? 2 * n_a : n_a;
     cudaStream_t st = ln.stream;
+    const bsl_params &P = ctx->P;
 
-    const u64 bases_a = a->offsets[n_a], bases_b = pe ? b->offsets[n_a] : 0;
-    u32 Lmax = max_len_of(a); if (pe) Lmax = std::max(Lmax, max_len_of(b));
+    const u64 off0_a = a->offsets[first], off0_b = pe ? b->offsets[first] : 0;
+    const u64 bases_a = a->offsets[first + n_a] - off0_a, bases_b = pe ? b->offsets[first + n_a] - off0_b : 0;
+    u32 Lmax = max_len_of(a, first, n_a); if (pe) Lmax = std::max(Lmax, max_len_of(b, first, n_a));
     if (Lmax > BSL_MAX_READLEN) Lmax = BSL_MAX_READLEN;       // longer reads are flagged filtered by prepare_reads; the CLI truncates like the reference
     const u32 Wb = std::max(1u, (Lmax + 31) / 32);
     const u32 cap = 32;
@@ -699,91 +989,139 @@ int bsl_align_impl(bsl_ctx *ctx, const bsl_batch *a, const bsl_batch *b, bsl_hit
         if (need > ln.cap_slots) {
             size_t ncap = std::max(need, ln.cap_slots + ln.cap_slots / 2);
             cudaFree(ln.d_off); cudaFree(ln.d_index); cudaFree(ln.d_rawlen); cudaFree(ln.d_meta); cudaFree(ln.d_cnt); cudaFree(ln.d_sched); cudaFree(ln.d_stat);
+            cudaFree(ln.d_minlvl); cudaFree(ln.d_slot_item); cudaFree(ln.d_slot_flag); cudaFree(ln.d_flag_list);
             cudaFree(ln.d_list[0]); cudaFree(ln.d_list[1]); cudaFree(ln.d_pe_list[0]); cudaFree(ln.d_pe_list[1]); cudaFree(ln.d_heavy_list); cudaFree(ln.d_out); cudaFree(ln.d_pair);
             ln.cap_slots = 0;
             CUDA_TRY(cudaMalloc(&ln.d_off, (ncap + 4) * 8)); CUDA_TRY(cudaMalloc(&ln.d_index, ncap * 4)); CUDA_TRY(cudaMalloc(&ln.d_rawlen, ncap * 2));
             CUDA_TRY(cudaMalloc(&ln.d_meta, ncap * sizeof(SlotMeta))); CUDA_TRY(cudaMalloc(&ln.d_cnt, ncap * sizeof(SlotCounts))); CUDA_TRY(cudaMalloc(&ln.d_sched, ncap * 32)); CUDA_TRY(cudaMalloc(&ln.d_stat, ncap * sizeof(uint2)));
+            CUDA_TRY(cudaMalloc(&ln.d_minlvl, ncap)); CUDA_TRY(cudaMalloc(&ln.d_slot_item, ncap * 2 * sizeof(uint2))); CUDA_TRY(cudaMalloc(&ln.d_slot_flag, ncap * 4)); CUDA_TRY(cudaMalloc(&ln.d_flag_list, ncap * 4));
             for (int k = 0; k < 2; k++) { CUDA_TRY(cudaMalloc(&ln.d_list[k], ncap * 4)); CUDA_TRY(cudaMalloc(&ln.d_pe_list[k], ncap * 4)); }
             CUDA_TRY(cudaMalloc(&ln.d_heavy_list, ncap * 4)); CUDA_TRY(cudaMalloc(&ln.d_out, ncap * sizeof(bsl_hit))); CUDA_TRY(cudaMalloc(&ln.d_pair, ncap * sizeof(bsl_pair)));
             ln.cap_slots = ncap;
         }
     }
-    c0 = ln.cap_words; if ((rc = grow(ctx, &ln.d_planes, &c0, (size_t)n_slots * 6 * Wb))) return rc; ln.cap_words = c0;
+    c0 = ln.cap_words; if ((rc = grow(ctx, &ln.d_planes, &c0, (size_t)n_slots * 6 * Wb + 16))) return rc; ln.cap_words = c0;
     c0 = ln.cap_hits; if ((rc = grow(ctx, &ln.d_hits, &c0, (size_t)n_slots * cap_main))) return rc; ln.cap_hits = c0;
-    const bool want_all = ctx->P.report_repeat_hits == 2 && all_a && (!pe || all_b) && all_cap > 0;
+    // per-round scratch: flat candidate space (1 bit per candidate) and item headers
+    const u32 nch = P.chains == 1 ? 2 : 1;
+    const u64 worst_slot = 2ull * P.index_interval * std::max<u32>(ctx->di.maxk, 1);      // candidates one read can have in one round
+    const char *env_cc = getenv("BSL_CAND_CAP");
+    u64 want_cands = env_cc ? (u64)atoll(env_cc) : std::max<u64>(96ull * n_slots, 1ull << 22);
+    want_cands = std::max<u64>(want_cands, 2 * worst_slot + CHUNK);
+    want_cands = std::min<u64>(want_cands, 0xfff00000ull);
+    want_cands = (want_cands + CHUNK - 1) / CHUNK * CHUNK;
+    if (2 * worst_slot + CHUNK > want_cands) { set_error(ctx, "over-represented k-mer cut-off %u is too large for the 32-bit candidate space", ctx->di.maxk); return BSL_ELIMIT; }
+    const u64 want_items = std::min<u64>((u64)n_slots * nch * P.index_interval, want_cands) + 16;
+    c0 = ln.cap_bitmap; if ((rc = grow(ctx, &ln.d_bitmap, &c0, (size_t)(want_cands / 32 + 8)))) return rc;
+    if (c0 != ln.cap_bitmap || !ln.d_chunk_first) { cudaFree(ln.d_chunk_first); ln.d_chunk_first = nullptr; CUDA_TRY(cudaMalloc(&ln.d_chunk_first, (c0 * 32 / CHUNK + 8) * 4)); }
+    ln.cap_bitmap = c0;
+    c0 = ln.cap_items; if ((rc = grow(ctx, &ln.d_hdr, &c0, (size_t)want_items))) return rc; ln.cap_items = c0;
+    const bool want_all = P.report_repeat_hits == 2 && all_a && (!pe || all_b) && all_cap > 0;
+    const u64 sub_cap = all_cap > all_off ? all_cap - all_off : 0;      // room left in the caller's all-hits arrays
     if (want_all) {
-        if (all_cap > ln.cap_all) { cudaFree(ln.d_all[0]); cudaFree(ln.d_all[1]); ln.cap_all = 0;
-            CUDA_TRY(cudaMalloc(&ln.d_all[0], all_cap * sizeof(bsl_hit))); CUDA_TRY(cudaMalloc(&ln.d_all[1], all_cap * sizeof(bsl_hit))); ln.cap_all = all_cap; }
+        const u64 dcap = std::max<u64>(sub_cap, 1);
+        if (dcap > ln.cap_all) { cudaFree(ln.d_all[0]); cudaFree(ln.d_all[1]); ln.cap_all = 0;
+            CUDA_TRY(cudaMalloc(&ln.d_all[0], dcap * sizeof(bsl_hit))); CUDA_TRY(cudaMalloc(&ln.d_all[1], dcap * sizeof(bsl_hit))); ln.cap_all = dcap; }
     }
 
     // ---- kernel arguments
     KArgs A; memset(&A, 0, sizeof A);
     A.di = ctx->di; A.tab = (const DevTables *)ctx->d_tables;
-    const bsl_params &P = ctx->P;
     A.s = P.seed_size; A.I = P.index_interval; A.gap = P.gap; A.w = P.max_num_hits; A.min_insert = P.min_insert; A.max_insert = P.max_insert;
     A.chains = P.chains; A.report = P.report_repeat_hits; A.randseed = P.randseed; A.max_ns = P.max_ns; A.min_read_size = P.min_read_size; A.single = ctx->rule.single;
     A.n_slots = n_slots; A.n_a = n_a; A.pe = pe; A.readset_a = a->readset; A.readset_b = pe ? b->readset : 0;
-    A.bases = ln.d_bases; A.off = ln.d_off; A.index = ln.d_index; A.rawlen = ln.d_rawlen; A.first_index_a = a->first_index; A.first_index_b = pe ? b->first_index : 0;
+    A.bases = ln.d_bases; A.off = ln.d_off; A.index = ln.d_index; A.rawlen = ln.d_rawlen; A.first_index_a = a->first_index + first; A.first_index_b = pe ? b->first_index + first : 0;
+    A.off_base_a = off0_a; A.off_base_b = off0_b; A.all_off = all_off;
     A.bases_b_shift = bases_a; A.has_index = (a->index != nullptr) && (!pe || b->index != nullptr); A.has_rawlen = (a->raw_len != nullptr) && (!pe || b->raw_len != nullptr);
-    A.Wb = Wb; A.planes = ln.d_planes; A.sched = ln.d_sched; A.meta = ln.d_meta; A.cnt = ln.d_cnt; A.stat = ln.d_stat; A.hits = ln.d_hits; A.cap = cap_main; A.ctr = ln.d_ctr;
-    A.out = ln.d_out; A.pair_out = ln.d_pair; A.all_a = want_all ? ln.d_all[0] : nullptr; A.all_b = want_all ? ln.d_all[1] : nullptr; A.all_cap = want_all ? all_cap : 0;
+    A.Wb = Wb; A.planes = ln.d_planes; A.sched = ln.d_sched; A.meta = ln.d_meta; A.cnt = ln.d_cnt; A.stat = ln.d_stat; A.minlvl = ln.d_minlvl;
+    A.hits = ln.d_hits; A.cap = cap_main; A.ctr = ln.d_ctr;
+    A.hdr = ln.d_hdr; A.cap_items = (u32)std::min<u64>(want_items - 16, 0xffffffffu); A.cap_cands = (u32)want_cands;
+    A.slot_item = ln.d_slot_item; A.slot_flag = ln.d_slot_flag; A.flag_list = ln.d_flag_list; A.chunk_first = ln.d_chunk_first; A.bitmap = ln.d_bitmap;
+    A.out = ln.d_out; A.pair_out = ln.d_pair; A.all_a = want_all ? ln.d_all[0] : nullptr; A.all_b = want_all ? ln.d_all[1] : nullptr; A.all_cap = want_all ? sub_cap : 0;
 
     // ---- H2D
     CUDA_TRY(cudaEventRecord(ln.ev[0], st));
     CUDA_TRY(cudaMemsetAsync(ln.d_ctr, 0, sizeof(DevCounters), st));
     if (!resident) {
-    CUDA_TRY(cudaMemcpyAsync(ln.d_bases, a->bases, bases_a, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(ln.d_off, a->offsets, (size_t)(n_a + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ln.d_bases, a->bases + off0_a, bases_a, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ln.d_off, a->offsets + first, (size_t)(n_a + 1) * 8, cudaMemcpyHostToDevice, st));
     if (pe) {
-        CUDA_TRY(cudaMemcpyAsync(ln.d_bases + bases_a, b->bases, bases_b, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(ln.d_off + (n_a + 1), b->offsets, (size_t)(n_a + 1) * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ln.d_bases + bases_a, b->bases + off0_b, bases_b, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ln.d_off + (n_a + 1), b->offsets + first, (size_t)(n_a + 1) * 8, cudaMemcpyHostToDevice, st));
     }
     }
     if (pe) CUDA_TRY(cudaMemsetAsync(ln.d_pair, 0, (size_t)n_a * sizeof(bsl_pair), st));
-    if (A.has_index && !resident) { CUDA_TRY(cudaMemcpyAsync(ln.d_index, a->index, (size_t)n_a * 4, cudaMemcpyHostToDevice, st));
-        if (pe) CUDA_TRY(cudaMemcpyAsync(ln.d_index + n_a, b->index, (size_t)n_a * 4, cudaMemcpyHostToDevice, st)); }
-    if (A.has_rawlen && !resident) { CUDA_TRY(cudaMemcpyAsync(ln.d_rawlen, a->raw_len, (size_t)n_a * 2, cudaMemcpyHostToDevice, st));
-        if (pe) CUDA_TRY(cudaMemcpyAsync(ln.d_rawlen + n_a, b->raw_len, (size_t)n_a * 2, cudaMemcpyHostToDevice, st)); }
+    if (A.has_index && !resident) { CUDA_TRY(cudaMemcpyAsync(ln.d_index, a->index + first, (size_t)n_a * 4, cudaMemcpyHostToDevice, st));
+        if (pe) CUDA_TRY(cudaMemcpyAsync(ln.d_index + n_a, b->index + first, (size_t)n_a * 4, cudaMemcpyHostToDevice, st)); }
+    if (A.has_rawlen && !resident) { CUDA_TRY(cudaMemcpyAsync(ln.d_rawlen, a->raw_len + first, (size_t)n_a * 2, cudaMemcpyHostToDevice, st));
+        if (pe) CUDA_TRY(cudaMemcpyAsync(ln.d_rawlen + n_a, b->raw_len + first, (size_t)n_a * 2, cudaMemcpyHostToDevice, st)); }
 
     u64 launches = 0;
-    const int grid_p = ctx->sm_count * 8;
+    const int sms = ctx->sm_count;
     CUDA_TRY(cudaEventRecord(ln.ev[1], st));
-    prepare_reads<<<std::min<u32>((n_slots + PREP_WARPS - 1) / PREP_WARPS, (u32)grid_p * 4), PREP_WARPS * 32, 0, st>>>(A); launches++;
+    prepare_reads<<<std::min<u32>((n_slots + PREP_WARPS - 1) / PREP_WARPS, (u32)sms * 16), PREP_WARPS * 32, 0, st>>>(A); launches++;
     build_lists<<<(std::max(n_slots, n_a) + 255) / 256, 256, 0, st>>>(A, ln.d_list[0], ln.d_pe_list[0]); launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ln.ev[2], st));
 
     const u32 G = P.gap;
     const u32 NW = (31 + 2 * G + Lmax + 31) / 32; const u32 NWS = NW | 1u;
-    const size_t smem = (size_t)ROUND_WARPS * (32 * NWS + 48) * 8;
+    const size_t smem_r = (size_t)ROUND_WARPS * (32 * NWS + 48) * 8;
+    const u32 NP = ctx->rule.single ? 2 : 3;
+    const size_t smem_v = (size_t)CHUNK * NP * Wb * 8;
+    const u32 KIT = ((31 + Lmax + 31) / 32 + 1 + 7) / 8;
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(search_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        cudaFuncSetAttribute(search_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr_set = true; }
+    if (!attr_set) {
+        cudaFuncSetAttribute(reduce_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(reduce_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(verify_candidates<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        cudaFuncSetAttribute(verify_candidates<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        cudaFuncSetAttribute(verify_candidates<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        cudaFuncSetAttribute(verify_candidates<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+        attr_set = true;
+    }
     const u32 rounds_se = std::min<u32>((Lmax + 1 >= P.index_interval + P.seed_size) ? (Lmax + 1 - P.index_interval) / P.seed_size : 0, 16);
-    const int grid_r = ctx->sm_count * 4;
-
-    int nev = 0; std::vector<char> ev_kind;           // per-launch CUDA-event pairs: 's' search_round, 'p' pair_round
-    auto ev_begin = [&](char kind) { if (nev + 2 <= (int)(sizeof ln.evk / sizeof ln.evk[0])) { cudaEventRecord(ln.evk[nev], st); ev_kind.push_back(kind); } };
-    auto ev_end = [&]() { if (nev + 2 <= (int)(sizeof ln.evk / sizeof ln.evk[0])) { cudaEventRecord(ln.evk[nev + 1], st); nev += 2; } };
-    auto run_passes = [&](KArgs &K) -> int {
-        // SE rounds (stop rule inside the kernel)
-        KArgs Kse = K; Kse.pe = 0;
-        for (u32 r = 0; r < rounds_se; r++) {
-            ev_begin('s');
-            if (ctx->rule.single) search_round<true><<<grid_r, ROUND_WARPS * 32, smem, st>>>(Kse, r, ln.d_list[r & 1], ln.d_list[(r + 1) & 1], r, NW, NWS);
-            else search_round<false><<<grid_r, ROUND_WARPS * 32, smem, st>>>(Kse, r, ln.d_list[r & 1], ln.d_list[(r + 1) & 1], r, NW, NWS);
-            ev_end(); launches++;
+    const int vkind = (ctx->rule.single ? 0 : 2) + (G ? 1 : 0);
+    if (!ctx->occ_verify[vkind]) {
+        int occ = 0; cudaError_t oe;
+        switch (vkind) {
+            case 0: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<true, false>, VF_THREADS, smem_v); break;
+            case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<true, true>, VF_THREADS, smem_v); break;
+            case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<false, false>, VF_THREADS, smem_v); break;
+            default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<false, true>, VF_THREADS, smem_v); break;
         }
+        ctx->occ_verify[vkind] = (oe == cudaSuccess && occ > 0) ? occ : 4;
+    }
+    const int grid_l = sms * 8, grid_v = sms * ctx->occ_verify[vkind], grid_r = sms * 4;      // persistent grids: a multiple of the SM count
+
+    int nev = 0; std::vector<char> ev_kind;           // per-launch CUDA-event pairs: 'l' seed_lookup, 'v' verify, 'r' reduce, 'p' pair_round
+    const int max_ev = (int)(sizeof ln.evk / sizeof ln.evk[0]);
+    auto ev_begin = [&](char kind) { if (nev + 2 <= max_ev) { cudaEventRecord(ln.evk[nev], st); ev_kind.push_back(kind); } };
+    auto ev_end = [&]() { if (nev + 2 <= max_ev) { cudaEventRecord(ln.evk[nev + 1], st); nev += 2; } };
+    auto search = [&](KArgs &K, bool as_pe, u32 r, const u32 *lin, u32 *lout, u32 ci) {
+        ev_begin('l');
+        if (as_pe) seed_lookup<true><<<grid_l, LK_THREADS, 0, st>>>(K, r, lin, lout, ci);
+        else seed_lookup<false><<<grid_l, LK_THREADS, 0, st>>>(K, r, lin, lout, ci);
+        ev_end();
+        ev_begin('v');
+        if (ctx->rule.single) { if (G) verify_candidates<true, true><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, KIT); else verify_candidates<true, false><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, KIT); }
+        else { if (G) verify_candidates<false, true><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, KIT); else verify_candidates<false, false><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, KIT); }
+        ev_end();
+        ev_begin('r');
+        if (ctx->rule.single) reduce_round<true><<<grid_r, ROUND_WARPS * 32, smem_r, st>>>(K, r, ci, NW, NWS);
+        else reduce_round<false><<<grid_r, ROUND_WARPS * 32, smem_r, st>>>(K, r, ci, NW, NWS);
+        ev_end();
+        launches += 3;
+    };
+    auto run_passes = [&](KArgs &K) -> int {
+        // SE rounds (stop rule evaluated by the next round's seed_lookup)
+        KArgs Kse = K; Kse.pe = 0;
+        for (u32 r = 0; r < rounds_se; r++) search(Kse, false, r, ln.d_list[r & 1], ln.d_list[(r + 1) & 1], r);
         if (K.pe) {
             for (u32 r = 0; r <= BSL_MAXSNPS; r++) {
-                if (r < rounds_se) {
-                    ev_begin('s');
-                    if (ctx->rule.single) search_round<true><<<grid_r, ROUND_WARPS * 32, smem, st>>>(K, r, ln.d_pe_list[r & 1], nullptr, 20 + r, NW, NWS);
-                    else search_round<false><<<grid_r, ROUND_WARPS * 32, smem, st>>>(K, r, ln.d_pe_list[r & 1], nullptr, 20 + r, NW, NWS);
-                    ev_end(); launches++;
-                }
+                if (r < rounds_se) search(K, true, r, ln.d_pe_list[r & 1], nullptr, 20 + r);
                 ev_begin('p');
-                pair_round<<<ctx->sm_count * 4, 128, 0, st>>>(K, r, ln.d_pe_list[r & 1], ln.d_pe_list[(r + 1) & 1], 20 + r);
+                pair_round<<<sms * 4, 128, 0, st>>>(K, r, ln.d_pe_list[r & 1], ln.d_pe_list[(r + 1) & 1], 20 + r);
                 ev_end(); launches++;
             }
         }
@@ -791,6 +1129,7 @@ int bsl_align_impl(bsl_ctx *ctx, const bsl_batch *a, const bsl_batch *b, bsl_hit
         if (e != cudaSuccess) { set_error(ctx, "kernel launch failed: %s", cudaGetErrorString(e)); return BSL_ECUDA; }
         return 0;
     };
+    if (smem_v > 128 * 1024) { set_error(ctx, "read planes do not fit the verify staging buffer"); return BSL_ELIMIT; }
     if ((rc = run_passes(A))) return rc;
     CUDA_TRY(cudaEventRecord(ln.ev[3], st));
     finalize_reads<<<(n_slots + 255) / 256, 256, 0, st>>>(A, nullptr, 0); launches++;
@@ -809,13 +1148,14 @@ int bsl_align_impl(bsl_ctx *ctx, const bsl_batch *a, const bsl_batch *b, bsl_hit
         const u32 hcap = std::min<u32>(16 * P.max_num_hits + 32, 65535u);
         const u32 per_item = pe ? 2 : 1;
         u32 chunk = (u32)std::max<u64>(1, (1ull << 30) / ((u64)hcap * 16 * per_item));
+        chunk = (u32)std::min<u64>(chunk, std::max<u64>(1, (want_cands - CHUNK) / (worst_slot * per_item)));     // the candidate space must hold every read of the chunk
         chunk = std::min(chunk, n_heavy);
         c0 = ln.cap_heavy_hits; if ((rc = grow(ctx, &ln.d_heavy_hits, &c0, (size_t)chunk * per_item * hcap))) return rc; ln.cap_heavy_hits = c0;
         KArgs H = A; H.hits = ln.d_heavy_hits; H.cap = hcap;
-        u32 *d_slots = ln.d_list[0];     // reused after the rounds as scratch for finalize's slot list (rounds use it first, so take pe_list[1]... see below)
+        u32 *d_slots = ln.d_list[0];
         for (u32 first = 0; first < n_heavy; first += chunk) {
             const u32 count = std::min(chunk, n_heavy - first);
-            CUDA_TRY(cudaMemsetAsync(ln.d_ctr->active, 0, sizeof(u32) * 80, st));
+            CUDA_TRY(cudaMemsetAsync(ln.d_ctr->rc, 0, sizeof(ln.d_ctr->rc), st));
             reset_heavy<<<(count + 127) / 128, 128, 0, st>>>(H, ln.d_heavy_list, first, count, ln.d_list[0], ln.d_pe_list[0]); launches++;
             if ((rc = run_passes(H))) return rc;
             d_slots = ln.d_list[0];
@@ -828,29 +1168,67 @@ int bsl_align_impl(bsl_ctx *ctx, const bsl_batch *a, const bsl_batch *b, bsl_hit
     CUDA_TRY(cudaEventRecord(ln.ev[4], st));
     // ---- D2H
     if (!resident) {
-    CUDA_TRY(cudaMemcpyAsync(out_a, ln.d_out, (size_t)n_a * sizeof(bsl_hit), cudaMemcpyDeviceToHost, st));
-    if (pe) { CUDA_TRY(cudaMemcpyAsync(out_b, ln.d_out + n_a, (size_t)n_a * sizeof(bsl_hit), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(out_pair, ln.d_pair, (size_t)n_a * sizeof(bsl_pair), cudaMemcpyDeviceToHost, st)); }
+    CUDA_TRY(cudaMemcpyAsync(out_a + first, ln.d_out, (size_t)n_a * sizeof(bsl_hit), cudaMemcpyDeviceToHost, st));
+    if (pe) { CUDA_TRY(cudaMemcpyAsync(out_b + first, ln.d_out + n_a, (size_t)n_a * sizeof(bsl_hit), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(out_pair + first, ln.d_pair, (size_t)n_a * sizeof(bsl_pair), cudaMemcpyDeviceToHost, st)); }
     }
     CUDA_TRY(cudaEventRecord(ln.ev[5], st));
     CUDA_TRY(cudaStreamSynchronize(st));
     DevCounters c2 = *ln.h_ctr;
     if (want_all && !resident) {
-        u64 na_ = std::min<u64>(c2.all_n, all_cap);
-        if (na_) { CUDA_TRY(cudaMemcpy(all_a, ln.d_all[0], na_ * sizeof(bsl_hit), cudaMemcpyDeviceToHost));
-            if (pe) CUDA_TRY(cudaMemcpy(all_b, ln.d_all[1], na_ * sizeof(bsl_hit), cudaMemcpyDeviceToHost)); }
-        if (n_all) *n_all = c2.all_n;
+        u64 na_ = std::min<u64>(c2.all_n, sub_cap);
+        if (na_) { CUDA_TRY(cudaMemcpy(all_a + all_off, ln.d_all[0], na_ * sizeof(bsl_hit), cudaMemcpyDeviceToHost));
+            if (pe) CUDA_TRY(cudaMemcpy(all_b + all_off, ln.d_all[1], na_ * sizeof(bsl_hit), cudaMemcpyDeviceToHost)); }
     }
-    float ms_pack = 0, ms_search = 0, ms_pair = 0, ms_total = 0, ms_dev = 0; u64 n_search = 0;
+    if (all_made) *all_made = c2.all_n;
+    float ms_pack = 0, ms_total = 0, ms_dev = 0; double ms_l = 0, ms_v = 0, ms_r = 0, ms_p = 0; u64 n_v = 0;
     cudaEventElapsedTime(&ms_pack, ln.ev[1], ln.ev[2]); cudaEventElapsedTime(&ms_total, ln.ev[0], ln.ev[5]); cudaEventElapsedTime(&ms_dev, ln.ev[1], ln.ev[4]);
-    for (int k = 0; k + 1 < nev; k += 2) { float t = 0; cudaEventElapsedTime(&t, ln.evk[k], ln.evk[k + 1]); if (ev_kind[k / 2] == 's') { ms_search += t; n_search++; } else ms_pair += t; }
-    {
-        std::lock_guard<std::mutex> g(ctx->stats_mu);
-        bsl_stats &S = ctx->stats; memset(&S, 0, sizeof S);
-        S.reads = n_slots; S.seed_lookups = c2.seed_lookups; S.candidates = c2.candidates; S.hits_added = c2.hits_added; S.heavy_reads = heavy_total;
-        S.ms_pack = ms_pack; S.ms_search = ms_search; S.ms_pair = ms_pair; S.ms_total = ms_total; S.ms_device = ms_dev; S.kernel_launches = launches; S.search_launches = n_search;
-        const u32 Wd = (Lmax + 31) / 32 + 1 + (G ? 1 : 0);
-        S.verify_bytes = c2.candidates * (4 + 8ull * Wd);
+    for (int k = 0; k + 1 < nev; k += 2) {
+        float t = 0; cudaEventElapsedTime(&t, ln.evk[k], ln.evk[k + 1]);
+        switch (ev_kind[k / 2]) { case 'l': ms_l += t; break; case 'v': ms_v += t; n_v++; break; case 'r': ms_r += t; break; default: ms_p += t; }
     }
+    {
+        bsl_stats &S = *acc;
+        S.reads += n_slots; S.seed_lookups += c2.seed_lookups; S.candidates += c2.candidates; S.hits_added += c2.hits_added; S.heavy_reads += heavy_total;
+        S.ms_pack += ms_pack; S.ms_search += ms_l + ms_v + ms_r; S.ms_pair += ms_p; S.ms_total += ms_total; S.ms_device += ms_dev; S.kernel_launches += launches; S.search_launches += n_v;
+        S.ms_lookup += ms_l; S.ms_verify += ms_v; S.ms_reduce += ms_r;
+        const u32 Wd = (Lmax + 31) / 32 + 1 + (G ? 1 : 0);      // 4 + 8 W bytes per candidate, W+1 words with -g
+        S.verify_bytes += c2.candidates * (4 + 8ull * Wd);
+    }
+    return 0;
+}
+
+int bsl_align_impl(bsl_ctx *ctx, const bsl_batch *a, const bsl_batch *b, bsl_hit *out_a, bsl_hit *out_b, bsl_pair *out_pair,
+                   bsl_hit *all_a, bsl_hit *all_b, u64 all_cap, u64 *n_all, int resident) {
+    if (!ctx->has_index) { set_error(ctx, "bsl_align: no index (call bsl_index_build first)"); return BSL_ESTATE; }
+    if (!a || (!resident && (!out_a || (b && (!out_b || !out_pair))))) { set_error(ctx, "bsl_align: null argument"); return BSL_EINVAL; }
+    if (b && a->n != b->n) { set_error(ctx, "bsl_align_pe: batches differ in size (%u vs %u)", a->n, b->n); return BSL_EINVAL; }
+    if (n_all) *n_all = 0;
+    const u32 n = a->n; const bool pe = b != nullptr;
+    if (n == 0) return 0;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    // pick a lane
+    Lane *lnp = nullptr; std::unique_lock<std::mutex> lk;
+    for (int t = 0; t < 2 && !lnp; t++) { std::unique_lock<std::mutex> l(ctx->lanes[t].mu, std::try_to_lock); if (l.owns_lock()) { lk = std::move(l); lnp = &ctx->lanes[t]; } }
+    if (!lnp) { lk = std::unique_lock<std::mutex>(ctx->lanes[0].mu); lnp = &ctx->lanes[0]; }
+    Lane &ln = *lnp;
+    int rc = ensure_lane(ctx, ln); if (rc) return rc;
+    // sub-ranges: a search round may create at most MAX_ITEMS_PER_ROUND items (slots x enabled chains x -I look-ups)
+    const bsl_params &P = ctx->P;
+    const u32 per_read = (P.chains == 1 ? 2u : 1u) * P.index_interval * (pe ? 2u : 1u);
+    u32 sub = std::max<u32>(1024u, MAX_ITEMS_PER_ROUND / per_read);
+    const char *env_sub = getenv("BSL_SUB_BATCH"); if (env_sub && atoi(env_sub) > 0) sub = (u32)atoi(env_sub);
+    if (resident && n > sub) { set_error(ctx, "bsl_align_rerun: the batch was split into sub-ranges and is not resident"); return BSL_ESTATE; }
+    bsl_stats acc; memset(&acc, 0, sizeof acc);
+    u64 all_off = 0;
+    for (u32 first = 0; first < n; first += sub) {
+        const u32 cnt = std::min(sub, n - first);
+        u64 made = 0;
+        rc = align_range(ctx, ln, a, b, first, cnt, out_a, out_b, out_pair, all_a, all_b, all_cap, all_off, &made, resident, &acc);
+        if (rc) return rc;
+        all_off += made;
+    }
+    if (n_all) *n_all = all_off;
+    { std::lock_guard<std::mutex> g(ctx->stats_mu); ctx->stats = acc; }
     return 0;
 }

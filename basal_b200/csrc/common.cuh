@@ -111,10 +111,35 @@ struct __align__(16) SlotMeta {
 struct SlotCounts { u16 c[2][16]; };   // hits per read chain and mismatch level
 
 // ---- work counters -------------------------------------------------------------------------
+// one non-empty seed bucket visited in a search round ("item"): owns the flat candidate range [base, base+m)
+struct __align__(16) ItemHdr {
+    u32 base;     // first flat candidate index of the bucket walk
+    u32 m;        // bucket size (KmerLoc2::n[0])
+    u32 b0;       // first entry in loc[]
+    u32 nfwd;     // forward-strand entries come first (n[1])
+    u32 rot;      // myrand(read index) % m : where the cyclic walk starts (align.cpp:293)
+    u32 pack;     // h | L<<9 | thr<<18 | phase<<22 | chain<<26
+    u32 slot;
+    u32 pad;
+};
+#define IH_H(p)     ((p) & 511u)
+#define IH_L(p)     (((p) >> 9) & 511u)
+#define IH_THR(p)   (((p) >> 18) & 15u)
+#define IH_PHASE(p) (((p) >> 22) & 15u)
+#define IH_CHAIN(p) (((p) >> 26) & 1u)
+
+// per search round (SE rounds use index r, PE rounds 20+r)
+struct RoundCtr {
+    unsigned long long alloc;   // items<<40 | candidates allocated by seed_lookup
+    unsigned long long limit_inv; // 0, or ~(allocation state at which the flat candidate space ran out)
+    u32 active;                 // length of the list this round consumes
+    u32 flagged;                // reads with at least one marked candidate
+    u32 work;                   // work-stealing cursor of reduce_round
+    u32 pad;
+};
 struct DevCounters {
     unsigned long long seed_lookups, candidates, hits_added, heavy, all_n;
-    u32 active[40];      // active-list lengths per round (ping-pong by index)
-    u32 work[40];        // work-stealing cursors per round
+    RoundCtr rc[40];
     u32 overflow_n;
 };
 

@@ -13,16 +13,18 @@
 struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
-    cudaEvent_t evk[160] = {};   // per-launch timing of search_round / pair_round
+    cudaEvent_t evk[640] = {};   // per-launch timing of search_round / pair_round
     std::mutex mu;
     // capacities
-    size_t cap_slots = 0, cap_bases = 0, cap_words = 0, cap_hits = 0, cap_heavy_hits = 0, cap_pairs = 0;
+    size_t cap_slots = 0, cap_bases = 0, cap_words = 0, cap_hits = 0, cap_heavy_hits = 0, cap_pairs = 0, cap_bitmap = 0, cap_items = 0;
     // device buffers
     u8 *d_bases = nullptr; u64 *d_off = nullptr; u32 *d_index = nullptr; u16 *d_rawlen = nullptr;
     SlotMeta *d_meta = nullptr; SlotCounts *d_cnt = nullptr; uint2 *d_stat = nullptr; u8 *d_sched = nullptr; u64 *d_planes = nullptr;
     DevHit *d_hits = nullptr; DevHit *d_heavy_hits = nullptr;
     u32 *d_list[2] = {nullptr, nullptr}; u32 *d_heavy_list = nullptr; u32 *d_pe_list[2] = {nullptr, nullptr};
     bsl_hit *d_out = nullptr; bsl_pair *d_pair = nullptr; bsl_hit *d_all[2] = {nullptr, nullptr}; size_t cap_all = 0;
+    u8 *d_minlvl = nullptr; uint2 *d_slot_item = nullptr; u32 *d_slot_flag = nullptr; u32 *d_flag_list = nullptr;
+    ItemHdr *d_hdr = nullptr; u32 *d_chunk_first = nullptr; u32 *d_bitmap = nullptr;      // per-round flat candidate space
     DevCounters *d_ctr = nullptr;
     // pinned staging
     DevCounters *h_ctr = nullptr;
@@ -46,6 +48,7 @@ struct bsl_ctx {
     std::mutex stats_mu;
     char err[512];
     int sm_count = BSL_SM_COUNT;
+    int occ_verify[4] = {0, 0, 0, 0};   // resident CTAs per SM of the verify_candidates variants
 };
 
 static inline void set_error(bsl_ctx *ctx, const char *fmt, ...) {

@@ -123,13 +123,16 @@ typedef struct bsl_stats {
     uint64_t hits_added;
     uint64_t heavy_reads;    /* reads re-run on the large-capacity path                             */
     double   ms_pack;        /* CUDA-event ms of pack+seed-select kernels                           */
-    double   ms_search;      /* CUDA-event ms of the round (seed lookup + verify + gap + reduce)    */
+    double   ms_search;      /* ms_lookup + ms_verify + ms_reduce                                   */
     double   ms_pair;        /* CUDA-event ms of the mate-pairing kernels                           */
     double   ms_total;       /* first H2D to last D2H                                               */
     uint64_t kernel_launches;
     uint64_t verify_bytes;   /* candidates x (4 + 8 W) algorithmic bytes               */
     double   ms_device;      /* first kernel to last kernel (inputs resident, records still on device) */
-    uint64_t search_launches;/* search_round launches inside ms_search                               */
+    uint64_t search_launches;/* verify_candidates launches inside ms_verify                          */
+    double   ms_lookup;      /* CUDA-event ms of seed_lookup (bucket look-ups of every round)         */
+    double   ms_verify;      /* CUDA-event ms of verify_candidates (the roofline kernel)              */
+    double   ms_reduce;      /* CUDA-event ms of reduce_round (AddHit replay + gap search)            */
 } bsl_stats;
 
 /* -- context ---------------------------------------------------------------------------- */

@@ -93,3 +93,35 @@ def test_pe_matches_oracle(cid, rule, extra):
     helpers.assert_records_equal(ga, wa, "mate 1 records")
     helpers.assert_records_equal(gb, wb, "mate 2 records")
     gpu.close(); orc.close()
+
+
+@pytest.mark.parametrize("env", [{"BSL_SUB_BATCH": "3000"}, {"BSL_CAND_CAP": "60000"}, {"BSL_HIT_CAP": "2"},
+                                 {"BSL_SUB_BATCH": "1500", "BSL_CAND_CAP": "30000", "BSL_HIT_CAP": "3"}])
+@pytest.mark.parametrize("pe", [False, True])
+def test_capacity_paths_match_oracle(env, pe, monkeypatch):
+    """Sub-ranges, a flat candidate space that runs out (reads re-run on the large-capacity path) and tiny hit
+    lists must not change a single record."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    if pe:
+        cfg, chrs, m1, m2 = helpers.small_case(2, 0.001, limit=8000)
+        params = helpers.flags_to_params(cfg, {"g": 1, "n": 1})
+        gpu, orc = _build_both(cfg, chrs, params)
+        a = capi.ReadBatch.from_matrix(m1, readset=1); b = capi.ReadBatch.from_matrix(m2, readset=2)
+        ga, gb, gp = gpu.align_pe(a, b); wa, wb, wp = orc.align_pe(a, b)
+        helpers.assert_records_equal(gp, wp, "pair records", fields=["n_pairs", "insert", "chain", "na", "nb"])
+        helpers.assert_records_equal(ga, wa, "mate 1 records"); helpers.assert_records_equal(gb, wb, "mate 2 records")
+    else:
+        cfg, chrs, m1, _ = helpers.small_case(3, 0.002, limit=12000)
+        params = helpers.flags_to_params(cfg, {"r": 2})
+        gpu, orc = _build_both(cfg, chrs, params)
+        batch = capi.ReadBatch.from_matrix(m1, readset=0, first_index=0)
+        got, gall = gpu.align_se(batch, all_cap=400000); want, wall = orc.align_se(batch, all_cap=400000)
+        helpers.assert_records_equal(got, want, "SE records")
+        assert len(gall) == int(got["n_hits"][got["status"] == capi.BSL_ST_MULTI].sum())      # the product lists repeat hits only; the oracle also lists unique ones
+        for i in np.flatnonzero(got["status"] == capi.BSL_ST_MULTI)[:2000]:
+            g = gall[got["all_first"][i]: got["all_first"][i] + got["n_hits"][i]]; w = wall[want["all_first"][i]: want["all_first"][i] + want["n_hits"][i]]
+            assert np.array_equal(g["loc"], w["loc"]) and np.array_equal(g["chr"], w["chr"])
+        gs, os_ = gpu.stats(), orc.stats()
+        assert gs.seed_lookups == os_.seed_lookups and gs.candidates == os_.candidates
+    gpu.close(); orc.close()
