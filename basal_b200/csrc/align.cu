@@ -217,26 +217,35 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prepare_reads(const __grid_co
                 st0 = ii ? (u32)key & 31u : 0;
                 if (ii && (u32)(key >> 32) == 0xffffffffu) st0 = 0;     // every sum is 2^32-1: `<` never fires, start stays 0
             }
-            // ---- AdjustSeedStartArray (align.cpp:500-524) + ranking: sequential by construction, lane 0
-            if (lane == 0) {
-                u32 st[16];
-                for (u32 j = 0; j < nseg; j++) st[j] = st0;
-                for (u32 t = 0; t < nseg; t++) {
-                    u32 ptr = (t & 1) ? nseg - 1 - t / 2 : t / 2;
-                    u32 lo = ptr == 0 ? 0 : st[ptr - 1], hi = ptr == nseg - 1 ? ii : st[ptr + 1];
-                    st[ptr] = lo; u32 b = 0xffffffffu;
-                    for (u32 v = lo; v <= hi; v++) { u32 tt = (u32)sm.cs[ptr][v]; if (tt < b) { b = tt; st[ptr] = v; } }
+            // ---- AdjustSeedStartArray (align.cpp:500-524): the nseg steps are sequential, the argmin of each step is
+            //      spread over the lanes (lane v holds candidate start v; first minimum wins like the reference's `<`)
+            u32 my_st = st0;                                   // lane j < nseg holds start[j]
+            for (u32 t = 0; t < nseg; t++) {
+                const u32 ptr = (t & 1) ? nseg - 1 - t / 2 : t / 2;
+                const u32 lo = ptr == 0 ? 0 : __shfl_sync(0xffffffffu, my_st, ptr - 1);
+                const u32 hi = ptr == nseg - 1 ? ii : __shfl_sync(0xffffffffu, my_st, (ptr + 1) & 31u);
+                unsigned long long key = ~0ULL;
+                if (lane >= lo && lane <= hi && lane < 16) key = ((unsigned long long)(u32)sm.cs[ptr][lane] << 32) | lane;
+                for (u32 o = 8; o; o >>= 1) { const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o); if (k2 < key) key = k2; }
+                key = __shfl_sync(0xffffffffu, key, 0);
+                // every value 2^32-1 (or an empty range lo > hi): `tt < b` never fires and start stays at lo
+                const u32 pick = (key == ~0ULL || (u32)(key >> 32) == 0xffffffffu) ? lo : (u32)key & 31u;
+                if (lane == ptr) my_st = pick;
+            }
+            // ---- rank segments by (count as int, segment): keys are unique, so the rank is a count of smaller keys
+            {
+                const int kx = lane < nseg ? sm.cs[lane][my_st & 15u] : 0;
+                u32 rank = 0;
+                for (u32 y = 0; y < nseg; y++) { const int ky = __shfl_sync(0xffffffffu, kx, y); rank += (ky < kx || (ky == kx && y < lane)) ? 1u : 0u; }
+                // sched byte t = segment of rank t | its start << 4
+                const u32 mine = lane < nseg ? (lane | (my_st << 4)) : 0u;
+                u32 wv[4] = {0, 0, 0, 0};
+                for (u32 y = 0; y < nseg; y++) {
+                    const u32 r_y = __shfl_sync(0xffffffffu, rank, y), v_y = __shfl_sync(0xffffffffu, mine, y);
+                    wv[0] |= (r_y < 4) ? v_y << (8 * r_y) : 0u; wv[1] |= (r_y >= 4 && r_y < 8) ? v_y << (8 * (r_y - 4)) : 0u;
+                    wv[2] |= (r_y >= 8 && r_y < 12) ? v_y << (8 * (r_y - 8)) : 0u; wv[3] |= (r_y >= 12) ? v_y << (8 * (r_y - 12)) : 0u;
                 }
-                // rank segments by (count as int, segment) — keys are unique, any sort gives the same order
-                u8 ord[16]; for (u32 j = 0; j < nseg; j++) ord[j] = (u8)j;
-                for (u32 a = 1; a < nseg; a++) { u8 x = ord[a]; int kx = sm.cs[x][st[x]]; int b2 = (int)a - 1;
-                    while (b2 >= 0) { u8 y = ord[b2]; int ky = sm.cs[y][st[y]]; if (ky < kx || (ky == kx && y < x)) break; ord[b2 + 1] = y; b2--; }
-                    ord[b2 + 1] = x; }
-                u8 *sc = A.sched + ((u64)slot * 2 + c) * 16;
-                uint4 pk; u32 wv[4] = {0, 0, 0, 0};
-                for (u32 t = 0; t < 16; t++) { u32 v = t < nseg ? (u32)(ord[t] | (st[ord[t]] << 4)) : 0u; wv[t >> 2] |= v << (8 * (t & 3)); }
-                pk.x = wv[0]; pk.y = wv[1]; pk.z = wv[2]; pk.w = wv[3];
-                *(uint4 *)sc = pk;
+                if (lane == 0) { uint4 pk; pk.x = wv[0]; pk.y = wv[1]; pk.z = wv[2]; pk.w = wv[3]; *(uint4 *)(A.sched + ((u64)slot * 2 + c) * 16) = pk; }
             }
             __syncwarp();
         }
@@ -379,104 +388,161 @@ __global__ void __launch_bounds__(LK_THREADS) seed_lookup(const __grid_constant_
 // verify_candidates : CountMismatch / CountMismatch_new over the flat candidate space
 // ------------------------------------------------------------------------------------------------
 #define VF_THREADS 256
+#define VF_ITMAX 128u        // items whose read planes are staged at a time (a chunk with more items is done in groups)
+#define VF_PADF 4u           // zero words in front of every staged stream (read positions -64..-1)
 
-// 32 bases of a zero-extended read plane starting at SIGNED base position p0
-__device__ __forceinline__ u64 rextract(const u64 *pl, int p0, int Wb) {
-    const int w = p0 >> 5; const u32 o = ((u32)p0 & 31u) * 2;
-    const u64 a = (w >= 0 && w < Wb) ? pl[w] : 0ULL;
-    const u64 b = (w + 1 >= 0 && w + 1 < Wb) ? pl[w + 1] : 0ULL;
-    return o ? ((a << o) | (b >> (64 - o))) : a;
-}
-// digit mask (01 per base) of the bases k of a word whose read position p0+k lies in [0, hs)
-__device__ __forceinline__ u64 posmask(int p0, int hs) {
-    const int lo = p0 < 0 ? -p0 : 0, hi = (hs - p0) < 32 ? (hs - p0) : 32;
-    if (hi <= lo) return 0ULL;
-    u64 mk = 0x5555555555555555ULL >> (2 * lo);
-    if (hi < 32) mk &= ~(0x5555555555555555ULL >> (2 * hi));
-    return mk;
+// Staged read planes: every item owns NPL streams of ST 32-bit words in LOGICAL order (word j = bases 16j..16j+15,
+// first base in the top bits), with VF_PADF zero words in front and zeros behind, so that a window of the read at ANY
+// base position in [-64, 16*(ST-VF_PADF)) is two plain loads and a funnel shift: no bounds tests in the inner loop.
+//   stream 0: N-mask reduced to one bit per base (01 = ACGT) — what the mismatch digits are ANDed with before the popcount
+//   stream 1: read bases (2-bit codes)
+//   stream 2: convert-to mask (multi-way / '-' rules only)
+//   last    : prefix mask 01 for read positions < h+s (only with -g: GapAlign's first test, align.cpp:353-360)
+__device__ __forceinline__ u32 vf_fsh(u32 a, u32 b, u32 sh) { return __funnelshift_l(b, a, sh); }   // (a:b) << sh, upper word; sh in [0,31]
+
+// mismatch digits (either bit of a digit set) of 16 bases: reference half-word r against read half-word q / convert mask cm
+template <bool SINGLE>
+__device__ __forceinline__ u32 vf_diff(u32 q, u32 cm, u32 r) {
+    const u32 xc = ~(r << 1) | r | 0x55555555u;                          // XC64: digit 01 -> 01, else 11
+    u32 d;
+    if (SINGLE) d = (q & xc) ^ r;                                        // align.h:126-128
+    else { const u32 m2 = xc | cm; const u32 m3 = m2 & (((m2 & 0xAAAAAAAAu) >> 1) | ((m2 & 0x55555555u) << 1)); d = ((~m3 & m2) | (m3 & q)) ^ r; }   // align.h:210-236
+    return d | (d >> 1);                                                 // caller ANDs with a 01-per-base mask
 }
 
 template <bool SINGLE, bool GAP>
-__global__ void __launch_bounds__(VF_THREADS) verify_candidates(const __grid_constant__ KArgs A, u32 ci, u32 KIT) {
-    extern __shared__ u64 vsm[];                          // staged read planes: item x plane x word
-    __shared__ u32 s_base[CHUNK + 1], s_m[CHUNK], s_b0[CHUNK], s_nfwd[CHUNK], s_rot[CHUNK], s_pack[CHUNK], s_slot[CHUNK];
-    __shared__ u32 s_bits[CHUNK / 32], s_push[CHUNK], s_npush, s_pbase;
-    constexpr u32 NP = SINGLE ? 2 : 3;
+__global__ void __launch_bounds__(VF_THREADS, 3) verify_candidates(const __grid_constant__ KArgs A, u32 ci, u32 KIT, u32 ST) {
+    extern __shared__ u32 vsm[];                          // staged streams: item x stream x ST
+    __shared__ uint4 s_ha[CHUNK], s_hb[CHUNK];            // item headers {base, m, b0, nfwd} {rot, pack, slot, -}
+    __shared__ u32 s_mask[CHUNK / 32], s_pref[CHUNK / 32 + 1], s_bits[CHUNK / 32], s_push[CHUNK], s_npush, s_pbase;
+    constexpr u32 NPL = 2 + (SINGLE ? 0 : 1) + (GAP ? 1 : 0);
+    constexpr u32 PL_CM = 2, PL_PM = SINGLE ? 2 : 3;
     RoundCtr *rc = A.ctr->rc + ci;
     const unsigned long long al = min(rc->alloc, ~rc->limit_inv);
     const u32 n_cands = (u32)(al & ALLOC_MASK), n_items = (u32)(al >> ALLOC_SHIFT);
     const u32 n_chunks = (n_cands + CHUNK - 1) / CHUNK;
-    const u32 t = threadIdx.x, lane = t & 31u, q = t & 3u;
-    const int Wb = (int)A.Wb;
-    const u32 PW = NP * A.Wb;
+    const u32 t = threadIdx.x, lane = t & 31u, wid = t >> 5, q = t & 3u;
+    const u32 IST = NPL * ST;
     for (u32 chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         const u32 cbeg = chunk * CHUNK, cend = min(cbeg + CHUNK, n_cands);
         const u32 first = A.chunk_first[chunk];
-        // ---- stage the headers of the items that overlap this chunk (their bases are increasing)
+        // ---- headers of the items that overlap this chunk (their bases are increasing)
         bool mine = false; uint4 ha, hb;
         if (first + t < n_items) { const uint4 *src = (const uint4 *)(A.hdr + first + t); ha = src[0]; mine = (t == 0) || ha.x < cend; if (mine) hb = src[1]; }
+        if (t < CHUNK / 32) { s_mask[t] = 0; s_bits[t] = 0; }
+        if (t == 0) s_npush = 0;
         const u32 n_it = (u32)__syncthreads_count(mine);
-        if (mine) { s_base[t] = ha.x; s_m[t] = ha.y; s_b0[t] = ha.z; s_nfwd[t] = ha.w; s_rot[t] = hb.x; s_pack[t] = hb.y; s_slot[t] = hb.z; }
-        if (t == 0) { s_base[n_it] = 0xffffffffu; s_npush = 0; }
-        if (t < CHUNK / 32) s_bits[t] = 0;
-        __syncthreads();
-        // ---- stage their read planes
-        for (u32 x = t; x < n_it * PW; x += VF_THREADS) {
-            const u32 it = x / PW, r = x - it * PW;
-            vsm[x] = A.planes[((u64)s_slot[it] * 2 + IH_CHAIN(s_pack[it])) * 3 * A.Wb + r];
+        if (mine) {
+            s_ha[t] = ha; s_hb[t] = hb;
+            const u32 pos = ha.x > cbeg ? ha.x - cbeg : 0u;                  // first candidate of the item inside the chunk
+            atomicOr(&s_mask[pos >> 5], 1u << (pos & 31u));
         }
         __syncthreads();
-        // ---- 4 lanes per candidate, 64 candidates per pass
-#pragma unroll 2
-        for (u32 pass = 0; pass < CHUNK / 64; pass++) {
-            const u32 cidx = pass * 64 + (t >> 2), idx = cbeg + cidx;
-            const bool valid = idx < cend;
-            u32 snp = 0, pre = 0, thr = 0, it = 0;
-            if (valid) {
-                u32 lo = 0, hi = n_it;
-                while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (s_base[mid] <= idx) lo = mid; else hi = mid; }
-                it = lo;
-                const u32 m_ = s_m[it]; u32 e = s_rot[it] + (idx - s_base[it]); if (e >= m_) e -= m_;
-                const u32 sig = e >= s_nfwd[it] ? 1u : 0u;
-                const u32 pack = s_pack[it]; const u32 h = IH_H(pack), L = IH_L(pack); thr = IH_THR(pack);
-                const u32 g = __ldg(A.di.loc + s_b0[it] + e) - h;                      // _hit.loc (align.cpp:297)
-                const u32 word0 = g >> 5, wb = word0 & ~1u, nwc = ((g & 31u) + L + 31u) >> 5;
-                const int rel = (int)(g - 32u * wb);
-                const u64 *P = A.di.plane[sig];
-                const u64 *rp = vsm + (size_t)it * PW;
-                const int hs = (int)(h + A.s);
-                for (u32 kk = 0; kk < KIT; kk++) {
-                    const u32 wq = wb + 8 * kk + 2 * q;
-                    if (wq + 1 >= word0 && wq < word0 + nwc) {
-                        const ulonglong2 r2 = __ldg((const ulonglong2 *)(P + wq));
+        if (t == 0) { u32 acc = 0; for (u32 w = 0; w < CHUNK / 32; w++) { s_pref[w] = acc; acc += __popc(s_mask[w]); } }
+        for (u32 grp = 0; grp < n_it; grp += VF_ITMAX) {
+            const u32 n_g = min(VF_ITMAX, n_it - grp);
+            if (grp) __syncthreads();                                        // the previous group is done with the staging buffer
+            // ---- stage the streams of this group's items: one warp per (item, stream) row
+            for (u32 row = wid; row < n_g * NPL; row += VF_THREADS / 32) {
+                const u32 it = row / NPL, pl = row - it * NPL;
+                const uint4 xb = s_hb[grp + it];
+                const u32 *src = (const u32 *)(A.planes + ((u64)xb.z * 2 + IH_CHAIN(xb.y)) * 3 * A.Wb + (pl == 0 ? 1u : pl == 1 ? 0u : 2u) * A.Wb);
+                const u32 hs = IH_H(xb.y) + A.s;
+                for (u32 wi = lane; wi < ST; wi += 32) {
+                    u32 v = 0; const u32 j = wi - VF_PADF;
+                    if (wi >= VF_PADF && j < 2 * A.Wb) {
+                        if (GAP && pl == PL_PM) v = hs >= 16 * j + 16 ? 0x55555555u : (hs <= 16 * j ? 0u : 0x55555555u & (0xffffffffu << (32 - 2 * (hs - 16 * j))));
+                        else { v = src[j ^ 1u]; if (pl == 0) v &= 0x55555555u; }    // logical word j = high half first
+                    }
+                    vsm[(size_t)it * IST + pl * ST + wi] = v;
+                }
+            }
+            __syncthreads();
+            // ---- 4 lanes per candidate, 64 candidates per pass; the 4 passes are interleaved so that their loc and
+            //      window loads are all in flight before the first popcount
+            u32 itx[CHUNK / 64], locv[CHUNK / 64]; bool act[CHUNK / 64];
 #pragma unroll
-                        for (u32 z = 0; z < 2; z++) {
-                            const u64 r = z ? r2.y : r2.x;
-                            const int p0 = 32 * (int)(8 * kk + 2 * q + z) - rel;
-                            const u64 qv = rextract(rp, p0, Wb), nv = rextract(rp + Wb, p0, Wb);
-                            const u64 cv = SINGLE ? 0ULL : rextract(rp + 2 * Wb, p0, Wb);
-                            const u64 d = bsl_pairs(bsl_diff<SINGLE>(qv, cv, r));
-                            snp += __popcll(d & nv);
-                            if (GAP) pre += __popcll(d & posmask(p0, hs));
+            for (u32 pass = 0; pass < CHUNK / 64; pass++) {
+                const u32 cidx = pass * 64 + (t >> 2), idx = cbeg + cidx;
+                const u32 w = cidx >> 5;
+                const u32 it = s_pref[w] + __popc(s_mask[w] & (0xffffffffu >> (31u - (cidx & 31u)))) - 1u;
+                act[pass] = idx < cend && it >= grp && it < grp + n_g;
+                itx[pass] = it; locv[pass] = 0;
+                if (act[pass]) {
+                    const uint4 xa = s_ha[it]; const u32 rot = s_hb[it].x;
+                    u32 e = rot + (idx - xa.x); if (e >= xa.y) e -= xa.y;
+                    locv[pass] = __ldg(A.di.loc + xa.z + e);
+                }
+            }
+            ulonglong2 win[CHUNK / 64];
+#pragma unroll
+            for (u32 pass = 0; pass < CHUNK / 64; pass++) {
+                win[pass] = make_ulonglong2(0ULL, 0ULL);
+                if (act[pass]) {
+                    const u32 it = itx[pass], idx = cbeg + pass * 64 + (t >> 2);
+                    const uint4 xa = s_ha[it]; const uint4 xb = s_hb[it];
+                    u32 e = xb.x + (idx - xa.x); if (e >= xa.y) e -= xa.y;
+                    const u32 sig = e >= xa.w ? 1u : 0u;
+                    const u32 g = locv[pass] - IH_H(xb.y);                                  // _hit.loc (align.cpp:297)
+                    const u32 word0 = g >> 5, wb = word0 & ~1u, nwc = ((g & 31u) + IH_L(xb.y) + 31u) >> 5;
+                    const u32 wq = wb + 2 * q;
+                    if (wq + 1 >= word0 && wq < word0 + nwc) win[pass] = __ldg((const ulonglong2 *)(A.di.plane[sig] + wq));
+                }
+            }
+#pragma unroll
+            for (u32 pass = 0; pass < CHUNK / 64; pass++) {
+                u32 snp = 0, pre = 0, thr = 0;
+                if (act[pass]) {
+                    const u32 it = itx[pass], idx = cbeg + pass * 64 + (t >> 2);
+                    const uint4 xa = s_ha[it]; const uint4 xb = s_hb[it];
+                    u32 e = xb.x + (idx - xa.x); if (e >= xa.y) e -= xa.y;
+                    const u32 sig = e >= xa.w ? 1u : 0u;
+                    const u32 g = locv[pass] - IH_H(xb.y);
+                    const u32 word0 = g >> 5, wb = word0 & ~1u, nwc = ((g & 31u) + IH_L(xb.y) + 31u) >> 5;
+                    const u32 rel = g - 32u * wb;                                           // 0..63
+                    thr = IH_THR(xb.y);
+                    const u32 sh = ((0u - rel) & 15u) * 2u;
+                    const u32 *S = vsm + (size_t)(it - grp) * IST;
+                    const u64 *P = A.di.plane[sig];
+                    for (u32 kk = 0; kk < KIT; kk++) {
+                        const u32 z = 8 * kk + 2 * q;                                       // my two reference words: z, z+1
+                        ulonglong2 r2 = win[pass];
+                        if (kk) { const u32 wq = wb + z; r2 = make_ulonglong2(0ULL, 0ULL); if (wq + 1 >= word0 && wq < word0 + nwc) r2 = __ldg((const ulonglong2 *)(P + wq)); }
+                        const int i0 = ((32 * (int)z - (int)rel) >> 4) + (int)VF_PADF;       // stream word holding read position 32z - rel
+                        const u32 *Sn = S + i0;
+                        const u32 n0 = Sn[0], n1 = Sn[1], n2 = Sn[2], n3 = Sn[3], n4 = Sn[4];
+                        const u32 *Sq = Sn + ST;
+                        const u32 q0 = Sq[0], q1 = Sq[1], q2 = Sq[2], q3 = Sq[3], q4 = Sq[4];
+                        u32 c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+                        if (!SINGLE) { const u32 *Sc = Sn + PL_CM * ST; c0 = Sc[0]; c1 = Sc[1]; c2 = Sc[2]; c3 = Sc[3]; c4 = Sc[4]; }
+                        const u32 d0 = vf_diff<SINGLE>(vf_fsh(q0, q1, sh), vf_fsh(c0, c1, sh), (u32)(r2.x >> 32));
+                        const u32 d1 = vf_diff<SINGLE>(vf_fsh(q1, q2, sh), vf_fsh(c1, c2, sh), (u32)r2.x);
+                        const u32 d2 = vf_diff<SINGLE>(vf_fsh(q2, q3, sh), vf_fsh(c2, c3, sh), (u32)(r2.y >> 32));
+                        const u32 d3 = vf_diff<SINGLE>(vf_fsh(q3, q4, sh), vf_fsh(c3, c4, sh), (u32)r2.y);
+                        snp += __popc((d0 & vf_fsh(n0, n1, sh)) | ((d1 & vf_fsh(n1, n2, sh)) << 1)) + __popc((d2 & vf_fsh(n2, n3, sh)) | ((d3 & vf_fsh(n3, n4, sh)) << 1));
+                        if (GAP) {
+                            const u32 *Sp = Sn + PL_PM * ST;
+                            const u32 p0 = Sp[0], p1 = Sp[1], p2 = Sp[2], p3 = Sp[3], p4 = Sp[4];
+                            pre += __popc((d0 & vf_fsh(p0, p1, sh)) | ((d1 & vf_fsh(p1, p2, sh)) << 1)) + __popc((d2 & vf_fsh(p2, p3, sh)) | ((d3 & vf_fsh(p3, p4, sh)) << 1));
                         }
                     }
                 }
-            }
-            u32 v = snp | (pre << 16);
-            v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
-            snp = v & 0xffffu; pre = v >> 16;
-            // could this candidate add a hit?  ungapped: snp <= thr.  gapped: GapAlign's first test (align.cpp:353-360)
-            const bool mark = valid && q == 0 && (snp <= thr || (GAP && thr >= 2 && pre < thr - 1));
-            const u32 bal = __ballot_sync(0xffffffffu, mark);
-            if (bal) {
-                if (lane == 0) {
-                    u32 byte = 0;
+                u32 v = snp | (pre << 16);
+                v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+                snp = v & 0xffffu; pre = v >> 16;
+                // could this candidate add a hit?  ungapped: snp <= thr.  gapped: GapAlign's first test (align.cpp:353-360)
+                const bool mark = act[pass] && q == 0 && (snp <= thr || (GAP && thr >= 2 && pre < thr - 1));
+                const u32 bal = __ballot_sync(0xffffffffu, mark);
+                if (bal) {
+                    if (lane == 0) {
+                        u32 byte = 0;
 #pragma unroll
-                    for (u32 b = 0; b < 8; b++) byte |= ((bal >> (4 * b)) & 1u) << b;
-                    const u32 c0 = pass * 64 + (t >> 5) * 8;
-                    atomicOr(&s_bits[c0 >> 5], byte << (c0 & 31u));
+                        for (u32 b = 0; b < 8; b++) byte |= ((bal >> (4 * b)) & 1u) << b;
+                        const u32 c0 = pass * 64 + (t >> 5) * 8;
+                        atomicOr(&s_bits[c0 >> 5], byte << (c0 & 31u));
+                    }
+                    if (mark) { const u32 slot = s_hb[itx[pass]].z; if (atomicExch(&A.slot_flag[slot], 1u) == 0u) { const u32 p = atomicAdd(&s_npush, 1u); s_push[p] = slot; } }
                 }
-                if (mark) { const u32 slot = s_slot[it]; if (atomicExch(&A.slot_flag[slot], 1u) == 0u) { const u32 p = atomicAdd(&s_npush, 1u); s_push[p] = slot; } }
             }
         }
         __syncthreads();
@@ -821,6 +887,212 @@ __global__ void pair_round(const __grid_constant__ KArgs A, u32 round, const u32
 }
 
 // ------------------------------------------------------------------------------------------------
+// pair_round_wide : the same replay with one WARP per pair, for pairs whose hit lists are long (reads from
+// repeat families on the large-capacity pass). The per-(chain, level) sub-lists are compacted into shared
+// memory, sorted by rank (stable, like sort_level), and the A x window(B) enumeration of GetPairs is spread
+// over the lanes; positions in the reference's enumeration order come from prefix sums, so the -w cut, the
+// -S pick and the -r 2 listing are the same pairs in the same order.
+// ------------------------------------------------------------------------------------------------
+#define PW_CAP 2048u        // longest sub-list the shared-memory path handles; longer ones take the serial path (lane 0)
+struct PairWideSmem {
+    union { DevHit stage[PW_CAP]; struct { u32 a_loc[PW_CAP], a_chr[PW_CAP], b_loc[PW_CAP], b_chr[PW_CAP]; } k; };
+    u16 ia[PW_CAP], ib[PW_CAP], wbs[PW_CAP], wbe[PW_CAP];
+    PairPick pick;
+};
+
+// indices (in list order) of the hits of `h[0..n)` tagged (chain, level) -> idx[]; returns how many (lists longer than PW_CAP are cut: caller checks n first)
+__device__ u32 pw_compact(const DevHit *h, u32 n, u32 chain, u32 level, u16 *idx, u32 lane) {
+    u32 c = 0;
+    for (u32 t = 0; t < n; t += 32) {
+        const u32 i = t + lane; const bool ok = i < n && tag_is(h[i].tag, chain, level);
+        const u32 bal = __ballot_sync(0xffffffffu, ok);
+        if (ok) idx[c + __popc(bal & ((1u << lane) - 1u))] = (u16)i;
+        c += __popc(bal);
+    }
+    __syncwarp();
+    return c;
+}
+
+__device__ void pw_sort_level(DevHit *h, u32 n, u32 chain, u32 level, PairWideSmem &sm, u32 lane) {
+    const u32 c = pw_compact(h, n, chain, level, sm.ia, lane);
+    if (c <= 1) return;
+    for (u32 x = lane; x < c; x += 32) sm.stage[x] = h[sm.ia[x]];
+    __syncwarp();
+    for (u32 x = lane; x < c; x += 32) {
+        const DevHit me = sm.stage[x]; const u64 kx = ((u64)HIT_CHR2(me.tag) << 32) | me.loc;
+        u32 rank = 0;
+        for (u32 f = 0; f < c; f++) { const u64 kf = ((u64)HIT_CHR2(sm.stage[f].tag) << 32) | sm.stage[f].loc; rank += (kf < kx || (kf == kx && f < x)) ? 1u : 0u; }
+        h[sm.ia[rank]] = me;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ bool pw_valid(const KArgs &A, u32 chain, u32 chra, u32 aloc, u32 bloc, u32 La, u32 Lb, u32 &ins) {
+    const bool a_first = chain == 0 ? !(chra & 1u) : (chra & 1u);
+    u32 s0, e0;
+    if (a_first) { s0 = aloc; e0 = bloc + Lb; } else { s0 = bloc; e0 = aloc + La; }
+    ins = e0 - s0;
+    return ins >= A.min_insert && ins <= A.max_insert;
+}
+
+// warp version of get_pairs; every argument and the return value are warp-uniform
+__device__ u32 pw_get_pairs(const KArgs &A, PairWideSmem &sm, u32 lane, const DevHit *ha, u32 nA, u32 Ba, u32 La, const DevHit *hb, u32 nB, u32 Bb, u32 Lb,
+                            u32 na, u32 nb, u32 &cnt_level, int mode, u32 target, u64 all_base) {
+    if (na > Ba || nb > Bb) return 0;
+    u32 npair = 0;
+    for (u32 chain = 0; chain < 2; chain++) {
+        const u32 cA = pw_compact(ha, nA, chain, na, sm.ia, lane);
+        if (cA == 0) continue;
+        const u32 cB = pw_compact(hb, nB, 1 - chain, nb, sm.ib, lane);
+        if (cB == 0) continue;
+        for (u32 x = lane; x < cA; x += 32) { const DevHit t = ha[sm.ia[x]]; sm.k.a_loc[x] = t.loc; sm.k.a_chr[x] = HIT_CHR2(t.tag); }
+        for (u32 x = lane; x < cB; x += 32) { const DevHit t = hb[sm.ib[x]]; sm.k.b_loc[x] = t.loc; sm.k.b_chr[x] = HIT_CHR2(t.tag); }
+        __syncwarp();
+        // windows of B per A element: the two-pointer walk of GetPairs (state carried from element to element)
+        {
+            u32 chra = ~0u, bs = 0, be = 0;
+            for (u32 x = 0; x < cA; x++) {
+                const u32 ca = sm.k.a_chr[x];
+                if (ca != chra) {
+                    chra = ca;
+                    u32 t = be; bs = cB;
+                    for (; t < cB; t += 32) { const u32 bal = __ballot_sync(0xffffffffu, t + lane < cB && sm.k.b_chr[t + lane] >= chra); if (bal) { bs = t + __ffs(bal) - 1; break; } }
+                    t = bs; be = cB;
+                    for (; t < cB; t += 32) { const u32 bal = __ballot_sync(0xffffffffu, t + lane < cB && sm.k.b_chr[t + lane] > chra); if (bal) { be = t + __ffs(bal) - 1; break; } }
+                }
+                if (lane == 0) { sm.wbs[x] = (u16)bs; sm.wbe[x] = (u16)be; }
+            }
+        }
+        __syncwarp();
+        for (u32 x0 = 0; x0 < cA; x0 += 32) {
+            const u32 x = x0 + lane; u32 cnt = 0, aloc = 0, chra = 0, bs = 0, be = 0;
+            if (x < cA) {
+                aloc = sm.k.a_loc[x]; chra = sm.k.a_chr[x]; bs = sm.wbs[x]; be = sm.wbe[x];
+                for (u32 j = bs; j < be; j++) { u32 ins; cnt += pw_valid(A, chain, chra, aloc, sm.k.b_loc[j], La, Lb, ins) ? 1u : 0u; }
+            }
+            u32 incl = cnt;
+            for (u32 o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const u32 tile = __shfl_sync(0xffffffffu, incl, 31);
+            if (tile == 0) continue;
+            const u32 room = cnt_level >= A.w ? 1u : A.w - cnt_level;          // pairs this call may still take before GetPairs returns
+            const u32 take = min(tile, room);
+            if (mode == 1 && cnt) {
+                u32 q = incl - cnt;                                          // order of my first pair within the tile
+                for (u32 j = bs; j < be && q < take; j++) {
+                    u32 ins;
+                    if (!pw_valid(A, chain, chra, aloc, sm.k.b_loc[j], La, Lb, ins)) continue;
+                    const u32 pos = cnt_level + q;
+                    const DevHit ta = ha[sm.ia[x]], tb = hb[sm.ib[j]];
+                    if (A.report == 2 && A.all_a && all_base + pos < A.all_cap) {
+                        bsl_hit ra, rb; memset(&ra, 0, sizeof ra); memset(&rb, 0, sizeof rb);
+                        ra.loc = ta.loc; ra.chr = HIT_CHR2(ta.tag); ra.gap_size = (int)ta.gap; ra.gap_pos = (u16)ta.gp; ra.nm = (u8)na; ra.read_chain = (u8)chain; ra.read_len = (u16)La; ra.status = BSL_ST_PAIRED; ra.all_first = ins;
+                        rb.loc = tb.loc; rb.chr = HIT_CHR2(tb.tag); rb.gap_size = (int)tb.gap; rb.gap_pos = (u16)tb.gp; rb.nm = (u8)nb; rb.read_chain = (u8)(1 - chain); rb.read_len = (u16)Lb; rb.status = BSL_ST_PAIRED; rb.all_first = ins;
+                        A.all_a[all_base + pos] = ra; A.all_b[all_base + pos] = rb;
+                    }
+                    if (pos == target) { PairPick &pk = sm.pick; pk.found = 1; pk.chain = chain; pk.na = na; pk.nb = nb; pk.insert = ins; pk.a = ta; pk.b = tb; }
+                    q++;
+                }
+            }
+            cnt_level += take; npair += take;
+            if (take == room) { __syncwarp(); return npair; }               // cnt_level reached -w: GetPairs returns
+        }
+        __syncwarp();
+    }
+    return npair;
+}
+
+__global__ void __launch_bounds__(32) pair_round_wide(const __grid_constant__ KArgs A, u32 round, const u32 *list_in, u32 *list_out, u32 ci) {
+    extern __shared__ __align__(16) unsigned char pw_raw[];
+    PairWideSmem &sm = *reinterpret_cast<PairWideSmem *>(pw_raw);
+    RoundCtr *rc = A.ctr->rc + ci;
+    const u32 n_items = rc->active, lane = threadIdx.x;
+    for (u32 k = blockIdx.x; k < n_items; k += gridDim.x) {
+        const u32 p = list_in[k]; const u32 sa = p, sb = p + A.n_a;
+        const SlotMeta ma = A.meta[sa], mb = A.meta[sb];
+        __syncwarp();
+        if ((ma.flags | mb.flags) & SF_OVERFLOW) {
+            if (lane == 0) { if (!(ma.flags & SF_OVERFLOW)) A.meta[sa].flags = ma.flags | SF_OVERFLOW; if (!(mb.flags & SF_OVERFLOW)) A.meta[sb].flags = mb.flags | SF_OVERFLOW; }
+            continue;
+        }
+        DevHit *ha = A.hits + (u64)ma.item * A.cap, *hb = A.hits + (u64)mb.item * A.cap;
+        const u32 nA = ma.nhit, nB = mb.nhit, Ba = ma.B, Bb = mb.B, La = ma.len, Lb = mb.len;
+        const u32 i = round;
+        u32 total = 0, best = 0xffffffffu, best_cnt = 0;
+        const bool wide = nA <= PW_CAP && nB <= PW_CAP;
+        if (wide) {
+            if (i <= Ba) { pw_sort_level(ha, nA, 0, i, sm, lane); pw_sort_level(ha, nA, 1, i, sm, lane); }
+            if (i <= Bb) { pw_sort_level(hb, nB, 0, i, sm, lane); pw_sort_level(hb, nB, 1, i, sm, lane); }
+            if (nA && nB) {
+                u32 c = 0; total += pw_get_pairs(A, sm, lane, ha, nA, Ba, La, hb, nB, Bb, Lb, i, i, c, 0, 0, 0);
+                if (c) { best = 2 * i; best_cnt = c; }
+                for (u32 j = 0; j < i; j++) {
+                    u32 cj = 0;
+                    total += pw_get_pairs(A, sm, lane, ha, nA, Ba, La, hb, nB, Bb, Lb, i, j, cj, 0, 0, 0);
+                    total += pw_get_pairs(A, sm, lane, ha, nA, Ba, La, hb, nB, Bb, Lb, j, i, cj, 0, 0, 0);
+                    if (cj && i + j < best) { best = i + j; best_cnt = cj; }
+                }
+            }
+        } else {
+            if (lane == 0) {
+                if (i <= Ba) { sort_level(ha, nA, 0, i); sort_level(ha, nA, 1, i); }
+                if (i <= Bb) { sort_level(hb, nB, 0, i); sort_level(hb, nB, 1, i); }
+                if (nA && nB) {
+                    u32 c = 0; total += get_pairs(A, ha, nA, Ba, La, hb, nB, Bb, Lb, i, i, c, 0, 0, nullptr, 0);
+                    if (c) { best = 2 * i; best_cnt = c; }
+                    for (u32 j = 0; j < i; j++) {
+                        u32 cj = 0;
+                        total += get_pairs(A, ha, nA, Ba, La, hb, nB, Bb, Lb, i, j, cj, 0, 0, nullptr, 0);
+                        total += get_pairs(A, ha, nA, Ba, La, hb, nB, Bb, Lb, j, i, cj, 0, 0, nullptr, 0);
+                        if (cj && i + j < best) { best = i + j; best_cnt = cj; }
+                    }
+                }
+            }
+            total = __shfl_sync(0xffffffffu, total, 0); best = __shfl_sync(0xffffffffu, best, 0); best_cnt = __shfl_sync(0xffffffffu, best_cnt, 0);
+        }
+        if (total == 0) {
+            if (lane == 0 && round < max(Ba, Bb)) { const u32 pos = atomicAdd(&rc[1].active, 1u); list_out[pos] = p; }
+            continue;
+        }
+        bsl_pair pr; memset(&pr, 0, sizeof pr); pr.n_pairs = best_cnt;
+        if (best_cnt > 1 && A.report == 0) { if (lane == 0) A.pair_out[p] = pr; continue; }
+        const u32 target = best_cnt == 1 ? 0 : ma.rnd % best_cnt;
+        u64 all_base = 0;
+        if (A.report == 2 && A.all_a) {
+            if (lane == 0) all_base = atomicAdd(&A.ctr->all_n, (unsigned long long)best_cnt);
+            all_base = __shfl_sync(0xffffffffu, all_base, 0); pr.all_first = (u32)(all_base + A.all_off);
+        }
+        if (lane == 0) sm.pick.found = 0;
+        __syncwarp();
+        if (wide) {
+            u32 c = 0;
+            if (best == 2 * i) pw_get_pairs(A, sm, lane, ha, nA, Ba, La, hb, nB, Bb, Lb, i, i, c, 1, target, all_base);
+            else { const u32 j = best - i;
+                pw_get_pairs(A, sm, lane, ha, nA, Ba, La, hb, nB, Bb, Lb, i, j, c, 1, target, all_base);
+                pw_get_pairs(A, sm, lane, ha, nA, Ba, La, hb, nB, Bb, Lb, j, i, c, 1, target, all_base); }
+        } else if (lane == 0) {
+            u32 c = 0; PairPick pk; pk.found = 0;
+            if (best == 2 * i) get_pairs(A, ha, nA, Ba, La, hb, nB, Bb, Lb, i, i, c, 1, target, &pk, all_base);
+            else { const u32 j = best - i;
+                get_pairs(A, ha, nA, Ba, La, hb, nB, Bb, Lb, i, j, c, 1, target, &pk, all_base);
+                get_pairs(A, ha, nA, Ba, La, hb, nB, Bb, Lb, j, i, c, 1, target, &pk, all_base); }
+            sm.pick = pk;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            const PairPick pk = sm.pick;
+            pr.insert = pk.insert; pr.chain = (u8)pk.chain; pr.na = (u8)pk.na; pr.nb = (u8)pk.nb;
+            A.pair_out[p] = pr;
+            bsl_hit oa, ob; memset(&oa, 0, sizeof oa); memset(&ob, 0, sizeof ob);
+            fill_record(oa, pk.a, pk.chain, pk.na); fill_record(ob, pk.b, 1 - pk.chain, pk.nb);
+            oa.status = ob.status = BSL_ST_PAIRED; oa.n_hits = ob.n_hits = best_cnt; oa.read_len = (u16)La; ob.read_len = (u16)Lb; oa.max_snp = (u8)Ba; ob.max_snp = (u8)Bb;
+            A.out[sa] = oa; A.out[sb] = ob;
+            A.meta[sa].flags = ma.flags | SF_DONE; A.meta[sb].flags = mb.flags | SF_DONE;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // finalize_reads : StringAlign / StringAlignUnpair selection (align.cpp:583-612, pairs.cpp:232-259)
 // ------------------------------------------------------------------------------------------------
 __global__ void finalize_reads(const __grid_constant__ KArgs A, const u32 *only_list, u32 only_n) {
@@ -1068,10 +1340,13 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     const u32 NW = (31 + 2 * G + Lmax + 31) / 32; const u32 NWS = NW | 1u;
     const size_t smem_r = (size_t)ROUND_WARPS * (32 * NWS + 48) * 8;
     const u32 NP = ctx->rule.single ? 2 : 3;
-    const size_t smem_v = (size_t)CHUNK * NP * Wb * 8;
     const u32 KIT = ((31 + Lmax + 31) / 32 + 1 + 7) / 8;
+    const u32 NPL = NP + (G ? 1 : 0);
+    const u32 ST = VF_PADF + std::max<u32>(2 * Wb, 16 * KIT + 1);        // words per staged stream (verify_candidates)
+    const size_t smem_v = (size_t)VF_ITMAX * NPL * ST * 4;
     static bool attr_set = false;
     if (!attr_set) {
+        cudaFuncSetAttribute(pair_round_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairWideSmem));
         cudaFuncSetAttribute(reduce_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         cudaFuncSetAttribute(reduce_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         cudaFuncSetAttribute(verify_candidates<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
@@ -1104,8 +1379,8 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
         else seed_lookup<false><<<grid_l, LK_THREADS, 0, st>>>(K, r, lin, lout, ci);
         ev_end();
         ev_begin('v');
-        if (ctx->rule.single) { if (G) verify_candidates<true, true><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, KIT); else verify_candidates<true, false><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, KIT); }
-        else { if (G) verify_candidates<false, true><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, KIT); else verify_candidates<false, false><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, KIT); }
+        if (ctx->rule.single) { if (G) verify_candidates<true, true><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, KIT, ST); else verify_candidates<true, false><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, KIT, ST); }
+        else { if (G) verify_candidates<false, true><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, KIT, ST); else verify_candidates<false, false><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, KIT, ST); }
         ev_end();
         ev_begin('r');
         if (ctx->rule.single) reduce_round<true><<<grid_r, ROUND_WARPS * 32, smem_r, st>>>(K, r, ci, NW, NWS);
@@ -1121,7 +1396,8 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
             for (u32 r = 0; r <= BSL_MAXSNPS; r++) {
                 if (r < rounds_se) search(K, true, r, ln.d_pe_list[r & 1], nullptr, 20 + r);
                 ev_begin('p');
-                pair_round<<<sms * 4, 128, 0, st>>>(K, r, ln.d_pe_list[r & 1], ln.d_pe_list[(r + 1) & 1], 20 + r);
+                if (K.hits == ln.d_heavy_hits) pair_round_wide<<<sms * 4, 32, sizeof(PairWideSmem), st>>>(K, r, ln.d_pe_list[r & 1], ln.d_pe_list[(r + 1) & 1], 20 + r);
+                else pair_round<<<sms * 4, 128, 0, st>>>(K, r, ln.d_pe_list[r & 1], ln.d_pe_list[(r + 1) & 1], 20 + r);
                 ev_end(); launches++;
             }
         }
