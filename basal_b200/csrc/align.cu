@@ -59,6 +59,7 @@ struct KArgs {
     u32 *flag_list;                // slots with marked candidates
     u32 *chunk_first;              // first item overlapping each chunk of the flat candidate space
     u32 *bitmap;                   // 1 bit per flat candidate
+    u32 *flat_loc;                 // seed-table entry of every flat candidate (the bucket walks, in visiting order)
     bsl_hit *out; bsl_pair *pair_out; bsl_hit *all_a; bsl_hit *all_b; u64 all_cap;
 };
 
@@ -66,6 +67,17 @@ __device__ __forceinline__ u64 plane_extract(const u64 *pl, u32 p) {     // 32 b
     u32 w = p >> 5, o = (p & 31u) * 2;
     u64 x = pl[w] << o;
     if (o) x |= pl[w + 1] >> (64 - o);
+    return x;
+}
+
+// Read planes live in global memory as "streams": 64-bit words with their halves swapped, so that the same bytes read
+// as a u32 array are in logical order (u32 j = bases 16j..16j+15, first base in the top bits), which is what
+// verify_candidates stages. Plane order per (slot, chain): bases, N-mask reduced to 01 per ACGT base, convert-to mask.
+__device__ __forceinline__ u64 swap32(u64 x) { return (x << 32) | (x >> 32); }
+__device__ __forceinline__ u64 stream_extract(const u64 *pl, u32 p) {    // plane_extract over a stream in global memory
+    u32 w = p >> 5, o = (p & 31u) * 2;
+    u64 x = swap32(pl[w]) << o;
+    if (o) x |= swap32(pl[w + 1]) >> (64 - o);
     return x;
 }
 
@@ -164,7 +176,7 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prepare_reads(const __grid_co
                 sm.pl[0][lane] = q; sm.pl[1][lane] = nm; sm.pl[2][lane] = cm;
                 if (lane < A.Wb) {
                     u64 *dst = A.planes + ((u64)slot * 2 + c) * 3 * A.Wb;
-                    dst[lane] = q; dst[A.Wb + lane] = nm; dst[2 * A.Wb + lane] = cm;
+                    dst[lane] = swap32(q); dst[A.Wb + lane] = swap32(nm & 0x5555555555555555ULL); dst[2 * A.Wb + lane] = swap32(cm);    // stream layout, see KArgs::planes
                 }
             }
             if (lane < 16) sm.need[lane] = 0;
@@ -326,7 +338,7 @@ __global__ void __launch_bounds__(LK_THREADS) seed_lookup(const __grid_constant_
             pq = A.planes + ((u64)slot * 2 + c) * 3 * A.Wb;
             for (u32 i = 0; i < A.I; i++) {
                 const u32 h = T->prof[j][i] + stj - i;
-                const u32 kmer = bsl_xt((u32)(plane_extract(pq, h) >> shs));
+                const u32 kmer = bsl_xt((u32)(stream_extract(pq, h) >> shs));
                 const u32 pm = A.di.bucket[2 * kmer + 2] - A.di.bucket[2 * kmer];
                 if (pm != 0 && pm <= A.di.maxk) { tot += pm; nne++; }
             }
@@ -357,27 +369,49 @@ __global__ void __launch_bounds__(LK_THREADS) seed_lookup(const __grid_constant_
         u32 it = s_ibase + wi0 + xi - nne, cb = s_cbase + wc0 + xc - tot;
         // ---- per-slot bookkeeping (the two chain threads of a slot are neighbouring lanes)
         const u32 tot_o = __shfl_xor_sync(0xffffffffu, tot, 1), se_o = __shfl_xor_sync(0xffffffffu, (u32)search, 1);
+        if (act && c == 0) A.slot_flag[slot] = 0;                                       // reduce_round visits every listed slot and skips the unflagged ones
         if (c == 0 && (search || se_o)) {
             if (ok) {
                 uint2 ss = A.stat[slot]; ss.x += A.I * ((u32)search + se_o); ss.y += tot + tot_o; A.stat[slot] = ss;
-                A.slot_flag[slot] = 0;
             } else { A.meta[slot].flags = m.flags | SF_OVERFLOW; atomicAdd(&A.ctr->overflow_n, 1u); }
         }
-        // ---- pass 2: item headers
-        if (search && ok) {
-            A.slot_item[(u64)slot * 2 + c] = make_uint2(it, nne);
-            for (u32 i = 0; i < A.I && nne; i++) {
+        // ---- pass 2: item headers, and the bucket walk itself: the entries of every non-empty bucket are copied, in
+        //      visiting order (cyclic from rot, align.cpp:293-296), to flat_loc[base..base+m), so that verification
+        //      reads its loc entries as a plain stream. A warp expands the buckets of its lanes together.
+        if (search && ok) A.slot_item[(u64)slot * 2 + c] = make_uint2(it, nne);
+        for (u32 i = 0; i < A.I; i++) {
+            u32 x_cb = 0, x_pm = 0, x_e0 = 0, x_rot = 0;
+            if (search && ok && nne) {
                 const u32 h = T->prof[j][i] + stj - i;
-                const u32 kmer = bsl_xt((u32)(plane_extract(pq, h) >> shs));
+                const u32 kmer = bsl_xt((u32)(stream_extract(pq, h) >> shs));
                 const u32 e0 = A.di.bucket[2 * kmer], e1 = A.di.bucket[2 * kmer + 1], e2 = A.di.bucket[2 * kmer + 2];
                 const u32 pm = e2 - e0;
-                if (pm == 0 || pm > A.di.maxk) continue;
-                uint4 a, b;
-                a.x = cb; a.y = pm; a.z = e0; a.w = e1 - e0;
-                b.x = m.rnd % pm; b.y = h | ((u32)m.len << 9) | ((u32)m.thr << 18) | (i << 22) | (c << 26); b.z = slot; b.w = 0;
-                uint4 *dst = (uint4 *)(A.hdr + it); dst[0] = a; dst[1] = b;
-                for (u32 cc = (cb + CHUNK - 1) / CHUNK; (u64)cc * CHUNK < (u64)cb + pm; cc++) A.chunk_first[cc] = it;
-                cb += pm; it++;
+                if (pm != 0 && pm <= A.di.maxk) {
+                    uint4 a, b;
+                    a.x = cb; a.y = pm; a.z = e0; a.w = e1 - e0;
+                    b.x = m.rnd % pm; b.y = h | ((u32)m.len << 9) | ((u32)m.thr << 18) | (i << 22) | (c << 26); b.z = slot; b.w = 0;
+                    uint4 *dst = (uint4 *)(A.hdr + it); dst[0] = a; dst[1] = b;
+                    for (u32 cc = (cb + CHUNK - 1) / CHUNK; (u64)cc * CHUNK < (u64)cb + pm; cc++) A.chunk_first[cc] = it;
+                    x_cb = cb; x_pm = pm; x_e0 = e0; x_rot = b.x;
+                    cb += pm; it++;
+                }
+            }
+            u32 todo = __ballot_sync(0xffffffffu, x_pm != 0);
+            while (todo) {                                   // 8 buckets per trip: their gathers are all in flight before the first store
+                u32 v[8], dst[8];
+#pragma unroll
+                for (u32 b = 0; b < 8; b++) {
+                    dst[b] = 0xffffffffu;
+                    if (todo) {
+                        const u32 l = __ffs(todo) - 1; todo &= todo - 1;
+                        const u32 ycb = __shfl_sync(0xffffffffu, x_cb, l), ypm = __shfl_sync(0xffffffffu, x_pm, l);
+                        const u32 ye0 = __shfl_sync(0xffffffffu, x_e0, l), yrot = __shfl_sync(0xffffffffu, x_rot, l);
+                        if (lane < ypm) { u32 e = yrot + lane; if (e >= ypm) e -= ypm; v[b] = __ldg(A.di.loc + ye0 + e); dst[b] = ycb + lane; }
+                        for (u32 tt = lane + 32; tt < ypm; tt += 32) { u32 e = yrot + tt; if (e >= ypm) e -= ypm; A.flat_loc[ycb + tt] = __ldg(A.di.loc + ye0 + e); }
+                    }
+                }
+#pragma unroll
+                for (u32 b = 0; b < 8; b++) if (dst[b] != 0xffffffffu) A.flat_loc[dst[b]] = v[b];
             }
         }
         __syncthreads();
@@ -410,118 +444,163 @@ __device__ __forceinline__ u32 vf_diff(u32 q, u32 cm, u32 r) {
     return d | (d >> 1);                                                 // caller ANDs with a 01-per-base mask
 }
 
-template <bool SINGLE, bool GAP>
+#define VF_EAGER 96u         // item headers every CTA prefetches for its next chunk (a chunk with more items loads the rest on demand)
+
+// one pass = 64 candidates of the chunk, 4 lanes each. K1: every window fits the 8 reference words the 4 lanes fetch at
+// once (reads up to 191 bases); otherwise each lane walks KIT groups of 8 words.
+template <bool SINGLE, bool GAP, bool K1>
 __global__ void __launch_bounds__(VF_THREADS, 3) verify_candidates(const __grid_constant__ KArgs A, u32 ci, u32 KIT, u32 ST) {
     extern __shared__ u32 vsm[];                          // staged streams: item x stream x ST
     __shared__ uint4 s_ha[CHUNK], s_hb[CHUNK];            // item headers {base, m, b0, nfwd} {rot, pack, slot, -}
-    __shared__ u32 s_mask[CHUNK / 32], s_pref[CHUNK / 32 + 1], s_bits[CHUNK / 32], s_push[CHUNK], s_npush, s_pbase;
-    constexpr u32 NPL = 2 + (SINGLE ? 0 : 1) + (GAP ? 1 : 0);
-    constexpr u32 PL_CM = 2, PL_PM = SINGLE ? 2 : 3;
+    __shared__ u32 s_mask[CHUNK / 32], s_bits[CHUNK / 32];
+    constexpr u32 NP = SINGLE ? 2 : 3;                    // streams copied from global memory: bases, N-mask, (convert-to mask)
+    constexpr u32 NPL = NP + (GAP ? 1 : 0);               // + prefix mask
+    constexpr u32 PL_NM = 1, PL_CM = 2, PL_PM = NP;
+    constexpr u32 NPASS = CHUNK / 64;
     RoundCtr *rc = A.ctr->rc + ci;
     const unsigned long long al = min(rc->alloc, ~rc->limit_inv);
     const u32 n_cands = (u32)(al & ALLOC_MASK), n_items = (u32)(al >> ALLOC_SHIFT);
     const u32 n_chunks = (n_cands + CHUNK - 1) / CHUNK;
     const u32 t = threadIdx.x, lane = t & 31u, wid = t >> 5, q = t & 3u;
-    const u32 IST = NPL * ST;
-    for (u32 chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const u32 IST = NPL * ST, W2 = 2 * A.Wb, D = NP * W2;
+    if (blockIdx.x >= n_chunks) return;
+    // the pads of every stream stay zero for the whole kernel: staging only ever writes the data words
+    for (u32 x = t; x < VF_ITMAX * IST; x += VF_THREADS) vsm[x] = 0;
+    // ---- software pipeline over this CTA's chunks: the headers of the next chunk are loaded while this one is verified
+    u32 chunk = blockIdx.x, first = A.chunk_first[chunk];
+    uint4 ha = make_uint4(0, 0, 0, 0), hb = ha; bool have = false;
+    if (t < VF_EAGER && first + t < n_items) { const uint4 *src = (const uint4 *)(A.hdr + first + t); ha = __ldg(src); hb = __ldg(src + 1); have = true; }
+    u32 nchunk = chunk + gridDim.x, nfirst = nchunk < n_chunks ? A.chunk_first[nchunk] : 0u;
+    u32 cloc[NPASS];                                      // seed-table entries of my 4 candidates (flat_loc is a plain stream)
+#pragma unroll
+    for (u32 pass = 0; pass < NPASS; pass++) { const u32 idx = chunk * CHUNK + pass * 64 + (t >> 2); cloc[pass] = idx < n_cands ? __ldg(A.flat_loc + idx) : 0u; }
+    for (; chunk < n_chunks;) {
         const u32 cbeg = chunk * CHUNK, cend = min(cbeg + CHUNK, n_cands);
-        const u32 first = A.chunk_first[chunk];
-        // ---- headers of the items that overlap this chunk (their bases are increasing)
-        bool mine = false; uint4 ha, hb;
-        if (first + t < n_items) { const uint4 *src = (const uint4 *)(A.hdr + first + t); ha = src[0]; mine = (t == 0) || ha.x < cend; if (mine) hb = src[1]; }
+        bool mine = have && (t == 0 || ha.x < cend);
         if (t < CHUNK / 32) { s_mask[t] = 0; s_bits[t] = 0; }
-        if (t == 0) s_npush = 0;
-        const u32 n_it = (u32)__syncthreads_count(mine);
+        u32 n_it = (u32)__syncthreads_count(mine);
+        if (n_it == VF_EAGER) {                                                  // (rare) more items than were prefetched
+            if (t >= VF_EAGER && first + t < n_items) { const uint4 *src = (const uint4 *)(A.hdr + first + t); ha = __ldg(src); mine = ha.x < cend; if (mine) hb = __ldg(src + 1); }
+            n_it = (u32)__syncthreads_count(mine);
+        }
         if (mine) {
+            hb.w = (hb.z * 2 + IH_CHAIN(hb.y)) * 3 * A.Wb;                   // first word of the item's read streams
             s_ha[t] = ha; s_hb[t] = hb;
             const u32 pos = ha.x > cbeg ? ha.x - cbeg : 0u;                  // first candidate of the item inside the chunk
             atomicOr(&s_mask[pos >> 5], 1u << (pos & 31u));
         }
+        // prefetch for the next chunk (consumed at the top of the next iteration)
+        uint4 pa = make_uint4(0, 0, 0, 0), pb = pa; bool phave = false;
+        if (nchunk < n_chunks && t < VF_EAGER && nfirst + t < n_items) { const uint4 *src = (const uint4 *)(A.hdr + nfirst + t); pa = __ldg(src); pb = __ldg(src + 1); phave = true; }
+        const u32 nnchunk = nchunk + gridDim.x; const u32 nnfirst = nnchunk < n_chunks ? __ldg(A.chunk_first + nnchunk) : 0u;
+        u32 nloc[NPASS];
+#pragma unroll
+        for (u32 pass = 0; pass < NPASS; pass++) { const u32 idx = nchunk * CHUNK + pass * 64 + (t >> 2); nloc[pass] = (nchunk < n_chunks && idx < n_cands) ? __ldg(A.flat_loc + idx) : 0u; }
         __syncthreads();
-        if (t == 0) { u32 acc = 0; for (u32 w = 0; w < CHUNK / 32; w++) { s_pref[w] = acc; acc += __popc(s_mask[w]); } }
+        // item of candidate c = (number of item starts at positions <= c) - 1: prefix popcounts of the start mask.
+        // The candidates of my pass p sit in mask word 2p + (t >> 7).
+        u32 wpre[NPASS], wmsk[NPASS];
+        {
+            u32 acc = 0;
+#pragma unroll
+            for (u32 ww = 0; ww < CHUNK / 32; ww++) {
+                const u32 mk = s_mask[ww];
+                if ((ww & 1u) == (t >> 7)) { wpre[ww >> 1] = acc; wmsk[ww >> 1] = mk; }
+                acc += __popc(mk);
+            }
+        }
         for (u32 grp = 0; grp < n_it; grp += VF_ITMAX) {
             const u32 n_g = min(VF_ITMAX, n_it - grp);
             if (grp) __syncthreads();                                        // the previous group is done with the staging buffer
-            // ---- stage the streams of this group's items: one warp per (item, stream) row
-            for (u32 row = wid; row < n_g * NPL; row += VF_THREADS / 32) {
-                const u32 it = row / NPL, pl = row - it * NPL;
-                const uint4 xb = s_hb[grp + it];
-                const u32 *src = (const u32 *)(A.planes + ((u64)xb.z * 2 + IH_CHAIN(xb.y)) * 3 * A.Wb + (pl == 0 ? 1u : pl == 1 ? 0u : 2u) * A.Wb);
-                const u32 hs = IH_H(xb.y) + A.s;
-                for (u32 wi = lane; wi < ST; wi += 32) {
-                    u32 v = 0; const u32 j = wi - VF_PADF;
-                    if (wi >= VF_PADF && j < 2 * A.Wb) {
-                        if (GAP && pl == PL_PM) v = hs >= 16 * j + 16 ? 0x55555555u : (hs <= 16 * j ? 0u : 0x55555555u & (0xffffffffu << (32 - 2 * (hs - 16 * j))));
-                        else { v = src[j ^ 1u]; if (pl == 0) v &= 0x55555555u; }    // logical word j = high half first
-                    }
-                    vsm[(size_t)it * IST + pl * ST + wi] = v;
-                }
-            }
-            __syncthreads();
-            // ---- 4 lanes per candidate, 64 candidates per pass; the 4 passes are interleaved so that their loc and
-            //      window loads are all in flight before the first popcount
-            u32 itx[CHUNK / 64], locv[CHUNK / 64]; bool act[CHUNK / 64];
+            // ---- 4 lanes per candidate, 64 candidates per pass; the window gathers of all passes are issued first
+            //      (they are the long pole: random DRAM sectors), the staging copies right behind them
+            u32 itx[NPASS], gv[NPASS];            // itx: item | reference strand << 16 | active << 17 ; gv: alignment start g
+            ulonglong2 win[NPASS];
 #pragma unroll
-            for (u32 pass = 0; pass < CHUNK / 64; pass++) {
+            for (u32 pass = 0; pass < NPASS; pass++) {
                 const u32 cidx = pass * 64 + (t >> 2), idx = cbeg + cidx;
-                const u32 w = cidx >> 5;
-                const u32 it = s_pref[w] + __popc(s_mask[w] & (0xffffffffu >> (31u - (cidx & 31u)))) - 1u;
-                act[pass] = idx < cend && it >= grp && it < grp + n_g;
-                itx[pass] = it; locv[pass] = 0;
-                if (act[pass]) {
-                    const uint4 xa = s_ha[it]; const u32 rot = s_hb[it].x;
-                    u32 e = rot + (idx - xa.x); if (e >= xa.y) e -= xa.y;
-                    locv[pass] = __ldg(A.di.loc + xa.z + e);
-                }
-            }
-            ulonglong2 win[CHUNK / 64];
-#pragma unroll
-            for (u32 pass = 0; pass < CHUNK / 64; pass++) {
-                win[pass] = make_ulonglong2(0ULL, 0ULL);
-                if (act[pass]) {
-                    const u32 it = itx[pass], idx = cbeg + pass * 64 + (t >> 2);
-                    const uint4 xa = s_ha[it]; const uint4 xb = s_hb[it];
+                const u32 it = wpre[pass] + __popc(wmsk[pass] & (0xffffffffu >> (31u - (cidx & 31u)))) - 1u;
+                itx[pass] = it; gv[pass] = 0; win[pass] = make_ulonglong2(0ULL, 0ULL);
+                if (idx < cend && it >= grp && it < grp + n_g) {
+                    const uint4 xa = s_ha[it]; const uint2 xb = *(const uint2 *)&s_hb[it];
                     u32 e = xb.x + (idx - xa.x); if (e >= xa.y) e -= xa.y;
-                    const u32 sig = e >= xa.w ? 1u : 0u;
-                    const u32 g = locv[pass] - IH_H(xb.y);                                  // _hit.loc (align.cpp:297)
-                    const u32 word0 = g >> 5, wb = word0 & ~1u, nwc = ((g & 31u) + IH_L(xb.y) + 31u) >> 5;
-                    const u32 wq = wb + 2 * q;
+                    const u32 sig = e >= xa.w ? 1u : 0u;                                    // forward-strand entries come first (align.cpp:296)
+                    itx[pass] = it | (sig << 16) | 0x20000u;
+                    const u32 g = cloc[pass] - IH_H(xb.y);                                  // _hit.loc (align.cpp:297)
+                    gv[pass] = g;
+                    const u32 word0 = g >> 5, nwc = ((g & 31u) + IH_L(xb.y) + 31u) >> 5;
+                    const u32 wq = (word0 & ~1u) + 2 * q;
                     if (wq + 1 >= word0 && wq < word0 + nwc) win[pass] = __ldg((const ulonglong2 *)(A.di.plane[sig] + wq));
                 }
             }
+            // ---- stage the streams of this group's items: a warp copies the D contiguous data words of an item
+            //      (coalesced), four items per warp in flight
+            for (u32 l = lane; l < D; l += 32) {
+                const u32 pl = l / W2, so = pl * ST + VF_PADF + (l - pl * W2);
+                for (u32 m0 = wid; m0 < n_g; m0 += 4 * (VF_THREADS / 32)) {
+                    u32 v[4];
 #pragma unroll
-            for (u32 pass = 0; pass < CHUNK / 64; pass++) {
+                    for (u32 b = 0; b < 4; b++) {
+                        const u32 it = m0 + b * (VF_THREADS / 32);
+                        if (it < n_g) v[b] = __ldg((const u32 *)(A.planes + s_hb[grp + it].w) + l);
+                    }
+#pragma unroll
+                    for (u32 b = 0; b < 4; b++) { const u32 it = m0 + b * (VF_THREADS / 32); if (it < n_g) vsm[(size_t)it * IST + so] = v[b]; }
+                }
+            }
+            if (GAP) {
+                for (u32 j = lane; j < W2; j += 32)
+                    for (u32 it = wid; it < n_g; it += VF_THREADS / 32) {
+                        const u32 hs = IH_H(s_hb[grp + it].y) + A.s;
+                        vsm[(size_t)it * IST + PL_PM * ST + VF_PADF + j] = hs >= 16 * j + 16 ? 0x55555555u : (hs <= 16 * j ? 0u : 0x55555555u & (0xffffffffu << (32 - 2 * (hs - 16 * j))));
+                    }
+            }
+            // ---- L2 prefetch for the NEXT chunk (its headers, loaded at the top of this iteration, have arrived by now):
+            //      the read streams of every item, so that the staging copies of the next iteration hit L2 instead of DRAM
+            if (grp == 0 && phave) {
+                const u32 ncend = min(nchunk * CHUNK + CHUNK, n_cands);
+                if (t == 0 || pa.x < ncend) {
+                    const char *pp = (const char *)(A.planes + (size_t)(pb.z * 2 + IH_CHAIN(pb.y)) * 3 * A.Wb);
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(pp));
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(pp + 4 * D - 4));
+                }
+            }
+            __syncthreads();                                                                // staged streams visible
+#pragma unroll
+            for (u32 pass = 0; pass < NPASS; pass++) {
                 u32 snp = 0, pre = 0, thr = 0;
-                if (act[pass]) {
-                    const u32 it = itx[pass], idx = cbeg + pass * 64 + (t >> 2);
-                    const uint4 xa = s_ha[it]; const uint4 xb = s_hb[it];
-                    u32 e = xb.x + (idx - xa.x); if (e >= xa.y) e -= xa.y;
-                    const u32 sig = e >= xa.w ? 1u : 0u;
-                    const u32 g = locv[pass] - IH_H(xb.y);
-                    const u32 word0 = g >> 5, wb = word0 & ~1u, nwc = ((g & 31u) + IH_L(xb.y) + 31u) >> 5;
+                const bool act = (itx[pass] & 0x20000u) != 0;
+                if (act) {
+                    const u32 it = itx[pass] & 0xffffu;
+                    const u32 pack = s_hb[it].y;
+                    const u32 g = gv[pass];
+                    const u32 word0 = g >> 5, wb = word0 & ~1u;
                     const u32 rel = g - 32u * wb;                                           // 0..63
-                    thr = IH_THR(xb.y);
+                    thr = IH_THR(pack);
                     const u32 sh = ((0u - rel) & 15u) * 2u;
                     const u32 *S = vsm + (size_t)(it - grp) * IST;
-                    const u64 *P = A.di.plane[sig];
-                    for (u32 kk = 0; kk < KIT; kk++) {
+                    const u32 nk = K1 ? 1u : KIT;
+                    for (u32 kk = 0; kk < nk; kk++) {
                         const u32 z = 8 * kk + 2 * q;                                       // my two reference words: z, z+1
                         ulonglong2 r2 = win[pass];
-                        if (kk) { const u32 wq = wb + z; r2 = make_ulonglong2(0ULL, 0ULL); if (wq + 1 >= word0 && wq < word0 + nwc) r2 = __ldg((const ulonglong2 *)(P + wq)); }
+                        if (!K1 && kk) {
+                            const u32 nwc = ((g & 31u) + IH_L(pack) + 31u) >> 5; const u32 wq = wb + z;
+                            r2 = make_ulonglong2(0ULL, 0ULL); if (wq + 1 >= word0 && wq < word0 + nwc) r2 = __ldg((const ulonglong2 *)(A.di.plane[(itx[pass] >> 16) & 1u] + wq));
+                        }
                         const int i0 = ((32 * (int)z - (int)rel) >> 4) + (int)VF_PADF;       // stream word holding read position 32z - rel
-                        const u32 *Sn = S + i0;
-                        const u32 n0 = Sn[0], n1 = Sn[1], n2 = Sn[2], n3 = Sn[3], n4 = Sn[4];
-                        const u32 *Sq = Sn + ST;
+                        const u32 *Sq = S + i0;
                         const u32 q0 = Sq[0], q1 = Sq[1], q2 = Sq[2], q3 = Sq[3], q4 = Sq[4];
+                        const u32 *Sn = Sq + PL_NM * ST;
+                        const u32 n0 = Sn[0], n1 = Sn[1], n2 = Sn[2], n3 = Sn[3], n4 = Sn[4];
                         u32 c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
-                        if (!SINGLE) { const u32 *Sc = Sn + PL_CM * ST; c0 = Sc[0]; c1 = Sc[1]; c2 = Sc[2]; c3 = Sc[3]; c4 = Sc[4]; }
+                        if (!SINGLE) { const u32 *Sc = Sq + PL_CM * ST; c0 = Sc[0]; c1 = Sc[1]; c2 = Sc[2]; c3 = Sc[3]; c4 = Sc[4]; }
                         const u32 d0 = vf_diff<SINGLE>(vf_fsh(q0, q1, sh), vf_fsh(c0, c1, sh), (u32)(r2.x >> 32));
                         const u32 d1 = vf_diff<SINGLE>(vf_fsh(q1, q2, sh), vf_fsh(c1, c2, sh), (u32)r2.x);
                         const u32 d2 = vf_diff<SINGLE>(vf_fsh(q2, q3, sh), vf_fsh(c2, c3, sh), (u32)(r2.y >> 32));
                         const u32 d3 = vf_diff<SINGLE>(vf_fsh(q3, q4, sh), vf_fsh(c3, c4, sh), (u32)r2.y);
                         snp += __popc((d0 & vf_fsh(n0, n1, sh)) | ((d1 & vf_fsh(n1, n2, sh)) << 1)) + __popc((d2 & vf_fsh(n2, n3, sh)) | ((d3 & vf_fsh(n3, n4, sh)) << 1));
                         if (GAP) {
-                            const u32 *Sp = Sn + PL_PM * ST;
+                            const u32 *Sp = Sq + PL_PM * ST;
                             const u32 p0 = Sp[0], p1 = Sp[1], p2 = Sp[2], p3 = Sp[3], p4 = Sp[4];
                             pre += __popc((d0 & vf_fsh(p0, p1, sh)) | ((d1 & vf_fsh(p1, p2, sh)) << 1)) + __popc((d2 & vf_fsh(p2, p3, sh)) | ((d3 & vf_fsh(p3, p4, sh)) << 1));
                         }
@@ -531,29 +610,24 @@ __global__ void __launch_bounds__(VF_THREADS, 3) verify_candidates(const __grid_
                 v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
                 snp = v & 0xffffu; pre = v >> 16;
                 // could this candidate add a hit?  ungapped: snp <= thr.  gapped: GapAlign's first test (align.cpp:353-360)
-                const bool mark = act[pass] && q == 0 && (snp <= thr || (GAP && thr >= 2 && pre < thr - 1));
-                const u32 bal = __ballot_sync(0xffffffffu, mark);
-                if (bal) {
+                const bool mark = act && q == 0 && (snp <= thr || (GAP && thr >= 2 && pre < thr - 1));
+                u32 x = __ballot_sync(0xffffffffu, mark);
+                if (x) {
+                    if (mark) A.slot_flag[s_hb[itx[pass] & 0xffffu].z] = 1u;                // reduce_round replays this read
                     if (lane == 0) {
-                        u32 byte = 0;
-#pragma unroll
-                        for (u32 b = 0; b < 8; b++) byte |= ((bal >> (4 * b)) & 1u) << b;
+                        x = (x | (x >> 3)) & 0x03030303u; x = (x | (x >> 6)) & 0x000F000Fu; x = (x | (x >> 12)) & 0xFFu;   // bit 4b -> bit b
                         const u32 c0 = pass * 64 + (t >> 5) * 8;
-                        atomicOr(&s_bits[c0 >> 5], byte << (c0 & 31u));
+                        atomicOr(&s_bits[c0 >> 5], x << (c0 & 31u));
                     }
-                    if (mark) { const u32 slot = s_hb[itx[pass]].z; if (atomicExch(&A.slot_flag[slot], 1u) == 0u) { const u32 p = atomicAdd(&s_npush, 1u); s_push[p] = slot; } }
                 }
             }
         }
         __syncthreads();
         if (t < CHUNK / 32) A.bitmap[(cbeg >> 5) + t] = s_bits[t];
-        const u32 np = s_npush;
-        if (np) {
-            if (t == 0) s_pbase = atomicAdd(&rc->flagged, np);
-            __syncthreads();
-            if (t < np) A.flag_list[s_pbase + t] = s_push[t];
-        }
         __syncthreads();
+        chunk = nchunk; first = nfirst; ha = pa; hb = pb; have = phave; nchunk = nnchunk; nfirst = nnfirst;
+#pragma unroll
+        for (u32 pass = 0; pass < NPASS; pass++) cloc[pass] = nloc[pass];
     }
 }
 
@@ -645,21 +719,29 @@ __device__ int add_hit(const KArgs &A, WarpCtx &S, u32 lane, u32 level, u32 g, u
 }
 
 template <bool SINGLE>
-__global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_constant__ KArgs A, u32 round, u32 ci, u32 NW, u32 NWS) {
+__global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_constant__ KArgs A, u32 round, u32 ci, u32 NW, u32 NWS, const u32 *list, u32 list_ci, u32 as_pe) {
     extern __shared__ u64 smem[];
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     u64 *win_all = smem + (size_t)wid * (32 * NWS + 48);
     u64 *pq = win_all + 32 * NWS, *pn = pq + 16, *pc = pn + 16;
     RoundCtr *rc = A.ctr->rc + ci;
-    const u32 n_items = rc->flagged;
+    // every slot searched in this round: SE = the compacted list seed_lookup wrote, PE = both mates of every listed pair;
+    // a warp takes 32 of them at a time and replays those verify_candidates flagged
+    const u32 n_entries = A.ctr->rc[list_ci].active << (as_pe ? 1 : 0);
+    const u32 batch = min(32u, max(1u, n_entries / (gridDim.x * ROUND_WARPS * 4)));      // few entries (the large-capacity pass): one per grab, for balance
     const u32 G = A.gap;
     unsigned long long st_hits = 0;
     for (;;) {
-        u32 k = 0;
-        if (lane == 0) k = atomicAdd(&rc->work, 1u);
-        k = __shfl_sync(0xffffffffu, k, 0);
-        if (k >= n_items) break;
-        const u32 slot = A.flag_list[k];
+        u32 k0 = 0;
+        if (lane == 0) k0 = atomicAdd(&rc->work, batch);
+        k0 = __shfl_sync(0xffffffffu, k0, 0);
+        if (k0 >= n_entries) break;
+        u32 my_slot = 0; bool flagged = false;
+        if (lane < batch && k0 + lane < n_entries) { const u32 kk = k0 + lane; my_slot = as_pe ? list[kk >> 1] + (kk & 1u) * A.n_a : list[kk]; flagged = A.slot_flag[my_slot] != 0u; }
+        u32 todo = __ballot_sync(0xffffffffu, flagged);
+      while (todo) {
+        const u32 src_lane = __ffs(todo) - 1; todo &= todo - 1;
+        const u32 slot = __shfl_sync(0xffffffffu, my_slot, src_lane);
         SlotMeta m = A.meta[slot];
         WarpCtx S; S.L = m.len; S.W = (S.L + 31) >> 5; S.thr = m.thr; S.nhit = m.nhit; S.cap = A.cap; S.overflow = false;
         S.hits = A.hits + (u64)m.item * A.cap;
@@ -689,7 +771,7 @@ __global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_co
             if (lane < 16) {
                 const u64 *src = A.planes + ((u64)slot * 2 + c) * 3 * A.Wb;
                 bool in = lane < A.Wb;
-                pq[lane] = in ? src[lane] : 0; pn[lane] = in ? src[A.Wb + lane] : 0; pc[lane] = in ? src[2 * A.Wb + lane] : 0;
+                pq[lane] = in ? swap32(src[lane]) : 0; pn[lane] = in ? swap32(src[A.Wb + lane]) : 0; pc[lane] = in ? swap32(src[2 * A.Wb + lane]) : 0;   // pn: 01 per ACGT base
             }
             __syncwarp();
             for (u32 tile = 0; tile < total && !stop_all; tile += 32) {
@@ -706,7 +788,7 @@ __global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_co
                 if (valid) {
                     u32 e = crot + t; if (e >= cm_) e -= cm_;
                     sig = e >= cnf ? 1u : 0u;
-                    g = A.di.loc[cb0 + e] - ch;                                 // _hit.loc (align.cpp:297)
+                    g = A.flat_loc[flat] - ch;                                  // _hit.loc (align.cpp:297)
                     const u32 gb = g - G; const u32 word0 = gb >> 5; rel = (gb & 31u) + G;      // window starts at word0; alignment starts `rel` bases into it
                     const u64 *P = A.di.plane[sig] + word0;
                     for (u32 w = 0; w < NW; w++) win[w] = __ldg(P + w);
@@ -715,8 +797,8 @@ __global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_co
                 if (valid) {
                     snp = 0;
                     for (u32 i = 0; i < W; i++) {                              // CountMismatch / CountMismatch_new
-                        u64 d = bsl_diff<SINGLE>(pq[i], pc[i], ref_word(win, NW, rel, i)) & pn[i];
-                        snp += __popcll(bsl_pairs(d));
+                        const u64 d = bsl_diff<SINGLE>(pq[i], pc[i], ref_word(win, NW, rel, i));
+                        snp += __popcll(bsl_pairs(d) & pn[i]);
                     }
                     if (G) gres = gap_search<SINGLE>(win, NW, rel, pq, pc, L, W, endmask, S.thr, ch, A.s, G);
                 }
@@ -755,6 +837,8 @@ __global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_co
             const u32 lv = (nz | (nz >> 16)) & 0xffffu;
             A.minlvl[slot] = lv ? (u8)(__ffs(lv) - 1) : (u8)255;
         }
+        __syncwarp();
+      }
     }
     if (lane == 0 && st_hits) atomicAdd(&A.ctr->hits_added, st_hits);
 }
@@ -1187,7 +1271,7 @@ template <typename T> int grow(bsl_ctx *ctx, T **p, size_t *cap, size_t need, bo
 void bsl_lane_free(Lane &ln) {
     cudaFree(ln.d_bases); cudaFree(ln.d_off); cudaFree(ln.d_index); cudaFree(ln.d_rawlen); cudaFree(ln.d_meta); cudaFree(ln.d_cnt); cudaFree(ln.d_sched); cudaFree(ln.d_stat);
     cudaFree(ln.d_minlvl); cudaFree(ln.d_slot_item); cudaFree(ln.d_slot_flag); cudaFree(ln.d_flag_list);
-    cudaFree(ln.d_hdr); cudaFree(ln.d_chunk_first); cudaFree(ln.d_bitmap);
+    cudaFree(ln.d_hdr); cudaFree(ln.d_chunk_first); cudaFree(ln.d_bitmap); cudaFree(ln.d_flat_loc);
     cudaFree(ln.d_planes); cudaFree(ln.d_hits); cudaFree(ln.d_heavy_hits); cudaFree(ln.d_list[0]); cudaFree(ln.d_list[1]); cudaFree(ln.d_heavy_list);
     cudaFree(ln.d_pe_list[0]); cudaFree(ln.d_pe_list[1]); cudaFree(ln.d_out); cudaFree(ln.d_pair); cudaFree(ln.d_all[0]); cudaFree(ln.d_all[1]); cudaFree(ln.d_ctr);
     if (ln.h_ctr) cudaFreeHost(ln.h_ctr);
@@ -1285,7 +1369,8 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     if (2 * worst_slot + CHUNK > want_cands) { set_error(ctx, "over-represented k-mer cut-off %u is too large for the 32-bit candidate space", ctx->di.maxk); return BSL_ELIMIT; }
     const u64 want_items = std::min<u64>((u64)n_slots * nch * P.index_interval, want_cands) + 16;
     c0 = ln.cap_bitmap; if ((rc = grow(ctx, &ln.d_bitmap, &c0, (size_t)(want_cands / 32 + 8)))) return rc;
-    if (c0 != ln.cap_bitmap || !ln.d_chunk_first) { cudaFree(ln.d_chunk_first); ln.d_chunk_first = nullptr; CUDA_TRY(cudaMalloc(&ln.d_chunk_first, (c0 * 32 / CHUNK + 8) * 4)); }
+    if (c0 != ln.cap_bitmap || !ln.d_chunk_first) { cudaFree(ln.d_chunk_first); ln.d_chunk_first = nullptr; CUDA_TRY(cudaMalloc(&ln.d_chunk_first, (c0 * 32 / CHUNK + 8) * 4));
+        cudaFree(ln.d_flat_loc); ln.d_flat_loc = nullptr; CUDA_TRY(cudaMalloc(&ln.d_flat_loc, (c0 * 32 + 2 * CHUNK) * 4)); }
     ln.cap_bitmap = c0;
     c0 = ln.cap_items; if ((rc = grow(ctx, &ln.d_hdr, &c0, (size_t)want_items))) return rc; ln.cap_items = c0;
     const bool want_all = P.report_repeat_hits == 2 && all_a && (!pe || all_b) && all_cap > 0;
@@ -1308,7 +1393,7 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     A.Wb = Wb; A.planes = ln.d_planes; A.sched = ln.d_sched; A.meta = ln.d_meta; A.cnt = ln.d_cnt; A.stat = ln.d_stat; A.minlvl = ln.d_minlvl;
     A.hits = ln.d_hits; A.cap = cap_main; A.ctr = ln.d_ctr;
     A.hdr = ln.d_hdr; A.cap_items = (u32)std::min<u64>(want_items - 16, 0xffffffffu); A.cap_cands = (u32)want_cands;
-    A.slot_item = ln.d_slot_item; A.slot_flag = ln.d_slot_flag; A.flag_list = ln.d_flag_list; A.chunk_first = ln.d_chunk_first; A.bitmap = ln.d_bitmap;
+    A.slot_item = ln.d_slot_item; A.slot_flag = ln.d_slot_flag; A.flag_list = ln.d_flag_list; A.chunk_first = ln.d_chunk_first; A.bitmap = ln.d_bitmap; A.flat_loc = ln.d_flat_loc;
     A.out = ln.d_out; A.pair_out = ln.d_pair; A.all_a = want_all ? ln.d_all[0] : nullptr; A.all_b = want_all ? ln.d_all[1] : nullptr; A.all_cap = want_all ? sub_cap : 0;
 
     // ---- H2D
@@ -1349,23 +1434,23 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
         cudaFuncSetAttribute(pair_round_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairWideSmem));
         cudaFuncSetAttribute(reduce_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         cudaFuncSetAttribute(reduce_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        cudaFuncSetAttribute(verify_candidates<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-        cudaFuncSetAttribute(verify_candidates<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-        cudaFuncSetAttribute(verify_candidates<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-        cudaFuncSetAttribute(verify_candidates<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+#define VF_ATTR(S_, G_, K_) cudaFuncSetAttribute(verify_candidates<S_, G_, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024)
+        VF_ATTR(true, false, true); VF_ATTR(true, false, false); VF_ATTR(true, true, true); VF_ATTR(true, true, false);
+        VF_ATTR(false, false, true); VF_ATTR(false, false, false); VF_ATTR(false, true, true); VF_ATTR(false, true, false);
+#undef VF_ATTR
         attr_set = true;
     }
     const u32 rounds_se = std::min<u32>((Lmax + 1 >= P.index_interval + P.seed_size) ? (Lmax + 1 - P.index_interval) / P.seed_size : 0, 16);
     const int vkind = (ctx->rule.single ? 0 : 2) + (G ? 1 : 0);
     if (!ctx->occ_verify[vkind]) {
         int occ = 0; cudaError_t oe;
-        switch (vkind) {
-            case 0: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<true, false>, VF_THREADS, smem_v); break;
-            case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<true, true>, VF_THREADS, smem_v); break;
-            case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<false, false>, VF_THREADS, smem_v); break;
-            default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<false, true>, VF_THREADS, smem_v); break;
+        switch (vkind) {                                 // the K1 and general variants have the same resource footprint
+            case 0: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<true, false, true>, VF_THREADS, smem_v); break;
+            case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<true, true, true>, VF_THREADS, smem_v); break;
+            case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<false, false, true>, VF_THREADS, smem_v); break;
+            default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<false, true, true>, VF_THREADS, smem_v); break;
         }
-        ctx->occ_verify[vkind] = (oe == cudaSuccess && occ > 0) ? occ : 4;
+        ctx->occ_verify[vkind] = (oe == cudaSuccess && occ > 0) ? occ : 3;
     }
     const int grid_l = sms * 8, grid_v = sms * ctx->occ_verify[vkind], grid_r = sms * 4;      // persistent grids: a multiple of the SM count
 
@@ -1373,18 +1458,27 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     const int max_ev = (int)(sizeof ln.evk / sizeof ln.evk[0]);
     auto ev_begin = [&](char kind) { if (nev + 2 <= max_ev) { cudaEventRecord(ln.evk[nev], st); ev_kind.push_back(kind); } };
     auto ev_end = [&]() { if (nev + 2 <= max_ev) { cudaEventRecord(ln.evk[nev + 1], st); nev += 2; } };
+    auto launch_verify = [&](KArgs &K, u32 ci) {
+#define VF_LAUNCH(S_, G_, K_) verify_candidates<S_, G_, K_><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, KIT, ST)
+        const bool k1 = KIT == 1;
+        if (ctx->rule.single) { if (G) { if (k1) VF_LAUNCH(true, true, true); else VF_LAUNCH(true, true, false); } else { if (k1) VF_LAUNCH(true, false, true); else VF_LAUNCH(true, false, false); } }
+        else { if (G) { if (k1) VF_LAUNCH(false, true, true); else VF_LAUNCH(false, true, false); } else { if (k1) VF_LAUNCH(false, false, true); else VF_LAUNCH(false, false, false); } }
+#undef VF_LAUNCH
+    };
     auto search = [&](KArgs &K, bool as_pe, u32 r, const u32 *lin, u32 *lout, u32 ci) {
         ev_begin('l');
         if (as_pe) seed_lookup<true><<<grid_l, LK_THREADS, 0, st>>>(K, r, lin, lout, ci);
         else seed_lookup<false><<<grid_l, LK_THREADS, 0, st>>>(K, r, lin, lout, ci);
         ev_end();
         ev_begin('v');
-        if (ctx->rule.single) { if (G) verify_candidates<true, true><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, KIT, ST); else verify_candidates<true, false><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, KIT, ST); }
-        else { if (G) verify_candidates<false, true><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, KIT, ST); else verify_candidates<false, false><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, KIT, ST); }
+        launch_verify(K, ci);
         ev_end();
         ev_begin('r');
-        if (ctx->rule.single) reduce_round<true><<<grid_r, ROUND_WARPS * 32, smem_r, st>>>(K, r, ci, NW, NWS);
-        else reduce_round<false><<<grid_r, ROUND_WARPS * 32, smem_r, st>>>(K, r, ci, NW, NWS);
+        {
+            const u32 *rl = as_pe ? lin : lout; const u32 rci = as_pe ? ci : ci + 1;
+            if (ctx->rule.single) reduce_round<true><<<grid_r, ROUND_WARPS * 32, smem_r, st>>>(K, r, ci, NW, NWS, rl, rci, as_pe ? 1u : 0u);
+            else reduce_round<false><<<grid_r, ROUND_WARPS * 32, smem_r, st>>>(K, r, ci, NW, NWS, rl, rci, as_pe ? 1u : 0u);
+        }
         ev_end();
         launches += 3;
     };

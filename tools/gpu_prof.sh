@@ -1,13 +1,16 @@
 #!/bin/bash
-# ncu --set full captures of the main kernels of one bench step (config 2). usage: bash tools/gpu_prof.sh <tag>
-TAG=${1:-x}
+# ncu --set full captures of chosen kernels of one bench step (config 2).
+# usage: bash tools/gpu_prof.sh <tag> "<kernel-regex>:<skip>:<count> ..."   [bench first: set BENCH_FIRST=1]
+TAG=${1:-x}; shift
+SPECS=${1:-"verify_candidates:9:2 reduce_round:9:1 prepare_reads:0:1"}
 mkdir -p gpurun_out
 export BENCH_SKIP_CPU=1
+if [ -n "$BENCH_FIRST" ]; then
+  timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench exit $?"; cat gpurun_out/bench_$TAG.json
+fi
 P="python bench.py --steps 1 --warmup 1"
-N="ncu --set full --clock-control none --import-source on -f"
-timeout 600 $N -k regex:verify_candidates -s 9 -c 2 -o gpurun_out/prof_verify_$TAG $P > gpurun_out/ncu_verify_$TAG.log 2>&1; echo "verify $?"
-timeout 600 $N -k regex:reduce_round -s 9 -c 2 -o gpurun_out/prof_reduce_$TAG $P > gpurun_out/ncu_reduce_$TAG.log 2>&1; echo "reduce $?"
-timeout 600 $N -k regex:prepare_reads -s 0 -c 1 -o gpurun_out/prof_prepare_$TAG $P > gpurun_out/ncu_prepare_$TAG.log 2>&1; echo "prepare $?"
-timeout 600 $N -k regex:seed_lookup -s 9 -c 1 -o gpurun_out/prof_lookup_$TAG $P > gpurun_out/ncu_lookup_$TAG.log 2>&1; echo "lookup $?"
-timeout 600 $N -k regex:pair_round -s 0 -c 1 -o gpurun_out/prof_pair_$TAG $P > gpurun_out/ncu_pair_$TAG.log 2>&1; echo "pair $?"
-ls -la gpurun_out
+for spec in $SPECS; do
+  IFS=: read -r K S C <<< "$spec"
+  timeout 900 ncu --set full --clock-control none --import-source on -f -k regex:$K -s $S -c $C -o gpurun_out/prof_${K}_$TAG $P > gpurun_out/ncu_${K}_$TAG.log 2>&1; echo "$K $?"
+done
+ls -la gpurun_out | tail -8
