@@ -99,13 +99,23 @@ __device__ __forceinline__ u64 weave(u32 hi, u32 lo) { return (spread32(__brev(h
 // ------------------------------------------------------------------------------------------------
 #define PREP_WARPS 8
 struct PrepSmem {
-    u32 bal[5][16];       // raw ballots per word: code hi, code lo, regular, conv hi, conv lo
-    u64 pl[3][17];
-    u32 hash[480];
-    u32 cntp[480];
-    int cs[16][16];
-    u32 need[16];
+    u32 bal[5][16];       // raw ballots per 32 bases: code hi, code lo, regular, conv hi, conv lo
+    u32 sq[36], sn[36];   // logical 32-bit words (16 bases each, first base in the top bits) of the bases / 01-per-ACGT planes, zero padded
+    u32 cntp[480];        // bucket size of the seed at read offset p (only offsets the schedule can touch)
+    u8  nflg[480];        // that seed contains a non-ACGT base
+    int cs[16][16];       // CountSeeds(segment, start)
+    u32 need[16];         // bitmap of the offsets the schedule can touch; depends on (L, nseg) only -> cached per warp
+    u16 plist[480];       // the same offsets as a list
+    u32 need_key, n_need;
+    u8  sbytes[16];
 };
+
+// 16 ballot bits (bit k = base k) -> 32-bit word with base k at bit 30-2k (the low bit of its 2-bit digit)
+__device__ __forceinline__ u32 spread16_rev(u32 b16) {
+    u32 x = __brev(b16) >> 16;
+    x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu; x = (x | (x << 2)) & 0x33333333u; x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
 
 __global__ void __launch_bounds__(PREP_WARPS * 32) prepare_reads(const __grid_constant__ KArgs A) {
     __shared__ PrepSmem sm_all[PREP_WARPS];
@@ -113,6 +123,8 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prepare_reads(const __grid_co
     PrepSmem &sm = sm_all[wid];
     const DevTables *T = A.tab;
     const u32 tabq0 = T->tab_code[0], tabq1 = T->tab_code[1], tabc0 = T->tab_conv[0], tabc1 = T->tab_conv[1];
+    if (lane == 0) sm.need_key = 0xffffffffu;
+    const u32 W2 = 2 * A.Wb;
     for (u32 slot = blockIdx.x * PREP_WARPS + wid; slot < A.n_slots; slot += gridDim.x * PREP_WARPS) {
         const bool mate_b = A.pe && slot >= A.n_a;
         const u32 r = mate_b ? slot - A.n_a : slot;
@@ -166,57 +178,72 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prepare_reads(const __grid_co
             }
             if (filtered) break;
             __syncwarp();
-            if (lane < 17) {
-                u64 q = 0, nm = 0, cm = 0;
-                if (lane < W) {
-                    q = weave(sm.bal[0][lane], sm.bal[1][lane]);
-                    const u64 rg = spread32(__brev(sm.bal[2][lane])); nm = rg | (rg << 1);
-                    cm = weave(sm.bal[3][lane], sm.bal[4][lane]);
+            // ---- weave the ballots into logical 32-bit words: global streams (see KArgs::planes) + shared copies for hashing
+            {
+                u32 *dst = (u32 *)(A.planes + ((u64)slot * 2 + c) * 3 * A.Wb);
+                for (u32 x = lane; x < 3 * W2; x += 32) {
+                    const u32 pl = x / W2, j = x - pl * W2;
+                    u32 v = 0;
+                    if (j < 2 * W) {
+                        const u32 sh16 = (j & 1u) * 16u, wv = j >> 1;
+                        if (pl == 0) v = (spread16_rev((sm.bal[0][wv] >> sh16) & 0xffffu) << 1) | spread16_rev((sm.bal[1][wv] >> sh16) & 0xffffu);
+                        else if (pl == 1) v = spread16_rev((sm.bal[2][wv] >> sh16) & 0xffffu);
+                        else v = (spread16_rev((sm.bal[3][wv] >> sh16) & 0xffffu) << 1) | spread16_rev((sm.bal[4][wv] >> sh16) & 0xffffu);
+                    }
+                    dst[x] = v;
+                    if (pl == 0) sm.sq[j] = v; else if (pl == 1) sm.sn[j] = v;
                 }
-                sm.pl[0][lane] = q; sm.pl[1][lane] = nm; sm.pl[2][lane] = cm;
-                if (lane < A.Wb) {
-                    u64 *dst = A.planes + ((u64)slot * 2 + c) * 3 * A.Wb;
-                    dst[lane] = swap32(q); dst[A.Wb + lane] = swap32(nm & 0x5555555555555555ULL); dst[2 * A.Wb + lane] = swap32(cm);    // stream layout, see KArgs::planes
-                }
+                if (lane < 4) { sm.sq[W2 + lane] = 0; sm.sn[W2 + lane] = 0; }
             }
-            if (lane < 16) sm.need[lane] = 0;
             __syncwarp();
             if (nseg == 0) continue;
-            // ---- seed hashes for every offset (xseed_array / xseedreg_array)
-            const u32 npos = L - A.s + 1; const u32 sh = 64 - 2 * A.s;
-            const u32 full = (A.s == 16) ? 0xffffffffu : ((1u << (2 * A.s)) - 1);
-            for (u32 p = lane; p < npos; p += 32) {
-                u32 x = (u32)(plane_extract(sm.pl[0], p) >> sh);
-                u32 m = (u32)(plane_extract(sm.pl[1], p) >> sh);
-                sm.hash[p] = bsl_xt(x) | ((m != full) ? 0x80000000u : 0u);
+            const u32 nv = ii + 1;
+            // ---- which offsets can the schedule touch: prof[j][i] + v - i for j < nseg, i < I, v <= ii. Cached per warp.
+            const u32 key = L | (nseg << 16);
+            if (sm.need_key != key) {
+                __syncwarp();
+                if (lane < 16) sm.need[lane] = 0;
+                __syncwarp();
+                const u32 tot = nseg * A.I * nv;
+                for (u32 t = lane; t < tot; t += 32) {
+                    const u32 v = t % nv, i = (t / nv) % A.I, j = t / (nv * A.I);
+                    const u32 p = T->prof[j][i] + v - i;
+                    atomicOr(&sm.need[p >> 5], 1u << (p & 31));
+                }
+                __syncwarp();
+                u32 base = 0;
+                for (u32 w = 0; w < 15; w++) {                           // list the set bits in increasing order
+                    const u32 bits = sm.need[w];
+                    if ((bits >> lane) & 1u) sm.plist[base + __popc(bits & ((1u << lane) - 1u))] = (u16)(32 * w + lane);
+                    base += __popc(bits);
+                }
+                if (lane == 0) { sm.n_need = base; sm.need_key = key; }
+                __syncwarp();
             }
-            // ---- which offsets can the schedule touch
-            const u32 nv = ii + 1, tot = nseg * A.I * nv;
-            for (u32 t = lane; t < tot; t += 32) {
-                u32 v = t % nv, i = (t / nv) % A.I, j = t / (nv * A.I);
-                u32 p = T->prof[j][i] + v - i;
-                atomicOr(&sm.need[p >> 5], 1u << (p & 31));
+            // ---- seed hash (xseed_array), N flag (xseedreg_array) and bucket size of every listed offset
+            const u32 n_need = sm.n_need;
+            const u32 full = (A.s == 16) ? 0x55555555u : (0x55555555u >> (32 - 2 * A.s)), shs = 32 - 2 * A.s;
+            for (u32 x = lane; x < n_need; x += 32) {
+                const u32 p = sm.plist[x], w = p >> 4, o = (p & 15u) * 2;
+                const u32 xq = __funnelshift_l(sm.sq[w + 1], sm.sq[w], o) >> shs, xn = __funnelshift_l(sm.sn[w + 1], sm.sn[w], o) >> shs;
+                const u32 k = bsl_xt(xq); const u32 c16 = A.di.cnt16[k];
+                sm.cntp[p] = (c16 == 0xFFFFu) ? A.di.bucket[2 * k + 2] - A.di.bucket[2 * k] : c16;
+                sm.nflg[p] = xn != full;
             }
             __syncwarp();
-            for (u32 p = lane; p < npos; p += 32) {
-                u32 cv = 0;
-                if (sm.need[p >> 5] >> (p & 31) & 1u) {
-                    u32 k = sm.hash[p] & 0x7fffffffu; u32 c16 = A.di.cnt16[k];
-                    cv = (c16 == 0xFFFFu) ? A.di.bucket[2 * k + 2] - A.di.bucket[2 * k] : c16;
+            // ---- CountSeeds(j, v) (align.cpp:526-540): lanes 0-15 / 16-31 take two segments per trip
+            for (u32 j0 = 0; j0 < nseg; j0 += 2) {
+                const u32 j = j0 + (lane >> 4), v = lane & 15u;
+                if (j < nseg && v < nv) {
+                    u32 total = 0, k = 0;
+                    for (u32 i = 0; i < A.I; i++) {
+                        const u32 p = T->prof[j][i] + v - i;
+                        if (sm.nflg[p]) k = 12;
+                        total += sm.cntp[p] << k;
+                    }
+                    if (total == 0) total = 9999999;
+                    sm.cs[j][v] = (int)total;
                 }
-                sm.cntp[p] = cv;
-            }
-            __syncwarp();
-            // ---- CountSeeds(j, v) (align.cpp:526-540)
-            for (u32 t = lane; t < nseg * nv; t += 32) {
-                u32 j = t / nv, v = t % nv, total = 0, k = 0;
-                for (u32 i = 0; i < A.I; i++) {
-                    u32 p = T->prof[j][i] + v - i;
-                    if (sm.hash[p] >> 31) k = 12;
-                    total += sm.cntp[p] << k;
-                }
-                if (total == 0) total = 9999999;
-                sm.cs[j][v] = (int)total;
             }
             __syncwarp();
             // ---- ReorderSeed (align.cpp:468-498): global start = first minimum of the column sums
@@ -224,10 +251,9 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prepare_reads(const __grid_co
             {
                 u32 colsum = 0xffffffffu;
                 if (lane < ii) { colsum = 0; for (u32 j = 0; j < nseg; j++) colsum += (u32)sm.cs[j][lane]; }
-                unsigned long long key = ((unsigned long long)colsum << 32) | lane;
-                for (u32 o = 16; o; o >>= 1) { unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o); if (k2 < key) key = k2; }
-                st0 = ii ? (u32)key & 31u : 0;
-                if (ii && (u32)(key >> 32) == 0xffffffffu) st0 = 0;     // every sum is 2^32-1: `<` never fires, start stays 0
+                const u32 mn = __reduce_min_sync(0xffffffffu, colsum);
+                const u32 who = __ballot_sync(0xffffffffu, colsum == mn);
+                st0 = (ii && mn != 0xffffffffu) ? (u32)__ffs(who) - 1u : 0u;          // every sum 2^32-1: `<` never fires, start stays 0
             }
             // ---- AdjustSeedStartArray (align.cpp:500-524): the nseg steps are sequential, the argmin of each step is
             //      spread over the lanes (lane v holds candidate start v; first minimum wins like the reference's `<`)
@@ -236,12 +262,12 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prepare_reads(const __grid_co
                 const u32 ptr = (t & 1) ? nseg - 1 - t / 2 : t / 2;
                 const u32 lo = ptr == 0 ? 0 : __shfl_sync(0xffffffffu, my_st, ptr - 1);
                 const u32 hi = ptr == nseg - 1 ? ii : __shfl_sync(0xffffffffu, my_st, (ptr + 1) & 31u);
-                unsigned long long key = ~0ULL;
-                if (lane >= lo && lane <= hi && lane < 16) key = ((unsigned long long)(u32)sm.cs[ptr][lane] << 32) | lane;
-                for (u32 o = 8; o; o >>= 1) { const unsigned long long k2 = __shfl_xor_sync(0xffffffffu, key, o); if (k2 < key) key = k2; }
-                key = __shfl_sync(0xffffffffu, key, 0);
+                u32 val = 0xffffffffu;
+                if (lane >= lo && lane <= hi && lane < 16) val = (u32)sm.cs[ptr][lane];
+                const u32 mn = __reduce_min_sync(0xffffffffu, val);
+                const u32 who = __ballot_sync(0xffffffffu, val == mn && lane >= lo && lane <= hi);
                 // every value 2^32-1 (or an empty range lo > hi): `tt < b` never fires and start stays at lo
-                const u32 pick = (key == ~0ULL || (u32)(key >> 32) == 0xffffffffu) ? lo : (u32)key & 31u;
+                const u32 pick = (mn == 0xffffffffu || who == 0) ? lo : (u32)__ffs(who) - 1u;
                 if (lane == ptr) my_st = pick;
             }
             // ---- rank segments by (count as int, segment): keys are unique, so the rank is a count of smaller keys
@@ -249,15 +275,11 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prepare_reads(const __grid_co
                 const int kx = lane < nseg ? sm.cs[lane][my_st & 15u] : 0;
                 u32 rank = 0;
                 for (u32 y = 0; y < nseg; y++) { const int ky = __shfl_sync(0xffffffffu, kx, y); rank += (ky < kx || (ky == kx && y < lane)) ? 1u : 0u; }
-                // sched byte t = segment of rank t | its start << 4
-                const u32 mine = lane < nseg ? (lane | (my_st << 4)) : 0u;
-                u32 wv[4] = {0, 0, 0, 0};
-                for (u32 y = 0; y < nseg; y++) {
-                    const u32 r_y = __shfl_sync(0xffffffffu, rank, y), v_y = __shfl_sync(0xffffffffu, mine, y);
-                    wv[0] |= (r_y < 4) ? v_y << (8 * r_y) : 0u; wv[1] |= (r_y >= 4 && r_y < 8) ? v_y << (8 * (r_y - 4)) : 0u;
-                    wv[2] |= (r_y >= 8 && r_y < 12) ? v_y << (8 * (r_y - 8)) : 0u; wv[3] |= (r_y >= 12) ? v_y << (8 * (r_y - 12)) : 0u;
-                }
-                if (lane == 0) { uint4 pk; pk.x = wv[0]; pk.y = wv[1]; pk.z = wv[2]; pk.w = wv[3]; *(uint4 *)(A.sched + ((u64)slot * 2 + c) * 16) = pk; }
+                if (lane < 16) sm.sbytes[lane] = 0;
+                __syncwarp();
+                if (lane < nseg) sm.sbytes[rank] = (u8)(lane | (my_st << 4));      // sched byte t = segment of rank t | its start << 4
+                __syncwarp();
+                if (lane < 4) ((u32 *)(A.sched + ((u64)slot * 2 + c) * 16))[lane] = ((const u32 *)sm.sbytes)[lane];
             }
             __syncwarp();
         }
