@@ -55,11 +55,12 @@ struct KArgs {
     // per-round scratch
     ItemHdr *hdr; u32 cap_items; u32 cap_cands;
     uint2 *slot_item;              // [slot*2+chain] = {first item, number of items} of this round
-    u32 *slot_flag;                // set by verify when a slot has a marked candidate
+    u32 *slot_flag;                // number of candidates verify marked for the slot in this round
     u32 *flag_list;                // slots with marked candidates
     u32 *chunk_first;              // first item overlapping each chunk of the flat candidate space
     u32 *bitmap;                   // 1 bit per flat candidate
     u32 *flat_loc;                 // seed-table entry of every flat candidate (the bucket walks, in visiting order)
+    uint4 *marks;                  // [slot][MK_CAP] the first marked candidates of a slot in this round: {flat index, g, snp | strand<<8 | chain<<9, -}
     bsl_hit *out; bsl_pair *pair_out; bsl_hit *all_a; bsl_hit *all_b; u64 all_cap;
 };
 
@@ -466,6 +467,7 @@ __device__ __forceinline__ u32 vf_diff(u32 q, u32 cm, u32 r) {
     return d | (d >> 1);                                                 // caller ANDs with a 01-per-base mask
 }
 
+#define MK_CAP 4u            // marked candidates per slot and round that reduce_fast can take
 #define VF_EAGER 96u         // item headers every CTA prefetches for its next chunk (a chunk with more items loads the rest on demand)
 
 // one pass = 64 candidates of the chunk, 4 lanes each. K1: every window fits the 8 reference words the 4 lanes fetch at
@@ -635,7 +637,11 @@ __global__ void __launch_bounds__(VF_THREADS, 3) verify_candidates(const __grid_
                 const bool mark = act && q == 0 && (snp <= thr || (GAP && thr >= 2 && pre < thr - 1));
                 u32 x = __ballot_sync(0xffffffffu, mark);
                 if (x) {
-                    if (mark) A.slot_flag[s_hb[itx[pass] & 0xffffu].z] = 1u;                // reduce_round replays this read
+                    if (mark) {                                                             // reduce_fast / reduce_round replay this read
+                        const uint4 xb = s_hb[itx[pass] & 0xffffu];
+                        const u32 pos = atomicAdd(&A.slot_flag[xb.z], 1u);
+                        if (!GAP && pos < MK_CAP) A.marks[(size_t)xb.z * MK_CAP + pos] = make_uint4(cbeg + pass * 64 + (t >> 2), gv[pass], snp | ((itx[pass] >> 16 & 1u) << 8) | (IH_CHAIN(xb.y) << 9), 0u);
+                    }
                     if (lane == 0) {
                         x = (x | (x >> 3)) & 0x03030303u; x = (x | (x >> 6)) & 0x000F000Fu; x = (x | (x >> 12)) & 0xFFu;   // bit 4b -> bit b
                         const u32 c0 = pass * 64 + (t >> 5) * 8;
@@ -651,6 +657,56 @@ __global__ void __launch_bounds__(VF_THREADS, 3) verify_candidates(const __grid_
 #pragma unroll
         for (u32 pass = 0; pass < NPASS; pass++) cloc[pass] = nloc[pass];
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reduce_fast : AddHit replay for the common case, one THREAD per read. A read whose marked candidates of this round
+// (at most MK_CAP, recorded by verify_candidates with their mismatch counts) cannot trigger the -w feedback and fit its
+// hit list needs no window gather and no warp: sort the marks into discovery order (= flat index), int2hit + AddHit
+// each (align.cpp:319-346, align.h:329-347). Everything else (long lists, -w in reach, -g) is left to reduce_round.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) reduce_fast(const __grid_constant__ KArgs A, const u32 *list, u32 list_ci, u32 as_pe) {
+    const u32 n_entries = A.ctr->rc[list_ci].active << (as_pe ? 1 : 0);
+    u32 added = 0;
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n_entries; k += gridDim.x * blockDim.x) {
+        const u32 slot = as_pe ? list[k >> 1] + (k & 1u) * A.n_a : list[k];
+        const u32 c = A.slot_flag[slot];
+        if (c == 0 || c > MK_CAP) continue;
+        SlotMeta m = A.meta[slot];
+        if (m.nhit + c >= A.w || m.nhit + c > A.cap) continue;            // a level could reach -w, or the list could overflow
+        uint4 e[MK_CAP];
+#pragma unroll
+        for (u32 i = 0; i < MK_CAP; i++) e[i] = i < c ? A.marks[(size_t)slot * MK_CAP + i] : make_uint4(0xffffffffu, 0, 0, 0);
+#pragma unroll
+        for (u32 i = 1; i < MK_CAP; i++)                                    // discovery order = flat candidate index
+#pragma unroll
+            for (u32 j = i; j > 0; j--) if (e[j].x < e[j - 1].x) { const uint4 tmp = e[j]; e[j] = e[j - 1]; e[j - 1] = tmp; }
+        DevHit *hits = A.hits + (u64)m.item * A.cap;
+        u32 nhit = m.nhit, minl = A.minlvl[slot];
+        const u32 L = m.len;
+#pragma unroll
+        for (u32 i = 0; i < MK_CAP; i++) {
+            if (i >= c) break;
+            const u32 g = e[i].y, snp = e[i].z & 0xffu, sig = (e[i].z >> 8) & 1u, chain = (e[i].z >> 9) & 1u;
+            if (snp > m.thr) continue;
+            u32 lo = 0, hi = A.di.nseq;
+            while (lo + 1 < hi) { const u32 mid = (lo + hi) >> 1; if (g >= A.di.anchor[mid]) lo = mid; else hi = mid; }
+            u32 x = g - A.di.anchor[lo], gp = 0;
+            if (sig) { x = A.di.rcoff[lo] - L - x; gp = L & 511u; }
+            if ((int)x < 0 || x + L > A.di.seqlen[lo]) continue;
+            bool dup = false;
+            for (u32 h = 0; h < nhit; h++) { const DevHit hh = hits[h]; if (hh.loc == x && HIT_GAPPED(hh.tag) == 0 && (HIT_CHR2(hh.tag) >> 1) == lo) { dup = true; break; } }
+            if (dup) continue;
+            DevHit hh; hh.loc = x; hh.tag = (lo * 2 + sig) | (snp << 20) | (chain << 24); hh.gap = 0; hh.gp = gp; hits[nhit++] = hh;
+            ((u16 *)&A.cnt[slot])[chain * 16 + snp]++;
+            minl = min(minl, snp);
+        }
+        added += nhit - m.nhit;
+        if (nhit != m.nhit) { A.meta[slot].nhit = (u16)nhit; A.minlvl[slot] = (u8)minl; }
+        A.slot_flag[slot] = 0;                                              // done: reduce_round skips it
+    }
+    for (u32 o = 16; o; o >>= 1) added += __shfl_xor_sync(0xffffffffu, added, o);
+    if ((threadIdx.x & 31u) == 0 && added) atomicAdd(&A.ctr->hits_added, (unsigned long long)added);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1292,7 +1348,7 @@ template <typename T> int grow(bsl_ctx *ctx, T **p, size_t *cap, size_t need, bo
 
 void bsl_lane_free(Lane &ln) {
     cudaFree(ln.d_bases); cudaFree(ln.d_off); cudaFree(ln.d_index); cudaFree(ln.d_rawlen); cudaFree(ln.d_meta); cudaFree(ln.d_cnt); cudaFree(ln.d_sched); cudaFree(ln.d_stat);
-    cudaFree(ln.d_minlvl); cudaFree(ln.d_slot_item); cudaFree(ln.d_slot_flag); cudaFree(ln.d_flag_list);
+    cudaFree(ln.d_minlvl); cudaFree(ln.d_slot_item); cudaFree(ln.d_slot_flag); cudaFree(ln.d_flag_list); cudaFree(ln.d_marks);
     cudaFree(ln.d_hdr); cudaFree(ln.d_chunk_first); cudaFree(ln.d_bitmap); cudaFree(ln.d_flat_loc);
     cudaFree(ln.d_planes); cudaFree(ln.d_hits); cudaFree(ln.d_heavy_hits); cudaFree(ln.d_list[0]); cudaFree(ln.d_list[1]); cudaFree(ln.d_heavy_list);
     cudaFree(ln.d_pe_list[0]); cudaFree(ln.d_pe_list[1]); cudaFree(ln.d_out); cudaFree(ln.d_pair); cudaFree(ln.d_all[0]); cudaFree(ln.d_all[1]); cudaFree(ln.d_ctr);
@@ -1367,12 +1423,12 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
         if (need > ln.cap_slots) {
             size_t ncap = std::max(need, ln.cap_slots + ln.cap_slots / 2);
             cudaFree(ln.d_off); cudaFree(ln.d_index); cudaFree(ln.d_rawlen); cudaFree(ln.d_meta); cudaFree(ln.d_cnt); cudaFree(ln.d_sched); cudaFree(ln.d_stat);
-            cudaFree(ln.d_minlvl); cudaFree(ln.d_slot_item); cudaFree(ln.d_slot_flag); cudaFree(ln.d_flag_list);
+            cudaFree(ln.d_minlvl); cudaFree(ln.d_slot_item); cudaFree(ln.d_slot_flag); cudaFree(ln.d_flag_list); cudaFree(ln.d_marks);
             cudaFree(ln.d_list[0]); cudaFree(ln.d_list[1]); cudaFree(ln.d_pe_list[0]); cudaFree(ln.d_pe_list[1]); cudaFree(ln.d_heavy_list); cudaFree(ln.d_out); cudaFree(ln.d_pair);
             ln.cap_slots = 0;
             CUDA_TRY(cudaMalloc(&ln.d_off, (ncap + 4) * 8)); CUDA_TRY(cudaMalloc(&ln.d_index, ncap * 4)); CUDA_TRY(cudaMalloc(&ln.d_rawlen, ncap * 2));
             CUDA_TRY(cudaMalloc(&ln.d_meta, ncap * sizeof(SlotMeta))); CUDA_TRY(cudaMalloc(&ln.d_cnt, ncap * sizeof(SlotCounts))); CUDA_TRY(cudaMalloc(&ln.d_sched, ncap * 32)); CUDA_TRY(cudaMalloc(&ln.d_stat, ncap * sizeof(uint2)));
-            CUDA_TRY(cudaMalloc(&ln.d_minlvl, ncap)); CUDA_TRY(cudaMalloc(&ln.d_slot_item, ncap * 2 * sizeof(uint2))); CUDA_TRY(cudaMalloc(&ln.d_slot_flag, ncap * 4)); CUDA_TRY(cudaMalloc(&ln.d_flag_list, ncap * 4));
+            CUDA_TRY(cudaMalloc(&ln.d_minlvl, ncap)); CUDA_TRY(cudaMalloc(&ln.d_slot_item, ncap * 2 * sizeof(uint2))); CUDA_TRY(cudaMalloc(&ln.d_slot_flag, ncap * 4)); CUDA_TRY(cudaMalloc(&ln.d_flag_list, ncap * 4)); CUDA_TRY(cudaMalloc(&ln.d_marks, ncap * MK_CAP * sizeof(uint4)));
             for (int k = 0; k < 2; k++) { CUDA_TRY(cudaMalloc(&ln.d_list[k], ncap * 4)); CUDA_TRY(cudaMalloc(&ln.d_pe_list[k], ncap * 4)); }
             CUDA_TRY(cudaMalloc(&ln.d_heavy_list, ncap * 4)); CUDA_TRY(cudaMalloc(&ln.d_out, ncap * sizeof(bsl_hit))); CUDA_TRY(cudaMalloc(&ln.d_pair, ncap * sizeof(bsl_pair)));
             ln.cap_slots = ncap;
@@ -1415,7 +1471,7 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     A.Wb = Wb; A.planes = ln.d_planes; A.sched = ln.d_sched; A.meta = ln.d_meta; A.cnt = ln.d_cnt; A.stat = ln.d_stat; A.minlvl = ln.d_minlvl;
     A.hits = ln.d_hits; A.cap = cap_main; A.ctr = ln.d_ctr;
     A.hdr = ln.d_hdr; A.cap_items = (u32)std::min<u64>(want_items - 16, 0xffffffffu); A.cap_cands = (u32)want_cands;
-    A.slot_item = ln.d_slot_item; A.slot_flag = ln.d_slot_flag; A.flag_list = ln.d_flag_list; A.chunk_first = ln.d_chunk_first; A.bitmap = ln.d_bitmap; A.flat_loc = ln.d_flat_loc;
+    A.slot_item = ln.d_slot_item; A.marks = ln.d_marks; A.slot_flag = ln.d_slot_flag; A.flag_list = ln.d_flag_list; A.chunk_first = ln.d_chunk_first; A.bitmap = ln.d_bitmap; A.flat_loc = ln.d_flat_loc;
     A.out = ln.d_out; A.pair_out = ln.d_pair; A.all_a = want_all ? ln.d_all[0] : nullptr; A.all_b = want_all ? ln.d_all[1] : nullptr; A.all_cap = want_all ? sub_cap : 0;
 
     // ---- H2D
@@ -1498,6 +1554,7 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
         ev_begin('r');
         {
             const u32 *rl = as_pe ? lin : lout; const u32 rci = as_pe ? ci : ci + 1;
+            if (!G) { reduce_fast<<<sms * 8, 256, 0, st>>>(K, rl, rci, as_pe ? 1u : 0u); launches++; }
             if (ctx->rule.single) reduce_round<true><<<grid_r, ROUND_WARPS * 32, smem_r, st>>>(K, r, ci, NW, NWS, rl, rci, as_pe ? 1u : 0u);
             else reduce_round<false><<<grid_r, ROUND_WARPS * 32, smem_r, st>>>(K, r, ci, NW, NWS, rl, rci, as_pe ? 1u : 0u);
         }

@@ -23,7 +23,7 @@ struct Lane {
     DevHit *d_hits = nullptr; DevHit *d_heavy_hits = nullptr;
     u32 *d_list[2] = {nullptr, nullptr}; u32 *d_heavy_list = nullptr; u32 *d_pe_list[2] = {nullptr, nullptr};
     bsl_hit *d_out = nullptr; bsl_pair *d_pair = nullptr; bsl_hit *d_all[2] = {nullptr, nullptr}; size_t cap_all = 0;
-    u8 *d_minlvl = nullptr; uint2 *d_slot_item = nullptr; u32 *d_slot_flag = nullptr; u32 *d_flag_list = nullptr;
+    u8 *d_minlvl = nullptr; uint2 *d_slot_item = nullptr; u32 *d_slot_flag = nullptr; u32 *d_flag_list = nullptr; uint4 *d_marks = nullptr;
     ItemHdr *d_hdr = nullptr; u32 *d_chunk_first = nullptr; u32 *d_bitmap = nullptr; u32 *d_flat_loc = nullptr;      // per-round flat candidate space
     DevCounters *d_ctr = nullptr;
     // pinned staging
