@@ -476,7 +476,8 @@ template <bool SINGLE, bool GAP, bool K1>
 __global__ void __launch_bounds__(VF_THREADS, 3) verify_candidates(const __grid_constant__ KArgs A, u32 ci, u32 KIT, u32 ST) {
     extern __shared__ u32 vsm[];                          // staged streams: item x stream x ST
     __shared__ uint4 s_ha[CHUNK], s_hb[CHUNK];            // item headers {base, m, b0, nfwd} {rot, pack, slot, -}
-    __shared__ u32 s_mask[CHUNK / 32], s_bits[CHUNK / 32];
+    __shared__ u32 s_mask[CHUNK / 32], s_bits[CHUNK / 32], s_nmk;
+    __shared__ uint4 s_mk[CHUNK];                         // marked candidates of the chunk: {flat index, g, snp | strand << 8 | chain << 9, slot}
     constexpr u32 NP = SINGLE ? 2 : 3;                    // streams copied from global memory: bases, N-mask, (convert-to mask)
     constexpr u32 NPL = NP + (GAP ? 1 : 0);               // + prefix mask
     constexpr u32 PL_NM = 1, PL_CM = 2, PL_PM = NP;
@@ -502,6 +503,7 @@ __global__ void __launch_bounds__(VF_THREADS, 3) verify_candidates(const __grid_
         const u32 cbeg = chunk * CHUNK, cend = min(cbeg + CHUNK, n_cands);
         bool mine = have && (t == 0 || ha.x < cend);
         if (t < CHUNK / 32) { s_mask[t] = 0; s_bits[t] = 0; }
+        if (t == 0) s_nmk = 0;
         u32 n_it = (u32)__syncthreads_count(mine);
         if (n_it == VF_EAGER) {                                                  // (rare) more items than were prefetched
             if (t >= VF_EAGER && first + t < n_items) { const uint4 *src = (const uint4 *)(A.hdr + first + t); ha = __ldg(src); mine = ha.x < cend; if (mine) hb = __ldg(src + 1); }
@@ -637,10 +639,9 @@ __global__ void __launch_bounds__(VF_THREADS, 3) verify_candidates(const __grid_
                 const bool mark = act && q == 0 && (snp <= thr || (GAP && thr >= 2 && pre < thr - 1));
                 u32 x = __ballot_sync(0xffffffffu, mark);
                 if (x) {
-                    if (mark) {                                                             // reduce_fast / reduce_round replay this read
+                    if (mark) {                                                             // collected per chunk, published below
                         const uint4 xb = s_hb[itx[pass] & 0xffffu];
-                        const u32 pos = atomicAdd(&A.slot_flag[xb.z], 1u);
-                        if (!GAP && pos < MK_CAP) A.marks[(size_t)xb.z * MK_CAP + pos] = make_uint4(cbeg + pass * 64 + (t >> 2), gv[pass], snp | ((itx[pass] >> 16 & 1u) << 8) | (IH_CHAIN(xb.y) << 9), 0u);
+                        s_mk[atomicAdd(&s_nmk, 1u)] = make_uint4(cbeg + pass * 64 + (t >> 2), gv[pass], snp | ((itx[pass] >> 16 & 1u) << 8) | (IH_CHAIN(xb.y) << 9), xb.z);
                     }
                     if (lane == 0) {
                         x = (x | (x >> 3)) & 0x03030303u; x = (x | (x >> 6)) & 0x000F000Fu; x = (x | (x >> 12)) & 0xFFu;   // bit 4b -> bit b
@@ -652,6 +653,11 @@ __global__ void __launch_bounds__(VF_THREADS, 3) verify_candidates(const __grid_
         }
         __syncthreads();
         if (t < CHUNK / 32) A.bitmap[(cbeg >> 5) + t] = s_bits[t];
+        if (t < s_nmk) {                                                                    // reduce_fast / reduce_round replay these reads
+            const uint4 mk = s_mk[t];
+            const u32 pos = atomicAdd(&A.slot_flag[mk.w], 1u);
+            if (!GAP && pos < MK_CAP) A.marks[(size_t)mk.w * MK_CAP + pos] = make_uint4(mk.x, mk.y, mk.z, 0u);
+        }
         __syncthreads();
         chunk = nchunk; first = nfirst; ha = pa; hb = pb; have = phave; nchunk = nnchunk; nfirst = nnfirst;
 #pragma unroll
