@@ -45,7 +45,7 @@ def _worker(rank, world, port, pe, out_path):
     import torch.distributed as dist
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        cfg, chrs, m1, m2 = helpers.small_case(2 if pe else 1, 0.0005 if pe else 0.004, limit=1001)
+        cfg, chrs, m1, m2 = helpers.small_case(2 if pe else 1, 0.0005 if pe else 0.02, limit=1001)
         params = helpers.flags_to_params(cfg, {"w": 3})
         cat, offs, lens = helpers.synth.reference_ascii(chrs)
         orc = helpers.oracle_context(params); orc.index_build(cat, offs, lens)       # every rank: its own replica of the index
