@@ -445,17 +445,21 @@ __global__ void __launch_bounds__(LK_THREADS) seed_lookup(const __grid_constant_
 // verify_candidates : CountMismatch / CountMismatch_new over the flat candidate space
 // ------------------------------------------------------------------------------------------------
 #define VF_THREADS 256
-#define VF_ITMAX 128u        // items whose read planes are staged at a time (a chunk with more items is done in groups)
-#define VF_PADF 4u           // zero words in front of every staged stream (read positions -64..-1)
+#define VF_ITMAX 128u        // items whose read streams are staged at a time (a chunk with more items is done in groups)
+#define MK_CAP 4u            // marked candidates per slot and round that reduce_fast can take
+#define VF_EAGER 96u         // item headers every CTA prefetches for its next chunk (a chunk with more items loads the rest on demand)
 
-// Staged read planes: every item owns NPL streams of ST 32-bit words in LOGICAL order (word j = bases 16j..16j+15,
-// first base in the top bits), with VF_PADF zero words in front and zeros behind, so that a window of the read at ANY
-// base position in [-64, 16*(ST-VF_PADF)) is two plain loads and a funnel shift: no bounds tests in the inner loop.
-//   stream 0: N-mask reduced to one bit per base (01 = ACGT) — what the mismatch digits are ANDed with before the popcount
-//   stream 1: read bases (2-bit codes)
+// One THREAD per candidate. The thread gathers the 32-byte sectors its reference window touches with 256-bit loads
+// (2-3 sectors for 150 bp), rotates them in registers so that the window starts at register 0, and walks the read's
+// words: reference half-words come out of the registers with one funnel shift each, read half-words come out of the
+// staged streams in shared memory as aligned 64-bit loads. NS = sectors a window can touch (3 up to 256 bp, 5 up to 480).
+//
+// Staged read streams: every item owns NPL streams of 2*Wb 32-bit words in LOGICAL order (word j = bases 16j..16j+15,
+// first base in the top bits), zero beyond the read:
+//   stream 0: read bases (2-bit codes)
+//   stream 1: N-mask reduced to one bit per base (01 = ACGT) — ANDed with the mismatch digits before the popcount
 //   stream 2: convert-to mask (multi-way / '-' rules only)
 //   last    : prefix mask 01 for read positions < h+s (only with -g: GapAlign's first test, align.cpp:353-360)
-__device__ __forceinline__ u32 vf_fsh(u32 a, u32 b, u32 sh) { return __funnelshift_l(b, a, sh); }   // (a:b) << sh, upper word; sh in [0,31]
 
 // mismatch digits (either bit of a digit set) of 16 bases: reference half-word r against read half-word q / convert mask cm
 template <bool SINGLE>
@@ -467,42 +471,39 @@ __device__ __forceinline__ u32 vf_diff(u32 q, u32 cm, u32 r) {
     return d | (d >> 1);                                                 // caller ANDs with a 01-per-base mask
 }
 
-#define MK_CAP 4u            // marked candidates per slot and round that reduce_fast can take
-#define VF_EAGER 96u         // item headers every CTA prefetches for its next chunk (a chunk with more items loads the rest on demand)
+__device__ __forceinline__ void ldg256(const u64 *p, u32 (&r)[8]) {     // one 32-byte sector -> 8 logical 32-bit words (first base in r[0]'s top bits)
+    u64 a, b, c, d;
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    r[0] = (u32)(a >> 32); r[1] = (u32)a; r[2] = (u32)(b >> 32); r[3] = (u32)b; r[4] = (u32)(c >> 32); r[5] = (u32)c; r[6] = (u32)(d >> 32); r[7] = (u32)d;
+}
 
-// one pass = 64 candidates of the chunk, 4 lanes each. K1: every window fits the 8 reference words the 4 lanes fetch at
-// once (reads up to 191 bases); otherwise each lane walks KIT groups of 8 words.
-template <bool SINGLE, bool GAP, bool K1>
-__global__ void __launch_bounds__(VF_THREADS, 3) verify_candidates(const __grid_constant__ KArgs A, u32 ci, u32 KIT, u32 ST) {
-    extern __shared__ u32 vsm[];                          // staged streams: item x stream x ST
-    __shared__ uint4 s_ha[CHUNK], s_hb[CHUNK];            // item headers {base, m, b0, nfwd} {rot, pack, slot, -}
-    __shared__ u32 s_mask[CHUNK / 32], s_bits[CHUNK / 32], s_nmk;
+template <bool SINGLE, bool GAP, int NS>
+__global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates(const __grid_constant__ KArgs A, u32 ci, u32 W) {
+    extern __shared__ u32 vsm[];                          // staged streams: item x stream x 2*Wb
+    __shared__ uint4 s_ha[CHUNK], s_hb[CHUNK];            // item headers {base, m, b0, nfwd} {rot, pack, slot, first word of the read streams}
+    __shared__ u32 s_mask[CHUNK / 32], s_nmk;
     __shared__ uint4 s_mk[CHUNK];                         // marked candidates of the chunk: {flat index, g, snp | strand << 8 | chain << 9, slot}
     constexpr u32 NP = SINGLE ? 2 : 3;                    // streams copied from global memory: bases, N-mask, (convert-to mask)
     constexpr u32 NPL = NP + (GAP ? 1 : 0);               // + prefix mask
     constexpr u32 PL_NM = 1, PL_CM = 2, PL_PM = NP;
-    constexpr u32 NPASS = CHUNK / 64;
+    constexpr int NR = 8 * NS;                            // logical 32-bit words of the gathered sectors
     RoundCtr *rc = A.ctr->rc + ci;
     const unsigned long long al = min(rc->alloc, ~rc->limit_inv);
     const u32 n_cands = (u32)(al & ALLOC_MASK), n_items = (u32)(al >> ALLOC_SHIFT);
     const u32 n_chunks = (n_cands + CHUNK - 1) / CHUNK;
-    const u32 t = threadIdx.x, lane = t & 31u, wid = t >> 5, q = t & 3u;
-    const u32 IST = NPL * ST, W2 = 2 * A.Wb, D = NP * W2;
+    const u32 t = threadIdx.x, lane = t & 31u, wid = t >> 5;
+    const u32 W2 = 2 * A.Wb, D = NP * W2, IST = NPL * W2;
     if (blockIdx.x >= n_chunks) return;
-    // the pads of every stream stay zero for the whole kernel: staging only ever writes the data words
-    for (u32 x = t; x < VF_ITMAX * IST; x += VF_THREADS) vsm[x] = 0;
-    // ---- software pipeline over this CTA's chunks: the headers of the next chunk are loaded while this one is verified
+    // ---- software pipeline over this CTA's chunks: the headers and loc entries of the next chunk are loaded while this one is verified
     u32 chunk = blockIdx.x, first = A.chunk_first[chunk];
     uint4 ha = make_uint4(0, 0, 0, 0), hb = ha; bool have = false;
     if (t < VF_EAGER && first + t < n_items) { const uint4 *src = (const uint4 *)(A.hdr + first + t); ha = __ldg(src); hb = __ldg(src + 1); have = true; }
     u32 nchunk = chunk + gridDim.x, nfirst = nchunk < n_chunks ? A.chunk_first[nchunk] : 0u;
-    u32 cloc[NPASS];                                      // seed-table entries of my 4 candidates (flat_loc is a plain stream)
-#pragma unroll
-    for (u32 pass = 0; pass < NPASS; pass++) { const u32 idx = chunk * CHUNK + pass * 64 + (t >> 2); cloc[pass] = idx < n_cands ? __ldg(A.flat_loc + idx) : 0u; }
+    u32 cloc = chunk * CHUNK + t < n_cands ? __ldg(A.flat_loc + chunk * CHUNK + t) : 0u;      // seed-table entry of my candidate (flat_loc is a plain stream)
     for (; chunk < n_chunks;) {
         const u32 cbeg = chunk * CHUNK, cend = min(cbeg + CHUNK, n_cands);
         bool mine = have && (t == 0 || ha.x < cend);
-        if (t < CHUNK / 32) { s_mask[t] = 0; s_bits[t] = 0; }
+        if (t < CHUNK / 32) s_mask[t] = 0;
         if (t == 0) s_nmk = 0;
         u32 n_it = (u32)__syncthreads_count(mine);
         if (n_it == VF_EAGER) {                                                  // (rare) more items than were prefetched
@@ -519,66 +520,58 @@ __global__ void __launch_bounds__(VF_THREADS, 3) verify_candidates(const __grid_
         uint4 pa = make_uint4(0, 0, 0, 0), pb = pa; bool phave = false;
         if (nchunk < n_chunks && t < VF_EAGER && nfirst + t < n_items) { const uint4 *src = (const uint4 *)(A.hdr + nfirst + t); pa = __ldg(src); pb = __ldg(src + 1); phave = true; }
         const u32 nnchunk = nchunk + gridDim.x; const u32 nnfirst = nnchunk < n_chunks ? __ldg(A.chunk_first + nnchunk) : 0u;
-        u32 nloc[NPASS];
-#pragma unroll
-        for (u32 pass = 0; pass < NPASS; pass++) { const u32 idx = nchunk * CHUNK + pass * 64 + (t >> 2); nloc[pass] = (nchunk < n_chunks && idx < n_cands) ? __ldg(A.flat_loc + idx) : 0u; }
+        const u32 nloc = (nchunk < n_chunks && nchunk * CHUNK + t < n_cands) ? __ldg(A.flat_loc + nchunk * CHUNK + t) : 0u;
         __syncthreads();
-        // item of candidate c = (number of item starts at positions <= c) - 1: prefix popcounts of the start mask.
-        // The candidates of my pass p sit in mask word 2p + (t >> 7).
-        u32 wpre[NPASS], wmsk[NPASS];
+        // ---- my candidate: item = (number of item starts at chunk positions <= t) - 1
+        const u32 idx = cbeg + t;
+        u32 it = 0;
         {
             u32 acc = 0;
 #pragma unroll
-            for (u32 ww = 0; ww < CHUNK / 32; ww++) {
-                const u32 mk = s_mask[ww];
-                if ((ww & 1u) == (t >> 7)) { wpre[ww >> 1] = acc; wmsk[ww >> 1] = mk; }
-                acc += __popc(mk);
-            }
+            for (u32 ww = 0; ww < CHUNK / 32; ww++) { const u32 mk = s_mask[ww]; if (ww < wid) acc += __popc(mk); else if (ww == wid) acc += __popc(mk & (0xffffffffu >> (31u - lane))); }
+            it = acc - 1u;
+        }
+        const bool act = idx < cend;
+        bool marked = false;
+        u32 g = 0, pack = 0, sig = 0, kk = 0, sh = 0;
+        u32 R[NR];
+#pragma unroll
+        for (int j = 0; j < NR; j++) R[j] = 0;
+        if (act) {
+            const uint4 xa = s_ha[it]; const uint2 xb = *(const uint2 *)&s_hb[it];
+            u32 e = xb.x + (idx - xa.x); if (e >= xa.y) e -= xa.y;
+            sig = e >= xa.w ? 1u : 0u;                                           // forward-strand entries come first (align.cpp:296)
+            pack = xb.y;
+            g = cloc - IH_H(pack);                                               // _hit.loc (align.cpp:297)
+            const u32 word0 = g >> 5, sb = word0 & ~3u;                          // first 64-bit word of the window, its 32-byte sector
+            const u32 nwc = ((g & 31u) + IH_L(pack) + 31u) >> 5;                 // 64-bit words the window touches
+            const u32 nsec = ((word0 & 3u) + nwc + 3u) >> 2;
+            kk = 2 * (word0 & 3u) + ((g & 31u) >> 4); sh = (g & 15u) * 2;        // window start = logical word kk, bit sh of the first sector
+            const u64 *P = A.di.plane[sig] + sb;
+#pragma unroll
+            for (int sct = 0; sct < NS; sct++) if ((u32)sct < nsec) { u32 r8[8]; ldg256(P + 4 * sct, r8);
+#pragma unroll
+                for (int j = 0; j < 8; j++) R[8 * sct + j] = r8[j]; }
         }
         for (u32 grp = 0; grp < n_it; grp += VF_ITMAX) {
             const u32 n_g = min(VF_ITMAX, n_it - grp);
             if (grp) __syncthreads();                                        // the previous group is done with the staging buffer
-            // ---- 4 lanes per candidate, 64 candidates per pass; the window gathers of all passes are issued first
-            //      (they are the long pole: random DRAM sectors), the staging copies right behind them
-            u32 itx[NPASS], gv[NPASS];            // itx: item | reference strand << 16 | active << 17 ; gv: alignment start g
-            ulonglong2 win[NPASS];
-#pragma unroll
-            for (u32 pass = 0; pass < NPASS; pass++) {
-                const u32 cidx = pass * 64 + (t >> 2), idx = cbeg + cidx;
-                const u32 it = wpre[pass] + __popc(wmsk[pass] & (0xffffffffu >> (31u - (cidx & 31u)))) - 1u;
-                itx[pass] = it; gv[pass] = 0; win[pass] = make_ulonglong2(0ULL, 0ULL);
-                if (idx < cend && it >= grp && it < grp + n_g) {
-                    const uint4 xa = s_ha[it]; const uint2 xb = *(const uint2 *)&s_hb[it];
-                    u32 e = xb.x + (idx - xa.x); if (e >= xa.y) e -= xa.y;
-                    const u32 sig = e >= xa.w ? 1u : 0u;                                    // forward-strand entries come first (align.cpp:296)
-                    itx[pass] = it | (sig << 16) | 0x20000u;
-                    const u32 g = cloc[pass] - IH_H(xb.y);                                  // _hit.loc (align.cpp:297)
-                    gv[pass] = g;
-                    const u32 word0 = g >> 5, nwc = ((g & 31u) + IH_L(xb.y) + 31u) >> 5;
-                    const u32 wq = (word0 & ~1u) + 2 * q;
-                    if (wq + 1 >= word0 && wq < word0 + nwc) win[pass] = __ldg((const ulonglong2 *)(A.di.plane[sig] + wq));
-                }
-            }
-            // ---- stage the streams of this group's items: a warp copies the D contiguous data words of an item
-            //      (coalesced), four items per warp in flight
+            // ---- stage the streams of this group's items: a warp copies the D contiguous words of an item (coalesced),
+            //      four items per warp in flight
             for (u32 l = lane; l < D; l += 32) {
-                const u32 pl = l / W2, so = pl * ST + VF_PADF + (l - pl * W2);
                 for (u32 m0 = wid; m0 < n_g; m0 += 4 * (VF_THREADS / 32)) {
                     u32 v[4];
 #pragma unroll
-                    for (u32 b = 0; b < 4; b++) {
-                        const u32 it = m0 + b * (VF_THREADS / 32);
-                        if (it < n_g) v[b] = __ldg((const u32 *)(A.planes + s_hb[grp + it].w) + l);
-                    }
+                    for (u32 b = 0; b < 4; b++) { const u32 i2 = m0 + b * (VF_THREADS / 32); if (i2 < n_g) v[b] = __ldg((const u32 *)(A.planes + s_hb[grp + i2].w) + l); }
 #pragma unroll
-                    for (u32 b = 0; b < 4; b++) { const u32 it = m0 + b * (VF_THREADS / 32); if (it < n_g) vsm[(size_t)it * IST + so] = v[b]; }
+                    for (u32 b = 0; b < 4; b++) { const u32 i2 = m0 + b * (VF_THREADS / 32); if (i2 < n_g) vsm[(size_t)i2 * IST + l] = v[b]; }
                 }
             }
             if (GAP) {
                 for (u32 j = lane; j < W2; j += 32)
-                    for (u32 it = wid; it < n_g; it += VF_THREADS / 32) {
-                        const u32 hs = IH_H(s_hb[grp + it].y) + A.s;
-                        vsm[(size_t)it * IST + PL_PM * ST + VF_PADF + j] = hs >= 16 * j + 16 ? 0x55555555u : (hs <= 16 * j ? 0u : 0x55555555u & (0xffffffffu << (32 - 2 * (hs - 16 * j))));
+                    for (u32 i2 = wid; i2 < n_g; i2 += VF_THREADS / 32) {
+                        const u32 hs = IH_H(s_hb[grp + i2].y) + A.s;
+                        vsm[(size_t)i2 * IST + PL_PM * W2 + j] = hs >= 16 * j + 16 ? 0x55555555u : (hs <= 16 * j ? 0u : 0x55555555u & (0xffffffffu << (32 - 2 * (hs - 16 * j))));
                     }
             }
             // ---- L2 prefetch for the NEXT chunk (its headers, loaded at the top of this iteration, have arrived by now):
@@ -592,76 +585,53 @@ __global__ void __launch_bounds__(VF_THREADS, 3) verify_candidates(const __grid_
                 }
             }
             __syncthreads();                                                                // staged streams visible
+            const bool now = act && it >= grp && it < grp + n_g;
+            u32 snp = 0, pre = 0;
+            if (now) {
+                // rotate the gathered words so that the window starts at R[0] (kk = 0..7 logical words)
+                if (kk & 4u) {
 #pragma unroll
-            for (u32 pass = 0; pass < NPASS; pass++) {
-                u32 snp = 0, pre = 0, thr = 0;
-                const bool act = (itx[pass] & 0x20000u) != 0;
-                if (act) {
-                    const u32 it = itx[pass] & 0xffffu;
-                    const u32 pack = s_hb[it].y;
-                    const u32 g = gv[pass];
-                    const u32 word0 = g >> 5, wb = word0 & ~1u;
-                    const u32 rel = g - 32u * wb;                                           // 0..63
-                    thr = IH_THR(pack);
-                    const u32 sh = ((0u - rel) & 15u) * 2u;
-                    const u32 *S = vsm + (size_t)(it - grp) * IST;
-                    const u32 nk = K1 ? 1u : KIT;
-                    for (u32 kk = 0; kk < nk; kk++) {
-                        const u32 z = 8 * kk + 2 * q;                                       // my two reference words: z, z+1
-                        ulonglong2 r2 = win[pass];
-                        if (!K1 && kk) {
-                            const u32 nwc = ((g & 31u) + IH_L(pack) + 31u) >> 5; const u32 wq = wb + z;
-                            r2 = make_ulonglong2(0ULL, 0ULL); if (wq + 1 >= word0 && wq < word0 + nwc) r2 = __ldg((const ulonglong2 *)(A.di.plane[(itx[pass] >> 16) & 1u] + wq));
-                        }
-                        const int i0 = ((32 * (int)z - (int)rel) >> 4) + (int)VF_PADF;       // stream word holding read position 32z - rel
-                        const u32 *Sq = S + i0;
-                        const u32 q0 = Sq[0], q1 = Sq[1], q2 = Sq[2], q3 = Sq[3], q4 = Sq[4];
-                        const u32 *Sn = Sq + PL_NM * ST;
-                        const u32 n0 = Sn[0], n1 = Sn[1], n2 = Sn[2], n3 = Sn[3], n4 = Sn[4];
-                        u32 c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
-                        if (!SINGLE) { const u32 *Sc = Sq + PL_CM * ST; c0 = Sc[0]; c1 = Sc[1]; c2 = Sc[2]; c3 = Sc[3]; c4 = Sc[4]; }
-                        const u32 d0 = vf_diff<SINGLE>(vf_fsh(q0, q1, sh), vf_fsh(c0, c1, sh), (u32)(r2.x >> 32));
-                        const u32 d1 = vf_diff<SINGLE>(vf_fsh(q1, q2, sh), vf_fsh(c1, c2, sh), (u32)r2.x);
-                        const u32 d2 = vf_diff<SINGLE>(vf_fsh(q2, q3, sh), vf_fsh(c2, c3, sh), (u32)(r2.y >> 32));
-                        const u32 d3 = vf_diff<SINGLE>(vf_fsh(q3, q4, sh), vf_fsh(c3, c4, sh), (u32)r2.y);
-                        snp += __popc((d0 & vf_fsh(n0, n1, sh)) | ((d1 & vf_fsh(n1, n2, sh)) << 1)) + __popc((d2 & vf_fsh(n2, n3, sh)) | ((d3 & vf_fsh(n3, n4, sh)) << 1));
-                        if (GAP) {
-                            const u32 *Sp = Sq + PL_PM * ST;
-                            const u32 p0 = Sp[0], p1 = Sp[1], p2 = Sp[2], p3 = Sp[3], p4 = Sp[4];
-                            pre += __popc((d0 & vf_fsh(p0, p1, sh)) | ((d1 & vf_fsh(p1, p2, sh)) << 1)) + __popc((d2 & vf_fsh(p2, p3, sh)) | ((d3 & vf_fsh(p3, p4, sh)) << 1));
-                        }
-                    }
+                    for (int j = 0; j + 4 < NR; j++) R[j] = R[j + 4];
                 }
-                u32 v = snp | (pre << 16);
-                v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
-                snp = v & 0xffffu; pre = v >> 16;
-                // could this candidate add a hit?  ungapped: snp <= thr.  gapped: GapAlign's first test (align.cpp:353-360)
-                const bool mark = act && q == 0 && (snp <= thr || (GAP && thr >= 2 && pre < thr - 1));
-                u32 x = __ballot_sync(0xffffffffu, mark);
-                if (x) {
-                    if (mark) {                                                             // collected per chunk, published below
-                        const uint4 xb = s_hb[itx[pass] & 0xffffu];
-                        s_mk[atomicAdd(&s_nmk, 1u)] = make_uint4(cbeg + pass * 64 + (t >> 2), gv[pass], snp | ((itx[pass] >> 16 & 1u) << 8) | (IH_CHAIN(xb.y) << 9), xb.z);
-                    }
-                    if (lane == 0) {
-                        x = (x | (x >> 3)) & 0x03030303u; x = (x | (x >> 6)) & 0x000F000Fu; x = (x | (x >> 12)) & 0xFFu;   // bit 4b -> bit b
-                        const u32 c0 = pass * 64 + (t >> 5) * 8;
-                        atomicOr(&s_bits[c0 >> 5], x << (c0 & 31u));
+                if (kk & 2u) {
+#pragma unroll
+                    for (int j = 0; j + 2 < NR; j++) R[j] = R[j + 2];
+                }
+                if (kk & 1u) {
+#pragma unroll
+                    for (int j = 0; j + 1 < NR; j++) R[j] = R[j + 1];
+                }
+                const u32 *S = vsm + (size_t)(it - grp) * IST;
+#pragma unroll
+                for (int i = 0; i < (NR - 8) / 2; i++) {                                    // read word i = logical words 2i, 2i+1
+                    if ((u32)i < W) {
+                        const uint2 qq = *(const uint2 *)(S + 2 * i), nn = *(const uint2 *)(S + PL_NM * W2 + 2 * i);
+                        uint2 cc = make_uint2(0u, 0u); if (!SINGLE) cc = *(const uint2 *)(S + PL_CM * W2 + 2 * i);
+                        const u32 r0 = __funnelshift_l(R[2 * i + 1], R[2 * i], sh), r1 = __funnelshift_l(R[2 * i + 2], R[2 * i + 1], sh);
+                        const u32 d0 = vf_diff<SINGLE>(qq.x, cc.x, r0), d1 = vf_diff<SINGLE>(qq.y, cc.y, r1);
+                        snp += __popc((d0 & nn.x) | ((d1 & nn.y) << 1));
+                        if (GAP) { const uint2 pp = *(const uint2 *)(S + PL_PM * W2 + 2 * i); pre += __popc((d0 & pp.x) | ((d1 & pp.y) << 1)); }
                     }
                 }
             }
+            // could this candidate add a hit?  ungapped: snp <= thr.  gapped: GapAlign's first test (align.cpp:353-360)
+            const u32 thr = IH_THR(pack);
+            const bool mark = now && (snp <= thr || (GAP && thr >= 2 && pre < thr - 1));
+            if (mark) { marked = true; s_mk[atomicAdd(&s_nmk, 1u)] = make_uint4(idx, g, snp | (sig << 8) | (IH_CHAIN(pack) << 9), s_hb[it].z); }
+        }
+        // ---- the warp's 32 verdicts are one word of the bitmap; marked candidates are published for reduce_fast / reduce_round
+        {
+            const u32 bal = __ballot_sync(0xffffffffu, marked);
+            if (lane == 0) A.bitmap[(cbeg >> 5) + wid] = bal;
         }
         __syncthreads();
-        if (t < CHUNK / 32) A.bitmap[(cbeg >> 5) + t] = s_bits[t];
-        if (t < s_nmk) {                                                                    // reduce_fast / reduce_round replay these reads
+        if (t < s_nmk) {
             const uint4 mk = s_mk[t];
             const u32 pos = atomicAdd(&A.slot_flag[mk.w], 1u);
             if (!GAP && pos < MK_CAP) A.marks[(size_t)mk.w * MK_CAP + pos] = make_uint4(mk.x, mk.y, mk.z, 0u);
         }
         __syncthreads();
-        chunk = nchunk; first = nfirst; ha = pa; hb = pb; have = phave; nchunk = nnchunk; nfirst = nnfirst;
-#pragma unroll
-        for (u32 pass = 0; pass < NPASS; pass++) cloc[pass] = nloc[pass];
+        chunk = nchunk; first = nfirst; ha = pa; hb = pb; have = phave; nchunk = nnchunk; nfirst = nnfirst; cloc = nloc;
     }
 }
 
@@ -1509,18 +1479,17 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     const u32 NW = (31 + 2 * G + Lmax + 31) / 32; const u32 NWS = NW | 1u;
     const size_t smem_r = (size_t)ROUND_WARPS * (32 * NWS + 48) * 8;
     const u32 NP = ctx->rule.single ? 2 : 3;
-    const u32 KIT = ((31 + Lmax + 31) / 32 + 1 + 7) / 8;
     const u32 NPL = NP + (G ? 1 : 0);
-    const u32 ST = VF_PADF + std::max<u32>(2 * Wb, 16 * KIT + 1);        // words per staged stream (verify_candidates)
-    const size_t smem_v = (size_t)VF_ITMAX * NPL * ST * 4;
+    const u32 Wr = (Lmax + 31) / 32;                                     // 64-bit words of the longest read
+    const bool ns3 = Wr + 1 + 3 <= 12;                                   // a window (Wr + 1 words at any of 4 word offsets) fits 3 sectors
+    const size_t smem_v = (size_t)VF_ITMAX * NPL * 2 * Wb * 4;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(pair_round_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairWideSmem));
         cudaFuncSetAttribute(reduce_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         cudaFuncSetAttribute(reduce_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-#define VF_ATTR(S_, G_, K_) cudaFuncSetAttribute(verify_candidates<S_, G_, K_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024)
-        VF_ATTR(true, false, true); VF_ATTR(true, false, false); VF_ATTR(true, true, true); VF_ATTR(true, true, false);
-        VF_ATTR(false, false, true); VF_ATTR(false, false, false); VF_ATTR(false, true, true); VF_ATTR(false, true, false);
+#define VF_ATTR(S_, G_) cudaFuncSetAttribute(verify_candidates<S_, G_, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); cudaFuncSetAttribute(verify_candidates<S_, G_, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024)
+        VF_ATTR(true, false); VF_ATTR(true, true); VF_ATTR(false, false); VF_ATTR(false, true);
 #undef VF_ATTR
         attr_set = true;
     }
@@ -1528,11 +1497,11 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     const int vkind = (ctx->rule.single ? 0 : 2) + (G ? 1 : 0);
     if (!ctx->occ_verify[vkind]) {
         int occ = 0; cudaError_t oe;
-        switch (vkind) {                                 // the K1 and general variants have the same resource footprint
-            case 0: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<true, false, true>, VF_THREADS, smem_v); break;
-            case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<true, true, true>, VF_THREADS, smem_v); break;
-            case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<false, false, true>, VF_THREADS, smem_v); break;
-            default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<false, true, true>, VF_THREADS, smem_v); break;
+        switch (vkind) {                                 // sized for the common 3-sector variant
+            case 0: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<true, false, 3>, VF_THREADS, smem_v); break;
+            case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<true, true, 3>, VF_THREADS, smem_v); break;
+            case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<false, false, 3>, VF_THREADS, smem_v); break;
+            default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<false, true, 3>, VF_THREADS, smem_v); break;
         }
         ctx->occ_verify[vkind] = (oe == cudaSuccess && occ > 0) ? occ : 3;
     }
@@ -1543,10 +1512,9 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     auto ev_begin = [&](char kind) { if (nev + 2 <= max_ev) { cudaEventRecord(ln.evk[nev], st); ev_kind.push_back(kind); } };
     auto ev_end = [&]() { if (nev + 2 <= max_ev) { cudaEventRecord(ln.evk[nev + 1], st); nev += 2; } };
     auto launch_verify = [&](KArgs &K, u32 ci) {
-#define VF_LAUNCH(S_, G_, K_) verify_candidates<S_, G_, K_><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, KIT, ST)
-        const bool k1 = KIT == 1;
-        if (ctx->rule.single) { if (G) { if (k1) VF_LAUNCH(true, true, true); else VF_LAUNCH(true, true, false); } else { if (k1) VF_LAUNCH(true, false, true); else VF_LAUNCH(true, false, false); } }
-        else { if (G) { if (k1) VF_LAUNCH(false, true, true); else VF_LAUNCH(false, true, false); } else { if (k1) VF_LAUNCH(false, false, true); else VF_LAUNCH(false, false, false); } }
+#define VF_LAUNCH(S_, G_) do { if (ns3) verify_candidates<S_, G_, 3><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, Wr); else verify_candidates<S_, G_, 5><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, Wr); } while (0)
+        if (ctx->rule.single) { if (G) VF_LAUNCH(true, true); else VF_LAUNCH(true, false); }
+        else { if (G) VF_LAUNCH(false, true); else VF_LAUNCH(false, false); }
 #undef VF_LAUNCH
     };
     auto search = [&](KArgs &K, bool as_pe, u32 r, const u32 *lin, u32 *lout, u32 ci) {
