@@ -1,4 +1,5 @@
 // api.cu — the extern "C" boundary declared in include/basal_gpu.h.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 

@@ -113,7 +113,7 @@ template <typename T> int dmalloc(bsl_ctx *ctx, T **p, size_t n) {
 void bsl_index_free_impl(bsl_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree((void *)ctx->di.plane[0]); cudaFree((void *)ctx->di.plane[1]); cudaFree((void *)ctx->di.bucket); cudaFree((void *)ctx->di.cnt16);
+    cudaFree((void *)ctx->di.plane[0]); cudaFree((void *)ctx->di.bucket); cudaFree((void *)ctx->di.cnt16);
     cudaFree((void *)ctx->di.loc); cudaFree((void *)ctx->di.anchor); cudaFree((void *)ctx->di.seqlen); cudaFree((void *)ctx->di.rcoff);
     memset(&ctx->di, 0, sizeof ctx->di); ctx->has_index = false;
 }
@@ -146,7 +146,8 @@ int bsl_index_build_impl(bsl_ctx *ctx, const u8 *cat, const u64 *off, const u32 
     u64 *d_fwd = nullptr, *d_rc = nullptr;
     int rc_ = 0;
     if ((rc_ = dmalloc(ctx, &d_ascii, bases + 64)) || (rc_ = dmalloc(ctx, &d_aoff, n + 1)) || (rc_ = dmalloc(ctx, &d_wstart, n + 1)) ||
-        (rc_ = dmalloc(ctx, &d_alen, n)) || (rc_ = dmalloc(ctx, &d_fwd, n_words)) || (rc_ = dmalloc(ctx, &d_rc, n_words))) return rc_;
+        (rc_ = dmalloc(ctx, &d_alen, n)) || (rc_ = dmalloc(ctx, &d_fwd, 2 * n_words))) return rc_;
+    d_rc = d_fwd + n_words;                 // both strand planes in one allocation: one L2 access-policy window covers them
     for (u32 c = 0; c < n; c++) CUDA_TRY(cudaMemcpy(d_ascii + aoff[c], cat + off[c], len[c], cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_aoff, aoff.data(), (n + 1) * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_wstart, wstart.data(), (n + 1) * 8, cudaMemcpyHostToDevice));
