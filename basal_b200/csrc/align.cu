@@ -732,16 +732,23 @@ __device__ u32 gap_search(const u64 *win, u32 NW, u32 rel, const u64 *q, const u
         }
         for (u32 k = n1; k < want; k++) PR[k] = (u16)L;
         const u32 rl = L - t - 1;
+        // first (i, j) in the reference's loop order with 6 <= P0[i] < rl, 6 <= PR[j] < rl, P0[i] + PR[j] - sh1 >= L.
+        // Both lists ascend, so for growing i the first admissible j only moves down: a two-pointer walk replaces the
+        // quadratic scan (the j the inner loop would stop at = first j with PR[j] >= max(6, L + sh1 - P0[i])).
+        u32 jj = 0; bool started = false;
         for (u32 i = 0; i < thr - t; i++) {
             u32 gp = P0[i];
             if (gp < 6 || gp >= rl) continue;
-            for (u32 j = 0; j < thr - t - i; j++) {
-                u32 m2 = PR[j];
-                if (m2 < 6 || m2 >= rl) continue;
-                if ((int)gp + (int)m2 - sh1 < (int)L) continue;
-                int clip = (int)gp + 6 - (int)L - sh1;
-                if (clip > 0) gp -= (u32)clip;
-                return (i + j + t) | ((u32)(sh + 4) << 8) | (gp << 16);
+            const int nd = (int)L + sh1 - (int)gp; const u32 need = nd > 6 ? (u32)nd : 6u;
+            if (!started) { while (jj < want && PR[jj] < need) jj++; started = true; }
+            else while (jj > 0 && PR[jj - 1] >= need) jj--;
+            if (jj < thr - t - i && jj < want) {
+                const u32 m2 = PR[jj];
+                if (m2 < rl) {
+                    int clip = (int)gp + 6 - (int)L - sh1;
+                    if (clip > 0) gp -= (u32)clip;
+                    return (i + jj + t) | ((u32)(sh + 4) << 8) | (gp << 16);
+                }
             }
         }
     }
@@ -1416,7 +1423,10 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     const u32 nch = P.chains == 1 ? 2 : 1;
     const u64 worst_slot = 2ull * P.index_interval * std::max<u32>(ctx->di.maxk, 1);      // candidates one read can have in one round
     const char *env_cc = getenv("BSL_CAND_CAP");
-    u64 want_cands = env_cc ? (u64)atoll(env_cc) : std::max<u64>(96ull * n_slots, 1ull << 22);
+    // flat candidate space of one round: sized for ~1.5x the expected bucket walks of every slot (mean bucket occupancy
+    // n_entries / K per look-up; 96 per slot at 500 Mb, ~430 at 3.1 Gb); reads that do not fit are re-run on the large-capacity pass
+    const u64 per_lookup = ctx->di.K ? ctx->di.n_entries / ctx->di.K + 1 : 1;
+    u64 want_cands = env_cc ? (u64)atoll(env_cc) : std::max<u64>(std::max<u64>(96ull * n_slots, 3ull * n_slots * P.index_interval * per_lookup / 2), 1ull << 22);
     want_cands = std::max<u64>(want_cands, 2 * worst_slot + CHUNK);
     want_cands = std::min<u64>(want_cands, 0xfff00000ull);
     want_cands = (want_cands + CHUNK - 1) / CHUNK * CHUNK;

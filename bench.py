@@ -301,9 +301,9 @@ def gpu_arm(args):
     e2e = total_reads / t_e2e
     peak, peak_src = peaks()
     achieved = (vbytes / 1e9) / (verify_ms / 1000.0) if verify_ms > 0 else 0.0
-    traffic = None
+    traffic = None                       # dram__bytes_read+write per verify_candidates launch, from the committed ncu --set full capture of this workload
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and CONFIG_ID == 2:
         try:
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
@@ -316,7 +316,7 @@ def gpu_arm(args):
                    "l2": "inputs larger than L2 (index 1.9 GB + 300 MB batch per step); no flush needed",
                    "timing": "CUDA events on the launching stream (first kernel to last kernel), max over ranks",
                    "index_build_s": round(t_index, 2), "parallelism": f"read-sharded x{world}, index replicated, no collective"},
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                 "ms_per_step": 1000.0 * t_e2e / args.steps, "note": f"bsl_align_pe from pinned host buffers, {N_INFLIGHT} caller threads (one lane = stream + buffers each)"},
         "gpu_launches": int(launches),
         "clocks": clk,
@@ -324,6 +324,7 @@ def gpu_arm(args):
                      "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                      "candidates_per_step": cands // max(args.steps, 1), "seed_lookups_per_step": lookups // max(args.steps, 1),
                      "bytes_per_candidate": (vbytes // cands) if cands else None, "launches_per_step": s_launch // max(args.steps, 1),
+                     "algorithmic_bytes_per_launch": (vbytes // s_launch) if s_launch else None,
                      "ms_verify_per_step": verify_ms / args.steps, "ms_lookup_per_step": lookup_ms / args.steps, "ms_reduce_per_step": reduce_ms / args.steps,
                      "ms_pack_per_step": pack_ms / args.steps, "ms_pair_per_step": pair_ms / args.steps,
                      "wall_ms_per_step": 1000.0 * t_wall / args.steps},
