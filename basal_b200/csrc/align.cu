@@ -356,10 +356,23 @@ __global__ void __launch_bounds__(LK_THREADS) seed_lookup(const __grid_constant_
         }
         // ---- pass 1: bucket sizes
         u32 tot = 0, nne = 0, j = 0, stj = 0; const u64 *pq = nullptr;
+        u32 ke0[4], ke1[4], ke2[4];                          // the look-ups of the first four phases stay in registers for pass 2
+#pragma unroll
+        for (u32 i = 0; i < 4; i++) { ke0[i] = 0; ke1[i] = 0; ke2[i] = 0; }
         if (search) {
             const u8 sc = A.sched[((u64)slot * 2 + c) * 16 + round]; j = sc & 15u; stj = sc >> 4;
             pq = A.planes + ((u64)slot * 2 + c) * 3 * A.Wb;
-            for (u32 i = 0; i < A.I; i++) {
+#pragma unroll
+            for (u32 i = 0; i < 4; i++) {
+                if (i < A.I) {
+                    const u32 h = T->prof[j][i] + stj - i;
+                    const u32 kmer = bsl_xt((u32)(stream_extract(pq, h) >> shs));
+                    ke0[i] = __ldg(A.di.bucket + 2 * kmer); ke1[i] = __ldg(A.di.bucket + 2 * kmer + 1); ke2[i] = __ldg(A.di.bucket + 2 * kmer + 2);
+                }
+            }
+#pragma unroll
+            for (u32 i = 0; i < 4; i++) { const u32 pm = ke2[i] - ke0[i]; if (i < A.I && pm != 0 && pm <= A.di.maxk) { tot += pm; nne++; } }
+            for (u32 i = 4; i < A.I; i++) {
                 const u32 h = T->prof[j][i] + stj - i;
                 const u32 kmer = bsl_xt((u32)(stream_extract(pq, h) >> shs));
                 const u32 pm = A.di.bucket[2 * kmer + 2] - A.di.bucket[2 * kmer];
@@ -406,8 +419,9 @@ __global__ void __launch_bounds__(LK_THREADS) seed_lookup(const __grid_constant_
             u32 x_cb = 0, x_pm = 0, x_e0 = 0, x_rot = 0;
             if (search && ok && nne) {
                 const u32 h = T->prof[j][i] + stj - i;
-                const u32 kmer = bsl_xt((u32)(stream_extract(pq, h) >> shs));
-                const u32 e0 = A.di.bucket[2 * kmer], e1 = A.di.bucket[2 * kmer + 1], e2 = A.di.bucket[2 * kmer + 2];
+                u32 e0, e1, e2;
+                if (i < 4) { e0 = i == 0 ? ke0[0] : i == 1 ? ke0[1] : i == 2 ? ke0[2] : ke0[3]; e1 = i == 0 ? ke1[0] : i == 1 ? ke1[1] : i == 2 ? ke1[2] : ke1[3]; e2 = i == 0 ? ke2[0] : i == 1 ? ke2[1] : i == 2 ? ke2[2] : ke2[3]; }
+                else { const u32 kmer = bsl_xt((u32)(stream_extract(pq, h) >> shs)); e0 = A.di.bucket[2 * kmer]; e1 = A.di.bucket[2 * kmer + 1]; e2 = A.di.bucket[2 * kmer + 2]; }
                 const u32 pm = e2 - e0;
                 if (pm != 0 && pm <= A.di.maxk) {
                     uint4 a, b;
@@ -974,6 +988,7 @@ __device__ void fill_record(bsl_hit &o, const DevHit &h, u32 chain, u32 level) {
     o.loc = h.loc; o.chr = HIT_CHR2(h.tag); o.gap_size = (int)h.gap; o.gap_pos = (u16)h.gp; o.nm = (u8)level; o.read_chain = (u8)chain;
 }
 
+#define PR_LOCAL 4u
 __global__ void pair_round(const __grid_constant__ KArgs A, u32 round, const u32 *list_in, u32 *list_out, u32 ci) {
     RoundCtr *rc = A.ctr->rc + ci;
     const u32 n_items = rc->active;
@@ -989,8 +1004,22 @@ __global__ void pair_round(const __grid_constant__ KArgs A, u32 round, const u32
         const u32 nA = ma.nhit, nB = mb.nhit, Ba = ma.B, Bb = mb.B, La = ma.len, Lb = mb.len;
         const u32 i = round;
         u32 total = 0, best = 0xffffffffu, best_cnt = 0;
+        // short lists (the usual case: one or two hits per mate) are replayed on a thread-local copy, so that the scans of
+        // sort_level / get_pairs are L1 hits instead of dependent global loads; sorted lists are written back
+        DevHit la[PR_LOCAL], lb[PR_LOCAL];
+        DevHit *ga = ha, *gb = hb;
+        const bool local = nA <= PR_LOCAL && nB <= PR_LOCAL;
+        if (local) {
+#pragma unroll
+            for (u32 x = 0; x < PR_LOCAL; x++) { if (x < nA) la[x] = ga[x]; if (x < nB) lb[x] = gb[x]; }
+            ha = la; hb = lb;
+        }
         if (i <= Ba) { sort_level(ha, nA, 0, i); sort_level(ha, nA, 1, i); }      // SortHits4PE happens even when the mate has no hit yet
         if (i <= Bb) { sort_level(hb, nB, 0, i); sort_level(hb, nB, 1, i); }
+        if (local) {
+            if (nA > 1 && i <= Ba) for (u32 x = 0; x < nA; x++) ga[x] = la[x];
+            if (nB > 1 && i <= Bb) for (u32 x = 0; x < nB; x++) gb[x] = lb[x];
+        }
         if (nA && nB) {
             // pass 1: count per level sum in the reference's call order
             u32 c = 0; total += get_pairs(A, ha, nA, Ba, La, hb, nB, Bb, Lb, i, i, c, 0, 0, nullptr, 0);
@@ -1554,7 +1583,7 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
                 if (r < rounds_se) search(K, true, r, ln.d_pe_list[r & 1], nullptr, 20 + r);
                 ev_begin('p');
                 if (K.hits == ln.d_heavy_hits) pair_round_wide<<<sms * 4, 32, sizeof(PairWideSmem), st>>>(K, r, ln.d_pe_list[r & 1], ln.d_pe_list[(r + 1) & 1], 20 + r);
-                else pair_round<<<sms * 4, 128, 0, st>>>(K, r, ln.d_pe_list[r & 1], ln.d_pe_list[(r + 1) & 1], 20 + r);
+                else pair_round<<<sms * 8, 128, 0, st>>>(K, r, ln.d_pe_list[r & 1], ln.d_pe_list[(r + 1) & 1], 20 + r);
                 ev_end(); launches++;
             }
         }
