@@ -491,12 +491,61 @@ __device__ __forceinline__ void ldg256(const u64 *p, u32 (&r)[8]) {     // one 3
     r[0] = (u32)(a >> 32); r[1] = (u32)a; r[2] = (u32)(b >> 32); r[3] = (u32)b; r[4] = (u32)(c >> 32); r[5] = (u32)c; r[6] = (u32)(d >> 32); r[7] = (u32)d;
 }
 
+// the 32-byte sectors of the reference window of a candidate at global coordinate g (read length L) -> R, 8 logical words
+// per sector; kk = logical word of the first sector the window starts in
+template <int NS>
+__device__ __forceinline__ void vf_gather(const u64 *plane, u32 g, u32 L, u32 (&R)[8 * NS], u32 &kk) {
+    const u32 word0 = g >> 5, sb = word0 & ~3u;                          // first 64-bit word of the window, its 32-byte sector
+    const u32 nwc = ((g & 31u) + L + 31u) >> 5;                          // 64-bit words the window touches
+    const u32 nsec = ((word0 & 3u) + nwc + 3u) >> 2;
+    kk = 2 * (word0 & 3u) + ((g & 31u) >> 4);
+    const u64 *P = plane + sb;
+#pragma unroll
+    for (int sct = 0; sct < NS; sct++) if ((u32)sct < nsec) { u32 r8[8]; ldg256(P + 4 * sct, r8);
+#pragma unroll
+        for (int j = 0; j < 8; j++) R[8 * sct + j] = r8[j]; }
+}
+
+// CountMismatch / CountMismatch_new of a whole read against the gathered window (R is rotated in place so that the window
+// starts at R[0]); S = the read's staged streams, sh = bit offset of the window start inside its half-word.
+// pre (only with GAP) = mismatches under the prefix mask stream
+template <bool SINGLE, bool GAP, int NS>
+__device__ __forceinline__ void vf_count(u32 (&R)[8 * NS], u32 kk, u32 sh, const u32 *S, u32 W, u32 W2, u32 &snp, u32 &pre) {
+    constexpr int NR = 8 * NS;
+    constexpr u32 NP = SINGLE ? 2 : 3, PL_NM = 1, PL_CM = 2, PL_PM = NP;
+    if (kk & 4u) {
+#pragma unroll
+        for (int j = 0; j + 4 < NR; j++) R[j] = R[j + 4];
+    }
+    if (kk & 2u) {
+#pragma unroll
+        for (int j = 0; j + 2 < NR; j++) R[j] = R[j + 2];
+    }
+    if (kk & 1u) {
+#pragma unroll
+        for (int j = 0; j + 1 < NR; j++) R[j] = R[j + 1];
+    }
+#pragma unroll
+    for (int i = 0; i < (NR - 8) / 2; i++) {                                    // read word i = logical words 2i, 2i+1
+        if ((u32)i < W) {
+            const uint2 qq = *(const uint2 *)(S + 2 * i), nn = *(const uint2 *)(S + PL_NM * W2 + 2 * i);
+            uint2 cc = make_uint2(0u, 0u); if (!SINGLE) cc = *(const uint2 *)(S + PL_CM * W2 + 2 * i);
+            const u32 r0 = __funnelshift_l(R[2 * i + 1], R[2 * i], sh), r1 = __funnelshift_l(R[2 * i + 2], R[2 * i + 1], sh);
+            const u32 d0 = vf_diff<SINGLE>(qq.x, cc.x, r0), d1 = vf_diff<SINGLE>(qq.y, cc.y, r1);
+            snp += __popc((d0 & nn.x) | ((d1 & nn.y) << 1));
+            if (GAP) { const uint2 pp = *(const uint2 *)(S + PL_PM * W2 + 2 * i); pre += __popc((d0 & pp.x) | ((d1 & pp.y) << 1)); }
+        }
+    }
+}
+
 template <bool SINGLE, bool GAP, int NS>
 __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates(const __grid_constant__ KArgs A, u32 ci, u32 W) {
     extern __shared__ u32 vsm[];                          // staged streams: item x stream x 2*Wb
     __shared__ uint4 s_ha[CHUNK], s_hb[CHUNK];            // item headers {base, m, b0, nfwd} {rot, pack, slot, first word of the read streams}
     __shared__ u32 s_mask[CHUNK / 32], s_nmk;
     __shared__ uint4 s_mk[CHUNK];                         // marked candidates of the chunk: {flat index, g, snp | strand << 8 | chain << 9, slot}
+    __shared__ uint2 s_sv[GAP ? 1 : CHUNK];               // candidates that passed the one-sector screen: {chunk position | item << 8 | strand << 16, g}
+    __shared__ u32 s_bits[CHUNK / 32], s_nsv;             // verdict bits of the chunk (screened path)
     constexpr u32 NP = SINGLE ? 2 : 3;                    // streams copied from global memory: bases, N-mask, (convert-to mask)
     constexpr u32 NPL = NP + (GAP ? 1 : 0);               // + prefix mask
     constexpr u32 PL_NM = 1, PL_CM = 2, PL_PM = NP;
@@ -517,7 +566,7 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
     for (; chunk < n_chunks;) {
         const u32 cbeg = chunk * CHUNK, cend = min(cbeg + CHUNK, n_cands);
         bool mine = have && (t == 0 || ha.x < cend);
-        if (t < CHUNK / 32) s_mask[t] = 0;
+        if (t < CHUNK / 32) { s_mask[t] = 0; s_bits[t] = 0; }
         if (t == 0) s_nmk = 0;
         u32 n_it = (u32)__syncthreads_count(mine);
         if (n_it == VF_EAGER) {                                                  // (rare) more items than were prefetched
@@ -547,29 +596,38 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
         }
         const bool act = idx < cend;
         bool marked = false;
-        u32 g = 0, pack = 0, sig = 0, kk = 0, sh = 0;
-        u32 R[NR];
+        u32 g = 0, pack = 0, sig = 0, kk = 0, sh = 0, dlt = 0, nh = 0;
+        u32 R[GAP ? NR : 8];                                                     // -g: the whole window; else the screened sector
 #pragma unroll
-        for (int j = 0; j < NR; j++) R[j] = 0;
+        for (int j = 0; j < (GAP ? NR : 8); j++) R[j] = 0;
         if (act) {
             const uint4 xa = s_ha[it]; const uint2 xb = *(const uint2 *)&s_hb[it];
             u32 e = xb.x + (idx - xa.x); if (e >= xa.y) e -= xa.y;
             sig = e >= xa.w ? 1u : 0u;                                           // forward-strand entries come first (align.cpp:296)
             pack = xb.y;
             g = cloc - IH_H(pack);                                               // _hit.loc (align.cpp:297)
-            const u32 word0 = g >> 5, sb = word0 & ~3u;                          // first 64-bit word of the window, its 32-byte sector
-            const u32 nwc = ((g & 31u) + IH_L(pack) + 31u) >> 5;                 // 64-bit words the window touches
-            const u32 nsec = ((word0 & 3u) + nwc + 3u) >> 2;
-            kk = 2 * (word0 & 3u) + ((g & 31u) >> 4); sh = (g & 15u) * 2;        // window start = logical word kk, bit sh of the first sector
-            const u64 *P = A.di.plane[sig] + sb;
+            sh = (g & 15u) * 2;
+            if constexpr (GAP) vf_gather<NS>(A.di.plane[sig], g, IH_L(pack), R, kk);
+            else {
+                // ---- screen: ONE 32-byte sector of the window (8 half-words of 16 bases). Read half-word i lines up with
+                //      reference half-words gh+i, gh+i+1; the sector starting o half-words before gh covers i in [0, 6-o],
+                //      the next one i in [8-o, 14-o]. Take the one that covers more of the read: a mismatch count over a
+                //      subset of the read's half-words is a lower bound of CountMismatch, so `> thr` here is final.
+                const u32 gh = g >> 4, o = gh & 7u;
+                nh = (IH_L(pack) + 15u) >> 4;
+                const u32 c0 = min(7u - o, nh), hi1 = min(14u - o, nh - 1u);
+                const u32 c1 = hi1 + o >= 8u ? hi1 + o - 7u : 0u;
+                const u32 k = c1 > c0 ? 1u : 0u;
+                dlt = k ? 8u - o : 0u - o;                                      // read half-word of sector half-word x = x + dlt
+                u32 r8[8]; ldg256(A.di.plane[sig] + ((gh - o) >> 1) + 4u * k, r8);
 #pragma unroll
-            for (int sct = 0; sct < NS; sct++) if ((u32)sct < nsec) { u32 r8[8]; ldg256(P + 4 * sct, r8);
-#pragma unroll
-                for (int j = 0; j < 8; j++) R[8 * sct + j] = r8[j]; }
+                for (int j = 0; j < 8; j++) R[j] = r8[j];
+            }
         }
         for (u32 grp = 0; grp < n_it; grp += VF_ITMAX) {
             const u32 n_g = min(VF_ITMAX, n_it - grp);
             if (grp) __syncthreads();                                        // the previous group is done with the staging buffer
+            if (!GAP && t == 0) s_nsv = 0;
             // ---- stage the streams of this group's items: a warp copies the D contiguous words of an item (coalesced),
             //      four items per warp in flight
             for (u32 l = lane; l < D; l += 32) {
@@ -600,45 +658,53 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
             }
             __syncthreads();                                                                // staged streams visible
             const bool now = act && it >= grp && it < grp + n_g;
-            u32 snp = 0, pre = 0;
-            if (now) {
-                // rotate the gathered words so that the window starts at R[0] (kk = 0..7 logical words)
-                if (kk & 4u) {
+            if constexpr (GAP) {
+                u32 snp = 0, pre = 0;
+                if (now) vf_count<SINGLE, GAP, NS>(R, kk, sh, vsm + (size_t)(it - grp) * IST, W, W2, snp, pre);
+                // could this candidate add a hit?  ungapped: snp <= thr.  gapped: GapAlign's first test (align.cpp:353-360)
+                const u32 thr = IH_THR(pack);
+                const bool mark = now && (snp <= thr || (thr >= 2 && pre < thr - 1));
+                if (mark) { marked = true; s_mk[atomicAdd(&s_nmk, 1u)] = make_uint4(idx, g, snp | (sig << 8) | (IH_CHAIN(pack) << 9), s_hb[it].z); }
+            } else {
+                if (now) {
+                    const u32 *S = vsm + (size_t)(it - grp) * IST;
+                    u32 snp = 0;
 #pragma unroll
-                    for (int j = 0; j + 4 < NR; j++) R[j] = R[j + 4];
+                    for (int x = 0; x < 7; x++) {
+                        const u32 i = (u32)x + dlt;
+                        if (i < nh) {
+                            const u32 r = __funnelshift_l(R[x + 1], R[x], sh);
+                            u32 cc = 0; if (!SINGLE) cc = S[PL_CM * W2 + i];
+                            snp += __popc(vf_diff<SINGLE>(S[i], cc, r) & S[PL_NM * W2 + i]);
+                        }
+                    }
+                    if (snp <= IH_THR(pack)) s_sv[atomicAdd(&s_nsv, 1u)] = make_uint2(t | ((it - grp) << 8) | (sig << 16), g);
                 }
-                if (kk & 2u) {
+                __syncthreads();
+                // ---- the few candidates that passed the screen: whole window, exact count
+                if (t < s_nsv) {
+                    const uint2 sv = s_sv[t];
+                    const u32 t2 = sv.x & 255u, it2 = grp + ((sv.x >> 8) & 255u), sig2 = (sv.x >> 16) & 1u, g2 = sv.y;
+                    const u32 pack2 = s_hb[it2].y;
+                    u32 Q[NR], kk2 = 0, snp = 0, pre = 0;
 #pragma unroll
-                    for (int j = 0; j + 2 < NR; j++) R[j] = R[j + 2];
-                }
-                if (kk & 1u) {
-#pragma unroll
-                    for (int j = 0; j + 1 < NR; j++) R[j] = R[j + 1];
-                }
-                const u32 *S = vsm + (size_t)(it - grp) * IST;
-#pragma unroll
-                for (int i = 0; i < (NR - 8) / 2; i++) {                                    // read word i = logical words 2i, 2i+1
-                    if ((u32)i < W) {
-                        const uint2 qq = *(const uint2 *)(S + 2 * i), nn = *(const uint2 *)(S + PL_NM * W2 + 2 * i);
-                        uint2 cc = make_uint2(0u, 0u); if (!SINGLE) cc = *(const uint2 *)(S + PL_CM * W2 + 2 * i);
-                        const u32 r0 = __funnelshift_l(R[2 * i + 1], R[2 * i], sh), r1 = __funnelshift_l(R[2 * i + 2], R[2 * i + 1], sh);
-                        const u32 d0 = vf_diff<SINGLE>(qq.x, cc.x, r0), d1 = vf_diff<SINGLE>(qq.y, cc.y, r1);
-                        snp += __popc((d0 & nn.x) | ((d1 & nn.y) << 1));
-                        if (GAP) { const uint2 pp = *(const uint2 *)(S + PL_PM * W2 + 2 * i); pre += __popc((d0 & pp.x) | ((d1 & pp.y) << 1)); }
+                    for (int j = 0; j < NR; j++) Q[j] = 0;
+                    vf_gather<NS>(A.di.plane[sig2], g2, IH_L(pack2), Q, kk2);
+                    vf_count<SINGLE, false, NS>(Q, kk2, (g2 & 15u) * 2, vsm + (size_t)(it2 - grp) * IST, W, W2, snp, pre);
+                    if (snp <= IH_THR(pack2)) {
+                        atomicOr(&s_bits[t2 >> 5], 1u << (t2 & 31u));
+                        s_mk[atomicAdd(&s_nmk, 1u)] = make_uint4(cbeg + t2, g2, snp | (sig2 << 8) | (IH_CHAIN(pack2) << 9), s_hb[it2].z);
                     }
                 }
             }
-            // could this candidate add a hit?  ungapped: snp <= thr.  gapped: GapAlign's first test (align.cpp:353-360)
-            const u32 thr = IH_THR(pack);
-            const bool mark = now && (snp <= thr || (GAP && thr >= 2 && pre < thr - 1));
-            if (mark) { marked = true; s_mk[atomicAdd(&s_nmk, 1u)] = make_uint4(idx, g, snp | (sig << 8) | (IH_CHAIN(pack) << 9), s_hb[it].z); }
         }
-        // ---- the warp's 32 verdicts are one word of the bitmap; marked candidates are published for reduce_fast / reduce_round
-        {
+        // ---- 32 verdicts are one word of the bitmap; marked candidates are published for reduce_fast / reduce_round
+        if (GAP) {
             const u32 bal = __ballot_sync(0xffffffffu, marked);
             if (lane == 0) A.bitmap[(cbeg >> 5) + wid] = bal;
         }
         __syncthreads();
+        if (!GAP && t < CHUNK / 32) A.bitmap[(cbeg >> 5) + t] = s_bits[t];
         if (t < s_nmk) {
             const uint4 mk = s_mk[t];
             const u32 pos = atomicAdd(&A.slot_flag[mk.w], 1u);
