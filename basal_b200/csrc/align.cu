@@ -57,7 +57,7 @@ struct KArgs {
     uint2 *slot_item;              // [slot*2+chain] = {first item, number of items} of this round
     u32 *slot_flag;                // number of candidates verify marked for the slot in this round
     u32 *flag_list;                // slots with marked candidates
-    u32 *chunk_first;              // first item overlapping each chunk of the flat candidate space
+    u32 *chunk_first;              // item that owns flat candidate 32 k, for every group k of 32 candidates
     u32 *bitmap;                   // 1 bit per flat candidate
     u32 *flat_loc;                 // seed-table entry of every flat candidate (the bucket walks, in visiting order)
     uint4 *marks;                  // [slot][MK_CAP] the first marked candidates of a slot in this round: {flat index, g, snp | strand<<8 | chain<<9, -}
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(LK_THREADS) seed_lookup(const __grid_constant_
                     a.x = cb; a.y = pm; a.z = e0; a.w = e1 - e0;
                     b.x = m.rnd % pm; b.y = h | ((u32)m.len << 9) | ((u32)m.thr << 18) | (i << 22) | (c << 26); b.z = slot; b.w = 0;
                     uint4 *dst = (uint4 *)(A.hdr + it); dst[0] = a; dst[1] = b;
-                    for (u32 cc = (cb + CHUNK - 1) / CHUNK; (u64)cc * CHUNK < (u64)cb + pm; cc++) A.chunk_first[cc] = it;
+                    for (u32 cc = (cb + 31u) / 32u; (u64)cc * 32u < (u64)cb + pm; cc++) A.chunk_first[cc] = it;
                     x_cb = cb; x_pm = pm; x_e0 = e0; x_rot = b.x;
                     cb += pm; it++;
                 }
@@ -558,10 +558,10 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
     const u32 W2 = 2 * A.Wb, D = NP * W2, IST = NPL * W2;
     if (blockIdx.x >= n_chunks) return;
     // ---- software pipeline over this CTA's chunks: the headers and loc entries of the next chunk are loaded while this one is verified
-    u32 chunk = blockIdx.x, first = A.chunk_first[chunk];
+    u32 chunk = blockIdx.x, first = A.chunk_first[chunk * (CHUNK / 32)];
     uint4 ha = make_uint4(0, 0, 0, 0), hb = ha; bool have = false;
     if (t < VF_EAGER && first + t < n_items) { const uint4 *src = (const uint4 *)(A.hdr + first + t); ha = __ldg(src); hb = __ldg(src + 1); have = true; }
-    u32 nchunk = chunk + gridDim.x, nfirst = nchunk < n_chunks ? A.chunk_first[nchunk] : 0u;
+    u32 nchunk = chunk + gridDim.x, nfirst = nchunk < n_chunks ? A.chunk_first[nchunk * (CHUNK / 32)] : 0u;
     u32 cloc = chunk * CHUNK + t < n_cands ? __ldg(A.flat_loc + chunk * CHUNK + t) : 0u;      // seed-table entry of my candidate (flat_loc is a plain stream)
     for (; chunk < n_chunks;) {
         const u32 cbeg = chunk * CHUNK, cend = min(cbeg + CHUNK, n_cands);
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
         // prefetch for the next chunk (consumed at the top of the next iteration)
         uint4 pa = make_uint4(0, 0, 0, 0), pb = pa; bool phave = false;
         if (nchunk < n_chunks && t < VF_EAGER && nfirst + t < n_items) { const uint4 *src = (const uint4 *)(A.hdr + nfirst + t); pa = __ldg(src); pb = __ldg(src + 1); phave = true; }
-        const u32 nnchunk = nchunk + gridDim.x; const u32 nnfirst = nnchunk < n_chunks ? __ldg(A.chunk_first + nnchunk) : 0u;
+        const u32 nnchunk = nchunk + gridDim.x; const u32 nnfirst = nnchunk < n_chunks ? __ldg(A.chunk_first + (size_t)nnchunk * (CHUNK / 32)) : 0u;
         const u32 nloc = (nchunk < n_chunks && nchunk * CHUNK + t < n_cands) ? __ldg(A.flat_loc + nchunk * CHUNK + t) : 0u;
         __syncthreads();
         // ---- my candidate: item = (number of item starts at chunk positions <= t) - 1
@@ -712,6 +712,144 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
         }
         __syncthreads();
         chunk = nchunk; first = nfirst; ha = pa; hb = pb; have = phave; nchunk = nnchunk; nfirst = nnfirst; cloc = nloc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// screen_candidates + verify_survivors : candidate verification without -g.
+//
+// screen_candidates is the roofline kernel. A WARP owns 32 consecutive flat candidates and never waits for another warp
+// (no block barriers): lanes load the headers of the items overlapping the group, every lane resolves its candidate's
+// item with one popcount, issues ONE 256-bit gather (the 32-byte sector of its reference window that covers most of the
+// read), the warp stages the items' read streams into its private slice of shared memory behind those gathers, and each
+// lane counts the mismatches of the read half-words the sector covers. That count is a lower bound of CountMismatch
+// (align.h:118-131 / 199-239: a sum over half-words, the same alignment), so a candidate above its threshold is
+// rejected for good; the rest (a few per cent) get bit = 1 in the bitmap. verify_survivors walks the set bits, gathers
+// the whole window and applies the exact count; it clears the bits that fail and records the marks.
+// ------------------------------------------------------------------------------------------------
+#define SC_WARPS 8
+template <bool SINGLE>
+__global__ void __launch_bounds__(SC_WARPS * 32, 5) screen_candidates(const __grid_constant__ KArgs A, u32 ci, u32 stage_items, u32 rcp_dw) {
+    extern __shared__ u32 ssm[];
+    constexpr u32 NP = SINGLE ? 2 : 3, PL_NM = 1, PL_CM = 2, FULL = 0xffffffffu;
+    const RoundCtr *rc = A.ctr->rc + ci;
+    const unsigned long long al = min(rc->alloc, ~rc->limit_inv);
+    const u32 n_cands = (u32)(al & ALLOC_MASK), n_items = (u32)(al >> ALLOC_SHIFT);
+    const u32 n_groups = (n_cands + 31u) >> 5;
+    const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const u32 W2 = 2 * A.Wb, D = NP * W2, DW = NP * A.Wb;
+    u32 *S0 = ssm + (size_t)wid * stage_items * D;
+    u64 *S64 = (u64 *)S0;
+    for (u32 grp = blockIdx.x * SC_WARPS + wid; grp < n_groups; grp += gridDim.x * SC_WARPS) {
+        const u32 gbeg = grp << 5, gend = min(gbeg + 32u, n_cands);
+        const u32 first = __ldg(A.chunk_first + grp);
+        const u32 last = grp + 1 < n_groups ? __ldg(A.chunk_first + grp + 1) : n_items - 1u;
+        const bool act = gbeg + lane < gend;
+        const u32 cloc = act ? __ldg(A.flat_loc + gbeg + lane) : 0u;
+        uint4 ha = make_uint4(FULL, 0, 0, 0), hb = make_uint4(0, 0, 0, 0);
+        const bool ld = first + lane <= last;
+        if (ld) { const uint4 *src = (const uint4 *)(A.hdr + first + lane); ha = __ldg(src); hb = __ldg(src + 1); }
+        const bool mine = ld && (lane == 0 || ha.x < gend);
+        const u32 pos = (mine && ha.x > gbeg) ? ha.x - gbeg : 0u;
+        const u32 mask = __reduce_or_sync(FULL, mine ? 1u << pos : 0u);
+        const u32 n_it = __popc(mask);
+        const u32 soff = (hb.z * 2 + IH_CHAIN(hb.y)) * 3 * A.Wb;                 // first 64-bit word of the item's read streams
+        const u32 it = __popc(mask & (FULL >> (31u - lane))) - 1u;               // my candidate's item = lane `it`
+        const u32 ibase = __shfl_sync(FULL, ha.x, it), im = __shfl_sync(FULL, ha.y, it), inf = __shfl_sync(FULL, ha.w, it);
+        const u32 irot = __shfl_sync(FULL, hb.x, it), pack = __shfl_sync(FULL, hb.y, it);
+        u32 e = irot + (gbeg + lane - ibase); if (e >= im) e -= im;
+        const u32 sig = e >= inf ? 1u : 0u;                                      // forward-strand entries come first (align.cpp:296)
+        const u32 g = cloc - IH_H(pack), sh = (g & 15u) * 2;                     // _hit.loc (align.cpp:297)
+        // ---- the sector: read half-word i lines up with reference half-words gh+i, gh+i+1; the sector that starts o
+        //      half-words before gh covers i in [0, 6-o], the next one i in [8-o, 14-o]; take the better covered one
+        const u32 gh = g >> 4, o = gh & 7u, nh = (IH_L(pack) + 15u) >> 4;
+        const u32 c0 = min(7u - o, nh), hi1 = min(14u - o, nh - 1u);
+        const u32 c1 = hi1 + o >= 8u ? hi1 + o - 7u : 0u;
+        const u32 k = c1 > c0 ? 1u : 0u;
+        const u32 dlt = k ? 8u - o : 0u - o;                                     // read half-word of sector half-word x = x + dlt
+        u32 R[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) R[j] = 0;
+        if (act) ldg256(A.di.plane[sig] + ((gh - o) >> 1) + 4u * k, R);
+        bool pass = false;
+        for (u32 s0 = 0; s0 < n_it; s0 += stage_items) {
+            const u32 nb = min(stage_items, n_it - s0), nw = nb * DW;
+            // ---- stage the read streams of items s0 .. s0+nb-1 (DW contiguous 64-bit words each), two trips in flight
+            for (u32 x0 = 0; x0 < nw; x0 += 64) {
+                const u32 xa = x0 + lane, xb = xa + 32u;
+                const u32 ia = min(__umulhi(xa, rcp_dw), nb - 1u), ib = min(__umulhi(xb, rcp_dw), nb - 1u);
+                const u32 sa = __shfl_sync(FULL, soff, s0 + ia), sb = __shfl_sync(FULL, soff, s0 + ib);
+                u64 va = 0, vb = 0;
+                if (xa < nw) va = __ldg(A.planes + sa + (xa - ia * DW));
+                if (xb < nw) vb = __ldg(A.planes + sb + (xb - ib * DW));
+                if (xa < nw) S64[xa] = va;
+                if (xb < nw) S64[xb] = vb;
+            }
+            __syncwarp();
+            if (act && it >= s0 && it < s0 + nb) {
+                const u32 *S = S0 + (size_t)(it - s0) * D;
+                u32 snp = 0;
+#pragma unroll
+                for (int x = 0; x < 7; x++) {
+                    const u32 i = (u32)x + dlt;
+                    if (i < nh) {
+                        const u32 r = __funnelshift_l(R[x + 1], R[x], sh);
+                        u32 cc = 0; if (!SINGLE) cc = S[PL_CM * W2 + i];
+                        snp += __popc(vf_diff<SINGLE>(S[i], cc, r) & S[PL_NM * W2 + i]);
+                    }
+                }
+                pass = snp <= IH_THR(pack);
+            }
+            __syncwarp();
+        }
+        const u32 bal = __ballot_sync(FULL, pass);
+        if (lane == 0) A.bitmap[grp] = bal;
+    }
+}
+
+template <bool SINGLE, int NS>
+__global__ void __launch_bounds__(128) verify_survivors(const __grid_constant__ KArgs A, u32 ci, u32 W) {
+    constexpr u32 FULL = 0xffffffffu;
+    constexpr int NR = 8 * NS;
+    const RoundCtr *rc = A.ctr->rc + ci;
+    const unsigned long long al = min(rc->alloc, ~rc->limit_inv);
+    const u32 n_cands = (u32)(al & ALLOC_MASK), n_items = (u32)(al >> ALLOC_SHIFT);
+    const u32 n_groups = (n_cands + 31u) >> 5;
+    const u32 lane = threadIdx.x & 31u;
+    const u32 nwarps = gridDim.x * (blockDim.x >> 5), warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const u32 W2 = 2 * A.Wb;
+    for (u32 w0 = warp * 32u; w0 < n_groups; w0 += nwarps * 32u) {
+        const u32 bits = w0 + lane < n_groups ? A.bitmap[w0 + lane] : 0u;
+        const u32 cnt = __popc(bits);
+        u32 incl = cnt;
+        for (u32 d = 1; d < 32; d <<= 1) { const u32 v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
+        const u32 excl = incl - cnt, total = __shfl_sync(FULL, incl, 31);
+        for (u32 base = 0; base < total; base += 32) {
+            const u32 j = base + lane;
+            u32 lo = 0;                                                          // lane that owns the j-th set bit: the last one with excl <= j
+            for (u32 step = 16; step; step >>= 1) { const u32 probe = lo + step; const u32 v = __shfl_sync(FULL, excl, probe & 31u); if (probe < 32u && v <= j) lo = probe; }
+            const u32 r = j - __shfl_sync(FULL, excl, lo), wb = __shfl_sync(FULL, bits, lo);
+            if (j < total) {
+                const u32 bit = __fns(wb, 0, (int)r + 1);
+                const u32 flat = ((w0 + lo) << 5) + bit;
+                u32 it = __ldg(A.chunk_first + (flat >> 5));
+                while (it + 1 < n_items && __ldg(&A.hdr[it + 1].base) <= flat) it++;
+                const uint4 *src = (const uint4 *)(A.hdr + it); const uint4 ha = __ldg(src), hb = __ldg(src + 1);
+                u32 e = hb.x + (flat - ha.x); if (e >= ha.y) e -= ha.y;
+                const u32 sig = e >= ha.w ? 1u : 0u, pack = hb.y, chain = IH_CHAIN(pack);
+                const u32 g = __ldg(A.flat_loc + flat) - IH_H(pack);
+                u32 Q[NR], kk = 0, snp = 0, pre = 0;
+#pragma unroll
+                for (int q = 0; q < NR; q++) Q[q] = 0;
+                vf_gather<NS>(A.di.plane[sig], g, IH_L(pack), Q, kk);
+                const u32 *S = (const u32 *)(A.planes + (size_t)(hb.z * 2 + chain) * 3 * A.Wb);
+                vf_count<SINGLE, false, NS>(Q, kk, (g & 15u) * 2, S, W, W2, snp, pre);
+                if (snp <= IH_THR(pack)) {
+                    const u32 pos = atomicAdd(&A.slot_flag[hb.z], 1u);
+                    if (pos < MK_CAP) A.marks[(size_t)hb.z * MK_CAP + pos] = make_uint4(flat, g, snp | (sig << 8) | (chain << 9), 0u);
+                } else atomicAnd(&A.bitmap[flat >> 5], ~(1u << bit));
+            }
+        }
     }
 }
 
@@ -1528,7 +1666,7 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     if (2 * worst_slot + CHUNK > want_cands) { set_error(ctx, "over-represented k-mer cut-off %u is too large for the 32-bit candidate space", ctx->di.maxk); return BSL_ELIMIT; }
     const u64 want_items = std::min<u64>((u64)n_slots * nch * P.index_interval, want_cands) + 16;
     c0 = ln.cap_bitmap; if ((rc = grow(ctx, &ln.d_bitmap, &c0, (size_t)(want_cands / 32 + 8)))) return rc;
-    if (c0 != ln.cap_bitmap || !ln.d_chunk_first) { cudaFree(ln.d_chunk_first); ln.d_chunk_first = nullptr; CUDA_TRY(cudaMalloc(&ln.d_chunk_first, (c0 * 32 / CHUNK + 8) * 4));
+    if (c0 != ln.cap_bitmap || !ln.d_chunk_first) { cudaFree(ln.d_chunk_first); ln.d_chunk_first = nullptr; CUDA_TRY(cudaMalloc(&ln.d_chunk_first, (c0 + 8) * 4));
         cudaFree(ln.d_flat_loc); ln.d_flat_loc = nullptr; CUDA_TRY(cudaMalloc(&ln.d_flat_loc, (c0 * 32 + 2 * CHUNK) * 4)); }
     ln.cap_bitmap = c0;
     c0 = ln.cap_items; if ((rc = grow(ctx, &ln.d_hdr, &c0, (size_t)want_items))) return rc; ln.cap_items = c0;
@@ -1616,7 +1754,27 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     const int max_ev = (int)(sizeof ln.evk / sizeof ln.evk[0]);
     auto ev_begin = [&](char kind) { if (nev + 2 <= max_ev) { cudaEventRecord(ln.evk[nev], st); ev_kind.push_back(kind); } };
     auto ev_end = [&]() { if (nev + 2 <= max_ev) { cudaEventRecord(ln.evk[nev + 1], st); nev += 2; } };
+    const u32 DWv = NP * Wb;                                             // 64-bit words of one item's read streams
+    const u32 stage_items = std::max<u32>(1, std::min<u32>(32, 640 / (2 * DWv)));
+    const size_t smem_s = (size_t)SC_WARPS * stage_items * 2 * DWv * 4;
+    const u32 rcp_dw = (u32)((0x100000000ull + DWv - 1) / DWv);
+    static const bool old_verify = getenv("BSL_VERIFY_OLD") != nullptr;
+    if (!ctx->occ_screen) {
+        int occ = 0;
+        cudaError_t oe = ctx->rule.single ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, screen_candidates<true>, SC_WARPS * 32, smem_s)
+                                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, screen_candidates<false>, SC_WARPS * 32, smem_s);
+        ctx->occ_screen = (oe == cudaSuccess && occ > 0) ? occ : 4;
+    }
+    const int grid_s = sms * ctx->occ_screen;
     auto launch_verify = [&](KArgs &K, u32 ci) {
+        if (!G && !old_verify) {
+            if (ctx->rule.single) screen_candidates<true><<<grid_s, SC_WARPS * 32, smem_s, st>>>(K, ci, stage_items, rcp_dw);
+            else screen_candidates<false><<<grid_s, SC_WARPS * 32, smem_s, st>>>(K, ci, stage_items, rcp_dw);
+            if (ctx->rule.single) { if (ns3) verify_survivors<true, 3><<<sms * 4, 128, 0, st>>>(K, ci, Wr); else verify_survivors<true, 5><<<sms * 4, 128, 0, st>>>(K, ci, Wr); }
+            else { if (ns3) verify_survivors<false, 3><<<sms * 4, 128, 0, st>>>(K, ci, Wr); else verify_survivors<false, 5><<<sms * 4, 128, 0, st>>>(K, ci, Wr); }
+            launches++;
+            return;
+        }
 #define VF_LAUNCH(S_, G_) do { if (ns3) verify_candidates<S_, G_, 3><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, Wr); else verify_candidates<S_, G_, 5><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, Wr); } while (0)
         if (ctx->rule.single) { if (G) VF_LAUNCH(true, true); else VF_LAUNCH(true, false); }
         else { if (G) VF_LAUNCH(false, true); else VF_LAUNCH(false, false); }

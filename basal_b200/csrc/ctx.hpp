@@ -49,6 +49,7 @@ struct bsl_ctx {
     char err[512];
     int sm_count = BSL_SM_COUNT;
     int occ_verify[4] = {0, 0, 0, 0};   // resident CTAs per SM of the verify_candidates variants
+    int occ_screen = 0;                 // resident CTAs per SM of screen_candidates
 };
 
 static inline void set_error(bsl_ctx *ctx, const char *fmt, ...) {
