@@ -728,9 +728,30 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
 // the whole window and applies the exact count; it clears the bits that fail and records the marks.
 // ------------------------------------------------------------------------------------------------
 #define SC_WARPS 8
+#define SC_QCAP 64u          // survivors a warp can hold (it empties the queue whenever 32 are waiting)
+
+// exact CountMismatch / CountMismatch_new of one survivor, one lane: reference half-words straight from the plane
+// (32-bit loads, L1/L2 hits: the screen just fetched the middle of the window), read streams from global memory
+template <bool SINGLE>
+__device__ __forceinline__ u32 exact_count(const KArgs &A, u32 g, u32 sig, u32 pack, u32 slot) {
+    const u32 W2 = 2 * A.Wb, gh = g >> 4, sh = (g & 15u) * 2, nh = (IH_L(pack) + 15u) >> 4;
+    const u32 *P = (const u32 *)A.di.plane[sig];                                 // logical half-word j of the plane = u32 word j ^ 1
+    const u32 *S = (const u32 *)(A.planes + (size_t)(slot * 2 + IH_CHAIN(pack)) * 3 * A.Wb);
+    u32 snp = 0, prev = __ldg(P + (gh ^ 1u));
+    for (u32 i = 0; i < nh; i++) {
+        const u32 next = __ldg(P + ((gh + i + 1u) ^ 1u));
+        const u32 r = __funnelshift_l(next, prev, sh);
+        u32 cc = 0; if (!SINGLE) cc = __ldg(S + 2 * W2 + i);
+        snp += __popc(vf_diff<SINGLE>(__ldg(S + i), cc, r) & __ldg(S + W2 + i));
+        prev = next;
+    }
+    return snp;
+}
+
 template <bool SINGLE>
 __global__ void __launch_bounds__(SC_WARPS * 32, 5) screen_candidates(const __grid_constant__ KArgs A, u32 ci, u32 stage_items, u32 rcp_dw) {
     extern __shared__ u32 ssm[];
+    __shared__ uint4 s_q[SC_WARPS][SC_QCAP];          // survivors waiting for the exact count: {flat index, g, pack, slot | strand << 31}
     constexpr u32 NP = SINGLE ? 2 : 3, PL_NM = 1, PL_CM = 2, FULL = 0xffffffffu;
     const RoundCtr *rc = A.ctr->rc + ci;
     const unsigned long long al = min(rc->alloc, ~rc->limit_inv);
@@ -740,6 +761,22 @@ __global__ void __launch_bounds__(SC_WARPS * 32, 5) screen_candidates(const __gr
     const u32 W2 = 2 * A.Wb, D = NP * W2, DW = NP * A.Wb;
     u32 *S0 = ssm + (size_t)wid * stage_items * D;
     u64 *S64 = (u64 *)S0;
+    uint4 *Q = s_q[wid];
+    u32 qn = 0;
+    // exact count of 32 queued survivors (or the `n` last ones when the kernel ends), one per lane; marks + bitmap bits
+    auto drain = [&](u32 from, u32 n) {
+        if (lane < n) {
+            const uint4 sv = Q[from + lane];
+            const u32 sig = sv.w >> 31, slot = sv.w & 0x7fffffffu;
+            const u32 snp = exact_count<SINGLE>(A, sv.y, sig, sv.z, slot);
+            if (snp <= IH_THR(sv.z)) {
+                atomicOr(&A.bitmap[sv.x >> 5], 1u << (sv.x & 31u));
+                const u32 pos = atomicAdd(&A.slot_flag[slot], 1u);
+                if (pos < MK_CAP) A.marks[(size_t)slot * MK_CAP + pos] = make_uint4(sv.x, sv.y, snp | (sig << 8) | (IH_CHAIN(sv.z) << 9), 0u);
+            }
+        }
+        __syncwarp();
+    };
     for (u32 grp = blockIdx.x * SC_WARPS + wid; grp < n_groups; grp += gridDim.x * SC_WARPS) {
         const u32 gbeg = grp << 5, gend = min(gbeg + 32u, n_cands);
         const u32 first = __ldg(A.chunk_first + grp);
@@ -749,6 +786,7 @@ __global__ void __launch_bounds__(SC_WARPS * 32, 5) screen_candidates(const __gr
         uint4 ha = make_uint4(FULL, 0, 0, 0), hb = make_uint4(0, 0, 0, 0);
         const bool ld = first + lane <= last;
         if (ld) { const uint4 *src = (const uint4 *)(A.hdr + first + lane); ha = __ldg(src); hb = __ldg(src + 1); }
+        if (lane == 0) A.bitmap[grp] = 0u;                                       // bits are set by drain()
         const bool mine = ld && (lane == 0 || ha.x < gend);
         const u32 pos = (mine && ha.x > gbeg) ? ha.x - gbeg : 0u;
         const u32 mask = __reduce_or_sync(FULL, mine ? 1u << pos : 0u);
@@ -756,7 +794,7 @@ __global__ void __launch_bounds__(SC_WARPS * 32, 5) screen_candidates(const __gr
         const u32 soff = (hb.z * 2 + IH_CHAIN(hb.y)) * 3 * A.Wb;                 // first 64-bit word of the item's read streams
         const u32 it = __popc(mask & (FULL >> (31u - lane))) - 1u;               // my candidate's item = lane `it`
         const u32 ibase = __shfl_sync(FULL, ha.x, it), im = __shfl_sync(FULL, ha.y, it), inf = __shfl_sync(FULL, ha.w, it);
-        const u32 irot = __shfl_sync(FULL, hb.x, it), pack = __shfl_sync(FULL, hb.y, it);
+        const u32 irot = __shfl_sync(FULL, hb.x, it), pack = __shfl_sync(FULL, hb.y, it), islot = __shfl_sync(FULL, hb.z, it);
         u32 e = irot + (gbeg + lane - ibase); if (e >= im) e -= im;
         const u32 sig = e >= inf ? 1u : 0u;                                      // forward-strand entries come first (align.cpp:296)
         const u32 g = cloc - IH_H(pack), sh = (g & 15u) * 2;                     // _hit.loc (align.cpp:297)
@@ -802,55 +840,16 @@ __global__ void __launch_bounds__(SC_WARPS * 32, 5) screen_candidates(const __gr
             }
             __syncwarp();
         }
+        // ---- survivors join the warp's queue; 32 waiting survivors are counted exactly, one per lane
         const u32 bal = __ballot_sync(FULL, pass);
-        if (lane == 0) A.bitmap[grp] = bal;
-    }
-}
-
-template <bool SINGLE, int NS>
-__global__ void __launch_bounds__(128) verify_survivors(const __grid_constant__ KArgs A, u32 ci, u32 W) {
-    constexpr u32 FULL = 0xffffffffu;
-    constexpr int NR = 8 * NS;
-    const RoundCtr *rc = A.ctr->rc + ci;
-    const unsigned long long al = min(rc->alloc, ~rc->limit_inv);
-    const u32 n_cands = (u32)(al & ALLOC_MASK), n_items = (u32)(al >> ALLOC_SHIFT);
-    const u32 n_groups = (n_cands + 31u) >> 5;
-    const u32 lane = threadIdx.x & 31u;
-    const u32 nwarps = gridDim.x * (blockDim.x >> 5), warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const u32 W2 = 2 * A.Wb;
-    for (u32 w0 = warp * 32u; w0 < n_groups; w0 += nwarps * 32u) {
-        const u32 bits = w0 + lane < n_groups ? A.bitmap[w0 + lane] : 0u;
-        const u32 cnt = __popc(bits);
-        u32 incl = cnt;
-        for (u32 d = 1; d < 32; d <<= 1) { const u32 v = __shfl_up_sync(FULL, incl, d); if (lane >= d) incl += v; }
-        const u32 excl = incl - cnt, total = __shfl_sync(FULL, incl, 31);
-        for (u32 base = 0; base < total; base += 32) {
-            const u32 j = base + lane;
-            u32 lo = 0;                                                          // lane that owns the j-th set bit: the last one with excl <= j
-            for (u32 step = 16; step; step >>= 1) { const u32 probe = lo + step; const u32 v = __shfl_sync(FULL, excl, probe & 31u); if (probe < 32u && v <= j) lo = probe; }
-            const u32 r = j - __shfl_sync(FULL, excl, lo), wb = __shfl_sync(FULL, bits, lo);
-            if (j < total) {
-                const u32 bit = __fns(wb, 0, (int)r + 1);
-                const u32 flat = ((w0 + lo) << 5) + bit;
-                u32 it = __ldg(A.chunk_first + (flat >> 5));
-                while (it + 1 < n_items && __ldg(&A.hdr[it + 1].base) <= flat) it++;
-                const uint4 *src = (const uint4 *)(A.hdr + it); const uint4 ha = __ldg(src), hb = __ldg(src + 1);
-                u32 e = hb.x + (flat - ha.x); if (e >= ha.y) e -= ha.y;
-                const u32 sig = e >= ha.w ? 1u : 0u, pack = hb.y, chain = IH_CHAIN(pack);
-                const u32 g = __ldg(A.flat_loc + flat) - IH_H(pack);
-                u32 Q[NR], kk = 0, snp = 0, pre = 0;
-#pragma unroll
-                for (int q = 0; q < NR; q++) Q[q] = 0;
-                vf_gather<NS>(A.di.plane[sig], g, IH_L(pack), Q, kk);
-                const u32 *S = (const u32 *)(A.planes + (size_t)(hb.z * 2 + chain) * 3 * A.Wb);
-                vf_count<SINGLE, false, NS>(Q, kk, (g & 15u) * 2, S, W, W2, snp, pre);
-                if (snp <= IH_THR(pack)) {
-                    const u32 pos = atomicAdd(&A.slot_flag[hb.z], 1u);
-                    if (pos < MK_CAP) A.marks[(size_t)hb.z * MK_CAP + pos] = make_uint4(flat, g, snp | (sig << 8) | (chain << 9), 0u);
-                } else atomicAnd(&A.bitmap[flat >> 5], ~(1u << bit));
-            }
+        if (bal) {
+            if (pass) Q[qn + __popc(bal & ((1u << lane) - 1u))] = make_uint4(gbeg + lane, g, pack, islot | (sig << 31));
+            qn += __popc(bal);
+            __syncwarp();
+            if (qn >= 32u) { qn -= 32u; drain(qn, 32u); }
         }
     }
+    if (qn) drain(0u, qn);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1770,9 +1769,6 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
         if (!G && !old_verify) {
             if (ctx->rule.single) screen_candidates<true><<<grid_s, SC_WARPS * 32, smem_s, st>>>(K, ci, stage_items, rcp_dw);
             else screen_candidates<false><<<grid_s, SC_WARPS * 32, smem_s, st>>>(K, ci, stage_items, rcp_dw);
-            if (ctx->rule.single) { if (ns3) verify_survivors<true, 3><<<sms * 4, 128, 0, st>>>(K, ci, Wr); else verify_survivors<true, 5><<<sms * 4, 128, 0, st>>>(K, ci, Wr); }
-            else { if (ns3) verify_survivors<false, 3><<<sms * 4, 128, 0, st>>>(K, ci, Wr); else verify_survivors<false, 5><<<sms * 4, 128, 0, st>>>(K, ci, Wr); }
-            launches++;
             return;
         }
 #define VF_LAUNCH(S_, G_) do { if (ns3) verify_candidates<S_, G_, 3><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, Wr); else verify_candidates<S_, G_, 5><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, Wr); } while (0)
