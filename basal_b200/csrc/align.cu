@@ -49,6 +49,7 @@ struct KArgs {
     u64 off_base_a, off_base_b;    // value of offsets[first] of the sub-range (offsets are passed as given)
     u64 all_off;                   // all-hits records already produced by earlier sub-ranges of this call
     u32 Wb;                        // words per plane in this batch
+    u32 *bits1;                    // [slot*2+chain][2*Wb]: low code bit per base, then ACGT mask per base (32 bases per word, first base in the top bit)
     u64 *planes; u8 *sched; SlotMeta *meta; SlotCounts *cnt; uint2 *stat; u8 *minlvl;   // stat: executed seed look-ups / candidates per slot
     DevHit *hits; u32 cap;         // hit pool and per-slot capacity
     DevCounters *ctr;
@@ -195,6 +196,20 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prepare_reads(const __grid_co
                     if (pl == 0) sm.sq[j] = v; else if (pl == 1) sm.sn[j] = v;
                 }
                 if (lane < 4) { sm.sq[W2 + lane] = 0; sm.sn[W2 + lane] = 0; }
+                // 1-bit streams for screen_bits (first base in the top bit): low code bits, ACGT mask, and both for the reversed read
+                u32 *b1 = A.bits1 + ((u64)slot * 2 + c) * 2 * W2;
+                if (lane < W2) {
+                    const u32 pl = lane < A.Wb ? 1 : 2, wv = lane < A.Wb ? lane : lane - A.Wb;
+                    b1[lane] = wv < W ? __brev(sm.bal[pl][wv]) : 0u;
+                    // reversed word wv holds bases L-1-32wv down to L-32-32wv = bits [off, off+32) of the ballot array
+                    const int off = (int)L - 32 - 32 * (int)wv; u32 rv = 0;
+                    if (off > -32) {
+                        const int w0 = off >> 5; const u32 sf = (u32)off & 31u;
+                        const u32 lo_ = w0 >= 0 ? sm.bal[pl][w0] : 0u, hi_ = (w0 + 1 < (int)W) ? sm.bal[pl][w0 + 1] : 0u;
+                        rv = __funnelshift_r(lo_, hi_, sf);
+                    }
+                    b1[W2 + lane] = rv;
+                }
             }
             __syncwarp();
             if (nseg == 0) continue;
@@ -730,23 +745,57 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
 #define SC_WARPS 8
 #define SC_QCAP 64u          // survivors a warp can hold (it empties the queue whenever 32 are waiting)
 
-// exact CountMismatch / CountMismatch_new of one survivor, one lane: reference half-words straight from the plane
-// (32-bit loads, L1/L2 hits: the screen just fetched the middle of the window), read streams from global memory
+// Exact count of up to 32 queued survivors {flat index, g, pack, slot | strand << 31}, one per lane. The warp copies
+// their 2-bit read streams (bases, ACGT mask, (convert-to mask): DW contiguous 64-bit words each) into its staging slice
+// with coalesced loads, then every lane walks the 32-byte sectors of its reference window with a one-word carry
+// (CountMismatch / CountMismatch_new, align.h:118-131 / 199-239). Passing candidates get their bitmap bit and a mark.
 template <bool SINGLE>
-__device__ __forceinline__ u32 exact_count(const KArgs &A, u32 g, u32 sig, u32 pack, u32 slot) {
-    const u32 W2 = 2 * A.Wb, gh = g >> 4, sh = (g & 15u) * 2, nh = (IH_L(pack) + 15u) >> 4;
-    const u32 *P = (const u32 *)A.di.plane[sig];                                 // logical half-word j of the plane = u32 word j ^ 1
-    const u32 *S = (const u32 *)(A.planes + (size_t)(slot * 2 + IH_CHAIN(pack)) * 3 * A.Wb);
-    u32 snp = 0, prev = __ldg(P + (gh ^ 1u));
-    for (u32 i = 0; i < nh; i++) {
-        const u32 next = __ldg(P + ((gh + i + 1u) ^ 1u));
-        const u32 r = __funnelshift_l(next, prev, sh);
-        u32 cc = 0; if (!SINGLE) cc = __ldg(S + 2 * W2 + i);
-        snp += __popc(vf_diff<SINGLE>(__ldg(S + i), cc, r) & __ldg(S + W2 + i));
-        prev = next;
+__device__ __forceinline__ void drain_exact(const KArgs &A, const uint4 *Q, u32 from, u32 n, u32 lane, u32 *S0, u32 stage_items, u32 rcp_dw) {
+    constexpr u32 FULL = 0xffffffffu, NP = SINGLE ? 2 : 3;
+    const u32 Wb = A.Wb, DW = NP * Wb, D = 2 * DW;
+    u64 *S64 = (u64 *)S0;
+    uint4 sv = make_uint4(0, 0, 0, 0);
+    if (lane < n) sv = Q[from + lane];
+    const u32 sig = sv.w >> 31, slot = sv.w & 0x7fffffffu;
+    const u32 qoff = (slot * 2 + IH_CHAIN(sv.z)) * 3 * Wb;
+    for (u32 b0 = 0; b0 < n; b0 += stage_items) {
+        const u32 nb = min(stage_items, n - b0), nw = nb * DW;
+        for (u32 x0 = 0; x0 < nw; x0 += 64) {
+            const u32 xa = x0 + lane, xb = xa + 32u;
+            const u32 ia = min(__umulhi(xa, rcp_dw), nb - 1u), ib = min(__umulhi(xb, rcp_dw), nb - 1u);
+            const u32 sa = __shfl_sync(FULL, qoff, b0 + ia), sb = __shfl_sync(FULL, qoff, b0 + ib);
+            u64 va = 0, vb = 0;
+            if (xa < nw) va = __ldg(A.planes + sa + (xa - ia * DW));
+            if (xb < nw) vb = __ldg(A.planes + sb + (xb - ib * DW));
+            if (xa < nw) S64[xa] = va;
+            if (xb < nw) S64[xb] = vb;
+        }
+        __syncwarp();
+        if (lane >= b0 && lane < b0 + nb) {
+            const u32 *S = S0 + (size_t)(lane - b0) * D;                         // read half-word i: bases S[i], mask S[2 Wb + i], convert-to S[4 Wb + i]
+            const u32 g = sv.y, gh = g >> 4, sh = (g & 15u) * 2, nh = (IH_L(sv.z) + 15u) >> 4, kk0 = gh & 7u;
+            const u64 *P = A.di.plane[sig] + ((gh >> 3) << 2);
+            const u32 nsec = (kk0 + nh + 8u) >> 3;
+            u32 prev = 0, snp = 0;
+            for (u32 sct = 0; sct < nsec; sct++) {
+                u32 r8[8]; ldg256(P + 4 * sct, r8);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const u32 i = 8 * sct + (u32)j - kk0 - 1u;                   // r8[j] is the second reference half-word of read half-word i
+                    if (i < nh) { u32 cc = 0; if (!SINGLE) cc = S[4 * Wb + i]; snp += __popc(vf_diff<SINGLE>(S[i], cc, __funnelshift_l(r8[j], prev, sh)) & S[2 * Wb + i]); }
+                    prev = r8[j];
+                }
+            }
+            if (snp <= IH_THR(sv.z)) {
+                atomicOr(&A.bitmap[sv.x >> 5], 1u << (sv.x & 31u));
+                const u32 pos = atomicAdd(&A.slot_flag[slot], 1u);
+                if (pos < MK_CAP) A.marks[(size_t)slot * MK_CAP + pos] = make_uint4(sv.x, g, snp | (sig << 8) | (IH_CHAIN(sv.z) << 9), 0u);
+            }
+        }
+        __syncwarp();
     }
-    return snp;
 }
+
 
 template <bool SINGLE>
 __global__ void __launch_bounds__(SC_WARPS * 32, 5) screen_candidates(const __grid_constant__ KArgs A, u32 ci, u32 stage_items, u32 rcp_dw) {
@@ -763,20 +812,7 @@ __global__ void __launch_bounds__(SC_WARPS * 32, 5) screen_candidates(const __gr
     u64 *S64 = (u64 *)S0;
     uint4 *Q = s_q[wid];
     u32 qn = 0;
-    // exact count of 32 queued survivors (or the `n` last ones when the kernel ends), one per lane; marks + bitmap bits
-    auto drain = [&](u32 from, u32 n) {
-        if (lane < n) {
-            const uint4 sv = Q[from + lane];
-            const u32 sig = sv.w >> 31, slot = sv.w & 0x7fffffffu;
-            const u32 snp = exact_count<SINGLE>(A, sv.y, sig, sv.z, slot);
-            if (snp <= IH_THR(sv.z)) {
-                atomicOr(&A.bitmap[sv.x >> 5], 1u << (sv.x & 31u));
-                const u32 pos = atomicAdd(&A.slot_flag[slot], 1u);
-                if (pos < MK_CAP) A.marks[(size_t)slot * MK_CAP + pos] = make_uint4(sv.x, sv.y, snp | (sig << 8) | (IH_CHAIN(sv.z) << 9), 0u);
-            }
-        }
-        __syncwarp();
-    };
+    auto drain = [&](u32 from, u32 n) { drain_exact<SINGLE>(A, Q, from, n, lane, S0, stage_items, rcp_dw); };
     for (u32 grp = blockIdx.x * SC_WARPS + wid; grp < n_groups; grp += gridDim.x * SC_WARPS) {
         const u32 gbeg = grp << 5, gend = min(gbeg + 32u, n_cands);
         const u32 first = __ldg(A.chunk_first + grp);
@@ -847,6 +883,157 @@ __global__ void __launch_bounds__(SC_WARPS * 32, 5) screen_candidates(const __gr
             qn += __popc(bal);
             __syncwarp();
             if (qn >= 32u) { qn -= 32u; drain(qn, 32u); }
+        }
+    }
+    if (qn) drain(0u, qn);
+}
+
+// ------------------------------------------------------------------------------------------------
+// screen_bits : the screen for single-conversion rules, on the ONE-BIT forward plane (DevIndex::bit1).
+//
+// A conversion never changes the low bit of a base's code (from = 01, to = 11), so "low bits differ" implies a mismatch
+// under CountMismatch (align.h:126-128) and the number of such positions over any part of the read is a lower bound of
+// its result. A 32-byte sector of bit1 holds 256 bases: one gather covers at least half of the window, and the whole
+// plane of a 500 Mb reference is 62.5 MB — it stays in L2, the gathers never reach DRAM. Candidates on the reverse
+// strand are screened on the same plane: rc position g+k of sequence i is the complement of forward position
+// 2*anchor_i + rc_offset_i - 1 - (g+k), complementing flips the low bit or not (DevIndex::flip), so the REVERSED read is
+// compared with the forward sector (one __brev per word). Sectors that hold a non-ACGT base, padding or margin
+// (DevIndex::nflag) and windows that cross a sequence boundary are not screened on that strand: they go straight to
+// the exact count. Same warp-autonomous structure and survivor queue as screen_candidates.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SC_WARPS * 32, 5) screen_bits(const __grid_constant__ KArgs A, u32 ci, u32 stage_items, u32 rcp_dw, u32 dbg) {   // dbg: tools/gpu_dbg.sh switches (1 no exact count, 2 no gather, 4 no staging loads); 0 in production
+    extern __shared__ u32 ssm[];
+    __shared__ uint4 s_q[SC_WARPS][SC_QCAP];
+    constexpr u32 FULL = 0xffffffffu;
+    const RoundCtr *rc = A.ctr->rc + ci;
+    const unsigned long long al = min(rc->alloc, ~rc->limit_inv);
+    const u32 n_cands = (u32)(al & ALLOC_MASK), n_items = (u32)(al >> ALLOC_SHIFT);
+    const u32 n_groups = (n_cands + 31u) >> 5;
+    const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    const u32 Wb = A.Wb, D = 4 * Wb, DW = 2 * Wb;        // staged item: low bits, ACGT mask, reversed low bits, reversed mask (Wb words each)
+    u32 *S0 = ssm + (size_t)wid * stage_items * D;
+    u64 *S64 = (u64 *)S0;
+    const u64 *bits64 = (const u64 *)A.bits1;
+    const u32 flipm = A.di.flip ? FULL : 0u;
+    uint4 *Q = s_q[wid];
+    u32 qn = 0;
+    auto drain = [&](u32 from, u32 n) { drain_exact<true>(A, Q, from, n, lane, S0, stage_items, rcp_dw); };
+    const u32 stride = gridDim.x * SC_WARPS;
+    u32 grp = blockIdx.x * SC_WARPS + wid;
+    if (grp >= n_groups) return;
+    // chunk_first of the groups this warp visits is loaded two visits ahead, so that the headers and loc entries of the
+    // next visit can be pulled into L2 while this one is screened
+    u32 f0 = __ldg(A.chunk_first + grp), l0 = grp + 1 < n_groups ? __ldg(A.chunk_first + grp + 1) : n_items - 1u;
+    u32 f1 = 0, l1 = 0;
+    if (grp + stride < n_groups) { f1 = __ldg(A.chunk_first + grp + stride); l1 = grp + stride + 1 < n_groups ? __ldg(A.chunk_first + grp + stride + 1) : n_items - 1u; }
+    for (; grp < n_groups; grp += stride) {
+        const u32 gbeg = grp << 5, gend = min(gbeg + 32u, n_cands);
+        const u32 first = f0, last = l0;
+        const bool act = gbeg + lane < gend;
+        const u32 cloc = act ? __ldg(A.flat_loc + gbeg + lane) : 0u;
+        uint4 ha = make_uint4(FULL, 0, 0, 0), hb = make_uint4(0, 0, 0, 0);
+        const bool ld = first + lane <= last;
+        if (ld) { const uint4 *src = (const uint4 *)(A.hdr + first + lane); ha = __ldg(src); hb = __ldg(src + 1); }
+        // ---- next visit: L2 prefetch of its headers and loc entries; chunk_first of the visit after it
+        f0 = f1; l0 = l1;
+        if (grp + stride < n_groups) {
+            if (f1 + lane <= l1) asm volatile("prefetch.global.L2 [%0];" :: "l"(A.hdr + f1 + lane));
+            if (lane == 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(A.flat_loc + ((size_t)(grp + stride) << 5)));
+            const u32 g2 = grp + 2 * stride;
+            if (g2 < n_groups) { f1 = __ldg(A.chunk_first + g2); l1 = g2 + 1 < n_groups ? __ldg(A.chunk_first + g2 + 1) : n_items - 1u; }
+        }
+        if (lane == 0) A.bitmap[grp] = 0u;                                       // bits are set by drain()
+        const bool mine = ld && (lane == 0 || ha.x < gend);
+        const u32 pos = (mine && ha.x > gbeg) ? ha.x - gbeg : 0u;
+        const u32 mask = __reduce_or_sync(FULL, mine ? 1u << pos : 0u);
+        const u32 n_it = __popc(mask);
+        const u32 soff = (hb.z * 2 + IH_CHAIN(hb.y)) * DW;                       // first 64-bit word of the item's 1-bit streams
+        const u32 it = __popc(mask & (FULL >> (31u - lane))) - 1u;               // my candidate's item = lane `it`
+        const u32 ibase = __shfl_sync(FULL, ha.x, it), im = __shfl_sync(FULL, ha.y, it), inf = __shfl_sync(FULL, ha.w, it);
+        const u32 irot = __shfl_sync(FULL, hb.x, it), pack = __shfl_sync(FULL, hb.y, it), islot = __shfl_sync(FULL, hb.z, it);
+        u32 e = irot + (gbeg + lane - ibase); if (e >= im) e -= im;
+        const u32 sig = e >= inf ? 1u : 0u;                                      // forward-strand entries come first (align.cpp:296)
+        const u32 g = cloc - IH_H(pack), L = IH_L(pack);                         // _hit.loc (align.cpp:297)
+        // ---- reverse-strand windows are mirrored onto the forward plane: which sequence owns g?
+        uint2 ce = make_uint2(0u, 0u);
+        if (act && sig) ce = __ldg(A.di.ctab + (g >> BSL_CTAB_SHIFT));
+        // ---- stage the 1-bit streams of the first items while that look-up is in flight
+        const u32 nb0 = min(stage_items, n_it), nw0 = nb0 * DW;
+        {
+            const u32 xa = lane, xb = lane + 32u;
+            const u32 ia = min(__umulhi(xa, rcp_dw), nb0 - 1u), ib = min(__umulhi(xb, rcp_dw), nb0 - 1u);
+            const u32 sa = __shfl_sync(FULL, soff, ia), sb = __shfl_sync(FULL, soff, ib);
+            u64 va = 0, vb = 0;
+            if (xa < nw0 && !(dbg & 4u)) va = __ldg(bits64 + sa + (xa - ia * DW));
+            if (xb < nw0 && !(dbg & 4u)) vb = __ldg(bits64 + sb + (xb - ib * DW));
+            u32 p0 = g; bool screen = act;
+            if (act && sig) {
+                if (ce.y == 0u) {                                                // a sequence boundary inside the block
+                    u32 lo = 0, hi = A.di.nseq;
+                    while (lo + 1 < hi) { const u32 mid = (lo + hi) >> 1; if (g >= __ldg(A.di.anchor + mid)) lo = mid; else hi = mid; }
+                    const u32 a0 = __ldg(A.di.anchor + lo), P = __ldg(A.di.rcoff + lo);
+                    ce = make_uint2(2u * a0 + P - 1u, a0 + P);
+                    if (g < a0) screen = false;                                  // in the leading margin
+                }
+                if ((u64)g + L > (u64)ce.y) screen = false;                      // crosses into the next sequence
+                p0 = ce.x - g - L + 1u;                                          // forward coordinate of the window's lowest base
+            }
+            // ---- the sector: read word i (32 bases; of the reversed read on the rc strand) lines up with plane words
+            //      pw+i, pw+i+1; the sector that starts o words before pw covers i in [0, 6-o], the next one [8-o, 14-o]
+            const u32 pw = p0 >> 5, o = pw & 7u, nW = (L + 31u) >> 5, sft = p0 & 31u;
+            const u32 c0 = min(7u - o, nW), hi1 = min(14u - o, nW - 1u);
+            const u32 c1 = hi1 + o >= 8u ? hi1 + o - 7u : 0u;
+            const u32 k = c1 > c0 ? 1u : 0u;
+            const u32 dlt = k ? 8u - o : 0u - o;                                 // read word of sector word x = x + dlt
+            const u32 sec = (pw >> 3) + k;
+            u32 R[8], nfl = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) R[j] = 0;
+            if (screen && !(dbg & 2u)) {
+                u64 a, b, c, d;
+                asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(A.di.bit1 + (size_t)sec * 8));
+                R[0] = (u32)a; R[1] = (u32)(a >> 32); R[2] = (u32)b; R[3] = (u32)(b >> 32); R[4] = (u32)c; R[5] = (u32)(c >> 32); R[6] = (u32)d; R[7] = (u32)(d >> 32);
+                if (sig) nfl = __ldg(A.di.nflag + (sec >> 5));
+            }
+            if (xa < nw0) S64[xa] = va;
+            if (xb < nw0) S64[xb] = vb;
+            bool pass = false;
+            for (u32 s0 = 0; s0 < n_it; s0 += stage_items) {
+                const u32 nb = min(stage_items, n_it - s0), nw = nb * DW;
+                for (u32 x0 = s0 ? 0u : 64u; x0 < nw; x0 += 64) {                // the first 64 words of the first batch are already on their way
+                    const u32 ya = x0 + lane, yb = ya + 32u;
+                    const u32 ja = min(__umulhi(ya, rcp_dw), nb - 1u), jb = min(__umulhi(yb, rcp_dw), nb - 1u);
+                    const u32 ta = __shfl_sync(FULL, soff, s0 + ja), tb = __shfl_sync(FULL, soff, s0 + jb);
+                    u64 wa = 0, wb = 0;
+                    if (ya < nw) wa = __ldg(bits64 + ta + (ya - ja * DW));
+                    if (yb < nw) wb = __ldg(bits64 + tb + (yb - jb * DW));
+                    if (ya < nw) S64[ya] = wa;
+                    if (yb < nw) S64[yb] = wb;
+                }
+                __syncwarp();
+                if (act && it >= s0 && it < s0 + nb) {
+                    if (!screen || (sig && ((nfl >> (sec & 31u)) & 1u))) pass = true;   // not screened on this strand: exact count decides
+                    else {
+                        const u32 *Lo = S0 + (size_t)(it - s0) * D + (sig ? 2 * Wb : 0u), *M = Lo + Wb;
+                        const u32 fm = sig ? flipm : 0u;
+                        u32 low = 0;
+#pragma unroll
+                        for (int x = 0; x < 7; x++) {
+                            const u32 i = (u32)x + dlt;
+                            if (i < nW) low += __popc((Lo[i] ^ __funnelshift_l(R[x + 1], R[x], sft) ^ fm) & M[i]);
+                        }
+                        pass = low <= IH_THR(pack);
+                    }
+                }
+                __syncwarp();
+            }
+            const u32 bal = __ballot_sync(FULL, pass);
+            if (bal) {
+                if (pass) Q[qn + __popc(bal & ((1u << lane) - 1u))] = make_uint4(gbeg + lane, g, pack, islot | (sig << 31));
+                qn += __popc(bal);
+                __syncwarp();
+                if (qn >= 32u) { qn -= 32u; if (!(dbg & 1u)) drain(qn, 32u); }
+            }
         }
     }
     if (qn) drain(0u, qn);
@@ -1564,7 +1751,7 @@ template <typename T> int grow(bsl_ctx *ctx, T **p, size_t *cap, size_t need, bo
 void bsl_lane_free(Lane &ln) {
     cudaFree(ln.d_bases); cudaFree(ln.d_off); cudaFree(ln.d_index); cudaFree(ln.d_rawlen); cudaFree(ln.d_meta); cudaFree(ln.d_cnt); cudaFree(ln.d_sched); cudaFree(ln.d_stat);
     cudaFree(ln.d_minlvl); cudaFree(ln.d_slot_item); cudaFree(ln.d_slot_flag); cudaFree(ln.d_flag_list); cudaFree(ln.d_marks);
-    cudaFree(ln.d_hdr); cudaFree(ln.d_chunk_first); cudaFree(ln.d_bitmap); cudaFree(ln.d_flat_loc);
+    cudaFree(ln.d_bits1); cudaFree(ln.d_hdr); cudaFree(ln.d_chunk_first); cudaFree(ln.d_bitmap); cudaFree(ln.d_flat_loc);
     cudaFree(ln.d_planes); cudaFree(ln.d_hits); cudaFree(ln.d_heavy_hits); cudaFree(ln.d_list[0]); cudaFree(ln.d_list[1]); cudaFree(ln.d_heavy_list);
     cudaFree(ln.d_pe_list[0]); cudaFree(ln.d_pe_list[1]); cudaFree(ln.d_out); cudaFree(ln.d_pair); cudaFree(ln.d_all[0]); cudaFree(ln.d_all[1]); cudaFree(ln.d_ctr);
     if (ln.h_ctr) cudaFreeHost(ln.h_ctr);
@@ -1650,6 +1837,7 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
         }
     }
     c0 = ln.cap_words; if ((rc = grow(ctx, &ln.d_planes, &c0, (size_t)n_slots * 6 * Wb + 16))) return rc; ln.cap_words = c0;
+    c0 = ln.cap_bits1; if ((rc = grow(ctx, &ln.d_bits1, &c0, (size_t)n_slots * 8 * Wb + 16))) return rc; ln.cap_bits1 = c0;
     c0 = ln.cap_hits; if ((rc = grow(ctx, &ln.d_hits, &c0, (size_t)n_slots * cap_main))) return rc; ln.cap_hits = c0;
     // per-round scratch: flat candidate space (1 bit per candidate) and item headers
     const u32 nch = P.chains == 1 ? 2 : 1;
@@ -1686,7 +1874,7 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     A.bases = ln.d_bases; A.off = ln.d_off; A.index = ln.d_index; A.rawlen = ln.d_rawlen; A.first_index_a = a->first_index + first; A.first_index_b = pe ? b->first_index + first : 0;
     A.off_base_a = off0_a; A.off_base_b = off0_b; A.all_off = all_off;
     A.bases_b_shift = bases_a; A.has_index = (a->index != nullptr) && (!pe || b->index != nullptr); A.has_rawlen = (a->raw_len != nullptr) && (!pe || b->raw_len != nullptr);
-    A.Wb = Wb; A.planes = ln.d_planes; A.sched = ln.d_sched; A.meta = ln.d_meta; A.cnt = ln.d_cnt; A.stat = ln.d_stat; A.minlvl = ln.d_minlvl;
+    A.Wb = Wb; A.planes = ln.d_planes; A.bits1 = ln.d_bits1; A.sched = ln.d_sched; A.meta = ln.d_meta; A.cnt = ln.d_cnt; A.stat = ln.d_stat; A.minlvl = ln.d_minlvl;
     A.hits = ln.d_hits; A.cap = cap_main; A.ctr = ln.d_ctr;
     A.hdr = ln.d_hdr; A.cap_items = (u32)std::min<u64>(want_items - 16, 0xffffffffu); A.cap_cands = (u32)want_cands;
     A.slot_item = ln.d_slot_item; A.marks = ln.d_marks; A.slot_flag = ln.d_slot_flag; A.flag_list = ln.d_flag_list; A.chunk_first = ln.d_chunk_first; A.bitmap = ln.d_bitmap; A.flat_loc = ln.d_flat_loc;
@@ -1765,7 +1953,20 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
         ctx->occ_screen = (oe == cudaSuccess && occ > 0) ? occ : 4;
     }
     const int grid_s = sms * ctx->occ_screen;
+    // 1-bit screen (single-conversion rules)
+    static const bool no_bits = getenv("BSL_NO_BITS") != nullptr;
+    static const u32 dbg_bits = getenv("BSL_DBG") ? (u32)atoi(getenv("BSL_DBG")) : 0u;
+    const bool use_bits = ctx->di.has_bit1 && !no_bits;
+    const u32 stage_items_b = std::max<u32>(2, std::min<u32>(32, 640 / (4 * Wb)));
+    const size_t smem_b = (size_t)SC_WARPS * stage_items_b * (4 * Wb) * 4;
+    const u32 rcp_b = (u32)((0x100000000ull + 2 * Wb - 1) / (2 * Wb));
+    if (!ctx->occ_bits) { int occ = 0; cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, screen_bits, SC_WARPS * 32, smem_b); ctx->occ_bits = (oe == cudaSuccess && occ > 0) ? occ : 4; }
+    const int grid_b = sms * ctx->occ_bits;
     auto launch_verify = [&](KArgs &K, u32 ci) {
+        if (!G && !old_verify && use_bits) {
+            screen_bits<<<grid_b, SC_WARPS * 32, smem_b, st>>>(K, ci, stage_items_b, rcp_b, dbg_bits);
+            return;
+        }
         if (!G && !old_verify) {
             if (ctx->rule.single) screen_candidates<true><<<grid_s, SC_WARPS * 32, smem_s, st>>>(K, ci, stage_items, rcp_dw);
             else screen_candidates<false><<<grid_s, SC_WARPS * 32, smem_s, st>>>(K, ci, stage_items, rcp_dw);

@@ -77,7 +77,16 @@ struct DevIndex {
     const u32 *rcoff;        // [nseq] RefTitle::rc_offset
     u32 nseq, K, maxk;
     u64 n_words, n_entries;
+    // screening plane (single-conversion rules): ONE bit per forward-strand base = the low bit of its 2-bit code, which
+    // the conversion cannot change (from = 01, to = 11). 32 bases per u32, first base in the top bit; n_words u32 words.
+    const u32 *bit1;
+    const u32 *nflag;        // 1 bit per 256-base sector of bit1: holds a non-ACGT base, padding or margin
+    const uint2 *ctab;       // per 2^20 global coordinates: {2*anchor + rc_offset - 1, anchor + rc_offset} of the sequence that owns
+                             // the whole block, {0, 0} when a boundary falls inside (then: binary search over anchor[])
+    u32 flip;                // low bit of code(complement(x)) = low bit of code(x) ^ flip
+    u32 has_bit1;
 };
+#define BSL_CTAB_SHIFT 16
 
 // ---- per-read ("slot") device state -------------------------------------------------------
 // hit record: 16 bytes

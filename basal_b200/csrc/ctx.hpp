@@ -19,7 +19,7 @@ struct Lane {
     size_t cap_slots = 0, cap_bases = 0, cap_words = 0, cap_hits = 0, cap_heavy_hits = 0, cap_pairs = 0, cap_bitmap = 0, cap_items = 0;
     // device buffers
     u8 *d_bases = nullptr; u64 *d_off = nullptr; u32 *d_index = nullptr; u16 *d_rawlen = nullptr;
-    SlotMeta *d_meta = nullptr; SlotCounts *d_cnt = nullptr; uint2 *d_stat = nullptr; u8 *d_sched = nullptr; u64 *d_planes = nullptr;
+    SlotMeta *d_meta = nullptr; SlotCounts *d_cnt = nullptr; uint2 *d_stat = nullptr; u8 *d_sched = nullptr; u64 *d_planes = nullptr; u32 *d_bits1 = nullptr; size_t cap_bits1 = 0;
     DevHit *d_hits = nullptr; DevHit *d_heavy_hits = nullptr;
     u32 *d_list[2] = {nullptr, nullptr}; u32 *d_heavy_list = nullptr; u32 *d_pe_list[2] = {nullptr, nullptr};
     bsl_hit *d_out = nullptr; bsl_pair *d_pair = nullptr; bsl_hit *d_all[2] = {nullptr, nullptr}; size_t cap_all = 0;
@@ -49,6 +49,7 @@ struct bsl_ctx {
     char err[512];
     int sm_count = BSL_SM_COUNT;
     int occ_verify[4] = {0, 0, 0, 0};   // resident CTAs per SM of the verify_candidates variants
+    int occ_bits = 0;                   // resident CTAs per SM of screen_bits
     int occ_screen = 0;                 // resident CTAs per SM of screen_candidates
 };
 

@@ -19,13 +19,15 @@ namespace {
 
 __constant__ u8 c_code[256];
 __constant__ u8 c_rcode[256];
+__constant__ u8 c_reg[256];
 
 // ---- pack both strand planes ---------------------------------------------------------------
 // One thread per 64-bit word of one sequence. Forward word w holds bases 32w..32w+31 (code 0
 // beyond the sequence: the reference pads with 'N'); reverse word w holds the complement codes
 // of padded positions P-1-32w .. P-32-32w (refbase.cpp:85-101).
 __global__ void pack_planes(const u8 *__restrict__ ascii, const u64 *__restrict__ aoff, const u32 *__restrict__ alen,
-                            const u64 *__restrict__ wstart, u32 nseq, u64 total_words, u64 *__restrict__ fwd, u64 *__restrict__ rc) {
+                            const u64 *__restrict__ wstart, u32 nseq, u64 total_words, u64 *__restrict__ fwd, u64 *__restrict__ rc,
+                            u32 *__restrict__ bit1, u32 *__restrict__ reg1) {
     u64 gw = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (gw >= total_words) return;
     u32 lo = 0, hi = nseq;                       // sequence containing word gw
@@ -33,15 +35,27 @@ __global__ void pack_planes(const u8 *__restrict__ ascii, const u64 *__restrict_
     u32 w = (u32)(gw - wstart[lo]); u32 n = alen[lo]; u32 nw = (u32)(wstart[lo + 1] - wstart[lo]); u32 P = nw * 32;
     const u8 *s = ascii + aoff[lo];
     u64 f = 0, r = 0;
-    u32 b0 = w * 32;
+    u32 b0 = w * 32, lowbits = 0, regular = 0;
 #pragma unroll 8
     for (u32 k = 0; k < 32; k++) {
         u32 p = b0 + k; u32 cf = p < n ? c_code[s[p]] : 0u;
         f = (f << 2) | cf;
+        lowbits = (lowbits << 1) | (cf & 1u);
+        regular = (regular << 1) | ((p < n && c_reg[s[p]]) ? 1u : 0u);
         u32 q = P - 1 - p; u32 cr = q < n ? c_rcode[s[q]] : 0u;
         r = (r << 2) | cr;
     }
     fwd[BSL_REF_MARGIN + gw] = f; rc[BSL_REF_MARGIN + gw] = r;
+    bit1[BSL_REF_MARGIN + gw] = lowbits; reg1[BSL_REF_MARGIN + gw] = regular;
+}
+
+// one bit per 256-base sector of the screening plane: set unless all 256 positions are ACGT bases of a sequence
+__global__ void sector_flags(const u32 *__restrict__ reg1, u64 n_sectors, u32 *__restrict__ nflag) {
+    u64 sct = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    if (sct < n_sectors) { const uint4 *p = (const uint4 *)(reg1 + sct * 8); uint4 a = p[0], b = p[1]; bad = (a.x & a.y & a.z & a.w & b.x & b.y & b.z & b.w) != 0xffffffffu; }
+    u32 bal = __ballot_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31u) == 0 && sct < n_sectors + 32) nflag[sct >> 5] = bal;
 }
 
 // ---- N/X run boundaries ----------------------------------------------------------------------
@@ -115,6 +129,7 @@ void bsl_index_free_impl(bsl_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaFree((void *)ctx->di.plane[0]); cudaFree((void *)ctx->di.bucket); cudaFree((void *)ctx->di.cnt16);
     cudaFree((void *)ctx->di.loc); cudaFree((void *)ctx->di.anchor); cudaFree((void *)ctx->di.seqlen); cudaFree((void *)ctx->di.rcoff);
+    cudaFree((void *)ctx->di.bit1); cudaFree((void *)ctx->di.nflag); cudaFree((void *)ctx->di.ctab);
     memset(&ctx->di, 0, sizeof ctx->di); ctx->has_index = false;
 }
 
@@ -140,7 +155,7 @@ int bsl_index_build_impl(bsl_ctx *ctx, const u8 *cat, const u64 *off, const u32 
     if (n_words * 32 >= (1ull << 32)) { set_error(ctx, "reference too large: concatenated coordinates must stay below 2^32 (refbase.cpp:222)"); return BSL_ELIMIT; }
     ctx->anchor[n] = (u32)((words + BSL_REF_MARGIN) * 32);
 
-    cudaMemcpyToSymbol(c_code, ctx->rule.code, 256); cudaMemcpyToSymbol(c_rcode, ctx->rule.rcode, 256);
+    cudaMemcpyToSymbol(c_code, ctx->rule.code, 256); cudaMemcpyToSymbol(c_rcode, ctx->rule.rcode, 256); cudaMemcpyToSymbol(c_reg, ctx->rule.reg, 256);
 
     u8 *d_ascii = nullptr; u64 *d_aoff = nullptr, *d_wstart = nullptr; u32 *d_alen = nullptr;
     u64 *d_fwd = nullptr, *d_rc = nullptr;
@@ -148,6 +163,11 @@ int bsl_index_build_impl(bsl_ctx *ctx, const u8 *cat, const u64 *off, const u32 
     if ((rc_ = dmalloc(ctx, &d_ascii, bases + 64)) || (rc_ = dmalloc(ctx, &d_aoff, n + 1)) || (rc_ = dmalloc(ctx, &d_wstart, n + 1)) ||
         (rc_ = dmalloc(ctx, &d_alen, n)) || (rc_ = dmalloc(ctx, &d_fwd, 2 * n_words))) return rc_;
     d_rc = d_fwd + n_words;                 // both strand planes in one allocation: one L2 access-policy window covers them
+    // screening plane + a temporary "is an ACGT base of a sequence" plane (margins and padding stay 0)
+    const u64 n_words8 = (n_words + 7) / 8 * 8, n_sectors = n_words8 / 8;
+    u32 *d_bit1 = nullptr, *d_reg1 = nullptr, *d_nflag = nullptr; uint2 *d_ctab = nullptr;
+    if ((rc_ = dmalloc(ctx, &d_bit1, n_words8 + 64)) || (rc_ = dmalloc(ctx, &d_reg1, n_words8 + 64)) || (rc_ = dmalloc(ctx, &d_nflag, n_sectors / 32 + 8))) return rc_;
+    CUDA_TRY(cudaMemset(d_bit1, 0, (n_words8 + 64) * 4)); CUDA_TRY(cudaMemset(d_reg1, 0, (n_words8 + 64) * 4));
     for (u32 c = 0; c < n; c++) CUDA_TRY(cudaMemcpy(d_ascii + aoff[c], cat + off[c], len[c], cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_aoff, aoff.data(), (n + 1) * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_wstart, wstart.data(), (n + 1) * 8, cudaMemcpyHostToDevice));
@@ -155,8 +175,12 @@ int bsl_index_build_impl(bsl_ctx *ctx, const u8 *cat, const u64 *off, const u32 
     CUDA_TRY(cudaMemset(d_fwd, 0, n_words * 8)); CUDA_TRY(cudaMemset(d_rc, 0, n_words * 8));
     {
         u64 blocks = (words + 255) / 256;
-        pack_planes<<<(unsigned)blocks, 256>>>(d_ascii, d_aoff, d_alen, d_wstart, n, words, d_fwd, d_rc);
+        pack_planes<<<(unsigned)blocks, 256>>>(d_ascii, d_aoff, d_alen, d_wstart, n, words, d_fwd, d_rc, d_bit1, d_reg1);
         CUDA_TRY(cudaGetLastError());
+        sector_flags<<<(unsigned)((n_sectors + 32 + 255) / 256), 256>>>(d_reg1, n_sectors, d_nflag);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(d_reg1); d_reg1 = nullptr;
     }
     // ---- UnmaskRegion blocks (refbase.cpp:103-128): GPU finds N/X run boundaries, host finishes
     const u32 tcap = 1u << 24;
@@ -255,7 +279,26 @@ int bsl_index_build_impl(bsl_ctx *ctx, const u8 *cat, const u64 *off, const u32 
     CUDA_TRY(cudaMemcpy(d_rcoff, ctx->rcoff.data(), n * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaDeviceSynchronize());
 
+    // ---- strand table for the screen: which sequence owns a block of 2^BSL_CTAB_SHIFT global coordinates
+    {
+        const u32 nblk = 1u << (32 - BSL_CTAB_SHIFT);
+        std::vector<uint2> ctab(nblk, make_uint2(0u, 0u));
+        for (u32 c = 0; c < n; c++) {
+            const u64 a0 = ctx->anchor[c], a1 = a0 + ctx->rcoff[c];          // [a0, a1) = coordinates of sequence c (both strands)
+            const u64 b0 = (a0 + (1ull << BSL_CTAB_SHIFT) - 1) >> BSL_CTAB_SHIFT, b1 = a1 >> BSL_CTAB_SHIFT;   // blocks wholly inside
+            for (u64 b = b0; b < b1 && b < nblk; b++) ctab[b] = make_uint2((u32)(2 * a0 + ctx->rcoff[c] - 1), (u32)a1);
+        }
+        if ((rc_ = dmalloc(ctx, &d_ctab, nblk))) return rc_;
+        CUDA_TRY(cudaMemcpy(d_ctab, ctab.data(), nblk * sizeof(uint2), cudaMemcpyHostToDevice));
+    }
     DevIndex &di = ctx->di;
+    di.bit1 = d_bit1; di.nflag = d_nflag; di.ctab = d_ctab;
+    {   // the screen needs: one convert-to base (from = 01, to = 11 share the low bit) and complement = XOR with a constant on the low bit
+        const u8 *cd = ctx->rule.code, *rd = ctx->rule.rcode;
+        const u32 f = (cd['A'] ^ rd['A']) & 1u;
+        const bool uniform = ((cd['C'] ^ rd['C']) & 1u) == f && ((cd['G'] ^ rd['G']) & 1u) == f && ((cd['T'] ^ rd['T']) & 1u) == f;
+        di.flip = f; di.has_bit1 = (ctx->rule.single && uniform) ? 1u : 0u;
+    }
     di.plane[0] = d_fwd; di.plane[1] = d_rc; di.bucket = d_bucket; di.cnt16 = d_cnt16; di.loc = d_loc;
     di.anchor = d_anchor; di.seqlen = d_len; di.rcoff = d_rcoff; di.nseq = n; di.K = K; di.maxk = maxk; di.n_words = n_words; di.n_entries = ne;
     memset(&ctx->info, 0, sizeof ctx->info);

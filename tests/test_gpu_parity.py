@@ -95,6 +95,31 @@ def test_pe_matches_oracle(cid, rule, extra):
     gpu.close(); orc.close()
 
 
+@pytest.mark.parametrize("cid,rule,extra", [(1, "C:T", {"n": 1}), (2, "A:G", {}), (1, "A:T", {"n": 1}), (2, "G:A", {"n": 1})])
+def test_large_sequences_match_oracle(cid, rule, extra):
+    """Three sequences of ~330 kb: windows whose 65 536-coordinate block lies wholly inside one sequence take the
+    strand-table path of the one-bit screen, the ones around the boundaries take the anchor search (both strands)."""
+    import dataclasses
+    cfg = dataclasses.replace(helpers.synth.baseline_config(cid, 0.02 if cid == 1 else 0.002), nchr=3)
+    chrs = helpers.synth.make_reference(cfg)
+    sim = helpers.synth.ReadSimulator(cfg, chrs)
+    m1, m2 = next(sim.chunks(limit=12000))
+    kw = dict(extra); kw["rule"] = rule
+    params = helpers.flags_to_params(cfg, kw)
+    gpu, orc = _build_both(cfg, chrs, params)
+    if m2 is None:
+        batch = capi.ReadBatch.from_matrix(m1, readset=0, first_index=0)
+        helpers.assert_records_equal(gpu.align_se(batch), orc.align_se(batch), f"SE {rule}")
+    else:
+        a = capi.ReadBatch.from_matrix(m1, readset=1); b = capi.ReadBatch.from_matrix(m2, readset=2)
+        ga, gb, gp = gpu.align_pe(a, b); wa, wb, wp = orc.align_pe(a, b)
+        helpers.assert_records_equal(gp, wp, "pair records", fields=["n_pairs", "insert", "chain", "na", "nb"])
+        helpers.assert_records_equal(ga, wa, "mate 1 records"); helpers.assert_records_equal(gb, wb, "mate 2 records")
+    gs, os_ = gpu.stats(), orc.stats()
+    assert gs.seed_lookups == os_.seed_lookups and gs.candidates == os_.candidates
+    gpu.close(); orc.close()
+
+
 @pytest.mark.parametrize("env", [{"BSL_SUB_BATCH": "3000"}, {"BSL_CAND_CAP": "60000"}, {"BSL_HIT_CAP": "2"},
                                  {"BSL_SUB_BATCH": "1500", "BSL_CAND_CAP": "30000", "BSL_HIT_CAP": "3"}])
 @pytest.mark.parametrize("pe", [False, True])
