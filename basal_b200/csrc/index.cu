@@ -161,8 +161,8 @@ int bsl_index_build_impl(bsl_ctx *ctx, const u8 *cat, const u64 *off, const u32 
     u64 *d_fwd = nullptr, *d_rc = nullptr;
     int rc_ = 0;
     if ((rc_ = dmalloc(ctx, &d_ascii, bases + 64)) || (rc_ = dmalloc(ctx, &d_aoff, n + 1)) || (rc_ = dmalloc(ctx, &d_wstart, n + 1)) ||
-        (rc_ = dmalloc(ctx, &d_alen, n)) || (rc_ = dmalloc(ctx, &d_fwd, 2 * n_words))) return rc_;
-    d_rc = d_fwd + n_words;                 // both strand planes in one allocation: one L2 access-policy window covers them
+        (rc_ = dmalloc(ctx, &d_alen, n)) || (rc_ = dmalloc(ctx, &d_fwd, 2 * ((n_words + 3) & ~3ull) + 8))) return rc_;
+    d_rc = d_fwd + ((n_words + 3) & ~3ull);   // 32-byte aligned: the kernels gather whole sectors of either plane                 // both strand planes in one allocation: one L2 access-policy window covers them
     // screening plane + a temporary "is an ACGT base of a sequence" plane (margins and padding stay 0)
     const u64 n_words8 = (n_words + 7) / 8 * 8, n_sectors = n_words8 / 8;
     u32 *d_bit1 = nullptr, *d_reg1 = nullptr, *d_nflag = nullptr; uint2 *d_ctab = nullptr;
