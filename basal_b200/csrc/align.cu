@@ -307,6 +307,169 @@ __global__ void __launch_bounds__(PREP_WARPS * 32) prepare_reads(const __grid_co
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// prepare_reads2 : the same outputs as prepare_reads, organised for issue-slot efficiency. A warp takes 32 reads:
+//   A. (lane per 64-bit plane word of any of the 32 reads) bases -> 2-bit code / ACGT / convert-to words and the 1-bit
+//      streams of both orientations, written to global memory and (codes, ACGT words) to the warp's shared slice;
+//   B. (lane per read) seed hashes and bucket sizes of every read offset the schedule can touch: segment j, offsets
+//      j*s .. j*s + I + ii - 1 (prof[j][i] + v - i lies in that range for every phase i and start v <= ii);
+//   C. (lane per read) ReorderSeed / AdjustSeedStartArray / the (count, segment) sort, literally (align.cpp:468-546),
+//      every CountSeeds evaluated on demand from the table of step B.
+// Shared memory per warp: 32 x (2 WQ + cap) words; odd strides keep the per-lane rows in different banks.
+// ------------------------------------------------------------------------------------------------
+#define P2_WARPS 4
+__global__ void __launch_bounds__(P2_WARPS * 32) prepare_reads2(const __grid_constant__ KArgs A, u32 WQ, u32 cap) {
+    extern __shared__ u32 psm[];
+    __shared__ u16 s_prof[16][16];
+    const DevTables *T = A.tab;
+    const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+    for (u32 x = threadIdx.x; x < 256; x += blockDim.x) s_prof[x >> 4][x & 15u] = T->prof[x >> 4][x & 15u];
+    __syncthreads();
+    u32 *wsm = psm + (size_t)wid * 32 * (2 * WQ + cap);
+    u32 *sq_all = wsm, *sn_all = wsm + 32 * WQ, *cp_all = wsm + 64 * WQ;
+    u32 *sq = sq_all + lane * WQ, *sn = sn_all + lane * WQ, *cp = cp_all + lane * cap;
+    const u32 Wb = A.Wb, W2 = 2 * Wb, I = A.I, s = A.s;
+    const u32 tabq[2] = {T->tab_code[0], T->tab_code[1]}, tabc[2] = {T->tab_conv[0], T->tab_conv[1]};
+    const u32 shs = 32 - 2 * s, full = (s == 16) ? 0x55555555u : (0x55555555u >> shs);
+    for (u32 slot0 = (blockIdx.x * P2_WARPS + wid) * 32u; slot0 < A.n_slots; slot0 += gridDim.x * P2_WARPS * 32u) {
+        const u32 slot = slot0 + lane;
+        const bool valid = slot < A.n_slots;
+        u64 b0 = 0; u32 Lraw = 0, readset = 0, index = 0;
+        if (valid) {
+            const bool mate_b = A.pe && slot >= A.n_a;
+            const u32 r = mate_b ? slot - A.n_a : slot;
+            const u64 *off = mate_b ? A.off + (A.n_a + 1) : A.off;
+            const u64 ob = mate_b ? A.off_base_b : A.off_base_a;
+            b0 = off[r] - ob + (mate_b ? A.bases_b_shift : 0);
+            Lraw = (u32)(off[r + 1] - off[r]);
+            readset = mate_b ? A.readset_b : A.readset_a;
+            index = A.has_index ? A.index[slot] : (mate_b ? A.first_index_b : A.first_index_a) + r;
+        }
+        const u32 L = Lraw > BSL_MAX_READLEN ? BSL_MAX_READLEN : Lraw;
+        const u32 W = (L + 31) >> 5;
+        u32 flags = 0;
+        if (valid) {
+            if ((A.chains == 1) || ((A.chains <= 1) == (readset < 2))) flags |= SF_CHAIN0;                       // align.cpp:83-84
+            if ((A.chains == 1) || ((A.chains <= 1) == (readset == 2))) flags |= SF_CHAIN1;
+        }
+        // per-level counters, stats: 32 slots x 64 bytes are contiguous
+        {
+            u32 *cz = (u32 *)(A.cnt + slot0); const u32 nz = min(32u, A.n_slots - slot0) * 16u;
+            for (u32 x = lane; x < nz; x += 32) cz[x] = 0;
+            if (valid) { A.stat[slot] = make_uint2(0u, 0u); A.minlvl[slot] = 255; }
+        }
+        u32 B = 0, nseg = 0; bool filtered = false, ns_known = false;
+        const u32 ii = (L + 1 >= I) ? (L + 1 - I) % s : 0;
+        const u32 wd = I + ii;                                                       // offsets per segment the schedule can touch
+        for (u32 c = 0; c < 2; c++) {
+            const bool en = valid && (flags & (c ? SF_CHAIN1 : SF_CHAIN0)) && !filtered;
+            if (!__any_sync(0xffffffffu, en)) continue;
+            // ---- A: one plane word (32 bases) of one read per lane and trip
+            const u32 tq = tabq[c], tc = tabc[c];
+            for (u32 idx = lane; idx < 32 * Wb; idx += 32) {
+                const u32 rl = idx / Wb, wv = idx - rl * Wb;
+                const u32 Lr = __shfl_sync(0xffffffffu, L, rl);
+                const u32 b0l = __shfl_sync(0xffffffffu, (u32)b0, rl), b0h = __shfl_sync(0xffffffffu, (u32)(b0 >> 32), rl);
+                const bool enr = __shfl_sync(0xffffffffu, (u32)en, rl) != 0;
+                if (!enr) continue;
+                const u8 *src = A.bases + (((u64)b0h << 32) | b0l);
+                u64 q = 0, nm = 0, cm = 0; u32 lo = 0, mk = 0, rlo = 0, rmk = 0;
+                const u32 p0 = wv * 32;
+                const u32 nbase = Lr > p0 ? min(32u, Lr - p0) : 0u;
+                for (u32 k = 0; k < nbase; k++) {
+                    const u32 p = p0 + k;
+                    const u32 ch = src[c ? Lr - 1 - p : p], ch2 = src[c ? p : Lr - 1 - p];       // chain c at position p; the same chain read backwards
+                    const u32 ix = (ch >> 1) & 3u, ix2 = (ch2 >> 1) & 3u;
+                    const bool reg = (ch & 0xDFu) == ((0x47544341u >> (8 * ix)) & 0xFFu), reg2 = (ch2 & 0xDFu) == ((0x47544341u >> (8 * ix2)) & 0xFFu);
+                    const u32 cq = reg ? (tq >> (2 * ix)) & 3u : 0u, cc = reg ? (tc >> (2 * ix)) & 3u : 0u;
+                    q = (q << 2) | cq; nm = (nm << 2) | (reg ? 1u : 0u); cm = (cm << 2) | cc;
+                    lo = (lo << 1) | (cq & 1u); mk = (mk << 1) | (reg ? 1u : 0u);
+                    rlo = (rlo << 1) | (reg2 ? (tq >> (2 * ix2)) & 1u : 0u); rmk = (rmk << 1) | (reg2 ? 1u : 0u);
+                }
+                if (nbase < 32) { const u32 sl = 32 - nbase; if (nbase == 0) { q = nm = cm = 0; lo = mk = rlo = rmk = 0; } else { q <<= 2 * sl; nm <<= 2 * sl; cm <<= 2 * sl; lo <<= sl; mk <<= sl; rlo <<= sl; rmk <<= sl; } }
+                const u32 slr = slot0 + rl;
+                u32 *dst = (u32 *)(A.planes + ((u64)slr * 2 + c) * 3 * Wb);           // streams: logical 32-bit words, see KArgs::planes
+                dst[2 * wv] = (u32)(q >> 32); dst[2 * wv + 1] = (u32)q;
+                dst[W2 + 2 * wv] = (u32)(nm >> 32); dst[W2 + 2 * wv + 1] = (u32)nm;
+                dst[2 * W2 + 2 * wv] = (u32)(cm >> 32); dst[2 * W2 + 2 * wv + 1] = (u32)cm;
+                u32 *b1 = A.bits1 + ((u64)slr * 2 + c) * 2 * W2;
+                b1[wv] = lo; b1[Wb + wv] = mk; b1[2 * Wb + wv] = rlo; b1[3 * Wb + wv] = rmk;
+                u32 *q_r = sq_all + rl * WQ, *n_r = sn_all + rl * WQ;
+                q_r[2 * wv] = (u32)(q >> 32); q_r[2 * wv + 1] = (u32)q; n_r[2 * wv] = (u32)(nm >> 32); n_r[2 * wv + 1] = (u32)nm;
+            }
+            if (lane < 32) { sq[W2] = 0; sq[W2 + 1] = 0; sq[W2 + 2] = 0; sn[W2] = 0; sn[W2 + 1] = 0; sn[W2 + 2] = 0; }
+            __syncwarp();
+            if (en && !ns_known) {
+                ns_known = true;
+                u32 acgt = 0; for (u32 j = 0; j < 2 * W; j++) acgt += __popc(sn[j]);
+                const u32 ns = L - acgt;
+                filtered = (L == 0) || (L < A.min_read_size) || (ns > A.max_ns) || (Lraw > BSL_MAX_READLEN);     // align.cpp:559-560
+                if (!filtered) {
+                    u32 raw = A.has_rawlen ? A.rawlen[slot] : L; if (raw == 0 || raw > BSL_MAX_READLEN) raw = L ? L : 1;
+                    B = (T->budget0[raw] + 1) * (L - 1) / raw;                                                    // align.cpp:561
+                    nseg = (L + 1 >= I + s) ? min((L + 1 - I) / s, B + 1) : 0;                                    // align.cpp:450
+                }
+            }
+            if (en && !filtered && nseg > 0) {
+                // ---- B: bucket sizes (bit 31 = the seed holds a non-ACGT base) of offsets j*s + d, d < wd; four gathers in flight
+                const u32 n_g = nseg * wd;
+                for (u32 j = 0; j < nseg; j++) {
+                    for (u32 d0 = 0; d0 < wd; d0 += 4) {
+                        u32 kmer[4], fl[4], c16[4];
+#pragma unroll
+                        for (u32 u = 0; u < 4; u++) {
+                            const u32 p = j * s + min(d0 + u, wd - 1), w = p >> 4, o = (p & 15u) * 2;
+                            const u32 xq = __funnelshift_l(sq[w + 1], sq[w], o) >> shs, xn = __funnelshift_l(sn[w + 1], sn[w], o) >> shs;
+                            kmer[u] = bsl_xt(xq); fl[u] = xn != full ? 0x80000000u : 0u;
+                            c16[u] = A.di.cnt16[kmer[u]];
+                        }
+#pragma unroll
+                        for (u32 u = 0; u < 4; u++) {
+                            if (d0 + u < wd) { const u32 m = c16[u] == 0xFFFFu ? A.di.bucket[2 * kmer[u] + 2] - A.di.bucket[2 * kmer[u]] : c16[u]; cp[j * wd + d0 + u] = (m & 0x7fffffffu) | fl[u]; }
+                        }
+                    }
+                }
+                // ---- C: CountSeeds(j, v) (align.cpp:526-540) from the table
+                auto count_seeds = [&](u32 j, u32 v) -> u32 {
+                    u32 total = 0, k = 0;
+                    for (u32 i = 0; i < I; i++) {
+                        const u32 e = cp[j * wd + (s_prof[j][i] + v - i - j * s)];
+                        if (e >> 31) k = 12;
+                        total += (e & 0x7fffffffu) << k;
+                    }
+                    return total == 0 ? 9999999u : total;
+                };
+                u32 *st = cp + n_g, *key = st + 16;
+                u32 st0 = 0, best = 0xffffffffu;                                   // ReorderSeed (align.cpp:468-498): first minimum of the column sums
+                for (u32 v = 0; v < ii; v++) { u32 tt = 0; for (u32 j = 0; j < nseg; j++) tt += count_seeds(j, v); if (tt < best) { best = tt; st0 = v; } }
+                for (u32 j = 0; j < nseg; j++) st[j] = st0;
+                for (u32 t = 0; t < nseg; t++) {                                   // AdjustSeedStartArray (align.cpp:500-524)
+                    const u32 ptr = (t & 1) ? nseg - 1 - t / 2 : t / 2;
+                    const u32 lo_ = ptr == 0 ? 0 : st[ptr - 1], hi_ = ptr == nseg - 1 ? ii : st[ptr + 1];
+                    u32 pick = lo_, b = 0xffffffffu;
+                    for (u32 x = lo_; x <= hi_; x++) { const u32 tt = count_seeds(ptr, x); if (tt < b) { b = tt; pick = x; } }
+                    st[ptr] = pick;
+                }
+                for (u32 j = 0; j < nseg; j++) key[j] = count_seeds(j, st[j]);
+                u32 sb[4] = {0, 0, 0, 0};                                          // sched byte t = segment of rank t | its start << 4
+                for (u32 j = 0; j < nseg; j++) {
+                    const int kj = (int)key[j]; u32 rank = 0;
+                    for (u32 y = 0; y < nseg; y++) { const int ky = (int)key[y]; rank += (ky < kj || (ky == kj && y < j)) ? 1u : 0u; }
+                    const u32 v = (j | (st[j] << 4)) << ((rank & 3u) * 8);
+                    if ((rank >> 2) == 0) sb[0] |= v; else if ((rank >> 2) == 1) sb[1] |= v; else if ((rank >> 2) == 2) sb[2] |= v; else sb[3] |= v;
+                }
+                *(uint4 *)(A.sched + ((u64)slot * 2 + c) * 16) = make_uint4(sb[0], sb[1], sb[2], sb[3]);
+            }
+            __syncwarp();
+        }
+        if (valid) {
+            if (filtered) flags |= SF_FILTERED;
+            SlotMeta m; m.rnd = bsl_rand(index, A.randseed); m.len = (u16)L; m.B = (u8)B; m.nseg = (u8)nseg; m.flags = (u8)flags; m.thr = (u8)B; m.nhit = 0; m.item = slot;
+            A.meta[slot] = m;
+        }
+    }
+}
+
 // Builds the first active lists. SE: every passing read. PE: full pairs -> pair list, lone passing mates -> SE list.
 __global__ void build_lists(const __grid_constant__ KArgs A, u32 *se_list, u32 *pe_list) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1796,8 +1959,20 @@ static int ensure_lane(bsl_ctx *ctx, Lane &ln) {
     return 0;
 }
 
-static u32 max_len_of(const bsl_batch *b, u32 first, u32 n) {
-    u32 mx = 0; for (u32 i = first; i < first + n; i++) { u64 l = b->offsets[i + 1] - b->offsets[i]; if (l > mx) mx = (u32)std::min<u64>(l, 0xffffffffu); } return mx;
+// longest read of a sub-range; *sched_max (optional) = the largest number of read offsets the seed schedule of one read can
+// touch: segments x (I + (L - I + 1) % s), segments <= (L - I + 1) / s (align.cpp:450, 476-480)
+static u32 max_len_of(const bsl_batch *b, u32 first, u32 n, const bsl_params *P = nullptr, u32 *sched_max = nullptr) {
+    u32 mx = 0, last = 0xffffffffu, sm = sched_max ? *sched_max : 0;
+    for (u32 i = first; i < first + n; i++) {
+        const u64 l = b->offsets[i + 1] - b->offsets[i];
+        if (l > mx) mx = (u32)std::min<u64>(l, 0xffffffffu);
+        if (P && (u32)l != last) {
+            last = (u32)l; const u32 L = (u32)std::min<u64>(l, BSL_MAX_READLEN), I = P->index_interval, s = P->seed_size;
+            if (L + 1 >= I + s) sm = std::max(sm, std::min<u32>((L + 1 - I) / s, 16) * (I + (L + 1 - I) % s));
+        }
+    }
+    if (sched_max) *sched_max = sm;
+    return mx;
 }
 
 // One sub-range [first, first+n_a) of the caller's batch on one lane. Sub-ranges keep the number of items a search
@@ -1811,7 +1986,8 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
 
     const u64 off0_a = a->offsets[first], off0_b = pe ? b->offsets[first] : 0;
     const u64 bases_a = a->offsets[first + n_a] - off0_a, bases_b = pe ? b->offsets[first + n_a] - off0_b : 0;
-    u32 Lmax = max_len_of(a, first, n_a); if (pe) Lmax = std::max(Lmax, max_len_of(b, first, n_a));
+    u32 sched_max = 0;
+    u32 Lmax = max_len_of(a, first, n_a, &P, &sched_max); if (pe) Lmax = std::max(Lmax, max_len_of(b, first, n_a, &P, &sched_max));
     if (Lmax > BSL_MAX_READLEN) Lmax = BSL_MAX_READLEN;       // longer reads are flagged filtered by prepare_reads; the CLI truncates like the reference
     const u32 Wb = std::max(1u, (Lmax + 31) / 32);
     const u32 cap = 32;
@@ -1900,7 +2076,23 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     u64 launches = 0;
     const int sms = ctx->sm_count;
     CUDA_TRY(cudaEventRecord(ln.ev[1], st));
-    prepare_reads<<<std::min<u32>((n_slots + PREP_WARPS - 1) / PREP_WARPS, (u32)sms * 16), PREP_WARPS * 32, 0, st>>>(A); launches++;
+    {
+        // prepare_reads2 needs 32 x (2 WQ + cap) words of shared memory per warp; cap = the largest number of read offsets the
+        // seed schedule of one read can touch (+ 32 for its start / key arrays). Very long reads with small -s fall back to
+        // the warp-per-read kernel.
+        static const bool prep_old = getenv("BSL_PREP_OLD") != nullptr;
+        const u32 WQ = 2 * Wb + 3;
+        const u32 cap = (sched_max + 32) | 1u;
+        const size_t smem_p = (size_t)P2_WARPS * 32 * (2 * WQ + cap) * 4;
+        if (!prep_old && smem_p <= 160 * 1024) {
+            static bool attr_p = false;
+            if (!attr_p) { cudaFuncSetAttribute(prepare_reads2, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_p = true; }
+            const u32 groups = (n_slots + 31) / 32;
+            prepare_reads2<<<std::min<u32>((groups + P2_WARPS - 1) / P2_WARPS, (u32)sms * 8), P2_WARPS * 32, smem_p, st>>>(A, WQ, cap);
+        } else
+            prepare_reads<<<std::min<u32>((n_slots + PREP_WARPS - 1) / PREP_WARPS, (u32)sms * 16), PREP_WARPS * 32, 0, st>>>(A);
+        launches++;
+    }
     build_lists<<<(std::max(n_slots, n_a) + 255) / 256, 256, 0, st>>>(A, ln.d_list[0], ln.d_pe_list[0]); launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ln.ev[2], st));

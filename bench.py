@@ -64,6 +64,13 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+VERIFY_KERNEL = {
+    0: "screen_bits (candidate verification: one-sector XOR/popcount screen on the 1-bit plane + exact masked XOR/popcount count of the survivors)",
+    3: "screen_candidates (candidate verification: one-sector masked XOR/popcount screen on the 2-bit planes + exact count of the survivors)",
+    4: "verify_candidates (candidate verification with -g: masked XOR/popcount over the whole gathered window)",
+}
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -76,7 +83,7 @@ class ClockSampler:
     def start(self):
         try:
             self.fh = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.gpu)],
                                          stdout=self.fh, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -266,6 +273,10 @@ def gpu_arm(args):
         call(i)
     run_e2e(N_INFLIGHT)          # warms the second lane's buffers
     # ---- e2e: K calls through the C-ABI with host buffers (H2D + kernels + D2H inside the timed region)
+    clocks = ClockSampler(local); clocks.start()          # samples every 20 ms across both timed regions (e2e, then kernels only)
+    time.sleep(0.5)                                       # nvidia-smi needs a moment before its first sample
+    for i in range(2):
+        call(i)
     barrier()
     t_e2e = run_e2e(args.steps)
     h2d = sum(x.bases.nbytes + x.offsets.nbytes for x in host[0] if x is not None)
@@ -276,7 +287,6 @@ def gpu_arm(args):
     for _ in range(2):
         ctx.align_rerun(a0, b0)
     barrier()
-    clocks = ClockSampler(local); clocks.start()
     dev_ms = search_ms = pack_ms = pair_ms = lookup_ms = verify_ms = reduce_ms = 0.0
     vbytes = cands = lookups = launches = s_launch = 0
     t0 = time.perf_counter()
@@ -320,7 +330,7 @@ def gpu_arm(args):
                 "ms_per_step": 1000.0 * t_e2e / args.steps, "note": f"bsl_align_pe from pinned host buffers, {N_INFLIGHT} caller threads (one lane = stream + buffers each)"},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": "verify_candidates (candidate verification: masked XOR/popcount over gathered reference windows)", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": VERIFY_KERNEL.get(cfg.cid, VERIFY_KERNEL[0]), "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                      "candidates_per_step": cands // max(args.steps, 1), "seed_lookups_per_step": lookups // max(args.steps, 1),
                      "bytes_per_candidate": (vbytes // cands) if cands else None, "launches_per_step": s_launch // max(args.steps, 1),
@@ -334,7 +344,7 @@ def gpu_arm(args):
             threads = os.cpu_count() or 1
             work = tempfile.mkdtemp(prefix="bench_cpu_")
             try:
-                sample = int(os.environ.get("BENCH_CPU_PAIRS", str(min(max(100_000, threads * 25_000), 1_000_000))))
+                sample = int(os.environ.get("BENCH_CPU_PAIRS", str(min(max(200_000, threads * 125_000), 2_000_000))))
                 if SCALE < 0.1:
                     sample = max(1000, int(sample * SCALE * 10))
                 log(f"cpu_baseline: reference binary, {sample} pairs, -p {threads}")
@@ -367,7 +377,7 @@ def _flag_kwargs(cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
