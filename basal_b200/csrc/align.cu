@@ -1,25 +1,28 @@
 // align.cu — batched read mapping on the GPU (replaces SingleAlign/PairAlign::Do_Batch).
 //
 // Kernels (all sm_100a integer / LSU work, no tensor cores):
-//   prepare_reads      warp per read: FilterReads, 2-bit planes for both chains (ballot transpose), rolling
-//                      seed hashes, bucket-size gathers and the seed schedule (ConvertBinaySeq + ReorderSeed)
+//   prepare_reads2     a warp takes 32 reads: FilterReads, 2-bit planes and 1-bit streams of both chains, seed hashes,
+//                      bucket-size gathers and the seed schedule (ConvertBinaySeq + ReorderSeed); prepare_reads is the
+//                      warp-per-read fallback for schedules that do not fit its shared memory
 //   build_lists        first active lists (SE reads / full pairs / lone mates)
 //   per search round r (= SnpAlign mode r of every still-active read, align.cpp:274-316):
-//     seed_lookup      thread per (read, chain): the I bucket look-ups of mode r; every non-empty bucket becomes
-//                      an "item" that owns a contiguous range of a flat candidate index space
-//     verify_candidates  THE roofline kernel: flat over candidates, 4 lanes per candidate, one 16-byte gather
-//                      per lane covering only the reference words the window needs, read bit planes staged in
-//                      shared memory, masked XOR/popcount (CountMismatch / CountMismatch_new), output = 1 bit
-//                      per candidate (could this candidate produce a hit?) + list of reads with a marked bit
-//     reduce_round     warp per read that has marked candidates: replays them in discovery order with the
-//                      reference's AddHit semantics (dedup, -w feedback on the threshold, abort) and runs the
-//                      single-gap search (GapAlign) on the marked candidates
-//     pair_round       PE: SortHits4PE + GetPairs replay for level r (thread per pair; block per pair on the
+//     seed_lookup      thread per (read, chain): the I bucket look-ups of mode r; every non-empty bucket becomes an
+//                      "item" that owns a contiguous range of a flat candidate space; the bucket walks are copied
+//                      out to flat_loc in visiting order
+//     screen_bits      THE roofline kernel (single-conversion rules, -g 0): warp per 32 candidates, one 32-byte gather
+//                      per candidate from the one-bit forward plane (L2 resident), XOR/popcount lower bound of
+//                      CountMismatch; survivors are counted exactly on the 2-bit planes (drain_exact)
+//     screen_candidates  the same for multi-way / '-' rules, on the 2-bit planes
+//     verify_candidates  -g > 0: whole window of every candidate (CountMismatch + GapAlign's first test), 1 bit per candidate
+//     reduce_fast      thread per read with <= 4 marked candidates: AddHit replay from the mark records
+//     reduce_round     warp per read: replays marked candidates in discovery order with the reference's AddHit
+//                      semantics (dedup, -w feedback on the threshold, abort) and runs the single-gap search (GapAlign)
+//     pair_round       PE: SortHits4PE + GetPairs replay for level r (thread per pair; warp per pair on the
 //                      large-capacity path)
 //   finalize_reads     lowest non-empty level, -S tie-break, result records
 //
 // Discovery order inside a read is preserved exactly: the flat candidate index of a read's candidates grows in
-// (chain, phase, rotated bucket index) order and reduce_round walks the marked bits in that order.
+// (chain, phase, rotated bucket index) order and the reducers walk the marked candidates in that order.
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -716,14 +719,14 @@ __device__ __forceinline__ void vf_count(u32 (&R)[8 * NS], u32 kk, u32 sh, const
     }
 }
 
-template <bool SINGLE, bool GAP, int NS>
+// Used with -g only (the screens below handle -g 0): GapAlign's first test needs the whole window of every candidate.
+template <bool SINGLE, int NS>
 __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates(const __grid_constant__ KArgs A, u32 ci, u32 W) {
+    constexpr bool GAP = true;
     extern __shared__ u32 vsm[];                          // staged streams: item x stream x 2*Wb
     __shared__ uint4 s_ha[CHUNK], s_hb[CHUNK];            // item headers {base, m, b0, nfwd} {rot, pack, slot, first word of the read streams}
     __shared__ u32 s_mask[CHUNK / 32], s_nmk;
     __shared__ uint4 s_mk[CHUNK];                         // marked candidates of the chunk: {flat index, g, snp | strand << 8 | chain << 9, slot}
-    __shared__ uint2 s_sv[GAP ? 1 : CHUNK];               // candidates that passed the one-sector screen: {chunk position | item << 8 | strand << 16, g}
-    __shared__ u32 s_bits[CHUNK / 32], s_nsv;             // verdict bits of the chunk (screened path)
     constexpr u32 NP = SINGLE ? 2 : 3;                    // streams copied from global memory: bases, N-mask, (convert-to mask)
     constexpr u32 NPL = NP + (GAP ? 1 : 0);               // + prefix mask
     constexpr u32 PL_NM = 1, PL_CM = 2, PL_PM = NP;
@@ -744,7 +747,7 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
     for (; chunk < n_chunks;) {
         const u32 cbeg = chunk * CHUNK, cend = min(cbeg + CHUNK, n_cands);
         bool mine = have && (t == 0 || ha.x < cend);
-        if (t < CHUNK / 32) { s_mask[t] = 0; s_bits[t] = 0; }
+        if (t < CHUNK / 32) s_mask[t] = 0;
         if (t == 0) s_nmk = 0;
         u32 n_it = (u32)__syncthreads_count(mine);
         if (n_it == VF_EAGER) {                                                  // (rare) more items than were prefetched
@@ -774,10 +777,10 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
         }
         const bool act = idx < cend;
         bool marked = false;
-        u32 g = 0, pack = 0, sig = 0, kk = 0, sh = 0, dlt = 0, nh = 0;
-        u32 R[GAP ? NR : 8];                                                     // -g: the whole window; else the screened sector
+        u32 g = 0, pack = 0, sig = 0, kk = 0, sh = 0;
+        u32 R[NR];
 #pragma unroll
-        for (int j = 0; j < (GAP ? NR : 8); j++) R[j] = 0;
+        for (int j = 0; j < NR; j++) R[j] = 0;
         if (act) {
             const uint4 xa = s_ha[it]; const uint2 xb = *(const uint2 *)&s_hb[it];
             u32 e = xb.x + (idx - xa.x); if (e >= xa.y) e -= xa.y;
@@ -785,27 +788,11 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
             pack = xb.y;
             g = cloc - IH_H(pack);                                               // _hit.loc (align.cpp:297)
             sh = (g & 15u) * 2;
-            if constexpr (GAP) vf_gather<NS>(A.di.plane[sig], g, IH_L(pack), R, kk);
-            else {
-                // ---- screen: ONE 32-byte sector of the window (8 half-words of 16 bases). Read half-word i lines up with
-                //      reference half-words gh+i, gh+i+1; the sector starting o half-words before gh covers i in [0, 6-o],
-                //      the next one i in [8-o, 14-o]. Take the one that covers more of the read: a mismatch count over a
-                //      subset of the read's half-words is a lower bound of CountMismatch, so `> thr` here is final.
-                const u32 gh = g >> 4, o = gh & 7u;
-                nh = (IH_L(pack) + 15u) >> 4;
-                const u32 c0 = min(7u - o, nh), hi1 = min(14u - o, nh - 1u);
-                const u32 c1 = hi1 + o >= 8u ? hi1 + o - 7u : 0u;
-                const u32 k = c1 > c0 ? 1u : 0u;
-                dlt = k ? 8u - o : 0u - o;                                      // read half-word of sector half-word x = x + dlt
-                u32 r8[8]; ldg256(A.di.plane[sig] + ((gh - o) >> 1) + 4u * k, r8);
-#pragma unroll
-                for (int j = 0; j < 8; j++) R[j] = r8[j];
-            }
+            vf_gather<NS>(A.di.plane[sig], g, IH_L(pack), R, kk);
         }
         for (u32 grp = 0; grp < n_it; grp += VF_ITMAX) {
             const u32 n_g = min(VF_ITMAX, n_it - grp);
             if (grp) __syncthreads();                                        // the previous group is done with the staging buffer
-            if (!GAP && t == 0) s_nsv = 0;
             // ---- stage the streams of this group's items: a warp copies the D contiguous words of an item (coalesced),
             //      four items per warp in flight
             for (u32 l = lane; l < D; l += 32) {
@@ -817,7 +804,7 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
                     for (u32 b = 0; b < 4; b++) { const u32 i2 = m0 + b * (VF_THREADS / 32); if (i2 < n_g) vsm[(size_t)i2 * IST + l] = v[b]; }
                 }
             }
-            if (GAP) {
+            {
                 for (u32 j = lane; j < W2; j += 32)
                     for (u32 i2 = wid; i2 < n_g; i2 += VF_THREADS / 32) {
                         const u32 hs = IH_H(s_hb[grp + i2].y) + A.s;
@@ -836,74 +823,36 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
             }
             __syncthreads();                                                                // staged streams visible
             const bool now = act && it >= grp && it < grp + n_g;
-            if constexpr (GAP) {
-                u32 snp = 0, pre = 0;
-                if (now) vf_count<SINGLE, GAP, NS>(R, kk, sh, vsm + (size_t)(it - grp) * IST, W, W2, snp, pre);
-                // could this candidate add a hit?  ungapped: snp <= thr.  gapped: GapAlign's first test (align.cpp:353-360)
-                const u32 thr = IH_THR(pack);
-                const bool mark = now && (snp <= thr || (thr >= 2 && pre < thr - 1));
-                if (mark) { marked = true; s_mk[atomicAdd(&s_nmk, 1u)] = make_uint4(idx, g, snp | (sig << 8) | (IH_CHAIN(pack) << 9), s_hb[it].z); }
-            } else {
-                if (now) {
-                    const u32 *S = vsm + (size_t)(it - grp) * IST;
-                    u32 snp = 0;
-#pragma unroll
-                    for (int x = 0; x < 7; x++) {
-                        const u32 i = (u32)x + dlt;
-                        if (i < nh) {
-                            const u32 r = __funnelshift_l(R[x + 1], R[x], sh);
-                            u32 cc = 0; if (!SINGLE) cc = S[PL_CM * W2 + i];
-                            snp += __popc(vf_diff<SINGLE>(S[i], cc, r) & S[PL_NM * W2 + i]);
-                        }
-                    }
-                    if (snp <= IH_THR(pack)) s_sv[atomicAdd(&s_nsv, 1u)] = make_uint2(t | ((it - grp) << 8) | (sig << 16), g);
-                }
-                __syncthreads();
-                // ---- the few candidates that passed the screen: whole window, exact count
-                if (t < s_nsv) {
-                    const uint2 sv = s_sv[t];
-                    const u32 t2 = sv.x & 255u, it2 = grp + ((sv.x >> 8) & 255u), sig2 = (sv.x >> 16) & 1u, g2 = sv.y;
-                    const u32 pack2 = s_hb[it2].y;
-                    u32 Q[NR], kk2 = 0, snp = 0, pre = 0;
-#pragma unroll
-                    for (int j = 0; j < NR; j++) Q[j] = 0;
-                    vf_gather<NS>(A.di.plane[sig2], g2, IH_L(pack2), Q, kk2);
-                    vf_count<SINGLE, false, NS>(Q, kk2, (g2 & 15u) * 2, vsm + (size_t)(it2 - grp) * IST, W, W2, snp, pre);
-                    if (snp <= IH_THR(pack2)) {
-                        atomicOr(&s_bits[t2 >> 5], 1u << (t2 & 31u));
-                        s_mk[atomicAdd(&s_nmk, 1u)] = make_uint4(cbeg + t2, g2, snp | (sig2 << 8) | (IH_CHAIN(pack2) << 9), s_hb[it2].z);
-                    }
-                }
-            }
+            u32 snp = 0, pre = 0;
+            if (now) vf_count<SINGLE, GAP, NS>(R, kk, sh, vsm + (size_t)(it - grp) * IST, W, W2, snp, pre);
+            // could this candidate add a hit?  ungapped: snp <= thr.  gapped: GapAlign's first test (align.cpp:353-360)
+            const u32 thr = IH_THR(pack);
+            const bool mark = now && (snp <= thr || (thr >= 2 && pre < thr - 1));
+            if (mark) { marked = true; s_mk[atomicAdd(&s_nmk, 1u)] = make_uint4(idx, g, snp | (sig << 8) | (IH_CHAIN(pack) << 9), s_hb[it].z); }
         }
         // ---- 32 verdicts are one word of the bitmap; marked candidates are published for reduce_fast / reduce_round
-        if (GAP) {
+        {
             const u32 bal = __ballot_sync(0xffffffffu, marked);
             if (lane == 0) A.bitmap[(cbeg >> 5) + wid] = bal;
         }
         __syncthreads();
-        if (!GAP && t < CHUNK / 32) A.bitmap[(cbeg >> 5) + t] = s_bits[t];
-        if (t < s_nmk) {
-            const uint4 mk = s_mk[t];
-            const u32 pos = atomicAdd(&A.slot_flag[mk.w], 1u);
-            if (!GAP && pos < MK_CAP) A.marks[(size_t)mk.w * MK_CAP + pos] = make_uint4(mk.x, mk.y, mk.z, 0u);
-        }
+        if (t < s_nmk) atomicAdd(&A.slot_flag[s_mk[t].w], 1u);          // reduce_round replays the flagged reads from the bitmap
         __syncthreads();
         chunk = nchunk; first = nfirst; ha = pa; hb = pb; have = phave; nchunk = nnchunk; nfirst = nnfirst; cloc = nloc;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// screen_candidates + verify_survivors : candidate verification without -g.
+// screen_candidates : candidate verification without -g, any conversion rule (2-bit planes).
 //
-// screen_candidates is the roofline kernel. A WARP owns 32 consecutive flat candidates and never waits for another warp
-// (no block barriers): lanes load the headers of the items overlapping the group, every lane resolves its candidate's
-// item with one popcount, issues ONE 256-bit gather (the 32-byte sector of its reference window that covers most of the
-// read), the warp stages the items' read streams into its private slice of shared memory behind those gathers, and each
-// lane counts the mismatches of the read half-words the sector covers. That count is a lower bound of CountMismatch
-// (align.h:118-131 / 199-239: a sum over half-words, the same alignment), so a candidate above its threshold is
-// rejected for good; the rest (a few per cent) get bit = 1 in the bitmap. verify_survivors walks the set bits, gathers
-// the whole window and applies the exact count; it clears the bits that fail and records the marks.
+// A WARP owns 32 consecutive flat candidates and never waits for another warp (no block barriers): lanes load the
+// headers of the items overlapping the group, every lane resolves its candidate's item with one popcount, issues ONE
+// 256-bit gather (the 32-byte sector of its reference window that covers most of the read), the warp stages the items'
+// read streams into its private slice of shared memory behind those gathers, and each lane counts the mismatches of
+// the read half-words the sector covers. That count is a lower bound of CountMismatch (align.h:118-131 / 199-239: a
+// sum over half-words, the same alignment), so a candidate above its threshold is rejected for good. The rest (a few
+// per cent) wait in a per-warp queue; whenever 32 are waiting they are counted exactly (drain_exact), one per lane.
+// Single-conversion rules use screen_bits (below) instead: the same structure on a one-bit plane that stays in L2.
 // ------------------------------------------------------------------------------------------------
 #define SC_WARPS 8
 #define SC_QCAP 64u          // survivors a warp can hold (it empties the queue whenever 32 are waiting)
@@ -2101,7 +2050,7 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     const u32 NW = (31 + 2 * G + Lmax + 31) / 32; const u32 NWS = NW | 1u;
     const size_t smem_r = (size_t)ROUND_WARPS * (32 * NWS + 48) * 8;
     const u32 NP = ctx->rule.single ? 2 : 3;
-    const u32 NPL = NP + (G ? 1 : 0);
+    const u32 NPL = NP + 1;                                               // verify_candidates (-g) stages a prefix-mask stream as well
     const u32 Wr = (Lmax + 31) / 32;                                     // 64-bit words of the longest read
     const bool ns3 = Wr + 1 + 3 <= 12;                                   // a window (Wr + 1 words at any of 4 word offsets) fits 3 sectors
     const size_t smem_v = (size_t)VF_ITMAX * NPL * 2 * Wb * 4;
@@ -2110,24 +2059,20 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
         cudaFuncSetAttribute(pair_round_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairWideSmem));
         cudaFuncSetAttribute(reduce_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         cudaFuncSetAttribute(reduce_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-#define VF_ATTR(S_, G_) cudaFuncSetAttribute(verify_candidates<S_, G_, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); cudaFuncSetAttribute(verify_candidates<S_, G_, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024)
-        VF_ATTR(true, false); VF_ATTR(true, true); VF_ATTR(false, false); VF_ATTR(false, true);
+#define VF_ATTR(S_) cudaFuncSetAttribute(verify_candidates<S_, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); cudaFuncSetAttribute(verify_candidates<S_, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024)
+        VF_ATTR(true); VF_ATTR(false);
 #undef VF_ATTR
         attr_set = true;
     }
     const u32 rounds_se = std::min<u32>((Lmax + 1 >= P.index_interval + P.seed_size) ? (Lmax + 1 - P.index_interval) / P.seed_size : 0, 16);
-    const int vkind = (ctx->rule.single ? 0 : 2) + (G ? 1 : 0);
-    if (!ctx->occ_verify[vkind]) {
-        int occ = 0; cudaError_t oe;
-        switch (vkind) {                                 // sized for the common 3-sector variant
-            case 0: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<true, false, 3>, VF_THREADS, smem_v); break;
-            case 1: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<true, true, 3>, VF_THREADS, smem_v); break;
-            case 2: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<false, false, 3>, VF_THREADS, smem_v); break;
-            default: oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<false, true, 3>, VF_THREADS, smem_v); break;
-        }
+    const int vkind = ctx->rule.single ? 0 : 1;
+    if (G && !ctx->occ_verify[vkind]) {
+        int occ = 0;                                     // sized for the common 3-sector variant
+        cudaError_t oe = ctx->rule.single ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<true, 3>, VF_THREADS, smem_v)
+                                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, verify_candidates<false, 3>, VF_THREADS, smem_v);
         ctx->occ_verify[vkind] = (oe == cudaSuccess && occ > 0) ? occ : 3;
     }
-    const int grid_l = sms * 8, grid_v = sms * ctx->occ_verify[vkind], grid_r = sms * 4;      // persistent grids: a multiple of the SM count
+    const int grid_l = sms * 8, grid_v = sms * std::max(ctx->occ_verify[vkind], 1), grid_r = sms * 4;      // persistent grids: a multiple of the SM count
 
     int nev = 0; std::vector<char> ev_kind;           // per-launch CUDA-event pairs: 'l' seed_lookup, 'v' verify, 'r' reduce, 'p' pair_round
     const int max_ev = (int)(sizeof ln.evk / sizeof ln.evk[0]);
@@ -2137,7 +2082,6 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     const u32 stage_items = std::max<u32>(1, std::min<u32>(32, 640 / (2 * DWv)));
     const size_t smem_s = (size_t)SC_WARPS * stage_items * 2 * DWv * 4;
     const u32 rcp_dw = (u32)((0x100000000ull + DWv - 1) / DWv);
-    static const bool old_verify = getenv("BSL_VERIFY_OLD") != nullptr;
     if (!ctx->occ_screen) {
         int occ = 0;
         cudaError_t oe = ctx->rule.single ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, screen_candidates<true>, SC_WARPS * 32, smem_s)
@@ -2155,19 +2099,14 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     if (!ctx->occ_bits) { int occ = 0; cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, screen_bits, SC_WARPS * 32, smem_b); ctx->occ_bits = (oe == cudaSuccess && occ > 0) ? occ : 4; }
     const int grid_b = sms * ctx->occ_bits;
     auto launch_verify = [&](KArgs &K, u32 ci) {
-        if (!G && !old_verify && use_bits) {
-            screen_bits<<<grid_b, SC_WARPS * 32, smem_b, st>>>(K, ci, stage_items_b, rcp_b, dbg_bits);
-            return;
-        }
-        if (!G && !old_verify) {
+        if (!G && use_bits) { screen_bits<<<grid_b, SC_WARPS * 32, smem_b, st>>>(K, ci, stage_items_b, rcp_b, dbg_bits); return; }
+        if (!G) {
             if (ctx->rule.single) screen_candidates<true><<<grid_s, SC_WARPS * 32, smem_s, st>>>(K, ci, stage_items, rcp_dw);
             else screen_candidates<false><<<grid_s, SC_WARPS * 32, smem_s, st>>>(K, ci, stage_items, rcp_dw);
             return;
         }
-#define VF_LAUNCH(S_, G_) do { if (ns3) verify_candidates<S_, G_, 3><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, Wr); else verify_candidates<S_, G_, 5><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, Wr); } while (0)
-        if (ctx->rule.single) { if (G) VF_LAUNCH(true, true); else VF_LAUNCH(true, false); }
-        else { if (G) VF_LAUNCH(false, true); else VF_LAUNCH(false, false); }
-#undef VF_LAUNCH
+        if (ctx->rule.single) { if (ns3) verify_candidates<true, 3><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, Wr); else verify_candidates<true, 5><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, Wr); }
+        else { if (ns3) verify_candidates<false, 3><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, Wr); else verify_candidates<false, 5><<<grid_v, VF_THREADS, smem_v, st>>>(K, ci, Wr); }
     };
     auto search = [&](KArgs &K, bool as_pe, u32 r, const u32 *lin, u32 *lout, u32 ci) {
         ev_begin('l');
