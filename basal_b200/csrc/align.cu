@@ -1211,7 +1211,11 @@ struct WarpCtx {
     // warp-uniform running state of one read (one SingleAlign object)
     u32 L, W, thr, nhit, chain, cap; u32 mycnt;     // mycnt: lane c*16+l holds hits[c][l]
     DevHit *hits; bool overflow;
+    u64 *keys; u32 kcap;                            // shared-memory copy of the dedup keys of hits[0 .. min(nhit, kcap))
 };
+#define RR_KEYS 512u         // dedup keys a warp keeps in shared memory (longer lists scan the rest in global memory)
+// what AddHit's std::set compares (align.h:334-339): forward coordinate, sequence, gapped or not
+__device__ __forceinline__ u64 hit_key(u32 loc, u32 seq, u32 gapped) { return (u64)loc | ((u64)(seq | (gapped << 20)) << 32); }
 
 // ref word aligned to read word i for an alignment starting at window-relative base `rel`
 __device__ __forceinline__ u64 ref_word(const u64 *win, u32 NW, u32 rel, u32 i) {
@@ -1273,20 +1277,29 @@ __device__ u32 gap_search(const u64 *win, u32 NW, u32 rel, const u64 *q, const u
 
 // AddHit + int2hit (align.h:329-347, align.cpp:319-346); all arguments warp-uniform.
 // returns 0 = continue, 1 = abort this SnpAlign call (level-0 list full, or storage overflow)
-__device__ int add_hit(const KArgs &A, WarpCtx &S, u32 lane, u32 level, u32 g, u32 sig, int sh, u32 gp) {
+__device__ __forceinline__ u32 seq_of(const KArgs &A, u32 g) {               // binary search of ref_anchor (align.cpp:320-327)
     u32 lo = 0, hi = A.di.nseq;
     while (lo + 1 < hi) { u32 mid = (lo + hi) >> 1; if (g >= A.di.anchor[mid]) lo = mid; else hi = mid; }
+    return lo;
+}
+__device__ int add_hit(const KArgs &A, WarpCtx &S, u32 lane, u32 level, u32 g, u32 lo, u32 sig, int sh, u32 gp) {
     u32 x = g - A.di.anchor[lo];
     if (sig) { x = A.di.rcoff[lo] - S.L - x; gp = (u32)((int)S.L + (sh < 0 ? sh : 0) - (int)gp); x -= (u32)sh; }
     gp &= 511u;
     if ((int)x < 0) return 0;
     if (x + S.L > A.di.seqlen[lo]) return 0;
     const u32 gapped = sh != 0;
+    const u64 key = hit_key(x, lo, gapped);
     bool dup = false;
-    for (u32 i = lane; i < S.nhit; i += 32) { DevHit hh = S.hits[i]; if (hh.loc == x && HIT_GAPPED(hh.tag) == gapped && (HIT_CHR2(hh.tag) >> 1) == lo) dup = true; }
+    const u32 nk = min(S.nhit, S.kcap);
+    for (u32 i = lane; i < nk; i += 32) dup |= S.keys[i] == key;
+    for (u32 i = nk + lane; i < S.nhit; i += 32) { DevHit hh = S.hits[i]; if (hh.loc == x && HIT_GAPPED(hh.tag) == gapped && (HIT_CHR2(hh.tag) >> 1) == lo) dup = true; }
     if (__any_sync(0xffffffffu, dup)) return 0;
     if (S.nhit >= S.cap) { S.overflow = true; return 1; }
-    if (lane == 0) { DevHit hh; hh.loc = x; hh.tag = (lo * 2 + sig) | (level << 20) | (S.chain << 24) | (gapped << 25); hh.gap = (u32)sh; hh.gp = gp; S.hits[S.nhit] = hh; }
+    if (lane == 0) {
+        DevHit hh; hh.loc = x; hh.tag = (lo * 2 + sig) | (level << 20) | (S.chain << 24) | (gapped << 25); hh.gap = (u32)sh; hh.gp = gp; S.hits[S.nhit] = hh;
+        if (S.nhit < S.kcap) S.keys[S.nhit] = key;
+    }
     S.nhit++;
     __syncwarp();
     if (lane == S.chain * 16 + level) S.mycnt++;
@@ -1299,8 +1312,8 @@ template <bool SINGLE>
 __global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_constant__ KArgs A, u32 round, u32 ci, u32 NW, u32 NWS, const u32 *list, u32 list_ci, u32 as_pe) {
     extern __shared__ u64 smem[];
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    u64 *win_all = smem + (size_t)wid * (32 * NWS + 48);
-    u64 *pq = win_all + 32 * NWS, *pn = pq + 16, *pc = pn + 16;
+    u64 *win_all = smem + (size_t)wid * (32 * NWS + 48 + RR_KEYS);
+    u64 *pq = win_all + 32 * NWS, *pn = pq + 16, *pc = pn + 16, *keys = pc + 16;
     RoundCtr *rc = A.ctr->rc + ci;
     // every slot searched in this round: SE = the compacted list seed_lookup wrote, PE = both mates of every listed pair;
     // a warp takes 32 of them at a time and replays those verify_candidates flagged
@@ -1323,6 +1336,10 @@ __global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_co
         WarpCtx S; S.L = m.len; S.W = (S.L + 31) >> 5; S.thr = m.thr; S.nhit = m.nhit; S.cap = A.cap; S.overflow = false;
         S.hits = A.hits + (u64)m.item * A.cap;
         S.mycnt = ((const u16 *)&A.cnt[slot])[lane];
+        S.keys = keys; S.kcap = RR_KEYS;
+        __syncwarp();
+        for (u32 i = lane; i < min(S.nhit, RR_KEYS); i += 32) { const DevHit hh = S.hits[i]; keys[i] = hit_key(hh.loc, HIT_CHR2(hh.tag) >> 1, HIT_GAPPED(hh.tag)); }
+        __syncwarp();
         const u32 L = S.L, W = S.W;
         const u32 lastb = L & 31u; const u64 endmask = lastb ? (~0ULL << (64 - 2 * lastb)) : ~0ULL;
         const u32 hits_before = S.nhit;
@@ -1381,16 +1398,19 @@ __global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_co
                 }
                 // ---- in-order reduction (AddHit semantics need the discovery order)
                 const u32 thr0 = S.thr;
-                u32 pending = __ballot_sync(0xffffffffu, valid && (snp <= thr0 || gres != GAP_NONE));
+                const bool cand = valid && (snp <= thr0 || gres != GAP_NONE);
+                const u32 myseq = cand ? seq_of(A, g) : 0u;                       // every lane finds the sequence of its own candidate
+                u32 pending = __ballot_sync(0xffffffffu, cand);
                 while (pending) {
                     const u32 l = __ffs(pending) - 1; pending &= pending - 1;
                     const u32 cg = __shfl_sync(0xffffffffu, g, l), csig = __shfl_sync(0xffffffffu, sig, l), csnp = __shfl_sync(0xffffffffu, snp, l);
+                    const u32 cseq = __shfl_sync(0xffffffffu, myseq, l);
                     bool ab = false;
-                    if (csnp <= S.thr) ab = add_hit(A, S, lane, csnp, cg, csig, 0, 0);
+                    if (csnp <= S.thr) ab = add_hit(A, S, lane, csnp, cg, cseq, csig, 0, 0);
                     if (G && !ab) {
                         if (S.thr != thr0 && lane == l) gres = gap_search<SINGLE>(win, NW, rel, pq, pc, L, W, endmask, S.thr, ch, A.s, G);
                         const u32 cres = __shfl_sync(0xffffffffu, gres, l);
-                        if (cres != GAP_NONE) ab = add_hit(A, S, lane, cres & 255u, cg, csig, (int)((cres >> 8) & 255u) - 4, cres >> 16);
+                        if (cres != GAP_NONE) ab = add_hit(A, S, lane, cres & 255u, cg, cseq, csig, (int)((cres >> 8) & 255u) - 4, cres >> 16);
                     }
                     if (ab) {                    // SnpAlign returns here: later phases / the other chain are never looked up
                         const u32 aitem = __shfl_sync(0xffffffffu, ph, l);
@@ -2048,7 +2068,7 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
 
     const u32 G = P.gap;
     const u32 NW = (31 + 2 * G + Lmax + 31) / 32; const u32 NWS = NW | 1u;
-    const size_t smem_r = (size_t)ROUND_WARPS * (32 * NWS + 48) * 8;
+    const size_t smem_r = (size_t)ROUND_WARPS * (32 * NWS + 48 + RR_KEYS) * 8;
     const u32 NP = ctx->rule.single ? 2 : 3;
     const u32 NPL = NP + 1;                                               // verify_candidates (-g) stages a prefix-mask stream as well
     const u32 Wr = (Lmax + 31) / 32;                                     // 64-bit words of the longest read
