@@ -344,7 +344,7 @@ def gpu_arm(args):
             threads = os.cpu_count() or 1
             work = tempfile.mkdtemp(prefix="bench_cpu_")
             try:
-                sample = int(os.environ.get("BENCH_CPU_PAIRS", str(min(max(200_000, threads * 125_000), 2_000_000))))
+                sample = int(os.environ.get("BENCH_CPU_PAIRS", str(min(max(200_000, threads * 62_500), 1_000_000))))
                 if SCALE < 0.1:
                     sample = max(1000, int(sample * SCALE * 10))
                 log(f"cpu_baseline: reference binary, {sample} pairs, -p {threads}")
