@@ -1275,6 +1275,37 @@ __device__ u32 gap_search(const u64 *win, u32 NW, u32 rel, const u64 *q, const u
     return GAP_NONE;
 }
 
+// A necessary condition of GapAlign finding anything (align.cpp:348-410), cheap enough to run for every candidate.
+// A gapped hit at shift d is a left part [0, gp) with i mismatches at shift 0 and a right part of m2 bases with j
+// mismatches at shift d, i, j <= thr - 2 and gp + m2 >= L - |d|. Cut the read at M = L / 2: either gp >= M, then the first
+// M bases hold at most thr - 2 mismatches at shift 0, or m2 >= L - G - M + 1 =: y, then the last y bases hold at most
+// thr - 2 mismatches at that shift. Mismatches are counted like MismatchPattern0/1 do (no N mask, align.h:133-196).
+template <bool SINGLE>
+__device__ bool gap_possible(const u64 *win, u32 NW, u32 rel, const u64 *q, const u64 *cm, u32 L, u32 W, u64 endmask, u32 thr, u32 G) {
+    if (thr < 2) return false;
+    const u32 M = L >> 1, start = G + M - 1;                                   // the last y = L - start bases
+    u32 a = 0;
+    for (u32 i = 0; i < W && 32 * i < M; i++) {
+        const u32 n = min(M - 32 * i, 32u);
+        u64 d = bsl_pairs(bsl_diff<SINGLE>(q[i], cm[i], ref_word(win, NW, rel, i))); if (i == W - 1) d &= endmask;
+        a += __popcll(d & (~0ULL << (64 - 2 * n)));
+    }
+    if (a <= thr - 2) return true;
+    for (u32 tt = 1; tt <= 2 * G; tt++) {
+        const u32 t = (tt + 1) >> 1; const int sh = (tt & 1) ? -(int)t : (int)t;
+        if (thr < 1 + t) break;
+        const u32 rel1 = (u32)((int)rel + sh);
+        u32 b = 0;
+        for (u32 i = start >> 5; i < W; i++) {
+            const u32 n0 = start > 32 * i ? start - 32 * i : 0u;                // bases of this word before the part
+            u64 d = bsl_pairs(bsl_diff<SINGLE>(q[i], cm[i], ref_word(win, NW, rel1, i))); if (i == W - 1) d &= endmask;
+            b += __popcll(n0 ? d & (~0ULL >> (2 * n0)) : d);
+        }
+        if (b <= thr - 2) return true;
+    }
+    return false;
+}
+
 // AddHit + int2hit (align.h:329-347, align.cpp:319-346); all arguments warp-uniform.
 // returns 0 = continue, 1 = abort this SnpAlign call (level-0 list full, or storage overflow)
 __device__ __forceinline__ u32 seq_of(const KArgs &A, u32 g) {               // binary search of ref_anchor (align.cpp:320-327)
@@ -1387,14 +1418,14 @@ __global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_co
                     const u64 *P = A.di.plane[sig] + word0;
                     for (u32 w = 0; w < NW; w++) win[w] = __ldg(P + w);
                 }
-                u32 snp = 0xffffu, gres = GAP_NONE;
+                u32 snp = 0xffffu, gres = GAP_NONE; bool gscr = false;
                 if (valid) {
                     snp = 0;
                     for (u32 i = 0; i < W; i++) {                              // CountMismatch / CountMismatch_new
                         const u64 d = bsl_diff<SINGLE>(pq[i], pc[i], ref_word(win, NW, rel, i));
                         snp += __popcll(bsl_pairs(d) & pn[i]);
                     }
-                    if (G) gres = gap_search<SINGLE>(win, NW, rel, pq, pc, L, W, endmask, S.thr, ch, A.s, G);
+                    if (G) { gscr = gap_possible<SINGLE>(win, NW, rel, pq, pc, L, W, endmask, S.thr, G); if (gscr) gres = gap_search<SINGLE>(win, NW, rel, pq, pc, L, W, endmask, S.thr, ch, A.s, G); }
                 }
                 // ---- in-order reduction (AddHit semantics need the discovery order)
                 const u32 thr0 = S.thr;
@@ -1408,7 +1439,7 @@ __global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_co
                     bool ab = false;
                     if (csnp <= S.thr) ab = add_hit(A, S, lane, csnp, cg, cseq, csig, 0, 0);
                     if (G && !ab) {
-                        if (S.thr != thr0 && lane == l) gres = gap_search<SINGLE>(win, NW, rel, pq, pc, L, W, endmask, S.thr, ch, A.s, G);
+                        if (S.thr != thr0 && lane == l && gscr) gres = gap_search<SINGLE>(win, NW, rel, pq, pc, L, W, endmask, S.thr, ch, A.s, G);
                         const u32 cres = __shfl_sync(0xffffffffu, gres, l);
                         if (cres != GAP_NONE) ab = add_hit(A, S, lane, cres & 255u, cg, cseq, csig, (int)((cres >> 8) & 255u) - 4, cres >> 16);
                     }
