@@ -1013,7 +1013,7 @@ __global__ void __launch_bounds__(SC_WARPS * 32, 5) screen_candidates(const __gr
 // (DevIndex::nflag) and windows that cross a sequence boundary are not screened on that strand: they go straight to
 // the exact count. Same warp-autonomous structure and survivor queue as screen_candidates.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SC_WARPS * 32, 5) screen_bits(const __grid_constant__ KArgs A, u32 ci, u32 stage_items, u32 rcp_dw, u32 dbg) {   // dbg: tools/gpu_dbg.sh switches (1 no exact count, 2 no gather, 4 no staging loads); 0 in production
+__global__ void __launch_bounds__(SC_WARPS * 32, 4) screen_bits(const __grid_constant__ KArgs A, u32 ci, u32 stage_items, u32 rcp_dw, u32 dbg) {   // dbg: tools/gpu_dbg.sh switches (1 no exact count, 2 no gather, 4 no staging loads); 0 in production
     extern __shared__ u32 ssm[];
     __shared__ uint4 s_q[SC_WARPS][SC_QCAP];
     constexpr u32 FULL = 0xffffffffu;
@@ -1033,24 +1033,30 @@ __global__ void __launch_bounds__(SC_WARPS * 32, 5) screen_bits(const __grid_con
     const u32 stride = gridDim.x * SC_WARPS;
     u32 grp = blockIdx.x * SC_WARPS + wid;
     if (grp >= n_groups) return;
-    // chunk_first of the groups this warp visits is loaded two visits ahead, so that the headers and loc entries of the
-    // next visit can be pulled into L2 while this one is screened
+    // software pipeline over the groups this warp visits: the item headers and loc entries of the NEXT visit are loaded
+    // into registers while this one is screened, chunk_first one visit further ahead
+    auto load_hdr = [&](u32 first, u32 last, uint4 &ha, uint4 &hb) {
+        ha = make_uint4(FULL, 0, 0, 0); hb = make_uint4(0, 0, 0, 0);
+        if (first + lane <= last) { const uint4 *src = (const uint4 *)(A.hdr + first + lane); ha = __ldg(src); hb = __ldg(src + 1); }
+    };
     u32 f0 = __ldg(A.chunk_first + grp), l0 = grp + 1 < n_groups ? __ldg(A.chunk_first + grp + 1) : n_items - 1u;
     u32 f1 = 0, l1 = 0;
     if (grp + stride < n_groups) { f1 = __ldg(A.chunk_first + grp + stride); l1 = grp + stride + 1 < n_groups ? __ldg(A.chunk_first + grp + stride + 1) : n_items - 1u; }
+    uint4 pha, phb; load_hdr(f0, l0, pha, phb);
+    u32 pcloc = (grp << 5) + lane < n_cands ? __ldg(A.flat_loc + (grp << 5) + lane) : 0u;
     for (; grp < n_groups; grp += stride) {
         const u32 gbeg = grp << 5, gend = min(gbeg + 32u, n_cands);
         const u32 first = f0, last = l0;
         const bool act = gbeg + lane < gend;
-        const u32 cloc = act ? __ldg(A.flat_loc + gbeg + lane) : 0u;
-        uint4 ha = make_uint4(FULL, 0, 0, 0), hb = make_uint4(0, 0, 0, 0);
+        const u32 cloc = pcloc;
+        const uint4 ha = pha, hb = phb;
         const bool ld = first + lane <= last;
-        if (ld) { const uint4 *src = (const uint4 *)(A.hdr + first + lane); ha = __ldg(src); hb = __ldg(src + 1); }
-        // ---- next visit: L2 prefetch of its headers and loc entries; chunk_first of the visit after it
+        // ---- next visit: its headers and loc entries; chunk_first of the visit after it
         f0 = f1; l0 = l1;
         if (grp + stride < n_groups) {
-            if (f1 + lane <= l1) asm volatile("prefetch.global.L2 [%0];" :: "l"(A.hdr + f1 + lane));
-            if (lane == 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(A.flat_loc + ((size_t)(grp + stride) << 5)));
+            load_hdr(f0, l0, pha, phb);
+            const u32 nb_ = (grp + stride) << 5;
+            pcloc = nb_ + lane < n_cands ? __ldg(A.flat_loc + nb_ + lane) : 0u;
             const u32 g2 = grp + 2 * stride;
             if (g2 < n_groups) { f1 = __ldg(A.chunk_first + g2); l1 = g2 + 1 < n_groups ? __ldg(A.chunk_first + g2 + 1) : n_items - 1u; }
         }
