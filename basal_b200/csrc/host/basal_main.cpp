@@ -1,8 +1,9 @@
 // basal_main.cpp — the `basal` command line on top of the C-ABI (include/basal_gpu.h).
 //
 // Drop-in for the reference binary's process contract (main.cpp:272-655): same flags in both
-// `-x v` and `-x=v` forms, same SAM header / records / stderr summary, `.bam` output piped
-// through an external `samtools view -bS -`.  The mapping itself happens on the GPU(s):
+// `-x v` and `-x=v` forms, same SAM header / records / stderr summary; `.bam` output is written by
+// bam_writer.hpp (BGZF blocks compressed by the worker threads; $BASAL_SAMTOOLS=1 pipes through an
+// external `samtools view -bS -` like the reference, main.cpp:505).  The mapping itself happens on the GPU(s):
 // this file only parses text, trims reads, batches them and prints result records.
 //
 //   reader thread  ->  batches of reads  ->  worker threads (bsl_align_se/pe on a GPU, then SAM text)
@@ -28,6 +29,7 @@
 #include <vector>
 
 #include "../../../include/basal_gpu.h"
+#include "bam_writer.hpp"
 
 typedef uint8_t u8; typedef uint16_t u16; typedef uint32_t u32; typedef uint64_t u64;
 static const char *kVersion = "1.8.1";
@@ -370,6 +372,7 @@ struct Pipeline {
     u64 next_ticket = 0, next_write = 0; u32 next_index; bool input_done = false;
     std::map<u64, std::string> done;
     FILE *out = nullptr;
+    bool bam_native = false; bam::Refs refs;          // -o x.bam without an external samtools
     Counters total; u64 reads_seen = 0;
     std::atomic<int> failed{0};
     size_t batch_reads;
@@ -475,7 +478,11 @@ struct Pipeline {
 
     void worker(int wid) {
         bsl_ctx *c = ctx[wid % ctx.size()]; Counters cn; Batch B;
-        while (!failed && load(B)) { process(B, c, cn); emit(B); }
+        while (!failed && load(B)) {
+            process(B, c, cn);
+            if (bam_native) { std::string blk; if (!bam::text_to_blocks(B.text, refs, blk)) { fprintf(stderr, "\ninternal error: malformed SAM record in BAM conversion\n"); failed = 1; } B.text.swap(blk); }
+            emit(B);
+        }
         std::lock_guard<std::mutex> g(out_mu);
         total.al += cn.al; total.un += cn.un; total.mu += cn.mu; total.pal += cn.pal; total.pun += cn.pun; total.pmu += cn.pmu;
         total.aal += cn.aal; total.aun += cn.aun; total.amu += cn.amu; total.bal += cn.bal; total.bun += cn.bun; total.bmu += cn.bmu;
@@ -548,21 +555,27 @@ int main(int argc, char **argv) {
     else {
         if (O.verbose >= 1 || pe) fprintf(stderr, "\tOutput file: %s\t (format: SAM%s)\n", O.o.c_str(), O.out_sam == 2 ? ", automatically convert to BAM" : "");
         FILE *probe = fopen(O.o.c_str(), "wb"); if (!probe) { fprintf(stderr, "\nfailed to open output file (check -o option): %s\n", O.o.c_str()); exit(1); } fclose(probe);
-        if (O.out_sam == 2) { std::string cmd = "samtools view -bS - >" + O.o; P.out = popen(cmd.c_str(), "w"); piped = P.out != nullptr; }   // main.cpp:505
+        if (O.out_sam == 2 && getenv("BASAL_SAMTOOLS")) { std::string cmd = "samtools view -bS - >" + O.o; P.out = popen(cmd.c_str(), "w"); piped = P.out != nullptr; }   // main.cpp:505
         if (!P.out) P.out = fopen(O.o.c_str(), "wb");
+        if (O.out_sam == 2 && !piped) { P.bam_native = true; for (size_t i = 0; i < R.names.size(); i++) P.refs.add(R.names[i], R.len[i]); }
     }
     static char obuf[8 << 20]; setvbuf(P.out, obuf, _IOFBF, sizeof obuf);
-    if (O.header) {                                                                                      // main.cpp:516-526
-        std::string h = "@HD\tVN:1.0\n";
-        for (size_t i = 0; i < R.names.size(); i++) { h += "@SQ\tSN:" + R.names[i] + "\tLN:"; append_u(h, R.len[i]); h.push_back('\n'); }
-        h += std::string("@PG\tID:BASAL\tVN:") + kVersion + "\tCL:\"" + O.cmdline + "\"\n";
-        fwrite(h.data(), 1, h.size(), P.out);
+    {
+        std::string h;
+        if (O.header) {                                                                                  // main.cpp:516-526
+            h = "@HD\tVN:1.0\n";
+            for (size_t i = 0; i < R.names.size(); i++) { h += "@SQ\tSN:" + R.names[i] + "\tLN:"; append_u(h, R.len[i]); h.push_back('\n'); }
+            h += std::string("@PG\tID:BASAL\tVN:") + kVersion + "\tCL:\"" + O.cmdline + "\"\n";
+        }
+        if (P.bam_native) { const std::string raw = bam::header_bytes(h, P.refs); std::string blk; bam::bgzf_append(raw.data(), raw.size(), blk); fwrite(blk.data(), 1, blk.size(), P.out); }
+        else if (!h.empty()) fwrite(h.data(), 1, h.size(), P.out);
     }
     {
         int nw = std::max<int>(O.procs, (int)P.ctx.size() * 2);
         std::vector<std::thread> th; for (int w = 0; w < nw; w++) th.emplace_back([&, w]() { P.worker(w); });
         for (auto &t : th) t.join();
     }
+    if (P.bam_native) { std::string e; bam::bgzf_eof(e); fwrite(e.data(), 1, e.size(), P.out); }
     if (piped) pclose(P.out); else if (P.out != stdout) fclose(P.out); else fflush(stdout);
     for (bsl_ctx *c : P.ctx) bsl_ctx_destroy(c);
     if (P.failed) return 2;

@@ -90,6 +90,25 @@ def test_cli_fasta_reads_and_stdout(data, tmp_path):
     assert got == want
 
 
+def test_cli_bam_output(data):
+    """`-o x.bam` is written natively (bam_writer.hpp): decoded, it holds the header and records of the SAM run."""
+    from test_bam_writer import decode_bam
+    cfg, d, paths = data[2]
+    args = _inputs(cfg, paths) + ["-S", "7", "-u", "-R"]
+    sam = helpers.run_cli(helpers.GPU_BIN, args, d, "bam_cmp.sam")            # without the @PG line
+    import subprocess
+    subprocess.run([helpers.GPU_BIN] + args + ["-o", "bam_cmp.bam"], cwd=d, check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    text, refs, recs = decode_bam(os.path.join(d, "bam_cmp.bam"))
+    hdr = [l for l in sam.splitlines() if l.startswith("@")]
+    body = [l for l in sam.splitlines() if l and not l.startswith("@")]
+    assert [l for l in text.splitlines() if not l.startswith("@PG")] == hdr
+    assert len(recs) == len(body) > 1000
+    for r, l in zip(recs, body):
+        f = l.split("\t")
+        assert [r["name"], r["flag"], r["rname"], r["pos"], r["mapq"], r["cigar"], r["pnext"], r["tlen"], r["seq"], r["qual"], r["tags"]] == \
+               [f[0], int(f[1]), f[2], int(f[3]), int(f[4]), f[5], int(f[7]), int(f[8]), f[9].upper(), f[10], f[11:]], l
+
+
 def test_cli_error_contract(data):
     import subprocess
     cfg, d, paths = data[1]
