@@ -180,6 +180,18 @@ struct GzReader {      // zlib reads plain and gzip files alike (the reference s
     void close() { if (f) gzclose(f); f = nullptr; }
     bool fill() { if (eof) return false; if (pos < len) { memmove(buf.data(), buf.data() + pos, len - pos); } len -= pos; pos = 0;
         int n = gzread(f, buf.data() + len, (unsigned)(buf.size() - len)); if (n <= 0) { eof = true; return len > 0; } len += (size_t)n; return true; }
+    // exactly n bytes (binary input); false when the stream ends first. dst may be null to skip
+    bool bytes(void *dst, size_t n) {
+        char *d = (char *)dst;
+        while (n) {
+            if (pos == len && !fill()) return false;
+            if (pos == len) return false;
+            const size_t k = std::min(n, len - pos);
+            if (d) { memcpy(d, buf.data() + pos, k); d += k; }
+            pos += k; n -= k;
+        }
+        return true;
+    }
     // next line without the terminator; false at EOF
     bool line(const char *&s, size_t &n) {
         for (;;) {
@@ -216,15 +228,49 @@ static bool load_reference(const std::string &path, Reference &R) {
 struct ReadRec { std::string name, seq, qual; u32 raw_len = 0; };
 
 struct ReadFile {
-    GzReader in; int format = -1;   // 0 fasta, 1 fastq
+    GzReader in; int format = -1;   // 0 fasta, 1 fastq, 3 bam (unaligned reads in a BAM file, reads.cpp:85-108)
+    int mate = 0;                   // BAM input of a paired run: both -a and -b name the same interleaved file; file #1 takes
+                                    // records 0, 2, 4, ... and file #2 records 1, 3, 5, ... (reads.cpp:88,107)
+    std::vector<char> rec;
     bool open(const std::string &p) {
         if (!in.open(p)) return false;
-        in.fill(); size_t i = 0; while (i < in.len && isspace((unsigned char)in.buf[i])) i++;
+        in.fill(); size_t i = 0;
+        if (in.len >= 4 && memcmp(in.buf.data(), "BAM\1", 4) == 0) {                 // zlib has already undone the BGZF layer
+            format = -1; int32_t l_text = 0, n_ref = 0;
+            if (!in.bytes(nullptr, 4) || !in.bytes(&l_text, 4) || l_text < 0 || !in.bytes(nullptr, (size_t)l_text) || !in.bytes(&n_ref, 4) || n_ref < 0) return true;
+            for (int32_t k = 0; k < n_ref; k++) { int32_t l_name = 0; if (!in.bytes(&l_name, 4) || l_name < 0 || !in.bytes(nullptr, (size_t)l_name + 4)) return true; }
+            format = 3; return true;
+        }
+        while (i < in.len && isspace((unsigned char)in.buf[i])) i++;
         if (i < in.len && in.buf[i] == '>') format = 0; else if (i < in.len && in.buf[i] == '@') format = 1; else format = -1;
+        return true;
+    }
+    const char *format_name() const { return format == 3 ? "BAM" : format == 1 ? "FASTQ" : "FASTA"; }
+    bool bam_record(ReadRec *r, const Options &O) {                                   // one alignment record; r == null skips it
+        int32_t bs = 0; if (!in.bytes(&bs, 4) || bs < 32) return false;
+        rec.resize((size_t)bs); if (!in.bytes(rec.data(), (size_t)bs)) return false;
+        if (!r) return true;
+        const unsigned char *b = (const unsigned char *)rec.data();
+        const u32 l_name = b[8], n_cig = (u32)b[12] | ((u32)b[13] << 8); u32 l_seq; memcpy(&l_seq, b + 16, 4);
+        const size_t o_name = 32, o_seq = o_name + l_name + 4ull * n_cig, o_qual = o_seq + (l_seq + 1) / 2;
+        if (o_qual + l_seq > (size_t)bs || l_name == 0) return false;
+        r->name.assign((const char *)b + o_name, strnlen((const char *)b + o_name, l_name));
+        const u32 n = std::min<u32>(l_seq, (u32)O.max_readlen);                           // reads.cpp:93
+        r->seq.resize(n); r->qual.resize(n);
+        for (u32 i = 0; i < n; i++) {
+            r->seq[i] = "=ACMGRSVTWYHKDBN"[(b[o_seq + i / 2] >> ((i & 1) ? 0 : 4)) & 15];  // bam_nt16_rev_table (reads.cpp:103)
+            r->qual[i] = (char)(b[o_qual + i] + 33);
+        }
         return true;
     }
     // ReadClass::LoadBatchReads (reads.cpp:42-84), line oriented
     bool next(ReadRec &r, const Options &O) {
+        if (format == 3) {
+            if (mate == 2 && !bam_record(nullptr, O)) return false;
+            if (!bam_record(&r, O)) return false;
+            if (mate == 1 && !bam_record(nullptr, O)) return false;
+            return true;
+        }
         const char *s; size_t n;
         do { if (!in.line(s, n)) return false; } while (n == 0);
         size_t i = 1; while (i < n && isspace((unsigned char)s[i])) i++; size_t j = i; while (j < n && !isspace((unsigned char)s[j])) j++;
@@ -512,6 +558,23 @@ int main(int argc, char **argv) {
     if (R.names.empty()) { fprintf(stderr, "\t(format: unknown)\nreference must be in FASTA format.\n"); exit(1); }
     if (O.verbose >= 1) fprintf(stderr, " \t(format: FASTA)\n[BASAL @%s] %zu reference seqs loaded, total size %llu bp. %ld secs passed\n", now_str(), R.names.size(), (unsigned long long)R.total, secs_passed());
 
+    // ---- $BASAL_PARSE_ONLY: run the read loader alone (no GPU) and print what it parsed as FASTQ, mates interleaved:
+    //      the CPU test hook of the host loader (FASTA / FASTQ / gz / BAM input, -L)
+    if (getenv("BASAL_PARSE_ONLY")) {
+        ReadFile fa, fb; const bool pe2 = !O.b.empty();
+        if (!fa.open(O.a) || fa.format < 0 || (pe2 && (!fb.open(O.b) || fb.format != fa.format))) { fprintf(stderr, "\t(format: unknown)\nUnknown input format.\n"); return 1; }
+        if (pe2) { fa.mate = 1; fb.mate = 2; }
+        fprintf(stderr, "format: %s\n", fa.format_name());
+        ReadRec ra, rb; std::string o;
+        while (fa.next(ra, O)) {
+            o += "@" + ra.name + "\n" + ra.seq + "\n+\n" + ra.qual + "\n";
+            if (pe2) { if (!fb.next(rb, O)) break; o += "@" + rb.name + "\n" + rb.seq + "\n+\n" + rb.qual + "\n"; }
+            if (o.size() > (1u << 20)) { fwrite(o.data(), 1, o.size(), stdout); o.clear(); }
+        }
+        fwrite(o.data(), 1, o.size(), stdout);
+        return 0;
+    }
+
     // ---- GPUs: every visible device holds a replica of the index
     int ngpu = 1; { const char *e = getenv("BASAL_GPUS"); if (e) ngpu = std::max(1, atoi(e)); else { const char *v = getenv("BASAL_ALL_GPUS"); if (v && atoi(v)) ngpu = 64; } }
     Pipeline P(O, R, T);
@@ -542,12 +605,14 @@ int main(int argc, char **argv) {
     if (O.verbose >= 1) fprintf(stderr, "[BASAL @%s] %s alignment(%zu GPU(s), %d host threads),\n", now_str(), pe ? "Pair-end" : "Single-end", P.ctx.size(), std::max(O.procs, 1));
     check_input(O.a, pe ? "failed to open read file #1 (check -a option): " : "failed to open read file (check -a option): ");
     if (!P.fa.open(O.a) || P.fa.format < 0) { fprintf(stderr, "\t(format: unknown)\nUnknown input format.\n"); exit(1); }
-    if (O.verbose >= 1) fprintf(stderr, "\tInput read file%s: %s \t(format: %s)\n", pe ? " #1" : "", O.a.c_str(), P.fa.format ? "FASTQ" : "FASTA");
+    if (pe) P.fa.mate = 1;
+    if (O.verbose >= 1) fprintf(stderr, "\tInput read file%s: %s \t(format: %s)\n", pe ? " #1" : "", O.a.c_str(), P.fa.format_name());
     if (pe) {
         check_input(O.b, "failed to open read file #2 (check -b option): ");
         if (!P.fb.open(O.b) || P.fb.format < 0) { fprintf(stderr, "\t(format: unknown)\nUnknown input format.\n"); exit(1); }
         if (P.fb.format != P.fa.format) { fprintf(stderr, "Input read file #1 and #2 should be in same format.\n"); exit(1); }
-        if (O.verbose >= 1) fprintf(stderr, "\tInput read file #2: %s \t(format: %s)\n", O.b.c_str(), P.fb.format ? "FASTQ" : "FASTA");
+        P.fb.mate = 2;
+        if (O.verbose >= 1) fprintf(stderr, "\tInput read file #2: %s \t(format: %s)\n", O.b.c_str(), P.fb.format_name());
     }
     { ReadRec skip; for (u32 i = 1; i < O.read_start; i++) { P.fa.next(skip, O); if (pe) P.fb.next(skip, O); } }     // InitIndex (reads.cpp:13-40)
     bool piped = false;

@@ -47,3 +47,71 @@ def test_range_checks():
 def test_usage():
     r = run()
     assert r.returncode == 1 and b"Usage:" in r.stderr
+
+
+# ------------------------------------------------------------------ the read loader alone ($BASAL_PARSE_ONLY, no GPU)
+
+SAM2BAM = os.path.join(helpers.ROOT, "basal_b200", "bin", "sam2bam")
+FQ2UBAM = os.path.join(helpers.ROOT, "tools", "fq2ubam.py")
+
+
+def parsed(tmp, *args):
+    import sys
+    env = dict(os.environ, BASAL_PARSE_ONLY="1")
+    r = subprocess.run([helpers.GPU_BIN] + list(args) + ["-M", "C:T", "-S", "7"], capture_output=True, timeout=60, env=env, cwd=tmp)
+    assert r.returncode == 0, r.stderr.decode()
+    body = r.stdout.decode().split("\n")
+    start = next(i for i, l in enumerate(body) if l.startswith("@"))          # SetAlign's two lines come first on stdout
+    return "\n".join(body[start:]), r.stderr.decode()
+
+
+def make_ubam(tmp, out, *fqs):
+    import sys
+    sam = os.path.join(tmp, out + ".sam")
+    with open(sam, "w") as fh:
+        subprocess.check_call([sys.executable, FQ2UBAM] + list(fqs), stdout=fh)
+    subprocess.check_call([SAM2BAM, sam, os.path.join(tmp, out)])
+
+
+@pytest.mark.skipif(not os.path.exists(SAM2BAM), reason="sam2bam not built")
+def test_loader_reads_fastq_gz_fasta_and_bam_alike(tmp_path):
+    import gzip
+    import shutil
+    tmp = str(tmp_path)
+    g = os.path.join(helpers.GOLDEN, "ct_se")
+    shutil.copy(os.path.join(g, "ref.fa"), tmp); shutil.copy(os.path.join(g, "reads.fq"), tmp)
+    with open(os.path.join(tmp, "reads.fq"), "rb") as a, gzip.open(os.path.join(tmp, "reads.fq.gz"), "wb") as b:
+        b.write(a.read())
+    make_ubam(tmp, "reads.bam", os.path.join(tmp, "reads.fq"))
+    fq, e1 = parsed(tmp, "-a", "reads.fq", "-d", "ref.fa")
+    gz, e2 = parsed(tmp, "-a", "reads.fq.gz", "-d", "ref.fa")
+    bam, e3 = parsed(tmp, "-a", "reads.bam", "-d", "ref.fa")
+    assert "format: FASTQ" in e1 and "format: FASTQ" in e2 and "format: BAM" in e3
+    src = open(os.path.join(tmp, "reads.fq")).read().split("\n")
+    src = "\n".join(l.split()[0] if i % 4 == 0 and l else l for i, l in enumerate(src))      # the name is the first token (reads.cpp:56)
+    assert fq == src and fq == gz == bam
+    cut, _ = parsed(tmp, "-a", "reads.bam", "-d", "ref.fa", "-L", "60")          # -L truncates sequence and qualities (reads.cpp:93)
+    recs = cut.strip().split("\n")
+    assert all(len(recs[i + 1]) == 60 and len(recs[i + 3]) == 60 for i in range(0, len(recs), 4))
+    fa_path = os.path.join(tmp, "reads.fa")
+    with open(fa_path, "w") as fh:
+        lines = fq.strip().split("\n")
+        for i in range(0, len(lines), 4):
+            fh.write(">" + lines[i][1:] + "\n" + lines[i + 1] + "\n")
+    fa, e4 = parsed(tmp, "-a", "reads.fa", "-d", "ref.fa")
+    assert "format: FASTA" in e4
+    assert [l for i, l in enumerate(fa.strip().split("\n")) if i % 4 < 2] == [l for i, l in enumerate(fq.strip().split("\n")) if i % 4 < 2]
+
+
+@pytest.mark.skipif(not os.path.exists(SAM2BAM), reason="sam2bam not built")
+def test_loader_paired_bam_is_one_interleaved_file(tmp_path):
+    """reads.cpp:88,107: with BAM input both -a and -b name the same interleaved file; file #1 takes the even records."""
+    import shutil
+    tmp = str(tmp_path)
+    g = os.path.join(helpers.GOLDEN, "ag_pe")
+    for f in ("ref.fa", "reads_1.fq", "reads_2.fq"):
+        shutil.copy(os.path.join(g, f), tmp)
+    make_ubam(tmp, "pairs.bam", os.path.join(tmp, "reads_1.fq"), os.path.join(tmp, "reads_2.fq"))
+    fq, _ = parsed(tmp, "-a", "reads_1.fq", "-b", "reads_2.fq", "-d", "ref.fa")
+    bam, err = parsed(tmp, "-a", "pairs.bam", "-b", "pairs.bam", "-d", "ref.fa")
+    assert "format: BAM" in err and fq == bam and fq.count("\n") > 2000

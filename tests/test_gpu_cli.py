@@ -109,6 +109,28 @@ def test_cli_bam_output(data):
                [f[0], int(f[1]), f[2], int(f[3]), int(f[4]), f[5], int(f[7]), int(f[8]), f[9].upper(), f[10], f[11:]], l
 
 
+@pytest.mark.parametrize("case", ["ct_se", "ag_pe"])
+def test_cli_bam_read_input(case, tmp_path):
+    """Unaligned BAM as read input (reads.cpp:85-108; a paired run names the same interleaved file twice). The expected
+    SAM is the committed golden one: the reference binary gives the same output for BAM and FASTQ input (checked in the
+    build container with oracle/_ref/basal on BAM files written by sam2bam)."""
+    import json
+    import shutil
+    import subprocess
+    import sys
+    g = os.path.join(helpers.GOLDEN, case); tmp = str(tmp_path)
+    spec = json.load(open(os.path.join(helpers.GOLDEN, "cases.json")))[case]
+    shutil.copy(os.path.join(g, "ref.fa"), tmp)
+    fqs = [os.path.join(g, a) for a in spec["args"] if a.endswith(".fq")]
+    with open(os.path.join(tmp, "u.sam"), "w") as fh:
+        subprocess.check_call([sys.executable, os.path.join(helpers.ROOT, "tools", "fq2ubam.py")] + fqs, stdout=fh)
+    subprocess.check_call([os.path.join(helpers.ROOT, "basal_b200", "bin", "sam2bam"), os.path.join(tmp, "u.sam"), os.path.join(tmp, "reads.bam")])
+    args = ["reads.bam" if a.endswith(".fq") else a for a in spec["args"]]
+    got = helpers.run_cli(helpers.GPU_BIN, args, tmp, "out.sam")
+    want = "".join(l for l in open(os.path.join(g, "expected.sam")) if not l.startswith("@PG"))
+    assert got == want
+
+
 def test_cli_error_contract(data):
     import subprocess
     cfg, d, paths = data[1]
