@@ -565,13 +565,16 @@ int main(int argc, char **argv) {
         if (!fa.open(O.a) || fa.format < 0 || (pe2 && (!fb.open(O.b) || fb.format != fa.format))) { fprintf(stderr, "\t(format: unknown)\nUnknown input format.\n"); return 1; }
         if (pe2) { fa.mate = 1; fb.mate = 2; }
         fprintf(stderr, "format: %s\n", fa.format_name());
-        ReadRec ra, rb; std::string o;
+        const bool count_only = strcmp(getenv("BASAL_PARSE_ONLY"), "count") == 0;      // loader throughput without the printing
+        ReadRec ra, rb; std::string o; u64 n_rec = 0, n_base = 0;
         while (fa.next(ra, O)) {
-            o += "@" + ra.name + "\n" + ra.seq + "\n+\n" + ra.qual + "\n";
-            if (pe2) { if (!fb.next(rb, O)) break; o += "@" + rb.name + "\n" + rb.seq + "\n+\n" + rb.qual + "\n"; }
+            n_rec++; n_base += ra.seq.size();
+            if (!count_only) o += "@" + ra.name + "\n" + ra.seq + "\n+\n" + ra.qual + "\n";
+            if (pe2) { if (!fb.next(rb, O)) break; n_rec++; n_base += rb.seq.size(); if (!count_only) o += "@" + rb.name + "\n" + rb.seq + "\n+\n" + rb.qual + "\n"; }
             if (o.size() > (1u << 20)) { fwrite(o.data(), 1, o.size(), stdout); o.clear(); }
         }
         fwrite(o.data(), 1, o.size(), stdout);
+        fprintf(stderr, "parsed %llu reads, %llu bases\n", (unsigned long long)n_rec, (unsigned long long)n_base);
         return 0;
     }
 
