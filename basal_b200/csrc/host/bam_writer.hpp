@@ -67,14 +67,14 @@ inline std::string header_bytes(const std::string &sam_header_text, const Refs &
     return o;
 }
 
-// UCSC binning scheme, as bam_reg2bin (end exclusive)
+// UCSC binning scheme of the BAM index (SAM specification section 5.3): the smallest bin of the 5-level hierarchy
+// (16 kb, 128 kb, 1 Mb, 8 Mb, 64 Mb windows; 512 Mb root) that contains [beg, end). Arithmetic shifts on purpose: an
+// unmapped record (pos -1, no CIGAR) lands in bin 4680 like in every samtools-written file.
 inline int reg2bin(int32_t beg, int32_t end) {
-    --end;
-    if (beg >> 14 == end >> 14) return ((1 << 15) - 1) / 7 + (beg >> 14);
-    if (beg >> 17 == end >> 17) return ((1 << 12) - 1) / 7 + (beg >> 17);
-    if (beg >> 20 == end >> 20) return ((1 << 9) - 1) / 7 + (beg >> 20);
-    if (beg >> 23 == end >> 23) return ((1 << 6) - 1) / 7 + (beg >> 23);
-    if (beg >> 26 == end >> 26) return ((1 << 3) - 1) / 7 + (beg >> 26);
+    static const struct { int shift, first; } level[5] = {{14, 4681}, {17, 585}, {20, 73}, {23, 9}, {26, 1}};
+    const int32_t last = end - 1;
+    for (const auto &lv : level)
+        if ((beg >> lv.shift) == (last >> lv.shift)) return lv.first + (beg >> lv.shift);
     return 0;
 }
 
