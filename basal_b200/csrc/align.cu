@@ -2280,7 +2280,7 @@ int bsl_align_impl(bsl_ctx *ctx, const bsl_batch *a, const bsl_batch *b, bsl_hit
     CUDA_TRY(cudaSetDevice(ctx->device));
     // pick a lane
     Lane *lnp = nullptr; std::unique_lock<std::mutex> lk;
-    for (int t = 0; t < 2 && !lnp; t++) { std::unique_lock<std::mutex> l(ctx->lanes[t].mu, std::try_to_lock); if (l.owns_lock()) { lk = std::move(l); lnp = &ctx->lanes[t]; } }
+    for (int t = 0; t < BSL_NLANES && !lnp; t++) { std::unique_lock<std::mutex> l(ctx->lanes[t].mu, std::try_to_lock); if (l.owns_lock()) { lk = std::move(l); lnp = &ctx->lanes[t]; } }
     if (!lnp) { lk = std::unique_lock<std::mutex>(ctx->lanes[0].mu); lnp = &ctx->lanes[0]; }
     Lane &ln = *lnp;
     int rc = ensure_lane(ctx, ln); if (rc) return rc;

@@ -9,7 +9,8 @@
 #include "common.cuh"
 
 // One "lane" = a CUDA stream plus every device/pinned buffer one in-flight batch needs,
-// so that two host threads can overlap H2D / kernels / D2H on one GPU.
+// so that several host threads can overlap H2D / kernels / D2H on one GPU.
+#define BSL_NLANES 3
 struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};
@@ -43,7 +44,7 @@ struct bsl_ctx {
     std::vector<u32> anchor, seqlen, rcoff;
     bsl_index_info info;
     // lanes
-    Lane lanes[2];
+    Lane lanes[BSL_NLANES];
     bsl_stats stats;
     std::mutex stats_mu;
     char err[512];

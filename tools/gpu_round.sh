@@ -11,5 +11,5 @@ fi
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench exit $?"
 cat gpurun_out/bench_$TAG.json
 BENCH_SKIP_CPU=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 1 --warmup 1 > gpurun_out/ncu_launch_$TAG.log 2>&1; echo "ncu launches exit $?"
-BENCH_SKIP_CPU=1 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:verify_candidates -s 2 -c 3 -o gpurun_out/prof_verify_$TAG -f python bench.py --steps 1 --warmup 1 > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full exit $?"
+BENCH_SKIP_CPU=1 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:screen_bits -s 9 -c 3 -o gpurun_out/prof_verify_$TAG -f python bench.py --steps 1 --warmup 1 > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full exit $?"
 ls -la gpurun_out
