@@ -639,7 +639,7 @@ int main(int argc, char **argv) {
         else if (!h.empty()) fwrite(h.data(), 1, h.size(), P.out);
     }
     {
-        int nw = std::max<int>(O.procs, (int)P.ctx.size() * 2);
+        int nw = std::max<int>(O.procs, (int)P.ctx.size() * 3);                 // three lanes per GPU context
         std::vector<std::thread> th; for (int w = 0; w < nw; w++) th.emplace_back([&, w]() { P.worker(w); });
         for (auto &t : th) t.join();
     }
