@@ -145,7 +145,18 @@ CASES = [
     ("acgt_se", "A:CGT", False, 100, 400, 0.05, False, ["-S", "7", "-w", "100", "-u"]),
     ("tdel_se", "T:-", False, 100, 400, 0.0, True, ["-S", "7", "-g", "3", "-u", "-R"]),
     ("gmulti_se", "G:ACT-", False, 100, 300, 0.05, True, ["-S", "9", "-g", "2", "-r", "0", "-u", "-n", "1"]),
+    # seed geometry extremes (SURVEY §8c vi); read lengths keep (L - I + 1) % s != 0 (trap 3)
+    ("ct_se_i1_s10", "C:T", False, 63, 300, 0.9, False, ["-S", "7", "-s", "10", "-I", "1", "-u"]),
+    ("ct_se_i16", "C:T", False, 100, 300, 0.9, False, ["-S", "7", "-I", "16", "-u"]),
+    ("ct_se_k", "C:T", False, 100, 300, 0.9, False, ["-S", "12345", "-k", "0.5", "-u"]),
+    # strands and filters on pairs (SURVEY §8c iv, vii)
+    ("ag_pe_n2", "A:G", True, 100, 300, 0.9, False, ["-S", "13", "-n", "2", "-u"]),
+    ("ag_pe_f0", "A:G", True, 100, 300, 0.9, False, ["-S", "7", "-f", "0", "-u"]),
+    # KNOWN GAP (cases.json "known_gap"): with -r 2 the reference lists EVERY hit of an unpaired multi-hit mate
+    # (pairs.cpp:232-305); the oracle and the CUDA path report the -S pick only. Pairs under -r 2 are listed in full.
+    ("ag_pe_r2", "A:G", True, 100, 300, 0.9, False, ["-S", "7", "-f", "0", "-u", "-r", "2"]),
 ]
+KNOWN_GAPS = {"ag_pe_r2"}
 
 
 def main():
@@ -173,6 +184,8 @@ def main():
                     out.write(line)
         os.unlink(os.path.join(d, "out.sam"))
         meta[name] = {"args": full, "paired": paired}
+        if name in KNOWN_GAPS:
+            meta[name]["known_gap"] = True
         print(name, sum(1 for _ in open(os.path.join(d, "expected.sam"))), "lines")
     with open(os.path.join(HERE, "cases.json"), "w") as fh:
         json.dump(meta, fh, indent=1, sort_keys=True)
