@@ -109,6 +109,27 @@ def test_cli_bam_output(data):
                [f[0], int(f[1]), f[2], int(f[3]), int(f[4]), f[5], int(f[7]), int(f[8]), f[9].upper(), f[10], f[11:]], l
 
 
+def _golden_cases():
+    import json
+    spec = json.load(open(os.path.join(helpers.GOLDEN, "cases.json")))
+    return [n for n in sorted(spec) if not spec[n].get("known_gap")]
+
+
+@pytest.mark.parametrize("case", _golden_cases())
+def test_cli_matches_golden(case, tmp_path):
+    """The CUDA `basal` on the committed golden inputs: SAM identical to what the reference binary printed
+    (tests/golden/make_golden.py), including the seed-geometry extremes (-s 10 -I 1, -I 16, -k 0.5)."""
+    import json
+    import shutil
+    g = os.path.join(helpers.GOLDEN, case); tmp = str(tmp_path)
+    spec = json.load(open(os.path.join(helpers.GOLDEN, "cases.json")))[case]
+    for f in os.listdir(g):
+        if f != "expected.sam":
+            shutil.copy(os.path.join(g, f), tmp)
+    got = helpers.run_cli(helpers.GPU_BIN, spec["args"], tmp, "out.sam")
+    assert got == open(os.path.join(g, "expected.sam")).read()
+
+
 @pytest.mark.parametrize("case", ["ct_se", "ag_pe"])
 def test_cli_bam_read_input(case, tmp_path):
     """Unaligned BAM as read input (reads.cpp:85-108; a paired run names the same interleaved file twice). The expected
