@@ -86,255 +86,80 @@ __device__ __forceinline__ u64 stream_extract(const u64 *pl, u32 p) {    // plan
     return x;
 }
 
-// spread bit k of x to bit 2k
-__device__ __forceinline__ u64 spread32(u32 v) {
-    u64 x = v;
-    x = (x | (x << 16)) & 0x0000FFFF0000FFFFULL;
-    x = (x | (x << 8)) & 0x00FF00FF00FF00FFULL;
-    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0FULL;
-    x = (x | (x << 2)) & 0x3333333333333333ULL;
-    x = (x | (x << 1)) & 0x5555555555555555ULL;
-    return x;
-}
-// ballot masks (bit l = base 32w+l) of the high and low code bits -> packed word (base k at bits 63-2k, 62-2k)
-__device__ __forceinline__ u64 weave(u32 hi, u32 lo) { return (spread32(__brev(hi)) << 1) | spread32(__brev(lo)); }
+// ------------------------------------------------------------------------------------------------
+// L2 cache-hint policies (createpolicy): `keep` for the tables every SM gathers from again and again (the one-byte
+// bucket-size table, the one-bit screening plane), `stream` for data that passes through once.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ u64 l2_policy_keep() { u64 p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ u64 l2_policy_stream() { u64 p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ u32 ldg_u8_hint(const u8 *p, u64 pol) { u32 v; asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v; }
+__device__ __forceinline__ uint2 ldg_v2_hint(const void *p, u64 pol) { uint2 v; asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol)); return v; }
 
 // ------------------------------------------------------------------------------------------------
-// prepare_reads
+// prepare_reads : FilterReads (align.cpp:548-563), read planes (ConvertBinaySeq / ConvertBinarySeq, align.cpp:79-226)
+// and the seed schedule (ReorderSeed / AdjustSeedStartArray / CountSeeds, align.cpp:468-546). A warp takes 32 reads:
+//   A.  (lane per 32-base plane word of any of the 32 reads) five aligned 8-byte loads cover the 32 ASCII bases of the
+//       word; four bases at a time are turned into 2-bit codes / ACGT flags / convert-to codes in registers (one PRMT
+//       looks up the expected letter, one the code) and packed with a multiply; the words go to global memory (2-bit
+//       streams, 1-bit streams) and to the warp's shared slice;
+//   A2. (same lanes) the 1-bit streams of the read taken backwards are bit-reversed funnel shifts of the forward ones;
+//   B.  (lane per read) per seed segment j: seed hashes and bucket sizes of the read offsets j*s .. j*s + I + ii - 1 (every
+//       offset prof[j][i] + v - i the schedule can touch), eight gathers from the one-byte size table in flight, then
+//       CountSeeds(j, v) for every start v <= ii from those sizes;
+//   C.  (lane per read) ReorderSeed / AdjustSeedStartArray / the (count, segment) sort, literally, as look-ups in the
+//       CountSeeds table of step B.
+// Shared memory per lane: 2 WQ + 2 Wb + wd + nseg (ii + 1) words, odd stride so that per-lane rows sit in different banks.
 // ------------------------------------------------------------------------------------------------
-#define PREP_WARPS 8
-struct PrepSmem {
-    u32 bal[5][16];       // raw ballots per 32 bases: code hi, code lo, regular, conv hi, conv lo
-    u32 sq[36], sn[36];   // logical 32-bit words (16 bases each, first base in the top bits) of the bases / 01-per-ACGT planes, zero padded
-    u32 cntp[480];        // bucket size of the seed at read offset p (only offsets the schedule can touch)
-    u8  nflg[480];        // that seed contains a non-ACGT base
-    int cs[16][16];       // CountSeeds(segment, start)
-    u32 need[16];         // bitmap of the offsets the schedule can touch; depends on (L, nseg) only -> cached per warp
-    u16 plist[480];       // the same offsets as a list
-    u32 need_key, n_need;
-    u8  sbytes[16];
-};
+#define PR_WARPS 4
+#define BASES_PAD 64        // bytes in front of and behind the batch's bases in device memory: load32 may touch up to 39 bytes either side
 
-// 16 ballot bits (bit k = base k) -> 32-bit word with base k at bit 30-2k (the low bit of its 2-bit digit)
-__device__ __forceinline__ u32 spread16_rev(u32 b16) {
-    u32 x = __brev(b16) >> 16;
-    x = (x | (x << 8)) & 0x00FF00FFu; x = (x | (x << 4)) & 0x0F0F0F0Fu; x = (x | (x << 2)) & 0x33333333u; x = (x | (x << 1)) & 0x55555555u;
-    return x;
+struct Conv4 { u32 cq, cc, r1; };      // per byte: 2-bit code, convert-to code, 0x01 for an ACGT letter
+// four ASCII bases (byte k = base k); valid01 has 0x01 in the bytes that belong to the read
+__device__ __forceinline__ Conv4 conv4(u32 w, u32 valid01, u32 tqb, u32 tcb) {
+    const u32 v = (w >> 1) & 0x03030303u;                                              // (ascii >> 1) & 3: A 0, C 1, T 2, G 3 in either case
+    const u32 t = (v | (v >> 4)) & 0x00330033u, sel = (t | (t >> 8)) & 0xFFFFu;         // one PRMT selector nibble per byte
+    const u32 y = (w & 0xDFDFDFDFu) ^ __byte_perm(0x47544341u, 0u, sel);               // zero byte <=> the letter is the A / C / T / G its bits select
+    const u32 z = ~(((y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | y) & 0x80808080u;
+    Conv4 o; o.r1 = (z >> 7) & valid01;
+    const u32 m3 = o.r1 * 3u;
+    o.cq = __byte_perm(tqb, 0u, sel) & m3; o.cc = __byte_perm(tcb, 0u, sel) & m3;
+    return o;
 }
+__device__ __forceinline__ u32 pack4x2(u32 x) { return (x * 0x40100401u) >> 24; }      // bytes b0..b3 (2 bits each) -> b0 b1 b2 b3, first base in the top bits
+__device__ __forceinline__ u32 pack4x1(u32 x) { return (x * 0x08040201u) >> 24; }      // bytes b0..b3 (1 bit each) -> 4 bits, first base in the top bit
+// 2-bit table indexed by (ascii >> 1) & 3 -> the same table with one byte per entry
+__device__ __forceinline__ u32 tab_bytes(u32 t2) { return (t2 & 3u) | ((t2 & 12u) << 6) | ((t2 & 48u) << 12) | ((t2 & 192u) << 18); }
 
-__global__ void __launch_bounds__(PREP_WARPS * 32) prepare_reads(const __grid_constant__ KArgs A) {
-    __shared__ PrepSmem sm_all[PREP_WARPS];
-    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    PrepSmem &sm = sm_all[wid];
-    const DevTables *T = A.tab;
-    const u32 tabq0 = T->tab_code[0], tabq1 = T->tab_code[1], tabc0 = T->tab_conv[0], tabc1 = T->tab_conv[1];
-    if (lane == 0) sm.need_key = 0xffffffffu;
-    const u32 W2 = 2 * A.Wb;
-    for (u32 slot = blockIdx.x * PREP_WARPS + wid; slot < A.n_slots; slot += gridDim.x * PREP_WARPS) {
-        const bool mate_b = A.pe && slot >= A.n_a;
-        const u32 r = mate_b ? slot - A.n_a : slot;
-        const u64 *off = mate_b ? A.off + (A.n_a + 1) : A.off;
-        const u64 ob = mate_b ? A.off_base_b : A.off_base_a;
-        const u64 b0 = off[r] - ob + (mate_b ? A.bases_b_shift : 0), b1 = off[r + 1] - ob + (mate_b ? A.bases_b_shift : 0);
-        const u32 Lraw = (u32)(b1 - b0);
-        const u32 L = Lraw > BSL_MAX_READLEN ? BSL_MAX_READLEN : Lraw;
-        const u32 readset = mate_b ? A.readset_b : A.readset_a;
-        const u32 index = A.has_index ? A.index[slot] : (mate_b ? A.first_index_b : A.first_index_a) + r;
-        const u32 W = (L + 31) >> 5;
-        u32 flags = 0;
-        if ((A.chains == 1) || ((A.chains <= 1) == (readset < 2))) flags |= SF_CHAIN0;                       // align.cpp:83-84
-        if ((A.chains == 1) || ((A.chains <= 1) == (readset == 2))) flags |= SF_CHAIN1;
-        // zero the per-level counters, stats
-        ((u16 *)&A.cnt[slot])[lane] = 0;
-        if (lane == 0) { A.stat[slot] = make_uint2(0u, 0u); A.minlvl[slot] = 255; }
-        u32 B = 0, nseg = 0; bool filtered = false; u32 ns_known = 0xffffffffu;
-        const u32 ii = (L + 1 >= A.I) ? (L + 1 - A.I) % A.s : 0;
-        for (u32 c = 0; c < 2 && !filtered; c++) {
-            if (!(flags & (c ? SF_CHAIN1 : SF_CHAIN0))) continue;
-            __syncwarp();
-            // ---- planes (ConvertBinaySeq / ConvertBinarySeq, align.cpp:79-226) by ballot transpose
-            const u32 tq = c ? tabq1 : tabq0, tc = c ? tabc1 : tabc0;
-            u32 ns = 0;
-            for (u32 wv = 0; wv < W; wv++) {
-                const u32 p = wv * 32 + lane;
-                u32 cq = 0, cc = 0; bool reg = false;
-                if (p < L) {
-                    const u8 ch = A.bases[b0 + (c ? L - 1 - p : p)];
-                    const u8 up = ch & 0xDFu;
-                    reg = (up == 'A') | (up == 'C') | (up == 'G') | (up == 'T');
-                    const u32 ix = (ch >> 1) & 3u;
-                    if (reg) { cq = (tq >> (2 * ix)) & 3u; cc = (tc >> (2 * ix)) & 3u; }
-                }
-                const u32 bh = __ballot_sync(0xffffffffu, cq & 2u), bl = __ballot_sync(0xffffffffu, cq & 1u), br = __ballot_sync(0xffffffffu, reg);
-                const u32 ch_ = __ballot_sync(0xffffffffu, cc & 2u), cl_ = __ballot_sync(0xffffffffu, cc & 1u);
-                const u32 inr = (L - wv * 32 >= 32) ? 0xffffffffu : ((1u << (L - wv * 32)) - 1u);
-                ns += __popc(~br & inr);
-                if (lane == 0) { sm.bal[0][wv] = bh; sm.bal[1][wv] = bl; sm.bal[2][wv] = br; sm.bal[3][wv] = ch_; sm.bal[4][wv] = cl_; }
-            }
-            if (ns_known == 0xffffffffu) {
-                ns_known = ns;
-                filtered = (L == 0) || (L < A.min_read_size) || (ns > A.max_ns) || (Lraw > BSL_MAX_READLEN);   // align.cpp:559-560
-                if (!filtered) {
-                    u32 raw = A.has_rawlen ? A.rawlen[slot] : L; if (raw == 0 || raw > BSL_MAX_READLEN) raw = L ? L : 1;
-                    B = (T->budget0[raw] + 1) * (L - 1) / raw;                                                    // align.cpp:561
-                    const u32 span = L + 1 - A.I;                                                                 // L >= I is implied by min_read_size
-                    nseg = (L + 1 >= A.I + A.s) ? min(span / A.s, B + 1) : 0;                                     // align.cpp:450
-                }
-            }
-            if (filtered) break;
-            __syncwarp();
-            // ---- weave the ballots into logical 32-bit words: global streams (see KArgs::planes) + shared copies for hashing
-            {
-                u32 *dst = (u32 *)(A.planes + ((u64)slot * 2 + c) * 3 * A.Wb);
-                for (u32 x = lane; x < 3 * W2; x += 32) {
-                    const u32 pl = x / W2, j = x - pl * W2;
-                    u32 v = 0;
-                    if (j < 2 * W) {
-                        const u32 sh16 = (j & 1u) * 16u, wv = j >> 1;
-                        if (pl == 0) v = (spread16_rev((sm.bal[0][wv] >> sh16) & 0xffffu) << 1) | spread16_rev((sm.bal[1][wv] >> sh16) & 0xffffu);
-                        else if (pl == 1) v = spread16_rev((sm.bal[2][wv] >> sh16) & 0xffffu);
-                        else v = (spread16_rev((sm.bal[3][wv] >> sh16) & 0xffffu) << 1) | spread16_rev((sm.bal[4][wv] >> sh16) & 0xffffu);
-                    }
-                    dst[x] = v;
-                    if (pl == 0) sm.sq[j] = v; else if (pl == 1) sm.sn[j] = v;
-                }
-                if (lane < 4) { sm.sq[W2 + lane] = 0; sm.sn[W2 + lane] = 0; }
-                // 1-bit streams for screen_bits (first base in the top bit): low code bits, ACGT mask, and both for the reversed read
-                u32 *b1 = A.bits1 + ((u64)slot * 2 + c) * 2 * W2;
-                if (lane < W2) {
-                    const u32 pl = lane < A.Wb ? 1 : 2, wv = lane < A.Wb ? lane : lane - A.Wb;
-                    b1[lane] = wv < W ? __brev(sm.bal[pl][wv]) : 0u;
-                    // reversed word wv holds bases L-1-32wv down to L-32-32wv = bits [off, off+32) of the ballot array
-                    const int off = (int)L - 32 - 32 * (int)wv; u32 rv = 0;
-                    if (off > -32) {
-                        const int w0 = off >> 5; const u32 sf = (u32)off & 31u;
-                        const u32 lo_ = w0 >= 0 ? sm.bal[pl][w0] : 0u, hi_ = (w0 + 1 < (int)W) ? sm.bal[pl][w0 + 1] : 0u;
-                        rv = __funnelshift_r(lo_, hi_, sf);
-                    }
-                    b1[W2 + lane] = rv;
-                }
-            }
-            __syncwarp();
-            if (nseg == 0) continue;
-            const u32 nv = ii + 1;
-            // ---- which offsets can the schedule touch: prof[j][i] + v - i for j < nseg, i < I, v <= ii. Cached per warp.
-            const u32 key = L | (nseg << 16);
-            if (sm.need_key != key) {
-                __syncwarp();
-                if (lane < 16) sm.need[lane] = 0;
-                __syncwarp();
-                const u32 tot = nseg * A.I * nv;
-                for (u32 t = lane; t < tot; t += 32) {
-                    const u32 v = t % nv, i = (t / nv) % A.I, j = t / (nv * A.I);
-                    const u32 p = T->prof[j][i] + v - i;
-                    atomicOr(&sm.need[p >> 5], 1u << (p & 31));
-                }
-                __syncwarp();
-                u32 base = 0;
-                for (u32 w = 0; w < 15; w++) {                           // list the set bits in increasing order
-                    const u32 bits = sm.need[w];
-                    if ((bits >> lane) & 1u) sm.plist[base + __popc(bits & ((1u << lane) - 1u))] = (u16)(32 * w + lane);
-                    base += __popc(bits);
-                }
-                if (lane == 0) { sm.n_need = base; sm.need_key = key; }
-                __syncwarp();
-            }
-            // ---- seed hash (xseed_array), N flag (xseedreg_array) and bucket size of every listed offset
-            const u32 n_need = sm.n_need;
-            const u32 full = (A.s == 16) ? 0x55555555u : (0x55555555u >> (32 - 2 * A.s)), shs = 32 - 2 * A.s;
-            for (u32 x = lane; x < n_need; x += 32) {
-                const u32 p = sm.plist[x], w = p >> 4, o = (p & 15u) * 2;
-                const u32 xq = __funnelshift_l(sm.sq[w + 1], sm.sq[w], o) >> shs, xn = __funnelshift_l(sm.sn[w + 1], sm.sn[w], o) >> shs;
-                const u32 k = bsl_xt(xq); const u32 c16 = A.di.cnt16[k];
-                sm.cntp[p] = (c16 == 0xFFFFu) ? A.di.bucket[2 * k + 2] - A.di.bucket[2 * k] : c16;
-                sm.nflg[p] = xn != full;
-            }
-            __syncwarp();
-            // ---- CountSeeds(j, v) (align.cpp:526-540): lanes 0-15 / 16-31 take two segments per trip
-            for (u32 j0 = 0; j0 < nseg; j0 += 2) {
-                const u32 j = j0 + (lane >> 4), v = lane & 15u;
-                if (j < nseg && v < nv) {
-                    u32 total = 0, k = 0;
-                    for (u32 i = 0; i < A.I; i++) {
-                        const u32 p = T->prof[j][i] + v - i;
-                        if (sm.nflg[p]) k = 12;
-                        total += sm.cntp[p] << k;
-                    }
-                    if (total == 0) total = 9999999;
-                    sm.cs[j][v] = (int)total;
-                }
-            }
-            __syncwarp();
-            // ---- ReorderSeed (align.cpp:468-498): global start = first minimum of the column sums
-            u32 st0 = 0;
-            {
-                u32 colsum = 0xffffffffu;
-                if (lane < ii) { colsum = 0; for (u32 j = 0; j < nseg; j++) colsum += (u32)sm.cs[j][lane]; }
-                const u32 mn = __reduce_min_sync(0xffffffffu, colsum);
-                const u32 who = __ballot_sync(0xffffffffu, colsum == mn);
-                st0 = (ii && mn != 0xffffffffu) ? (u32)__ffs(who) - 1u : 0u;          // every sum 2^32-1: `<` never fires, start stays 0
-            }
-            // ---- AdjustSeedStartArray (align.cpp:500-524): the nseg steps are sequential, the argmin of each step is
-            //      spread over the lanes (lane v holds candidate start v; first minimum wins like the reference's `<`)
-            u32 my_st = st0;                                   // lane j < nseg holds start[j]
-            for (u32 t = 0; t < nseg; t++) {
-                const u32 ptr = (t & 1) ? nseg - 1 - t / 2 : t / 2;
-                const u32 lo = ptr == 0 ? 0 : __shfl_sync(0xffffffffu, my_st, ptr - 1);
-                const u32 hi = ptr == nseg - 1 ? ii : __shfl_sync(0xffffffffu, my_st, (ptr + 1) & 31u);
-                u32 val = 0xffffffffu;
-                if (lane >= lo && lane <= hi && lane < 16) val = (u32)sm.cs[ptr][lane];
-                const u32 mn = __reduce_min_sync(0xffffffffu, val);
-                const u32 who = __ballot_sync(0xffffffffu, val == mn && lane >= lo && lane <= hi);
-                // every value 2^32-1 (or an empty range lo > hi): `tt < b` never fires and start stays at lo
-                const u32 pick = (mn == 0xffffffffu || who == 0) ? lo : (u32)__ffs(who) - 1u;
-                if (lane == ptr) my_st = pick;
-            }
-            // ---- rank segments by (count as int, segment): keys are unique, so the rank is a count of smaller keys
-            {
-                const int kx = lane < nseg ? sm.cs[lane][my_st & 15u] : 0;
-                u32 rank = 0;
-                for (u32 y = 0; y < nseg; y++) { const int ky = __shfl_sync(0xffffffffu, kx, y); rank += (ky < kx || (ky == kx && y < lane)) ? 1u : 0u; }
-                if (lane < 16) sm.sbytes[lane] = 0;
-                __syncwarp();
-                if (lane < nseg) sm.sbytes[rank] = (u8)(lane | (my_st << 4));      // sched byte t = segment of rank t | its start << 4
-                __syncwarp();
-                if (lane < 4) ((u32 *)(A.sched + ((u64)slot * 2 + c) * 16))[lane] = ((const u32 *)sm.sbytes)[lane];
-            }
-            __syncwarp();
-        }
-        if (filtered) flags |= SF_FILTERED;
-        if (lane == 0) {
-            SlotMeta m; m.rnd = bsl_rand(index, A.randseed); m.len = (u16)L; m.B = (u8)B; m.nseg = (u8)nseg; m.flags = (u8)flags; m.thr = (u8)B; m.nhit = 0; m.item = slot;
-            A.meta[slot] = m;
-        }
-    }
+// 32 bytes starting at p (any alignment) as eight little-endian words; touches [p & ~7, (p & ~7) + 40)
+__device__ __forceinline__ void load32(const u8 *p, u32 (&w)[8]) {
+    const u64 a = (u64)p; const uint2 *q = (const uint2 *)(a & ~7ull);
+    const uint2 x0 = __ldcs(q), x1 = __ldcs(q + 1), x2 = __ldcs(q + 2), x3 = __ldcs(q + 3), x4 = __ldcs(q + 4);
+    const u32 x[10] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y, x4.x, x4.y};
+    const bool odd = (a >> 2) & 1u; const u32 sh = ((u32)a & 3u) * 8u;
+    u32 y[9];
+#pragma unroll
+    for (int j = 0; j < 9; j++) y[j] = odd ? x[j + 1] : x[j];
+#pragma unroll
+    for (int j = 0; j < 8; j++) w[j] = __funnelshift_r(y[j], y[j + 1], sh);
 }
 
-// ------------------------------------------------------------------------------------------------
-// prepare_reads2 : the same outputs as prepare_reads, organised for issue-slot efficiency. A warp takes 32 reads:
-//   A. (lane per 64-bit plane word of any of the 32 reads) bases -> 2-bit code / ACGT / convert-to words and the 1-bit
-//      streams of both orientations, written to global memory and (codes, ACGT words) to the warp's shared slice;
-//   B. (lane per read) seed hashes and bucket sizes of every read offset the schedule can touch: segment j, offsets
-//      j*s .. j*s + I + ii - 1 (prof[j][i] + v - i lies in that range for every phase i and start v <= ii);
-//   C. (lane per read) ReorderSeed / AdjustSeedStartArray / the (count, segment) sort, literally (align.cpp:468-546),
-//      every CountSeeds evaluated on demand from the table of step B.
-// Shared memory per warp: 32 x (2 WQ + cap) words; odd strides keep the per-lane rows in different banks.
-// ------------------------------------------------------------------------------------------------
-#define P2_WARPS 4
-__global__ void __launch_bounds__(P2_WARPS * 32) prepare_reads2(const __grid_constant__ KArgs A, u32 WQ, u32 cap) {
+__global__ void __launch_bounds__(PR_WARPS * 32) prepare_reads(const __grid_constant__ KArgs A, u32 WQ, u32 WDM, u32 CSZ) {
     extern __shared__ u32 psm[];
     __shared__ u16 s_prof[16][16];
     const DevTables *T = A.tab;
     const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
     for (u32 x = threadIdx.x; x < 256; x += blockDim.x) s_prof[x >> 4][x & 15u] = T->prof[x >> 4][x & 15u];
     __syncthreads();
-    u32 *wsm = psm + (size_t)wid * 32 * (2 * WQ + cap);
-    u32 *sq_all = wsm, *sn_all = wsm + 32 * WQ, *cp_all = wsm + 64 * WQ;
-    u32 *sq = sq_all + lane * WQ, *sn = sn_all + lane * WQ, *cp = cp_all + lane * cap;
     const u32 Wb = A.Wb, W2 = 2 * Wb, I = A.I, s = A.s;
+    const u32 RS = (2 * WQ + 2 * Wb + WDM + CSZ) | 1u;                              // words per lane row
+    u32 *wsm = psm + (size_t)wid * 32 * RS;
+    u32 *row = wsm + lane * RS;
+    u32 *sq = row, *sn = row + WQ, *cw = row + 2 * WQ + 2 * Wb, *cs = cw + WDM;
     const u32 tabq[2] = {T->tab_code[0], T->tab_code[1]}, tabc[2] = {T->tab_conv[0], T->tab_conv[1]};
     const u32 shs = 32 - 2 * s, full = (s == 16) ? 0x55555555u : (0x55555555u >> shs);
-    for (u32 slot0 = (blockIdx.x * P2_WARPS + wid) * 32u; slot0 < A.n_slots; slot0 += gridDim.x * P2_WARPS * 32u) {
+    const u32 flipm = A.di.flip ? 0xffffffffu : 0u;
+    const u64 keep = l2_policy_keep();
+    for (u32 slot0 = (blockIdx.x * PR_WARPS + wid) * 32u; slot0 < A.n_slots; slot0 += gridDim.x * PR_WARPS * 32u) {
         const u32 slot = slot0 + lane;
         const bool valid = slot < A.n_slots;
         u64 b0 = 0; u32 Lraw = 0, readset = 0, index = 0;
@@ -363,12 +188,11 @@ __global__ void __launch_bounds__(P2_WARPS * 32) prepare_reads2(const __grid_con
         }
         u32 B = 0, nseg = 0; bool filtered = false, ns_known = false;
         const u32 ii = (L + 1 >= I) ? (L + 1 - I) % s : 0;
-        const u32 wd = I + ii;                                                       // offsets per segment the schedule can touch
         for (u32 c = 0; c < 2; c++) {
             const bool en = valid && (flags & (c ? SF_CHAIN1 : SF_CHAIN0)) && !filtered;
             if (!__any_sync(0xffffffffu, en)) continue;
             // ---- A: one plane word (32 bases) of one read per lane and trip
-            const u32 tq = tabq[c], tc = tabc[c];
+            const u32 tqb = tab_bytes(tabq[c]), tcb = tab_bytes(tabc[c]);
             for (u32 idx = lane; idx < 32 * Wb; idx += 32) {
                 const u32 rl = idx / Wb, wv = idx - rl * Wb;
                 const u32 Lr = __shfl_sync(0xffffffffu, L, rl);
@@ -376,32 +200,61 @@ __global__ void __launch_bounds__(P2_WARPS * 32) prepare_reads2(const __grid_con
                 const bool enr = __shfl_sync(0xffffffffu, (u32)en, rl) != 0;
                 if (!enr) continue;
                 const u8 *src = A.bases + (((u64)b0h << 32) | b0l);
-                u64 q = 0, nm = 0, cm = 0; u32 lo = 0, mk = 0, rlo = 0, rmk = 0;
                 const u32 p0 = wv * 32;
                 const u32 nbase = Lr > p0 ? min(32u, Lr - p0) : 0u;
-                for (u32 k = 0; k < nbase; k++) {
-                    const u32 p = p0 + k;
-                    const u32 ch = src[c ? Lr - 1 - p : p], ch2 = src[c ? p : Lr - 1 - p];       // chain c at position p; the same chain read backwards
-                    const u32 ix = (ch >> 1) & 3u, ix2 = (ch2 >> 1) & 3u;
-                    const bool reg = (ch & 0xDFu) == ((0x47544341u >> (8 * ix)) & 0xFFu), reg2 = (ch2 & 0xDFu) == ((0x47544341u >> (8 * ix2)) & 0xFFu);
-                    const u32 cq = reg ? (tq >> (2 * ix)) & 3u : 0u, cc = reg ? (tc >> (2 * ix)) & 3u : 0u;
-                    q = (q << 2) | cq; nm = (nm << 2) | (reg ? 1u : 0u); cm = (cm << 2) | cc;
-                    lo = (lo << 1) | (cq & 1u); mk = (mk << 1) | (reg ? 1u : 0u);
-                    rlo = (rlo << 1) | (reg2 ? (tq >> (2 * ix2)) & 1u : 0u); rmk = (rmk << 1) | (reg2 ? 1u : 0u);
+                u32 qh = 0, ql = 0, nh = 0, nl = 0, ch = 0, cl = 0, lo = 0, mk = 0;
+                if (nbase) {
+                    // chain 0: bases p0 .. p0+31 in order; chain 1: the reverse complement, i.e. bytes Lr-1-p0 down to Lr-32-p0
+                    u32 w[8];
+                    if (c == 0) load32(src + p0, w);
+                    else {
+                        u32 t[8]; load32(src + (long long)Lr - 32 - (long long)p0, t);       // may start before the read: those bytes are masked out below
+#pragma unroll
+                        for (int j = 0; j < 8; j++) w[j] = __byte_perm(t[7 - j], 0u, 0x0123u);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const u32 nb = nbase > 4u * j ? nbase - 4u * j : 0u;
+                        const u32 v01 = nb >= 4u ? 0x01010101u : (0x01010101u & ((1u << (8u * nb)) - 1u));
+                        const Conv4 k4 = conv4(w[j], v01, tqb, tcb);
+                        const u32 q8 = pack4x2(k4.cq), n8 = pack4x2(k4.r1), c8 = pack4x2(k4.cc);
+                        if (j < 4) { qh = (qh << 8) | q8; nh = (nh << 8) | n8; ch = (ch << 8) | c8; }
+                        else { ql = (ql << 8) | q8; nl = (nl << 8) | n8; cl = (cl << 8) | c8; }
+                        lo = (lo << 4) | pack4x1(k4.cq & 0x01010101u); mk = (mk << 4) | pack4x1(k4.r1);
+                    }
                 }
-                if (nbase < 32) { const u32 sl = 32 - nbase; if (nbase == 0) { q = nm = cm = 0; lo = mk = rlo = rmk = 0; } else { q <<= 2 * sl; nm <<= 2 * sl; cm <<= 2 * sl; lo <<= sl; mk <<= sl; rlo <<= sl; rmk <<= sl; } }
                 const u32 slr = slot0 + rl;
                 u32 *dst = (u32 *)(A.planes + ((u64)slr * 2 + c) * 3 * Wb);           // streams: logical 32-bit words, see KArgs::planes
-                dst[2 * wv] = (u32)(q >> 32); dst[2 * wv + 1] = (u32)q;
-                dst[W2 + 2 * wv] = (u32)(nm >> 32); dst[W2 + 2 * wv + 1] = (u32)nm;
-                dst[2 * W2 + 2 * wv] = (u32)(cm >> 32); dst[2 * W2 + 2 * wv + 1] = (u32)cm;
+                __stcs((uint2 *)(dst + 2 * wv), make_uint2(qh, ql));
+                __stcs((uint2 *)(dst + W2 + 2 * wv), make_uint2(nh, nl));
+                __stcs((uint2 *)(dst + 2 * W2 + 2 * wv), make_uint2(ch, cl));
                 u32 *b1 = A.bits1 + ((u64)slr * 2 + c) * 2 * W2;
-                b1[wv] = lo; b1[Wb + wv] = mk; b1[2 * Wb + wv] = rlo; b1[3 * Wb + wv] = rmk;
-                u32 *q_r = sq_all + rl * WQ, *n_r = sn_all + rl * WQ;
-                q_r[2 * wv] = (u32)(q >> 32); q_r[2 * wv + 1] = (u32)q; n_r[2 * wv] = (u32)(nm >> 32); n_r[2 * wv + 1] = (u32)nm;
+                __stcs((uint2 *)(b1 + 2 * wv), make_uint2(lo, mk));
+                u32 *r_ = wsm + rl * RS;
+                r_[2 * wv] = qh; r_[2 * wv + 1] = ql; r_[WQ + 2 * wv] = nh; r_[WQ + 2 * wv + 1] = nl;
+                r_[2 * WQ + wv] = lo; r_[2 * WQ + Wb + wv] = mk;
             }
-            if (lane < 32) { sq[W2] = 0; sq[W2 + 1] = 0; sq[W2 + 2] = 0; sn[W2] = 0; sn[W2 + 1] = 0; sn[W2 + 2] = 0; }
+            sq[W2] = 0; sq[W2 + 1] = 0; sq[W2 + 2] = 0; sn[W2] = 0; sn[W2 + 1] = 0; sn[W2 + 2] = 0;
             __syncwarp();
+            // ---- A2: the same two 1-bit streams for the read taken backwards (what screen_bits compares with a forward-plane
+            //      sector when the candidate lies on the reverse strand); the low bits carry the complement flip already
+            for (u32 idx = lane; idx < 32 * Wb; idx += 32) {
+                const u32 rl = idx / Wb, wv = idx - rl * Wb;
+                const u32 Lr = __shfl_sync(0xffffffffu, L, rl);
+                const bool enr = __shfl_sync(0xffffffffu, (u32)en, rl) != 0;
+                if (!enr) continue;
+                const u32 *blo = wsm + rl * RS + 2 * WQ, *bmk = blo + Wb;
+                const int s0 = (int)Lr - 32 - 32 * (int)wv;                            // reversed word wv = forward bases s0+31 down to s0
+                u32 rlo = 0, rmk = 0;
+                if (s0 > -32) {
+                    const int w0 = s0 >> 5; const u32 sf = (u32)s0 & 31u;
+                    const u32 la = w0 >= 0 ? __brev(blo[w0]) : 0u, lb = (w0 + 1 < (int)Wb) ? __brev(blo[w0 + 1]) : 0u;
+                    const u32 ma = w0 >= 0 ? __brev(bmk[w0]) : 0u, mb = (w0 + 1 < (int)Wb) ? __brev(bmk[w0 + 1]) : 0u;
+                    rlo = __funnelshift_r(la, lb, sf); rmk = __funnelshift_r(ma, mb, sf);
+                }
+                u32 *b1 = A.bits1 + ((u64)(slot0 + rl) * 2 + c) * 2 * W2;
+                __stcs((uint2 *)(b1 + W2 + 2 * wv), make_uint2(rlo ^ flipm, rmk));
+            }
             if (en && !ns_known) {
                 ns_known = true;
                 u32 acgt = 0; for (u32 j = 0; j < 2 * W; j++) acgt += __popc(sn[j]);
@@ -414,51 +267,52 @@ __global__ void __launch_bounds__(P2_WARPS * 32) prepare_reads2(const __grid_con
                 }
             }
             if (en && !filtered && nseg > 0) {
-                // ---- B: bucket sizes (bit 31 = the seed holds a non-ACGT base) of offsets j*s + d, d < wd; four gathers in flight
-                const u32 n_g = nseg * wd;
+                const u32 vmax = ii, wd = I + vmax, ncol = vmax + 1;
+                // ---- B: per segment, bucket sizes (bit 31 = the seed holds a non-ACGT base) of offsets j*s + d, d < wd, then
+                //      CountSeeds(j, v) (align.cpp:526-540) for every start v <= vmax
                 for (u32 j = 0; j < nseg; j++) {
-                    for (u32 d0 = 0; d0 < wd; d0 += 4) {
-                        u32 kmer[4], fl[4], c16[4];
+                    for (u32 d0 = 0; d0 < wd; d0 += 8) {
+                        u32 kmer[8], fl[8], c8[8];
 #pragma unroll
-                        for (u32 u = 0; u < 4; u++) {
+                        for (u32 u = 0; u < 8; u++) {
                             const u32 p = j * s + min(d0 + u, wd - 1), w = p >> 4, o = (p & 15u) * 2;
                             const u32 xq = __funnelshift_l(sq[w + 1], sq[w], o) >> shs, xn = __funnelshift_l(sn[w + 1], sn[w], o) >> shs;
                             kmer[u] = bsl_xt(xq); fl[u] = xn != full ? 0x80000000u : 0u;
-                            c16[u] = A.di.cnt16[kmer[u]];
+                            c8[u] = ldg_u8_hint(A.di.cnt8 + kmer[u], keep);
                         }
 #pragma unroll
-                        for (u32 u = 0; u < 4; u++) {
-                            if (d0 + u < wd) { const u32 m = c16[u] == 0xFFFFu ? A.di.bucket[2 * kmer[u] + 2] - A.di.bucket[2 * kmer[u]] : c16[u]; cp[j * wd + d0 + u] = (m & 0x7fffffffu) | fl[u]; }
+                        for (u32 u = 0; u < 8; u++) {
+                            if (d0 + u < wd) { const u32 m = c8[u] == 0xFFu ? __ldg(A.di.bucket + 2 * kmer[u] + 2) - __ldg(A.di.bucket + 2 * kmer[u]) : c8[u]; cw[d0 + u] = (m & 0x7fffffffu) | fl[u]; }
                         }
                     }
-                }
-                // ---- C: CountSeeds(j, v) (align.cpp:526-540) from the table
-                auto count_seeds = [&](u32 j, u32 v) -> u32 {
-                    u32 total = 0, k = 0;
-                    for (u32 i = 0; i < I; i++) {
-                        const u32 e = cp[j * wd + (s_prof[j][i] + v - i - j * s)];
-                        if (e >> 31) k = 12;
-                        total += (e & 0x7fffffffu) << k;
+                    for (u32 v = 0; v <= vmax; v++) {
+                        u32 total = 0, k = 0;
+                        for (u32 i = 0; i < I; i++) {
+                            const u32 e = cw[s_prof[j][i] + v - i - j * s];
+                            if (e >> 31) k = 12;
+                            total += (e & 0x7fffffffu) << k;
+                        }
+                        cs[j * ncol + v] = total == 0 ? 9999999u : total;
                     }
-                    return total == 0 ? 9999999u : total;
-                };
-                u32 *st = cp + n_g, *key = st + 16;
-                u32 st0 = 0, best = 0xffffffffu;                                   // ReorderSeed (align.cpp:468-498): first minimum of the column sums
-                for (u32 v = 0; v < ii; v++) { u32 tt = 0; for (u32 j = 0; j < nseg; j++) tt += count_seeds(j, v); if (tt < best) { best = tt; st0 = v; } }
-                for (u32 j = 0; j < nseg; j++) st[j] = st0;
+                }
+                // ---- C: ReorderSeed (align.cpp:468-498): first minimum of the column sums
+                u32 st0 = 0, best = 0xffffffffu;
+                for (u32 v = 0; v < ii; v++) { u32 tt = 0; for (u32 j = 0; j < nseg; j++) tt += cs[j * ncol + v]; if (tt < best) { best = tt; st0 = v; } }
+                u64 stp = 0;                                                       // start[j] in 4 bits each
+                for (u32 j = 0; j < nseg; j++) stp |= (u64)st0 << (4 * j);
                 for (u32 t = 0; t < nseg; t++) {                                   // AdjustSeedStartArray (align.cpp:500-524)
                     const u32 ptr = (t & 1) ? nseg - 1 - t / 2 : t / 2;
-                    const u32 lo_ = ptr == 0 ? 0 : st[ptr - 1], hi_ = ptr == nseg - 1 ? ii : st[ptr + 1];
+                    const u32 lo_ = ptr == 0 ? 0 : (u32)(stp >> (4 * (ptr - 1))) & 15u, hi_ = ptr == nseg - 1 ? ii : (u32)(stp >> (4 * (ptr + 1))) & 15u;
                     u32 pick = lo_, b = 0xffffffffu;
-                    for (u32 x = lo_; x <= hi_; x++) { const u32 tt = count_seeds(ptr, x); if (tt < b) { b = tt; pick = x; } }
-                    st[ptr] = pick;
+                    for (u32 x = lo_; x <= hi_; x++) { const u32 tt = cs[ptr * ncol + x]; if (tt < b) { b = tt; pick = x; } }
+                    stp = (stp & ~(15ull << (4 * ptr))) | ((u64)pick << (4 * ptr));
                 }
-                for (u32 j = 0; j < nseg; j++) key[j] = count_seeds(j, st[j]);
                 u32 sb[4] = {0, 0, 0, 0};                                          // sched byte t = segment of rank t | its start << 4
                 for (u32 j = 0; j < nseg; j++) {
-                    const int kj = (int)key[j]; u32 rank = 0;
-                    for (u32 y = 0; y < nseg; y++) { const int ky = (int)key[y]; rank += (ky < kj || (ky == kj && y < j)) ? 1u : 0u; }
-                    const u32 v = (j | (st[j] << 4)) << ((rank & 3u) * 8);
+                    const u32 stj = (u32)(stp >> (4 * j)) & 15u;
+                    const int kj = (int)cs[j * ncol + stj]; u32 rank = 0;          // pair<int,int> order: (count, segment)
+                    for (u32 y = 0; y < nseg; y++) { const int ky = (int)cs[y * ncol + ((u32)(stp >> (4 * y)) & 15u)]; rank += (ky < kj || (ky == kj && y < j)) ? 1u : 0u; }
+                    const u32 v = (j | (stj << 4)) << ((rank & 3u) * 8);
                     if ((rank >> 2) == 0) sb[0] |= v; else if ((rank >> 2) == 1) sb[1] |= v; else if ((rank >> 2) == 2) sb[2] |= v; else sb[3] |= v;
                 }
                 *(uint4 *)(A.sched + ((u64)slot * 2 + c) * 16) = make_uint4(sb[0], sb[1], sb[2], sb[3]);
@@ -605,12 +459,12 @@ __global__ void __launch_bounds__(LK_THREADS) seed_lookup(const __grid_constant_
                 else { const u32 kmer = bsl_xt((u32)(stream_extract(pq, h) >> shs)); e0 = A.di.bucket[2 * kmer]; e1 = A.di.bucket[2 * kmer + 1]; e2 = A.di.bucket[2 * kmer + 2]; }
                 const u32 pm = e2 - e0;
                 if (pm != 0 && pm <= A.di.maxk) {
-                    uint4 a, b;
-                    a.x = cb; a.y = pm; a.z = e0; a.w = e1 - e0;
-                    b.x = m.rnd % pm; b.y = h | ((u32)m.len << 9) | ((u32)m.thr << 18) | (i << 22) | (c << 26); b.z = slot; b.w = 0;
-                    uint4 *dst = (uint4 *)(A.hdr + it); dst[0] = a; dst[1] = b;
+                    // walk positions on the reverse strand: [x1, x2) (inv = 0) or all but [x1, x2) (inv = 1), see ItemHdr
+                    const u32 nf = e1 - e0, rot = m.rnd % pm;
+                    const u32 inv = rot < nf ? 0u : 1u, x1 = inv ? pm - rot : nf - rot, x2 = inv ? pm - rot + nf : pm - rot;
+                    *(uint4 *)(A.hdr + it) = make_uint4(cb, slot | (c << 22) | ((u32)m.thr << 23) | (inv << 27) | (i << 28), x1 | ((u32)m.len << 23), x2 | (h << 23));
                     for (u32 cc = (cb + 31u) / 32u; (u64)cc * 32u < (u64)cb + pm; cc++) A.chunk_first[cc] = it;
-                    x_cb = cb; x_pm = pm; x_e0 = e0; x_rot = b.x;
+                    x_cb = cb; x_pm = pm; x_e0 = e0; x_rot = rot;
                     cb += pm; it++;
                 }
             }
@@ -724,7 +578,7 @@ template <bool SINGLE, int NS>
 __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates(const __grid_constant__ KArgs A, u32 ci, u32 W) {
     constexpr bool GAP = true;
     extern __shared__ u32 vsm[];                          // staged streams: item x stream x 2*Wb
-    __shared__ uint4 s_ha[CHUNK], s_hb[CHUNK];            // item headers {base, m, b0, nfwd} {rot, pack, slot, first word of the read streams}
+    __shared__ uint4 s_ha[CHUNK];                         // item headers (ItemHdr)
     __shared__ u32 s_mask[CHUNK / 32], s_nmk;
     __shared__ uint4 s_mk[CHUNK];                         // marked candidates of the chunk: {flat index, g, snp | strand << 8 | chain << 9, slot}
     constexpr u32 NP = SINGLE ? 2 : 3;                    // streams copied from global memory: bases, N-mask, (convert-to mask)
@@ -740,10 +594,11 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
     if (blockIdx.x >= n_chunks) return;
     // ---- software pipeline over this CTA's chunks: the headers and loc entries of the next chunk are loaded while this one is verified
     u32 chunk = blockIdx.x, first = A.chunk_first[chunk * (CHUNK / 32)];
-    uint4 ha = make_uint4(0, 0, 0, 0), hb = ha; bool have = false;
-    if (t < VF_EAGER && first + t < n_items) { const uint4 *src = (const uint4 *)(A.hdr + first + t); ha = __ldg(src); hb = __ldg(src + 1); have = true; }
+    uint4 ha = make_uint4(0, 0, 0, 0); bool have = false;
+    if (t < VF_EAGER && first + t < n_items) { ha = __ldg((const uint4 *)(A.hdr + first + t)); have = true; }
     u32 nchunk = chunk + gridDim.x, nfirst = nchunk < n_chunks ? A.chunk_first[nchunk * (CHUNK / 32)] : 0u;
     u32 cloc = chunk * CHUNK + t < n_cands ? __ldg(A.flat_loc + chunk * CHUNK + t) : 0u;      // seed-table entry of my candidate (flat_loc is a plain stream)
+    auto stream_of = [&](u32 y) -> u32 { return (IH_SLOT(y) * 2 + IH_CHAIN(y)) * 3 * A.Wb; };   // first 64-bit word of an item's read streams
     for (; chunk < n_chunks;) {
         const u32 cbeg = chunk * CHUNK, cend = min(cbeg + CHUNK, n_cands);
         bool mine = have && (t == 0 || ha.x < cend);
@@ -751,18 +606,17 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
         if (t == 0) s_nmk = 0;
         u32 n_it = (u32)__syncthreads_count(mine);
         if (n_it == VF_EAGER) {                                                  // (rare) more items than were prefetched
-            if (t >= VF_EAGER && first + t < n_items) { const uint4 *src = (const uint4 *)(A.hdr + first + t); ha = __ldg(src); mine = ha.x < cend; if (mine) hb = __ldg(src + 1); }
+            if (t >= VF_EAGER && first + t < n_items) { ha = __ldg((const uint4 *)(A.hdr + first + t)); mine = ha.x < cend; }
             n_it = (u32)__syncthreads_count(mine);
         }
         if (mine) {
-            hb.w = (hb.z * 2 + IH_CHAIN(hb.y)) * 3 * A.Wb;                   // first word of the item's read streams
-            s_ha[t] = ha; s_hb[t] = hb;
+            s_ha[t] = ha;
             const u32 pos = ha.x > cbeg ? ha.x - cbeg : 0u;                  // first candidate of the item inside the chunk
             atomicOr(&s_mask[pos >> 5], 1u << (pos & 31u));
         }
         // prefetch for the next chunk (consumed at the top of the next iteration)
-        uint4 pa = make_uint4(0, 0, 0, 0), pb = pa; bool phave = false;
-        if (nchunk < n_chunks && t < VF_EAGER && nfirst + t < n_items) { const uint4 *src = (const uint4 *)(A.hdr + nfirst + t); pa = __ldg(src); pb = __ldg(src + 1); phave = true; }
+        uint4 pa = make_uint4(0, 0, 0, 0); bool phave = false;
+        if (nchunk < n_chunks && t < VF_EAGER && nfirst + t < n_items) { pa = __ldg((const uint4 *)(A.hdr + nfirst + t)); phave = true; }
         const u32 nnchunk = nchunk + gridDim.x; const u32 nnfirst = nnchunk < n_chunks ? __ldg(A.chunk_first + (size_t)nnchunk * (CHUNK / 32)) : 0u;
         const u32 nloc = (nchunk < n_chunks && nchunk * CHUNK + t < n_cands) ? __ldg(A.flat_loc + nchunk * CHUNK + t) : 0u;
         __syncthreads();
@@ -777,18 +631,17 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
         }
         const bool act = idx < cend;
         bool marked = false;
-        u32 g = 0, pack = 0, sig = 0, kk = 0, sh = 0;
+        u32 g = 0, hy = 0, sig = 0, kk = 0, sh = 0;
         u32 R[NR];
 #pragma unroll
         for (int j = 0; j < NR; j++) R[j] = 0;
         if (act) {
-            const uint4 xa = s_ha[it]; const uint2 xb = *(const uint2 *)&s_hb[it];
-            u32 e = xb.x + (idx - xa.x); if (e >= xa.y) e -= xa.y;
-            sig = e >= xa.w ? 1u : 0u;                                           // forward-strand entries come first (align.cpp:296)
-            pack = xb.y;
-            g = cloc - IH_H(pack);                                               // _hit.loc (align.cpp:297)
+            const uint4 xa = s_ha[it];
+            sig = ih_strand(idx - xa.x, xa.y, xa.z, xa.w);                       // forward-strand entries come first (align.cpp:296)
+            hy = xa.y;
+            g = cloc - IH_H(xa.w);                                               // _hit.loc (align.cpp:297)
             sh = (g & 15u) * 2;
-            vf_gather<NS>(A.di.plane[sig], g, IH_L(pack), R, kk);
+            vf_gather<NS>(A.di.plane[sig], g, IH_L(xa.z), R, kk);
         }
         for (u32 grp = 0; grp < n_it; grp += VF_ITMAX) {
             const u32 n_g = min(VF_ITMAX, n_it - grp);
@@ -799,7 +652,7 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
                 for (u32 m0 = wid; m0 < n_g; m0 += 4 * (VF_THREADS / 32)) {
                     u32 v[4];
 #pragma unroll
-                    for (u32 b = 0; b < 4; b++) { const u32 i2 = m0 + b * (VF_THREADS / 32); if (i2 < n_g) v[b] = __ldg((const u32 *)(A.planes + s_hb[grp + i2].w) + l); }
+                    for (u32 b = 0; b < 4; b++) { const u32 i2 = m0 + b * (VF_THREADS / 32); if (i2 < n_g) v[b] = __ldg((const u32 *)(A.planes + stream_of(s_ha[grp + i2].y)) + l); }
 #pragma unroll
                     for (u32 b = 0; b < 4; b++) { const u32 i2 = m0 + b * (VF_THREADS / 32); if (i2 < n_g) vsm[(size_t)i2 * IST + l] = v[b]; }
                 }
@@ -807,7 +660,7 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
             {
                 for (u32 j = lane; j < W2; j += 32)
                     for (u32 i2 = wid; i2 < n_g; i2 += VF_THREADS / 32) {
-                        const u32 hs = IH_H(s_hb[grp + i2].y) + A.s;
+                        const u32 hs = IH_H(s_ha[grp + i2].w) + A.s;
                         vsm[(size_t)i2 * IST + PL_PM * W2 + j] = hs >= 16 * j + 16 ? 0x55555555u : (hs <= 16 * j ? 0u : 0x55555555u & (0xffffffffu << (32 - 2 * (hs - 16 * j))));
                     }
             }
@@ -816,7 +669,7 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
             if (grp == 0 && phave) {
                 const u32 ncend = min(nchunk * CHUNK + CHUNK, n_cands);
                 if (t == 0 || pa.x < ncend) {
-                    const char *pp = (const char *)(A.planes + (size_t)(pb.z * 2 + IH_CHAIN(pb.y)) * 3 * A.Wb);
+                    const char *pp = (const char *)(A.planes + stream_of(pa.y));
                     asm volatile("prefetch.global.L2 [%0];" :: "l"(pp));
                     asm volatile("prefetch.global.L2 [%0];" :: "l"(pp + 4 * D - 4));
                 }
@@ -826,9 +679,9 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
             u32 snp = 0, pre = 0;
             if (now) vf_count<SINGLE, GAP, NS>(R, kk, sh, vsm + (size_t)(it - grp) * IST, W, W2, snp, pre);
             // could this candidate add a hit?  ungapped: snp <= thr.  gapped: GapAlign's first test (align.cpp:353-360)
-            const u32 thr = IH_THR(pack);
+            const u32 thr = IH_THR(hy);
             const bool mark = now && (snp <= thr || (thr >= 2 && pre < thr - 1));
-            if (mark) { marked = true; s_mk[atomicAdd(&s_nmk, 1u)] = make_uint4(idx, g, snp | (sig << 8) | (IH_CHAIN(pack) << 9), s_hb[it].z); }
+            if (mark) { marked = true; s_mk[atomicAdd(&s_nmk, 1u)] = make_uint4(idx, g, snp | (sig << 8) | (IH_CHAIN(hy) << 9), IH_SLOT(hy)); }
         }
         // ---- 32 verdicts are one word of the bitmap; marked candidates are published for reduce_fast / reduce_round
         {
@@ -838,7 +691,7 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
         __syncthreads();
         if (t < s_nmk) atomicAdd(&A.slot_flag[s_mk[t].w], 1u);          // reduce_round replays the flagged reads from the bitmap
         __syncthreads();
-        chunk = nchunk; first = nfirst; ha = pa; hb = pb; have = phave; nchunk = nnchunk; nfirst = nnfirst; cloc = nloc;
+        chunk = nchunk; first = nfirst; ha = pa; have = phave; nchunk = nnchunk; nfirst = nnfirst; cloc = nloc;
     }
 }
 
@@ -852,67 +705,47 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
 // the read half-words the sector covers. That count is a lower bound of CountMismatch (align.h:118-131 / 199-239: a
 // sum over half-words, the same alignment), so a candidate above its threshold is rejected for good. The rest (a few
 // per cent) wait in a per-warp queue; whenever 32 are waiting they are counted exactly (drain_exact), one per lane.
-// Single-conversion rules use screen_bits (below) instead: the same structure on a one-bit plane that stays in L2.
+// Single-conversion rules use screen_bits (below) instead: a pipelined version on a one-bit plane that stays in L2.
 // ------------------------------------------------------------------------------------------------
 #define SC_WARPS 8
 #define SC_QCAP 64u          // survivors a warp can hold (it empties the queue whenever 32 are waiting)
 
-// Exact count of up to 32 queued survivors {flat index, g, pack, slot | strand << 31}, one per lane. The warp copies
-// their 2-bit read streams (bases, ACGT mask, (convert-to mask): DW contiguous 64-bit words each) into its staging slice
-// with coalesced loads, then every lane walks the 32-byte sectors of its reference window with a one-word carry
-// (CountMismatch / CountMismatch_new, align.h:118-131 / 199-239). Passing candidates get their bitmap bit and a mark.
+// Exact count of one queued survivor per lane, sv = {flat index, g, ItemHdr::y with the STRAND in the inv bit, L}: the
+// whole CountMismatch / CountMismatch_new (align.h:118-131 / 199-239) over the 2-bit window, reference words and read
+// words straight from global memory (three independent loads per word, nothing staged). Passing candidates get their
+// bitmap bit and a mark record for reduce_fast.
 template <bool SINGLE>
-__device__ __forceinline__ void drain_exact(const KArgs &A, const uint4 *Q, u32 from, u32 n, u32 lane, u32 *S0, u32 stage_items, u32 rcp_dw) {
-    constexpr u32 FULL = 0xffffffffu, NP = SINGLE ? 2 : 3;
-    const u32 Wb = A.Wb, DW = NP * Wb, D = 2 * DW;
-    u64 *S64 = (u64 *)S0;
-    uint4 sv = make_uint4(0, 0, 0, 0);
-    if (lane < n) sv = Q[from + lane];
-    const u32 sig = sv.w >> 31, slot = sv.w & 0x7fffffffu;
-    const u32 qoff = (slot * 2 + IH_CHAIN(sv.z)) * 3 * Wb;
-    for (u32 b0 = 0; b0 < n; b0 += stage_items) {
-        const u32 nb = min(stage_items, n - b0), nw = nb * DW;
-        for (u32 x0 = 0; x0 < nw; x0 += 64) {
-            const u32 xa = x0 + lane, xb = xa + 32u;
-            const u32 ia = min(__umulhi(xa, rcp_dw), nb - 1u), ib = min(__umulhi(xb, rcp_dw), nb - 1u);
-            const u32 sa = __shfl_sync(FULL, qoff, b0 + ia), sb = __shfl_sync(FULL, qoff, b0 + ib);
-            u64 va = 0, vb = 0;
-            if (xa < nw) va = __ldg(A.planes + sa + (xa - ia * DW));
-            if (xb < nw) vb = __ldg(A.planes + sb + (xb - ib * DW));
-            if (xa < nw) S64[xa] = va;
-            if (xb < nw) S64[xb] = vb;
-        }
-        __syncwarp();
-        if (lane >= b0 && lane < b0 + nb) {
-            const u32 *S = S0 + (size_t)(lane - b0) * D;                         // read half-word i: bases S[i], mask S[2 Wb + i], convert-to S[4 Wb + i]
-            const u32 g = sv.y, gh = g >> 4, sh = (g & 15u) * 2, nh = (IH_L(sv.z) + 15u) >> 4, kk0 = gh & 7u;
-            const u64 *P = A.di.plane[sig] + ((gh >> 3) << 2);
-            const u32 nsec = (kk0 + nh + 8u) >> 3;
-            u32 prev = 0, snp = 0;
-            for (u32 sct = 0; sct < nsec; sct++) {
-                u32 r8[8]; ldg256(P + 4 * sct, r8);
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const u32 i = 8 * sct + (u32)j - kk0 - 1u;                   // r8[j] is the second reference half-word of read half-word i
-                    if (i < nh) { u32 cc = 0; if (!SINGLE) cc = S[4 * Wb + i]; snp += __popc(vf_diff<SINGLE>(S[i], cc, __funnelshift_l(r8[j], prev, sh)) & S[2 * Wb + i]); }
-                    prev = r8[j];
-                }
-            }
-            if (snp <= IH_THR(sv.z)) {
-                atomicOr(&A.bitmap[sv.x >> 5], 1u << (sv.x & 31u));
-                const u32 pos = atomicAdd(&A.slot_flag[slot], 1u);
-                if (pos < MK_CAP) A.marks[(size_t)slot * MK_CAP + pos] = make_uint4(sv.x, g, snp | (sig << 8) | (IH_CHAIN(sv.z) << 9), 0u);
-            }
-        }
-        __syncwarp();
+__device__ __forceinline__ void drain_exact(const KArgs &A, const uint4 sv, bool have) {
+    if (!have) return;
+    const u32 y = sv.z, sig = IH_INV(y), slot = IH_SLOT(y), chain = IH_CHAIN(y), L = sv.w, g = sv.y;
+    const u32 Wb = A.Wb, W = (L + 31u) >> 5;
+    const u64 *S = A.planes + ((u64)slot * 2 + chain) * 3 * Wb;                    // streams: bases, 01 per ACGT base, convert-to mask
+    const u64 *P = A.di.plane[sig] + (g >> 5);
+    const u32 off = (g & 31u) * 2;
+    u32 snp = 0;
+    u64 prev = __ldg(P);
+#pragma unroll 3
+    for (u32 i = 0; i < W; i++) {
+        const u64 next = __ldg(P + i + 1);
+        const u64 r = off ? (prev << off) | (next >> (64 - off)) : prev;
+        const u64 q = swap32(__ldg(S + i)), n = swap32(__ldg(S + Wb + i));
+        u64 cm = 0; if (!SINGLE) cm = swap32(__ldg(S + 2 * Wb + i));
+        snp += __popcll(bsl_pairs(bsl_diff<SINGLE>(q, cm, r)) & n);
+        prev = next;
+    }
+    if (snp <= IH_THR(y)) {
+        atomicOr(&A.bitmap[sv.x >> 5], 1u << (sv.x & 31u));
+        const u32 pos = atomicAdd(&A.slot_flag[slot], 1u);
+        if (pos < MK_CAP) A.marks[(size_t)slot * MK_CAP + pos] = make_uint4(sv.x, g, snp | (sig << 8) | (chain << 9), 0u);
     }
 }
-
+// queue entry of a survivor
+__device__ __forceinline__ uint4 survivor(u32 flat, u32 g, u32 hy, u32 sig, u32 L) { return make_uint4(flat, g, (hy & ~(1u << 27)) | (sig << 27), L); }
 
 template <bool SINGLE>
 __global__ void __launch_bounds__(SC_WARPS * 32, 5) screen_candidates(const __grid_constant__ KArgs A, u32 ci, u32 stage_items, u32 rcp_dw) {
     extern __shared__ u32 ssm[];
-    __shared__ uint4 s_q[SC_WARPS][SC_QCAP];          // survivors waiting for the exact count: {flat index, g, pack, slot | strand << 31}
+    __shared__ uint4 s_q[SC_WARPS][SC_QCAP];          // survivors waiting for the exact count
     constexpr u32 NP = SINGLE ? 2 : 3, PL_NM = 1, PL_CM = 2, FULL = 0xffffffffu;
     const RoundCtr *rc = A.ctr->rc + ci;
     const unsigned long long al = min(rc->alloc, ~rc->limit_inv);
@@ -924,31 +757,28 @@ __global__ void __launch_bounds__(SC_WARPS * 32, 5) screen_candidates(const __gr
     u64 *S64 = (u64 *)S0;
     uint4 *Q = s_q[wid];
     u32 qn = 0;
-    auto drain = [&](u32 from, u32 n) { drain_exact<SINGLE>(A, Q, from, n, lane, S0, stage_items, rcp_dw); };
     for (u32 grp = blockIdx.x * SC_WARPS + wid; grp < n_groups; grp += gridDim.x * SC_WARPS) {
         const u32 gbeg = grp << 5, gend = min(gbeg + 32u, n_cands);
         const u32 first = __ldg(A.chunk_first + grp);
         const u32 last = grp + 1 < n_groups ? __ldg(A.chunk_first + grp + 1) : n_items - 1u;
         const bool act = gbeg + lane < gend;
         const u32 cloc = act ? __ldg(A.flat_loc + gbeg + lane) : 0u;
-        uint4 ha = make_uint4(FULL, 0, 0, 0), hb = make_uint4(0, 0, 0, 0);
+        uint4 ha = make_uint4(FULL, 0, 0, 0);
         const bool ld = first + lane <= last;
-        if (ld) { const uint4 *src = (const uint4 *)(A.hdr + first + lane); ha = __ldg(src); hb = __ldg(src + 1); }
-        if (lane == 0) A.bitmap[grp] = 0u;                                       // bits are set by drain()
+        if (ld) ha = __ldg((const uint4 *)(A.hdr + first + lane));
+        if (lane == 0) A.bitmap[grp] = 0u;                                       // bits are set by drain_exact
         const bool mine = ld && (lane == 0 || ha.x < gend);
         const u32 pos = (mine && ha.x > gbeg) ? ha.x - gbeg : 0u;
         const u32 mask = __reduce_or_sync(FULL, mine ? 1u << pos : 0u);
         const u32 n_it = __popc(mask);
-        const u32 soff = (hb.z * 2 + IH_CHAIN(hb.y)) * 3 * A.Wb;                 // first 64-bit word of the item's read streams
+        const u32 soff = (IH_SLOT(ha.y) * 2 + IH_CHAIN(ha.y)) * 3 * A.Wb;         // first 64-bit word of the item's read streams
         const u32 it = __popc(mask & (FULL >> (31u - lane))) - 1u;               // my candidate's item = lane `it`
-        const u32 ibase = __shfl_sync(FULL, ha.x, it), im = __shfl_sync(FULL, ha.y, it), inf = __shfl_sync(FULL, ha.w, it);
-        const u32 irot = __shfl_sync(FULL, hb.x, it), pack = __shfl_sync(FULL, hb.y, it), islot = __shfl_sync(FULL, hb.z, it);
-        u32 e = irot + (gbeg + lane - ibase); if (e >= im) e -= im;
-        const u32 sig = e >= inf ? 1u : 0u;                                      // forward-strand entries come first (align.cpp:296)
-        const u32 g = cloc - IH_H(pack), sh = (g & 15u) * 2;                     // _hit.loc (align.cpp:297)
+        const u32 ibase = __shfl_sync(FULL, ha.x, it), hy = __shfl_sync(FULL, ha.y, it), hz = __shfl_sync(FULL, ha.z, it), hw = __shfl_sync(FULL, ha.w, it);
+        const u32 sig = ih_strand(gbeg + lane - ibase, hy, hz, hw);              // forward-strand entries come first (align.cpp:296)
+        const u32 g = cloc - IH_H(hw), sh = (g & 15u) * 2, L = IH_L(hz);         // _hit.loc (align.cpp:297)
         // ---- the sector: read half-word i lines up with reference half-words gh+i, gh+i+1; the sector that starts o
         //      half-words before gh covers i in [0, 6-o], the next one i in [8-o, 14-o]; take the better covered one
-        const u32 gh = g >> 4, o = gh & 7u, nh = (IH_L(pack) + 15u) >> 4;
+        const u32 gh = g >> 4, o = gh & 7u, nh = (L + 15u) >> 4;
         const u32 c0 = min(7u - o, nh), hi1 = min(14u - o, nh - 1u);
         const u32 c1 = hi1 + o >= 8u ? hi1 + o - 7u : 0u;
         const u32 k = c1 > c0 ? 1u : 0u;
@@ -984,109 +814,99 @@ __global__ void __launch_bounds__(SC_WARPS * 32, 5) screen_candidates(const __gr
                         snp += __popc(vf_diff<SINGLE>(S[i], cc, r) & S[PL_NM * W2 + i]);
                     }
                 }
-                pass = snp <= IH_THR(pack);
+                pass = snp <= IH_THR(hy);
             }
             __syncwarp();
         }
         // ---- survivors join the warp's queue; 32 waiting survivors are counted exactly, one per lane
         const u32 bal = __ballot_sync(FULL, pass);
         if (bal) {
-            if (pass) Q[qn + __popc(bal & ((1u << lane) - 1u))] = make_uint4(gbeg + lane, g, pack, islot | (sig << 31));
+            if (pass) Q[qn + __popc(bal & ((1u << lane) - 1u))] = survivor(gbeg + lane, g, hy, sig, L);
             qn += __popc(bal);
             __syncwarp();
-            if (qn >= 32u) { qn -= 32u; drain(qn, 32u); }
+            if (qn >= 32u) { qn -= 32u; drain_exact<SINGLE>(A, Q[qn + lane], true); __syncwarp(); }
         }
     }
-    if (qn) drain(0u, qn);
+    if (qn) drain_exact<SINGLE>(A, Q[min(lane, qn - 1u)], lane < qn);
 }
 
 // ------------------------------------------------------------------------------------------------
-// screen_bits : the screen for single-conversion rules, on the ONE-BIT forward plane (DevIndex::bit1).
+// screen_bits : the screen for single-conversion rules, on the ONE-BIT forward plane (DevIndex::bit1) — the roofline kernel.
 //
 // A conversion never changes the low bit of a base's code (from = 01, to = 11), so "low bits differ" implies a mismatch
 // under CountMismatch (align.h:126-128) and the number of such positions over any part of the read is a lower bound of
 // its result. A 32-byte sector of bit1 holds 256 bases: one gather covers at least half of the window, and the whole
-// plane of a 500 Mb reference is 62.5 MB — it stays in L2, the gathers never reach DRAM. Candidates on the reverse
-// strand are screened on the same plane: rc position g+k of sequence i is the complement of forward position
-// 2*anchor_i + rc_offset_i - 1 - (g+k), complementing flips the low bit or not (DevIndex::flip), so the REVERSED read is
-// compared with the forward sector (one __brev per word). Sectors that hold a non-ACGT base, padding or margin
-// (DevIndex::nflag) and windows that cross a sequence boundary are not screened on that strand: they go straight to
-// the exact count. Same warp-autonomous structure and survivor queue as screen_candidates.
+// plane of a 500 Mb reference is 62.5 MB. Candidates on the reverse strand are screened on the same plane: rc position
+// g+k of sequence i is the complement of forward position 2*anchor_i + rc_offset_i - 1 - (g+k), complementing flips the
+// low bit or not (DevIndex::flip, folded into the read's reversed stream by prepare_reads), so the REVERSED read is
+// compared with the forward sector. Sectors that hold a non-ACGT base, padding or margin (DevIndex::nflag) and windows
+// that cross a sequence boundary are not screened on that strand: they go straight to the exact count.
+//
+// A warp owns groups of 32 consecutive flat candidates (lane per candidate) and never waits for another warp. Its
+// groups move through a software pipeline, one stage per visit, so that every global load has a whole visit (or more)
+// to arrive before it is used:
+//   F  chunk_first of the group four visits ahead            (which items overlap the group)
+//   P  item headers + loc entries of the group three ahead   (16-byte ItemHdr per lane, 4-byte flat_loc per lane)
+//   B1 resolve each lane's item (one popcount over the "an item starts here" mask, four shuffles), strand, window start;
+//      reverse-strand lanes issue their strand-table look-up (ctab)
+//   B2 mirror reverse-strand windows, pick the sector, issue the 256-bit gather (and the nflag word)
+//   S  cp.async the items' 1-bit streams (16 Wb bytes per item: {low bits, ACGT mask} words forward, then reversed)
+//      into the warp's shared slice — issued after the previous group's compare has left the slice
+//   C  XOR / mask / popcount of <= 7 read words against funnel-shifted sector words; survivors join the warp's queue,
+//      32 waiting survivors are counted exactly (drain_exact), one per lane
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SC_WARPS * 32, 4) screen_bits(const __grid_constant__ KArgs A, u32 ci, u32 stage_items, u32 rcp_dw, u32 dbg) {   // dbg: tools/gpu_dbg.sh switches (1 no exact count, 2 no gather, 4 no staging loads); 0 in production
-    extern __shared__ u32 ssm[];
-    __shared__ uint4 s_q[SC_WARPS][SC_QCAP];
+#define SB_WARPS 8
+__device__ __forceinline__ void cp_async16(u32 smem_addr, const void *gptr) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smem_addr), "l"(gptr)); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void ldg256_keep(const u32 *p, u32 (&r)[8], u64 pol) {      // one 32-byte sector of the one-bit plane, L2 evict-last
+    u64 a, b, c, d;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p), "l"(pol));
+    r[0] = (u32)a; r[1] = (u32)(a >> 32); r[2] = (u32)b; r[3] = (u32)(b >> 32); r[4] = (u32)c; r[5] = (u32)(c >> 32); r[6] = (u32)d; r[7] = (u32)(d >> 32);
+}
+
+__global__ void __launch_bounds__(SB_WARPS * 32, 4) screen_bits(const __grid_constant__ KArgs A, u32 ci, u32 item_bytes) {
+    extern __shared__ __align__(16) unsigned char sbm[];                       // per warp: 32 staged items x item_bytes
+    __shared__ uint4 s_q[SB_WARPS][SC_QCAP];
     constexpr u32 FULL = 0xffffffffu;
     const RoundCtr *rc = A.ctr->rc + ci;
     const unsigned long long al = min(rc->alloc, ~rc->limit_inv);
     const u32 n_cands = (u32)(al & ALLOC_MASK), n_items = (u32)(al >> ALLOC_SHIFT);
-    const u32 n_groups = (n_cands + 31u) >> 5;
+    const int n_groups = (int)((n_cands + 31u) >> 5);
     const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    const u32 Wb = A.Wb, D = 4 * Wb, DW = 2 * Wb;        // staged item: low bits, ACGT mask, reversed low bits, reversed mask (Wb words each)
-    u32 *S0 = ssm + (size_t)wid * stage_items * D;
-    u64 *S64 = (u64 *)S0;
-    const u64 *bits64 = (const u64 *)A.bits1;
-    const u32 flipm = A.di.flip ? FULL : 0u;
+    const int stride = (int)(gridDim.x * SB_WARPS), g0 = (int)(blockIdx.x * SB_WARPS + wid);
+    if (g0 >= n_groups) return;
+    const u32 Wb = A.Wb, RB = 16u * Wb;                                        // bytes of one (slot, chain) record of bits1
+    unsigned char *S0 = sbm + (size_t)wid * 32u * item_bytes;
+    const u32 S0a = (u32)__cvta_generic_to_shared(S0);
+    const unsigned char *bits = (const unsigned char *)A.bits1;
+    const u64 keep = l2_policy_keep();
     uint4 *Q = s_q[wid];
     u32 qn = 0;
-    auto drain = [&](u32 from, u32 n) { drain_exact<true>(A, Q, from, n, lane, S0, stage_items, rcp_dw); };
-    const u32 stride = gridDim.x * SC_WARPS;
-    u32 grp = blockIdx.x * SC_WARPS + wid;
-    if (grp >= n_groups) return;
-    // software pipeline over the groups this warp visits: the item headers and loc entries of the NEXT visit are loaded
-    // into registers while this one is screened, chunk_first one visit further ahead
-    auto load_hdr = [&](u32 first, u32 last, uint4 &ha, uint4 &hb) {
-        ha = make_uint4(FULL, 0, 0, 0); hb = make_uint4(0, 0, 0, 0);
-        if (first + lane <= last) { const uint4 *src = (const uint4 *)(A.hdr + first + lane); ha = __ldg(src); hb = __ldg(src + 1); }
-    };
-    u32 f0 = __ldg(A.chunk_first + grp), l0 = grp + 1 < n_groups ? __ldg(A.chunk_first + grp + 1) : n_items - 1u;
-    u32 f1 = 0, l1 = 0;
-    if (grp + stride < n_groups) { f1 = __ldg(A.chunk_first + grp + stride); l1 = grp + stride + 1 < n_groups ? __ldg(A.chunk_first + grp + stride + 1) : n_items - 1u; }
-    uint4 pha, phb; load_hdr(f0, l0, pha, phb);
-    u32 pcloc = (grp << 5) + lane < n_cands ? __ldg(A.flat_loc + (grp << 5) + lane) : 0u;
-    for (; grp < n_groups; grp += stride) {
-        const u32 gbeg = grp << 5, gend = min(gbeg + 32u, n_cands);
-        const u32 first = f0, last = l0;
-        const bool act = gbeg + lane < gend;
-        const u32 cloc = pcloc;
-        const uint4 ha = pha, hb = phb;
-        const bool ld = first + lane <= last;
-        // ---- next visit: its headers and loc entries; chunk_first of the visit after it
-        f0 = f1; l0 = l1;
-        if (grp + stride < n_groups) {
-            load_hdr(f0, l0, pha, phb);
-            const u32 nb_ = (grp + stride) << 5;
-            pcloc = nb_ + lane < n_cands ? __ldg(A.flat_loc + nb_ + lane) : 0u;
-            const u32 g2 = grp + 2 * stride;
-            if (g2 < n_groups) { f1 = __ldg(A.chunk_first + g2); l1 = g2 + 1 < n_groups ? __ldg(A.chunk_first + g2 + 1) : n_items - 1u; }
-        }
-        if (lane == 0) A.bitmap[grp] = 0u;                                       // bits are set by drain()
-        const bool mine = ld && (lane == 0 || ha.x < gend);
-        const u32 pos = (mine && ha.x > gbeg) ? ha.x - gbeg : 0u;
-        const u32 mask = __reduce_or_sync(FULL, mine ? 1u << pos : 0u);
-        const u32 n_it = __popc(mask);
-        const u32 soff = (hb.z * 2 + IH_CHAIN(hb.y)) * DW;                       // first 64-bit word of the item's 1-bit streams
-        const u32 it = __popc(mask & (FULL >> (31u - lane))) - 1u;               // my candidate's item = lane `it`
-        const u32 ibase = __shfl_sync(FULL, ha.x, it), im = __shfl_sync(FULL, ha.y, it), inf = __shfl_sync(FULL, ha.w, it);
-        const u32 irot = __shfl_sync(FULL, hb.x, it), pack = __shfl_sync(FULL, hb.y, it), islot = __shfl_sync(FULL, hb.z, it);
-        u32 e = irot + (gbeg + lane - ibase); if (e >= im) e -= im;
-        const u32 sig = e >= inf ? 1u : 0u;                                      // forward-strand entries come first (align.cpp:296)
-        const u32 g = cloc - IH_H(pack), L = IH_L(pack);                         // _hit.loc (align.cpp:297)
-        // ---- reverse-strand windows are mirrored onto the forward plane: which sequence owns g?
-        uint2 ce = make_uint2(0u, 0u);
-        if (act && sig) ce = __ldg(A.di.ctab + (g >> BSL_CTAB_SHIFT));
-        // ---- stage the 1-bit streams of the first items while that look-up is in flight
-        const u32 nb0 = min(stage_items, n_it), nw0 = nb0 * DW;
-        {
-            const u32 xa = lane, xb = lane + 32u;
-            const u32 ia = min(__umulhi(xa, rcp_dw), nb0 - 1u), ib = min(__umulhi(xb, rcp_dw), nb0 - 1u);
-            const u32 sa = __shfl_sync(FULL, soff, ia), sb = __shfl_sync(FULL, soff, ib);
-            u64 va = 0, vb = 0;
-            if (xa < nw0 && !(dbg & 4u)) va = __ldg(bits64 + sa + (xa - ia * DW));
-            if (xb < nw0 && !(dbg & 4u)) vb = __ldg(bits64 + sb + (xb - ib * DW));
-            u32 p0 = g; bool screen = act;
+    auto group_of = [&](int k) -> int { return k < 0 ? -1 : g0 + k * stride; };
+    auto is_group = [&](int g) -> bool { return g >= 0 && g < n_groups; };
+
+    // ---- pipeline registers
+    u32 fP = 0, lP = 0;                                                        // F -> P
+    uint4 hB = make_uint4(FULL, 0, 0, 0); u32 clB = 0;                         // P -> B1
+    u32 g2 = 0, y2 = 0, m2 = 0, rec2 = FULL; uint2 ce2 = make_uint2(0u, 0u);   // B1 -> B2 (m: L | it << 9 | act << 14 | n_it << 15)
+    u32 R[8], nfl = 0, cx = 0, gC = 0, yC = 0, mC = 0;                         // B2 -> C  (cx: dlt+8 | sft << 5 | nW << 10 | screened << 14 | (sec & 31) << 15)
+#pragma unroll
+    for (int j = 0; j < 8; j++) R[j] = 0;
+    { const int g = g0; fP = __ldg(A.chunk_first + g); lP = g + 1 < n_groups ? __ldg(A.chunk_first + g + 1) : n_items - 1u; }      // F of the first group
+
+    for (int v = -3;; v++) {
+        const int GC = group_of(v), GB2 = group_of(v + 1), GB1 = group_of(v + 2), GP = group_of(v + 3), GF = group_of(v + 4);
+        if (v >= 0 && GC >= n_groups) break;
+        // ---- B2 (group v+1): sector choice and gather
+        u32 Rn[8], nfl_n = 0, cx_n = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) Rn[j] = 0;
+        if (is_group(GB2)) {
+            const u32 L = m2 & 511u, sig = IH_INV(y2), g = g2; const bool act = (m2 >> 14) & 1u;
+            u32 p0 = g; bool screen = act; uint2 ce = ce2;
             if (act && sig) {
-                if (ce.y == 0u) {                                                // a sequence boundary inside the block
+                if (ce.y == 0u) {                                                // a sequence boundary inside the 65 536-coordinate block
                     u32 lo = 0, hi = A.di.nseq;
                     while (lo + 1 < hi) { const u32 mid = (lo + hi) >> 1; if (g >= __ldg(A.di.anchor + mid)) lo = mid; else hi = mid; }
                     const u32 a0 = __ldg(A.di.anchor + lo), P = __ldg(A.di.rcoff + lo);
@@ -1096,65 +916,93 @@ __global__ void __launch_bounds__(SC_WARPS * 32, 4) screen_bits(const __grid_con
                 if ((u64)g + L > (u64)ce.y) screen = false;                      // crosses into the next sequence
                 p0 = ce.x - g - L + 1u;                                          // forward coordinate of the window's lowest base
             }
-            // ---- the sector: read word i (32 bases; of the reversed read on the rc strand) lines up with plane words
-            //      pw+i, pw+i+1; the sector that starts o words before pw covers i in [0, 6-o], the next one [8-o, 14-o]
+            // the sector: read word i (32 bases; of the reversed read on the rc strand) lines up with plane words pw+i, pw+i+1;
+            // the sector that starts o words before pw covers i in [0, 6-o], the next one [8-o, 14-o]
             const u32 pw = p0 >> 5, o = pw & 7u, nW = (L + 31u) >> 5, sft = p0 & 31u;
             const u32 c0 = min(7u - o, nW), hi1 = min(14u - o, nW - 1u);
             const u32 c1 = hi1 + o >= 8u ? hi1 + o - 7u : 0u;
             const u32 k = c1 > c0 ? 1u : 0u;
-            const u32 dlt = k ? 8u - o : 0u - o;                                 // read word of sector word x = x + dlt
+            const u32 dlt8 = k ? 16u - o : 8u - o;                               // (read word of sector word x) - x + 8
             const u32 sec = (pw >> 3) + k;
-            u32 R[8], nfl = 0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) R[j] = 0;
-            if (screen && !(dbg & 2u)) {
-                u64 a, b, c, d;
-                asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(A.di.bit1 + (size_t)sec * 8));
-                R[0] = (u32)a; R[1] = (u32)(a >> 32); R[2] = (u32)b; R[3] = (u32)(b >> 32); R[4] = (u32)c; R[5] = (u32)(c >> 32); R[6] = (u32)d; R[7] = (u32)(d >> 32);
-                if (sig) nfl = __ldg(A.di.nflag + (sec >> 5));
+            if (screen) {
+                ldg256_keep(A.di.bit1 + (size_t)sec * 8, Rn, keep);
+                if (sig) nfl_n = __ldg(A.di.nflag + (sec >> 5));
             }
-            if (xa < nw0) S64[xa] = va;
-            if (xb < nw0) S64[xb] = vb;
+            cx_n = dlt8 | (sft << 5) | (nW << 10) | ((screen ? 1u : 0u) << 14) | ((sec & 31u) << 15);
+        }
+        // ---- C (group v): compare
+        if (is_group(GC)) {
+            cp_async_wait_all();
+            __syncwarp();
+            const bool act = (mC >> 14) & 1u; const u32 it = (mC >> 9) & 31u, sig = IH_INV(yC);
             bool pass = false;
-            for (u32 s0 = 0; s0 < n_it; s0 += stage_items) {
-                const u32 nb = min(stage_items, n_it - s0), nw = nb * DW;
-                for (u32 x0 = s0 ? 0u : 64u; x0 < nw; x0 += 64) {                // the first 64 words of the first batch are already on their way
-                    const u32 ya = x0 + lane, yb = ya + 32u;
-                    const u32 ja = min(__umulhi(ya, rcp_dw), nb - 1u), jb = min(__umulhi(yb, rcp_dw), nb - 1u);
-                    const u32 ta = __shfl_sync(FULL, soff, s0 + ja), tb = __shfl_sync(FULL, soff, s0 + jb);
-                    u64 wa = 0, wb = 0;
-                    if (ya < nw) wa = __ldg(bits64 + ta + (ya - ja * DW));
-                    if (yb < nw) wb = __ldg(bits64 + tb + (yb - jb * DW));
-                    if (ya < nw) S64[ya] = wa;
-                    if (yb < nw) S64[yb] = wb;
-                }
-                __syncwarp();
-                if (act && it >= s0 && it < s0 + nb) {
-                    if (!screen || (sig && ((nfl >> (sec & 31u)) & 1u))) pass = true;   // not screened on this strand: exact count decides
-                    else {
-                        const u32 *Lo = S0 + (size_t)(it - s0) * D + (sig ? 2 * Wb : 0u), *M = Lo + Wb;
-                        const u32 fm = sig ? flipm : 0u;
-                        u32 low = 0;
+            if (act) {
+                if (!((cx >> 14) & 1u) || (sig && ((nfl >> ((cx >> 15) & 31u)) & 1u))) pass = true;     // not screened on this strand: the exact count decides
+                else {
+                    const uint2 *Sr = (const uint2 *)(S0 + (size_t)it * item_bytes + (sig ? 8u * Wb : 0u));   // {low bits, ACGT mask} per 32 bases
+                    const u32 sft = (cx >> 5) & 31u, nW = (cx >> 10) & 15u, d8 = cx & 31u;
+                    u32 low = 0;
 #pragma unroll
-                        for (int x = 0; x < 7; x++) {
-                            const u32 i = (u32)x + dlt;
-                            if (i < nW) low += __popc((Lo[i] ^ __funnelshift_l(R[x + 1], R[x], sft) ^ fm) & M[i]);
-                        }
-                        pass = low <= IH_THR(pack);
+                    for (int x = 0; x < 7; x++) {
+                        const u32 i = (u32)x + d8 - 8u;
+                        if (i < nW) { const uint2 lm = Sr[i]; low += __popc((lm.x ^ __funnelshift_l(R[x + 1], R[x], sft)) & lm.y); }
                     }
+                    pass = low <= IH_THR(yC);
                 }
-                __syncwarp();
             }
             const u32 bal = __ballot_sync(FULL, pass);
             if (bal) {
-                if (pass) Q[qn + __popc(bal & ((1u << lane) - 1u))] = make_uint4(gbeg + lane, g, pack, islot | (sig << 31));
+                if (pass) Q[qn + __popc(bal & ((1u << lane) - 1u))] = make_uint4(((u32)GC << 5) + lane, gC, yC, mC & 511u);
                 qn += __popc(bal);
                 __syncwarp();
-                if (qn >= 32u) { qn -= 32u; if (!(dbg & 1u)) drain(qn, 32u); }
+                if (qn >= 32u) { qn -= 32u; drain_exact<true>(A, Q[qn + lane], true); }
             }
         }
+        // ---- S (group v+1): its items' 1-bit streams into the slice the compare above has just left
+        __syncwarp();
+        if (is_group(GB2)) {
+            if (rec2 != FULL) {
+                const unsigned char *src = bits + (size_t)rec2 * RB; const u32 dst = S0a + lane * item_bytes;
+                for (u32 part = 0; part < Wb; part++) cp_async16(dst + 16u * part, src + 16u * part);
+            }
+            cp_async_commit();
+        }
+        // ---- B1 (group v+2): item of every candidate, strand, window start; strand-table look-up
+        u32 g1 = 0, y1 = 0, m1 = 0, rec1 = FULL; uint2 ce1 = make_uint2(0u, 0u);
+        if (is_group(GB1)) {
+            const u32 gbeg = (u32)GB1 << 5, gend = min(gbeg + 32u, n_cands);
+            const bool act = gbeg + lane < gend;
+            const bool mine = hB.x != FULL && (lane == 0 || hB.x < gend);
+            const u32 pos = (mine && hB.x > gbeg) ? hB.x - gbeg : 0u;
+            const u32 mask = __reduce_or_sync(FULL, mine ? 1u << pos : 0u);
+            const u32 it = __popc(mask & (FULL >> (31u - lane))) - 1u;           // my candidate's item = lane `it`
+            const u32 ibase = __shfl_sync(FULL, hB.x, it), hy = __shfl_sync(FULL, hB.y, it), hz = __shfl_sync(FULL, hB.z, it), hw = __shfl_sync(FULL, hB.w, it);
+            const u32 sig = ih_strand(gbeg + lane - ibase, hy, hz, hw);          // forward-strand entries come first (align.cpp:296)
+            g1 = clB - IH_H(hw);                                                 // _hit.loc (align.cpp:297)
+            y1 = (hy & ~(1u << 27)) | (sig << 27);
+            m1 = IH_L(hz) | (it << 9) | ((act ? 1u : 0u) << 14) | ((u32)__popc(mask) << 15);
+            if (act && sig) ce1 = __ldg(A.di.ctab + (g1 >> BSL_CTAB_SHIFT));
+            if (mine) rec1 = IH_SLOT(hB.y) * 2 + IH_CHAIN(hB.y);
+            if (lane == 0) A.bitmap[GB1] = 0u;                                   // bits are set by drain_exact
+        }
+        // ---- P (group v+3): headers and loc entries
+        uint4 hN = make_uint4(FULL, 0, 0, 0); u32 clN = 0;
+        if (is_group(GP)) {
+            if (fP + lane <= lP) hN = __ldg((const uint4 *)(A.hdr + fP + lane));
+            const u32 c = ((u32)GP << 5) + lane;
+            if (c < n_cands) clN = __ldg(A.flat_loc + c);
+        }
+        // ---- F (group v+4)
+        if (is_group(GF)) { fP = __ldg(A.chunk_first + GF); lP = GF + 1 < n_groups ? __ldg(A.chunk_first + GF + 1) : n_items - 1u; }
+        // ---- rotate
+#pragma unroll
+        for (int j = 0; j < 8; j++) R[j] = Rn[j];
+        nfl = nfl_n; cx = cx_n; gC = g2; yC = y2; mC = m2;
+        g2 = g1; y2 = y1; m2 = m1; rec2 = rec1; ce2 = ce1;
+        hB = hN; clB = clN;
     }
-    if (qn) drain(0u, qn);
+    __syncwarp();
+    if (qn) drain_exact<true>(A, Q[min(lane, qn - 1u)], lane < qn);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1352,6 +1200,8 @@ __global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_co
     u64 *win_all = smem + (size_t)wid * (32 * NWS + 48 + RR_KEYS);
     u64 *pq = win_all + 32 * NWS, *pn = pq + 16, *pc = pn + 16, *keys = pc + 16;
     RoundCtr *rc = A.ctr->rc + ci;
+    const unsigned long long al_rc = min(rc->alloc, ~rc->limit_inv);
+    const u32 n_cands_rc = (u32)(al_rc & ALLOC_MASK), n_items_rc = (u32)(al_rc >> ALLOC_SHIFT);
     // every slot searched in this round: SE = the compacted list seed_lookup wrote, PE = both mates of every listed pair;
     // a warp takes 32 of them at a time and replays those verify_candidates flagged
     const u32 n_entries = A.ctr->rc[list_ci].active << (as_pe ? 1 : 0);
@@ -1385,12 +1235,13 @@ __global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_co
             if (!(m.flags & (c ? SF_CHAIN1 : SF_CHAIN0))) continue;
             const uint2 si = A.slot_item[(u64)slot * 2 + c];
             const u32 ni = si.y;
-            // ---- the items (non-empty buckets) of this chain, one per lane
-            u32 pm = 0, pb0 = 0, pnf = 0, ph_h = 0, prot = 0, pphase = 0, pbase = 0;
+            // ---- the items (non-empty buckets) of this chain, one per lane; an item ends where the next one begins
+            u32 pm = 0, py = 0, pz = 0, pw_ = 0, ph_h = 0, pphase = 0, pbase = 0;
             if (lane < ni) {
-                const uint4 *src = (const uint4 *)(A.hdr + si.x + lane); const uint4 a = src[0], b = src[1];
-                pbase = a.x; pm = a.y; pb0 = a.z; pnf = a.w; prot = b.x; ph_h = IH_H(b.y); pphase = IH_PHASE(b.y);
-            }
+                const uint4 a = *(const uint4 *)(A.hdr + si.x + lane);
+                pbase = a.x; py = a.y; pz = a.z; pw_ = a.w; ph_h = IH_H(a.w); pphase = IH_PHASE(a.y);
+            } else if (lane == ni) pbase = si.x + ni < n_items_rc ? A.hdr[si.x + ni].base : n_cands_rc;
+            { const u32 nxt = __shfl_down_sync(0xffffffffu, pbase, 1); if (lane < ni) pm = nxt - pbase; }
             u32 incl = pm;
             for (u32 o = 1; o < 32; o <<= 1) { u32 v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
             const u32 poff = incl - pm; const u32 total = __shfl_sync(0xffffffffu, incl, 31);
@@ -1412,13 +1263,12 @@ __global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_co
                 u32 ph = 0;
                 for (u32 i = 1; i < ni; i++) { u32 o = __shfl_sync(0xffffffffu, poff, i); if (idx >= o) ph = i; }
                 const u32 t = idx - __shfl_sync(0xffffffffu, poff, ph);
-                const u32 cm_ = __shfl_sync(0xffffffffu, pm, ph), crot = __shfl_sync(0xffffffffu, prot, ph), cb0 = __shfl_sync(0xffffffffu, pb0, ph);
-                const u32 cnf = __shfl_sync(0xffffffffu, pnf, ph); const u32 ch = __shfl_sync(0xffffffffu, ph_h, ph);
+                const u32 cy = __shfl_sync(0xffffffffu, py, ph), cz = __shfl_sync(0xffffffffu, pz, ph), cw = __shfl_sync(0xffffffffu, pw_, ph);
+                const u32 ch = __shfl_sync(0xffffffffu, ph_h, ph);
                 u32 g = 0, sig = 0, rel = 0;
                 u64 *win = win_all + lane * NWS;
                 if (valid) {
-                    u32 e = crot + t; if (e >= cm_) e -= cm_;
-                    sig = e >= cnf ? 1u : 0u;
+                    sig = ih_strand(t, cy, cz, cw);                             // forward-strand entries come first (align.cpp:296)
                     g = A.flat_loc[flat] - ch;                                  // _hit.loc (align.cpp:297)
                     const u32 gb = g - G; const u32 word0 = gb >> 5; rel = (gb & 31u) + G;      // window starts at word0; alignment starts `rel` bases into it
                     const u64 *P = A.di.plane[sig] + word0;
@@ -1965,20 +1815,37 @@ static int ensure_lane(bsl_ctx *ctx, Lane &ln) {
     return 0;
 }
 
-// longest read of a sub-range; *sched_max (optional) = the largest number of read offsets the seed schedule of one read can
-// touch: segments x (I + (L - I + 1) % s), segments <= (L - I + 1) / s (align.cpp:450, 476-480)
-static u32 max_len_of(const bsl_batch *b, u32 first, u32 n, const bsl_params *P = nullptr, u32 *sched_max = nullptr) {
-    u32 mx = 0, last = 0xffffffffu, sm = sched_max ? *sched_max : 0;
+// longest read of a sub-range; dims (optional) = shared-memory row sizes of prepare_reads over the read lengths present:
+// dims[0] = most read offsets per seed segment the schedule can touch, I + (L - I + 1) % s; dims[1] = largest CountSeeds table,
+// segments x ((L - I + 1) % s + 1) with segments <= (L - I + 1) / s (align.cpp:450, 476-480)
+static u32 max_len_of(const bsl_batch *b, u32 first, u32 n, const bsl_params *P = nullptr, u32 *dims = nullptr) {
+    u32 mx = 0, last = 0xffffffffu;
     for (u32 i = first; i < first + n; i++) {
         const u64 l = b->offsets[i + 1] - b->offsets[i];
         if (l > mx) mx = (u32)std::min<u64>(l, 0xffffffffu);
-        if (P && (u32)l != last) {
+        if (P && dims && (u32)l != last) {
             last = (u32)l; const u32 L = (u32)std::min<u64>(l, BSL_MAX_READLEN), I = P->index_interval, s = P->seed_size;
-            if (L + 1 >= I + s) sm = std::max(sm, std::min<u32>((L + 1 - I) / s, 16) * (I + (L + 1 - I) % s));
+            if (L + 1 >= I + s) { const u32 ii = (L + 1 - I) % s; dims[0] = std::max(dims[0], I + ii); dims[1] = std::max(dims[1], std::min<u32>((L + 1 - I) / s, 16) * (ii + 1)); }
         }
     }
-    if (sched_max) *sched_max = sm;
     return mx;
+}
+
+// Opt-in shared-memory sizes are per device: done once per context (under its first lane's lock or any later one: idempotent).
+static int configure_kernels(bsl_ctx *ctx) {
+    std::lock_guard<std::mutex> g(ctx->stats_mu);
+    if (ctx->kernels_configured) return 0;
+    CUDA_TRY(cudaFuncSetAttribute(prepare_reads, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(screen_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(pair_round_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairWideSmem)));
+    CUDA_TRY(cudaFuncSetAttribute(reduce_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(reduce_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(verify_candidates<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(verify_candidates<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(verify_candidates<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(verify_candidates<false, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    ctx->kernels_configured = true;
+    return 0;
 }
 
 // One sub-range [first, first+n_a) of the caller's batch on one lane. Sub-ranges keep the number of items a search
@@ -1992,8 +1859,8 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
 
     const u64 off0_a = a->offsets[first], off0_b = pe ? b->offsets[first] : 0;
     const u64 bases_a = a->offsets[first + n_a] - off0_a, bases_b = pe ? b->offsets[first + n_a] - off0_b : 0;
-    u32 sched_max = 0;
-    u32 Lmax = max_len_of(a, first, n_a, &P, &sched_max); if (pe) Lmax = std::max(Lmax, max_len_of(b, first, n_a, &P, &sched_max));
+    u32 pdims[2] = {P.index_interval, 1};
+    u32 Lmax = max_len_of(a, first, n_a, &P, pdims); if (pe) Lmax = std::max(Lmax, max_len_of(b, first, n_a, &P, pdims));
     if (Lmax > BSL_MAX_READLEN) Lmax = BSL_MAX_READLEN;       // longer reads are flagged filtered by prepare_reads; the CLI truncates like the reference
     const u32 Wb = std::max(1u, (Lmax + 31) / 32);
     const u32 cap = 32;
@@ -2001,14 +1868,16 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
 
     // ---- buffers
     size_t c0;
-    c0 = ln.cap_bases; if ((rc = grow(ctx, &ln.d_bases, &c0, (size_t)(bases_a + bases_b + 16)))) return rc; ln.cap_bases = c0;
+    c0 = ln.cap_bases; if ((rc = grow(ctx, &ln.d_bases, &c0, (size_t)(bases_a + bases_b + 2 * BASES_PAD)))) return rc; ln.cap_bases = c0;
     {
         size_t need = n_slots + 2;
         if (need > ln.cap_slots) {
             size_t ncap = std::max(need, ln.cap_slots + ln.cap_slots / 2);
-            cudaFree(ln.d_off); cudaFree(ln.d_index); cudaFree(ln.d_rawlen); cudaFree(ln.d_meta); cudaFree(ln.d_cnt); cudaFree(ln.d_sched); cudaFree(ln.d_stat);
-            cudaFree(ln.d_minlvl); cudaFree(ln.d_slot_item); cudaFree(ln.d_slot_flag); cudaFree(ln.d_flag_list); cudaFree(ln.d_marks);
-            cudaFree(ln.d_list[0]); cudaFree(ln.d_list[1]); cudaFree(ln.d_pe_list[0]); cudaFree(ln.d_pe_list[1]); cudaFree(ln.d_heavy_list); cudaFree(ln.d_out); cudaFree(ln.d_pair);
+            // free-and-null first: a failed allocation below leaves the lane with null pointers and zero capacity, so the next call starts clean
+            auto drop = [](auto *&q) { cudaFree(q); q = nullptr; };
+            drop(ln.d_off); drop(ln.d_index); drop(ln.d_rawlen); drop(ln.d_meta); drop(ln.d_cnt); drop(ln.d_sched); drop(ln.d_stat);
+            drop(ln.d_minlvl); drop(ln.d_slot_item); drop(ln.d_slot_flag); drop(ln.d_flag_list); drop(ln.d_marks);
+            drop(ln.d_list[0]); drop(ln.d_list[1]); drop(ln.d_pe_list[0]); drop(ln.d_pe_list[1]); drop(ln.d_heavy_list); drop(ln.d_out); drop(ln.d_pair);
             ln.cap_slots = 0;
             CUDA_TRY(cudaMalloc(&ln.d_off, (ncap + 4) * 8)); CUDA_TRY(cudaMalloc(&ln.d_index, ncap * 4)); CUDA_TRY(cudaMalloc(&ln.d_rawlen, ncap * 2));
             CUDA_TRY(cudaMalloc(&ln.d_meta, ncap * sizeof(SlotMeta))); CUDA_TRY(cudaMalloc(&ln.d_cnt, ncap * sizeof(SlotCounts))); CUDA_TRY(cudaMalloc(&ln.d_sched, ncap * 32)); CUDA_TRY(cudaMalloc(&ln.d_stat, ncap * sizeof(uint2)));
@@ -2035,15 +1904,16 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     if (2 * worst_slot + CHUNK > want_cands) { set_error(ctx, "over-represented k-mer cut-off %u is too large for the 32-bit candidate space", ctx->di.maxk); return BSL_ELIMIT; }
     const u64 want_items = std::min<u64>((u64)n_slots * nch * P.index_interval, want_cands) + 16;
     c0 = ln.cap_bitmap; if ((rc = grow(ctx, &ln.d_bitmap, &c0, (size_t)(want_cands / 32 + 8)))) return rc;
-    if (c0 != ln.cap_bitmap || !ln.d_chunk_first) { cudaFree(ln.d_chunk_first); ln.d_chunk_first = nullptr; CUDA_TRY(cudaMalloc(&ln.d_chunk_first, (c0 + 8) * 4));
-        cudaFree(ln.d_flat_loc); ln.d_flat_loc = nullptr; CUDA_TRY(cudaMalloc(&ln.d_flat_loc, (c0 * 32 + 2 * CHUNK) * 4)); }
+    if (c0 != ln.cap_bitmap || !ln.d_chunk_first || !ln.d_flat_loc) {
+        cudaFree(ln.d_chunk_first); ln.d_chunk_first = nullptr; cudaFree(ln.d_flat_loc); ln.d_flat_loc = nullptr; ln.cap_bitmap = 0;
+        CUDA_TRY(cudaMalloc(&ln.d_chunk_first, (c0 + 8) * 4)); CUDA_TRY(cudaMalloc(&ln.d_flat_loc, (c0 * 32 + 2 * CHUNK) * 4)); }
     ln.cap_bitmap = c0;
     c0 = ln.cap_items; if ((rc = grow(ctx, &ln.d_hdr, &c0, (size_t)want_items))) return rc; ln.cap_items = c0;
     const bool want_all = P.report_repeat_hits == 2 && all_a && (!pe || all_b) && all_cap > 0;
     const u64 sub_cap = all_cap > all_off ? all_cap - all_off : 0;      // room left in the caller's all-hits arrays
     if (want_all) {
         const u64 dcap = std::max<u64>(sub_cap, 1);
-        if (dcap > ln.cap_all) { cudaFree(ln.d_all[0]); cudaFree(ln.d_all[1]); ln.cap_all = 0;
+        if (dcap > ln.cap_all) { cudaFree(ln.d_all[0]); cudaFree(ln.d_all[1]); ln.d_all[0] = ln.d_all[1] = nullptr; ln.cap_all = 0;
             CUDA_TRY(cudaMalloc(&ln.d_all[0], dcap * sizeof(bsl_hit))); CUDA_TRY(cudaMalloc(&ln.d_all[1], dcap * sizeof(bsl_hit))); ln.cap_all = dcap; }
     }
 
@@ -2053,7 +1923,7 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     A.s = P.seed_size; A.I = P.index_interval; A.gap = P.gap; A.w = P.max_num_hits; A.min_insert = P.min_insert; A.max_insert = P.max_insert;
     A.chains = P.chains; A.report = P.report_repeat_hits; A.randseed = P.randseed; A.max_ns = P.max_ns; A.min_read_size = P.min_read_size; A.single = ctx->rule.single;
     A.n_slots = n_slots; A.n_a = n_a; A.pe = pe; A.readset_a = a->readset; A.readset_b = pe ? b->readset : 0;
-    A.bases = ln.d_bases; A.off = ln.d_off; A.index = ln.d_index; A.rawlen = ln.d_rawlen; A.first_index_a = a->first_index + first; A.first_index_b = pe ? b->first_index + first : 0;
+    A.bases = ln.d_bases + BASES_PAD; A.off = ln.d_off; A.index = ln.d_index; A.rawlen = ln.d_rawlen; A.first_index_a = a->first_index + first; A.first_index_b = pe ? b->first_index + first : 0;
     A.off_base_a = off0_a; A.off_base_b = off0_b; A.all_off = all_off;
     A.bases_b_shift = bases_a; A.has_index = (a->index != nullptr) && (!pe || b->index != nullptr); A.has_rawlen = (a->raw_len != nullptr) && (!pe || b->raw_len != nullptr);
     A.Wb = Wb; A.planes = ln.d_planes; A.bits1 = ln.d_bits1; A.sched = ln.d_sched; A.meta = ln.d_meta; A.cnt = ln.d_cnt; A.stat = ln.d_stat; A.minlvl = ln.d_minlvl;
@@ -2066,10 +1936,10 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     CUDA_TRY(cudaEventRecord(ln.ev[0], st));
     CUDA_TRY(cudaMemsetAsync(ln.d_ctr, 0, sizeof(DevCounters), st));
     if (!resident) {
-    CUDA_TRY(cudaMemcpyAsync(ln.d_bases, a->bases + off0_a, bases_a, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ln.d_bases + BASES_PAD, a->bases + off0_a, bases_a, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(ln.d_off, a->offsets + first, (size_t)(n_a + 1) * 8, cudaMemcpyHostToDevice, st));
     if (pe) {
-        CUDA_TRY(cudaMemcpyAsync(ln.d_bases + bases_a, b->bases + off0_b, bases_b, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ln.d_bases + BASES_PAD + bases_a, b->bases + off0_b, bases_b, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(ln.d_off + (n_a + 1), b->offsets + first, (size_t)(n_a + 1) * 8, cudaMemcpyHostToDevice, st));
     }
     }
@@ -2083,20 +1953,12 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     const int sms = ctx->sm_count;
     CUDA_TRY(cudaEventRecord(ln.ev[1], st));
     {
-        // prepare_reads2 needs 32 x (2 WQ + cap) words of shared memory per warp; cap = the largest number of read offsets the
-        // seed schedule of one read can touch (+ 32 for its start / key arrays). Very long reads with small -s fall back to
-        // the warp-per-read kernel.
-        static const bool prep_old = getenv("BSL_PREP_OLD") != nullptr;
+        // prepare_reads keeps 2 WQ + 2 Wb + wd + nseg (ii + 1) words per read in shared memory (<= 200 KB per CTA for any -s / -I / length)
         const u32 WQ = 2 * Wb + 3;
-        const u32 cap = (sched_max + 32) | 1u;
-        const size_t smem_p = (size_t)P2_WARPS * 32 * (2 * WQ + cap) * 4;
-        if (!prep_old && smem_p <= 160 * 1024) {
-            static bool attr_p = false;
-            if (!attr_p) { cudaFuncSetAttribute(prepare_reads2, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_p = true; }
-            const u32 groups = (n_slots + 31) / 32;
-            prepare_reads2<<<std::min<u32>((groups + P2_WARPS - 1) / P2_WARPS, (u32)sms * 8), P2_WARPS * 32, smem_p, st>>>(A, WQ, cap);
-        } else
-            prepare_reads<<<std::min<u32>((n_slots + PREP_WARPS - 1) / PREP_WARPS, (u32)sms * 16), PREP_WARPS * 32, 0, st>>>(A);
+        const size_t smem_p = (size_t)PR_WARPS * 32 * ((2 * WQ + 2 * Wb + pdims[0] + pdims[1]) | 1u) * 4;
+        if (smem_p > 200 * 1024) { set_error(ctx, "seed schedule does not fit the shared memory of prepare_reads"); return BSL_ELIMIT; }
+        const u32 groups = (n_slots + 31) / 32;
+        prepare_reads<<<std::min<u32>((groups + PR_WARPS - 1) / PR_WARPS, (u32)sms * 16), PR_WARPS * 32, smem_p, st>>>(A, WQ, pdims[0], pdims[1]);
         launches++;
     }
     build_lists<<<(std::max(n_slots, n_a) + 255) / 256, 256, 0, st>>>(A, ln.d_list[0], ln.d_pe_list[0]); launches++;
@@ -2111,16 +1973,6 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     const u32 Wr = (Lmax + 31) / 32;                                     // 64-bit words of the longest read
     const bool ns3 = Wr + 1 + 3 <= 12;                                   // a window (Wr + 1 words at any of 4 word offsets) fits 3 sectors
     const size_t smem_v = (size_t)VF_ITMAX * NPL * 2 * Wb * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(pair_round_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairWideSmem));
-        cudaFuncSetAttribute(reduce_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        cudaFuncSetAttribute(reduce_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-#define VF_ATTR(S_) cudaFuncSetAttribute(verify_candidates<S_, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024); cudaFuncSetAttribute(verify_candidates<S_, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024)
-        VF_ATTR(true); VF_ATTR(false);
-#undef VF_ATTR
-        attr_set = true;
-    }
     const u32 rounds_se = std::min<u32>((Lmax + 1 >= P.index_interval + P.seed_size) ? (Lmax + 1 - P.index_interval) / P.seed_size : 0, 16);
     const int vkind = ctx->rule.single ? 0 : 1;
     if (G && !ctx->occ_verify[vkind]) {
@@ -2147,16 +1999,13 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     }
     const int grid_s = sms * ctx->occ_screen;
     // 1-bit screen (single-conversion rules)
-    static const bool no_bits = getenv("BSL_NO_BITS") != nullptr;
-    static const u32 dbg_bits = getenv("BSL_DBG") ? (u32)atoi(getenv("BSL_DBG")) : 0u;
-    const bool use_bits = ctx->di.has_bit1 && !no_bits;
-    const u32 stage_items_b = std::max<u32>(2, std::min<u32>(32, 640 / (4 * Wb)));
-    const size_t smem_b = (size_t)SC_WARPS * stage_items_b * (4 * Wb) * 4;
-    const u32 rcp_b = (u32)((0x100000000ull + 2 * Wb - 1) / (2 * Wb));
-    if (!ctx->occ_bits) { int occ = 0; cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, screen_bits, SC_WARPS * 32, smem_b); ctx->occ_bits = (oe == cudaSuccess && occ > 0) ? occ : 4; }
+    const bool use_bits = ctx->di.has_bit1 != 0;
+    const u32 item_bytes = 16 * Wb + 16;                                  // staged item: {low bits, ACGT mask} x Wb forward, x Wb reversed (+16: bank spread)
+    const size_t smem_b = (size_t)SB_WARPS * 32 * item_bytes;
+    if (!ctx->occ_bits || ctx->occ_bits_wb != Wb) { int occ = 0; cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, screen_bits, SB_WARPS * 32, smem_b); ctx->occ_bits = (oe == cudaSuccess && occ > 0) ? occ : 1; ctx->occ_bits_wb = Wb; }
     const int grid_b = sms * ctx->occ_bits;
     auto launch_verify = [&](KArgs &K, u32 ci) {
-        if (!G && use_bits) { screen_bits<<<grid_b, SC_WARPS * 32, smem_b, st>>>(K, ci, stage_items_b, rcp_b, dbg_bits); return; }
+        if (!G && use_bits) { screen_bits<<<grid_b, SB_WARPS * 32, smem_b, st>>>(K, ci, item_bytes); return; }
         if (!G) {
             if (ctx->rule.single) screen_candidates<true><<<grid_s, SC_WARPS * 32, smem_s, st>>>(K, ci, stage_items, rcp_dw);
             else screen_candidates<false><<<grid_s, SC_WARPS * 32, smem_s, st>>>(K, ci, stage_items, rcp_dw);
@@ -2284,10 +2133,12 @@ int bsl_align_impl(bsl_ctx *ctx, const bsl_batch *a, const bsl_batch *b, bsl_hit
     if (!lnp) { lk = std::unique_lock<std::mutex>(ctx->lanes[0].mu); lnp = &ctx->lanes[0]; }
     Lane &ln = *lnp;
     int rc = ensure_lane(ctx, ln); if (rc) return rc;
+    if ((rc = configure_kernels(ctx))) return rc;
+    if (ctx->di.maxk >= BSL_MAX_BUCKET) { set_error(ctx, "over-represented k-mer cut-off %u exceeds the largest bucket a walk can visit (%u)", ctx->di.maxk, BSL_MAX_BUCKET - 1); return BSL_ELIMIT; }
     // sub-ranges: a search round may create at most MAX_ITEMS_PER_ROUND items (slots x enabled chains x -I look-ups)
     const bsl_params &P = ctx->P;
     const u32 per_read = (P.chains == 1 ? 2u : 1u) * P.index_interval * (pe ? 2u : 1u);
-    u32 sub = std::max<u32>(1024u, MAX_ITEMS_PER_ROUND / per_read);
+    u32 sub = std::min<u32>(std::max<u32>(1024u, MAX_ITEMS_PER_ROUND / per_read), BSL_MAX_SLOTS / (pe ? 2u : 1u));
     const char *env_sub = getenv("BSL_SUB_BATCH"); if (env_sub && atoi(env_sub) > 0) sub = (u32)atoi(env_sub);
     if (resident && n > sub) { set_error(ctx, "bsl_align_rerun: the batch was split into sub-ranges and is not resident"); return BSL_ESTATE; }
     bsl_stats acc; memset(&acc, 0, sizeof acc);

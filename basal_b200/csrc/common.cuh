@@ -70,7 +70,7 @@ struct RuleTables {
 struct DevIndex {
     const u64 *plane[2];     // forward / reverse-complement 2-bit planes with 400-word margins
     const u32 *bucket;       // [2K+1]: bucket[2k]=first entry of k-mer k, bucket[2k+1]=end of its forward-strand entries
-    const u16 *cnt16;        // [K] saturating bucket sizes for seed selection (0xFFFF -> use bucket[])
+    const u8 *cnt8;          // [K] saturating bucket sizes for seed selection (0xFF -> use bucket[]); 43 MB at -s 16: L2 resident
     const u32 *loc;          // seed table entries (global coordinates), forward entries first per bucket
     const u32 *anchor;       // [nseq+1] ref_anchor (refbase.cpp:222-226)
     const u32 *seqlen;       // [nseq]
@@ -120,22 +120,27 @@ struct __align__(16) SlotMeta {
 struct SlotCounts { u16 c[2][16]; };   // hits per read chain and mismatch level
 
 // ---- work counters -------------------------------------------------------------------------
-// one non-empty seed bucket visited in a search round ("item"): owns the flat candidate range [base, base+m)
-struct __align__(16) ItemHdr {
-    u32 base;     // first flat candidate index of the bucket walk
-    u32 m;        // bucket size (KmerLoc2::n[0])
-    u32 b0;       // first entry in loc[]
-    u32 nfwd;     // forward-strand entries come first (n[1])
-    u32 rot;      // myrand(read index) % m : where the cyclic walk starts (align.cpp:293)
-    u32 pack;     // h | L<<9 | thr<<18 | phase<<22 | chain<<26
-    u32 slot;
-    u32 pad;
-};
-#define IH_H(p)     ((p) & 511u)
-#define IH_L(p)     (((p) >> 9) & 511u)
-#define IH_THR(p)   (((p) >> 18) & 15u)
-#define IH_PHASE(p) (((p) >> 22) & 15u)
-#define IH_CHAIN(p) (((p) >> 26) & 1u)
+// one non-empty seed bucket visited in a search round ("item"): owns the flat candidate range [base, base + m), where
+// base + m is the base of the next item (items and candidates are allocated by one packed counter, so item order is
+// candidate order). The cyclic bucket walk (align.cpp:293-296) starts at entry rot = myrand % m and forward-strand
+// entries come first in a bucket, so the walk positions t = flat index - base that lie on the reverse strand form ONE
+// interval [x1, x2) (inv = 0, rot < n_fwd) or everything but one interval (inv = 1): strand(t) = (x1 <= t < x2) ^ inv.
+//   y: slot (22) | chain << 22 | thr << 23 | inv << 27 | phase << 28
+//   z: x1 (23) | L << 23
+//   w: x2 (23) | h << 23            (h = read offset of the seed: candidate start g = loc - h, align.cpp:297)
+struct __align__(16) ItemHdr { u32 base, y, z, w; };
+#define IH_SLOT(y)  ((y) & 0x3FFFFFu)
+#define IH_CHAIN(y) (((y) >> 22) & 1u)
+#define IH_THR(y)   (((y) >> 23) & 15u)
+#define IH_INV(y)   (((y) >> 27) & 1u)
+#define IH_PHASE(y) ((y) >> 28)
+#define IH_X1(z)    ((z) & 0x7FFFFFu)
+#define IH_L(z)     ((z) >> 23)
+#define IH_X2(w)    ((w) & 0x7FFFFFu)
+#define IH_H(w)     ((w) >> 23)
+#define BSL_MAX_SLOTS (1u << 22)       // slots of one sub-range (ItemHdr::y)
+#define BSL_MAX_BUCKET (1u << 23)      // largest bucket a walk may visit (ItemHdr x1 / x2)
+__host__ __device__ __forceinline__ u32 ih_strand(u32 t, u32 y, u32 z, u32 w) { return ((t >= IH_X1(z) && t < IH_X2(w)) ? 1u : 0u) ^ IH_INV(y); }
 
 // per search round (SE rounds use index r, PE rounds 20+r)
 struct RoundCtr {

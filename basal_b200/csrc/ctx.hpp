@@ -50,7 +50,9 @@ struct bsl_ctx {
     char err[512];
     int sm_count = BSL_SM_COUNT;
     int occ_verify[4] = {0, 0, 0, 0};   // resident CTAs per SM of the verify_candidates variants
-    int occ_bits = 0;                   // resident CTAs per SM of screen_bits
+    int occ_bits = 0;                   // resident CTAs per SM of screen_bits (for occ_bits_wb words per read plane)
+    u32 occ_bits_wb = 0;
+    bool kernels_configured = false;    // opt-in shared-memory sizes set on this context's device
     int occ_screen = 0;                 // resident CTAs per SM of screen_candidates
 };
 

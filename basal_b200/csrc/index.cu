@@ -4,7 +4,7 @@
 //                   --nx_transitions--> N/X run boundaries (UnmaskRegion blocks finished on the host)
 //   blocks --gen_seeds--> (kmer*2+strand, global coordinate) for every I-th window
 //          --cub radix sort--> seed table `loc[]`   (stable: forward entries first, ascending)
-//          --bucket_bounds--> bucket[2K+1], cnt16[K]; counts --radix sort--> max_kmer_num
+//          --bucket_bounds--> bucket[2K+1], cnt8[K]; counts --radix sort--> max_kmer_num
 //
 // Reference behaviour restated here: refbase.cpp:63-128 (BinSeq/cBinSeq/UnmaskRegion),
 // :186-252 (anchors, margins), :254-255 (s_MakeSeed_1), :303-367 (count/alloc/cut-off),
@@ -102,11 +102,11 @@ __global__ void bucket_bounds(const u32 *__restrict__ keys, u64 n, u32 twoK, u32
     for (u32 j = prev; j < cur; j++) bucket[j] = (u32)i;
 }
 
-__global__ void bucket_counts(const u32 *__restrict__ bucket, u32 K, u32 *__restrict__ cnt, u16 *__restrict__ cnt16) {
+__global__ void bucket_counts(const u32 *__restrict__ bucket, u32 K, u32 *__restrict__ cnt, u8 *__restrict__ cnt8) {
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= K) return;
     u32 m = bucket[2 * k + 2] - bucket[2 * k];
-    cnt[k] = m; cnt16[k] = m >= 0xFFFFu ? (u16)0xFFFFu : (u16)m;
+    cnt[k] = m; cnt8[k] = m >= 0xFFu ? (u8)0xFFu : (u8)m;
 }
 
 __global__ void split_bucket(const u32 *__restrict__ bucket, u32 K, u32 *__restrict__ start, u32 *__restrict__ nfwd) {
@@ -127,7 +127,7 @@ template <typename T> int dmalloc(bsl_ctx *ctx, T **p, size_t n) {
 void bsl_index_free_impl(bsl_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree((void *)ctx->di.plane[0]); cudaFree((void *)ctx->di.bucket); cudaFree((void *)ctx->di.cnt16);
+    cudaFree((void *)ctx->di.plane[0]); cudaFree((void *)ctx->di.bucket); cudaFree((void *)ctx->di.cnt8);
     cudaFree((void *)ctx->di.loc); cudaFree((void *)ctx->di.anchor); cudaFree((void *)ctx->di.seqlen); cudaFree((void *)ctx->di.rcoff);
     cudaFree((void *)ctx->di.bit1); cudaFree((void *)ctx->di.nflag); cudaFree((void *)ctx->di.ctab);
     memset(&ctx->di, 0, sizeof ctx->di); ctx->has_index = false;
@@ -231,10 +231,10 @@ int bsl_index_build_impl(bsl_ctx *ctx, const u8 *cat, const u64 *off, const u32 
     u32 K = 1; for (u32 i = 0; i < s; i++) K *= 3;
 
     // ---- seeds -> sort -> table
-    SeedBlock *d_sb = nullptr; u32 *d_keys = nullptr, *d_vals = nullptr, *d_keys2 = nullptr, *d_loc = nullptr, *d_bucket = nullptr; u16 *d_cnt16 = nullptr;
+    SeedBlock *d_sb = nullptr; u32 *d_keys = nullptr, *d_vals = nullptr, *d_keys2 = nullptr, *d_loc = nullptr, *d_bucket = nullptr; u8 *d_cnt8 = nullptr;
     if ((rc_ = dmalloc(ctx, &d_sb, sb.size())) || (rc_ = dmalloc(ctx, &d_keys, ne)) || (rc_ = dmalloc(ctx, &d_vals, ne)) ||
         (rc_ = dmalloc(ctx, &d_keys2, ne)) || (rc_ = dmalloc(ctx, &d_loc, ne + 32)) || (rc_ = dmalloc(ctx, &d_bucket, 2 * (size_t)K + 2)) ||
-        (rc_ = dmalloc(ctx, &d_cnt16, K))) return rc_;
+        (rc_ = dmalloc(ctx, &d_cnt8, (size_t)K + 16))) return rc_;
     if (!sb.empty()) CUDA_TRY(cudaMemcpy(d_sb, sb.data(), sb.size() * sizeof(SeedBlock), cudaMemcpyHostToDevice));
     if (ne) {
         gen_seeds<<<(unsigned)((ne + 255) / 256), 256>>>(d_sb, (u32)sb.size(), ne, I, s, d_fwd, d_rc, d_keys, d_vals);
@@ -251,10 +251,10 @@ int bsl_index_build_impl(bsl_ctx *ctx, const u8 *cat, const u64 *off, const u32 
     bucket_bounds<<<(unsigned)((ne + 1 + 255) / 256), 256>>>(d_keys2, ne, 2 * K, d_bucket);
     CUDA_TRY(cudaGetLastError());
     cudaFree(d_keys); cudaFree(d_vals); cudaFree(d_sb);
-    // ---- counts, cnt16, over-represented k-mer cut-off (refbase.cpp:362-363)
+    // ---- counts, cnt8, over-represented k-mer cut-off (refbase.cpp:362-363)
     u32 *d_cnt = nullptr, *d_cnt_sorted = d_keys2;          // reuse: keys2 has >= K entries only if ne >= K; allocate otherwise
     if ((rc_ = dmalloc(ctx, &d_cnt, K))) return rc_;
-    bucket_counts<<<(K + 255) / 256, 256>>>(d_bucket, K, d_cnt, d_cnt16);
+    bucket_counts<<<(K + 255) / 256, 256>>>(d_bucket, K, d_cnt, d_cnt8);
     CUDA_TRY(cudaGetLastError());
     u32 *d_sorted = nullptr; if ((rc_ = dmalloc(ctx, &d_sorted, K))) return rc_;
     (void)d_cnt_sorted;
@@ -299,7 +299,7 @@ int bsl_index_build_impl(bsl_ctx *ctx, const u8 *cat, const u64 *off, const u32 
         const bool uniform = ((cd['C'] ^ rd['C']) & 1u) == f && ((cd['G'] ^ rd['G']) & 1u) == f && ((cd['T'] ^ rd['T']) & 1u) == f;
         di.flip = f; di.has_bit1 = (ctx->rule.single && uniform) ? 1u : 0u;
     }
-    di.plane[0] = d_fwd; di.plane[1] = d_rc; di.bucket = d_bucket; di.cnt16 = d_cnt16; di.loc = d_loc;
+    di.plane[0] = d_fwd; di.plane[1] = d_rc; di.bucket = d_bucket; di.cnt8 = d_cnt8; di.loc = d_loc;
     di.anchor = d_anchor; di.seqlen = d_len; di.rcoff = d_rcoff; di.nseq = n; di.K = K; di.maxk = maxk; di.n_words = n_words; di.n_entries = ne;
     memset(&ctx->info, 0, sizeof ctx->info);
     ctx->info.n_seq = n; ctx->info.n_kmers = K; ctx->info.sum_length = bases; ctx->info.n_words = n_words; ctx->info.n_entries = ne; ctx->info.max_kmer_num = maxk;

@@ -7,10 +7,11 @@
 // packed words the reference and the CUDA path use) so that it is an independent
 // statement of the *rules*, cf. SURVEY.md Appendix A/D.
 //
-// Parity pin: tests/test_oracle_vs_ref.py diffs this program's SAM against the
+// Parity pin: tests/test_oracle_golden.py diffs this program's SAM against the
 // unmodified reference binary (oracle/_ref/basal, built by oracle/Makefile.ref)
 // and against the committed fixtures in tests/golden/ (made by
-// tests/golden/make_golden.py from that binary).
+// tests/golden/make_golden.py from that binary); tools/fuzz_oracle.py does the same
+// on random flag combinations.
 //
 // Each function cites the reference file:line (under /root/reference) it follows.
 #include <algorithm>
@@ -94,8 +95,18 @@ static u32 myrand(u32 index, u32 seed) {
 // ---------------------------------------------------------------- reference + index
 struct Hit { u32 loc; u32 chr; int gap; u32 gp; };       // gHit (param.h:35-42); chr = 2*seq+strand
 
+// What a SingleAlign object keeps from read to read (align.h:73-77): the reference never clears xseed_start_offset,
+// xseed_array or xseedreg_array, so a read whose start-offset range is empty ((len - I + 1) % s == 0, align.cpp:476-480)
+// inherits the start offset of the last read (same object, same chain) that had a range, and seed positions beyond
+// len - s still hold the hashes of the last read that was long enough to write them (align.cpp:79-150). With -p 1 one
+// object (two for pairs: _sa / _sb) sees every read in input order, which is the deterministic behaviour restated here;
+// memory starts zeroed (the object lives on a fresh thread stack).
+struct Carry { u32 st0[2]; u32 xseed[2][512]; u8 xreg[2][512]; };
+
 struct Context {
     bsl_params P; Rule R;
+    Carry carry[3];                       // aligner objects by ReadInf::readset: 0 single-end, 1 mate #1 (_sa), 2 mate #2 (_sb)
+    bool keep_state = false;              // false: every orc_align_* call starts with fresh objects (like one bsl_align_* call)
     // reference (refbase.cpp:186-252)
     std::vector<std::string> names; std::vector<u32> len, rcoff, anchor;
     std::vector<u8> G[2];                 // one code per base, concatenated with margins, both strands
@@ -177,7 +188,7 @@ struct Shared {                 // state shared by the two chain views of a read
 struct View {
     const Context *C; Shared *S; u32 c;        // read chain
     std::vector<u8> q; std::vector<u8> isN, conv;
-    std::vector<u32> sh; std::vector<u8> sN;
+    u32 *sh; u8 *sN; u32 *st0;                 // xseed_array / xseedreg_array / xseed_start_offset of this chain: live in the Carry
     u32 st[MAXSNPS + 1]; std::pair<int, int> rank[MAXSNPS + 1];
 };
 
@@ -189,17 +200,17 @@ static u32 budget(const bsl_params &P, u32 raw_len, u32 len) {
     return (B + 1) * (len - 1) / raw_len;
 }
 
-static void make_view(View &v, const Context &C, Shared &S, const u8 *seq, u32 chain) {
+static void make_view(View &v, const Context &C, Carry &K, Shared &S, const u8 *seq, u32 chain) {
     const Rule &R = C.R; u32 L = S.L, s = C.P.seed_size;
     v.C = &C; v.S = &S; v.c = chain; v.q.resize(L); v.isN.resize(L); v.conv.resize(L);
+    v.sh = K.xseed[chain]; v.sN = K.xreg[chain]; v.st0 = &K.st0[chain];
     for (u32 k = 0; k < L; k++) {                                           // align.cpp:79-226
         u8 ch = chain ? seq[L - 1 - k] : seq[k];
         v.q[k] = chain ? R.rcode[ch] : R.code[ch];
         v.isN[k] = !R.reg[ch];
         v.conv[k] = (chain ? R.rconv[ch] : R.conv[ch]) == 1;
     }
-    v.sh.resize(L - s + 1); v.sN.resize(L - s + 1);
-    for (u32 p = 0; p + s <= L; p++) {
+    for (u32 p = 0; p + s <= L; p++) {                                      // entries beyond L - s keep what an earlier read wrote
         v.sh[p] = seed_hash(&v.q[p], s); u8 any = 0; for (u32 k = 0; k < s; k++) any |= v.isN[p + k]; v.sN[p] = any;
     }
 }
@@ -219,11 +230,12 @@ static int count_seeds(const View &v, u32 j, u32 st) {
 // ReorderSeed + AdjustSeedStartArray (align.cpp:468-524)
 static void schedule(View &v) {
     const Context &C = *v.C; u32 L = v.S->L, I = C.P.index_interval, s = C.P.seed_size, nseg = v.S->nseg;
-    u32 ii = (L - I + 1) % s, best = 0xffffffffu, st0 = 0;     // empty range: reference reads a stale value; 0 here (SURVEY trap 3)
+    u32 ii = (L - I + 1) % s, best = 0xffffffffu, st0 = *v.st0;  // empty range: the value the previous read left (SURVEY trap 3)
     for (u32 i = 0; i < ii; i++) {
         u32 tt = 0; for (u32 j = 0; j < nseg; j++) tt += (u32)count_seeds(v, j, i);
         if (tt < best) { best = tt; st0 = i; }
     }
+    *v.st0 = st0;
     for (u32 j = 0; j < nseg; j++) v.st[j] = st0;
     for (u32 t = 0; t < nseg; t++) {
         u32 ptr = (t % 2 == 0) ? t / 2 : nseg - 1 - t / 2;
@@ -324,7 +336,7 @@ static void chain_flags(const bsl_params &P, u32 readset, bool on[2]) {     // a
     on[1] = (P.chains == 1) || ((P.chains <= 1) == (readset == 2));
 }
 
-static bool prepare(ReadState &rs, const Context &C, const u8 *seq, u32 len, u32 raw_len, u32 index, u32 readset) {
+static bool prepare(ReadState &rs, Context &C, const u8 *seq, u32 len, u32 raw_len, u32 index, u32 readset) {
     const bsl_params &P = C.P; Shared &S = rs.S;
     rs.filtered = true; S.L = len; S.B = 0;
     if (len < P.min_read_size || len == 0) return false;
@@ -334,7 +346,7 @@ static bool prepare(ReadState &rs, const Context &C, const u8 *seq, u32 len, u32
     S.B = budget(P, raw_len, len); S.thr = S.B; S.Rnd = myrand(index, P.randseed);
     S.nseg = std::min((u32)((len - P.index_interval + 1) / P.seed_size), S.B + 1);   // align.cpp:450
     chain_flags(P, readset, S.on);
-    for (u32 c = 0; c < 2; c++) if (S.on[c]) { make_view(rs.v[c], C, S, seq, c); schedule(rs.v[c]); }
+    for (u32 c = 0; c < 2; c++) if (S.on[c]) { make_view(rs.v[c], C, C.carry[readset < 3 ? readset : 0], S, seq, c); schedule(rs.v[c]); }
     return true;
 }
 
@@ -428,7 +440,7 @@ struct orc_ctx { Context C; };
 extern "C" {
 
 int orc_ctx_create(orc_ctx **out, const bsl_params *p) {
-    orc_ctx *c = new orc_ctx(); c->C.P = *p; memset(&c->C.st, 0, sizeof c->C.st);
+    orc_ctx *c = new orc_ctx(); c->C.P = *p; memset(&c->C.st, 0, sizeof c->C.st); memset(c->C.carry, 0, sizeof c->C.carry);
     std::string rule = std::string(1, p->from_base) + ":" + p->to_bases;
     if (!make_rule(rule, c->C.R)) { fprintf(stderr, "%s\n", c->C.R.err.c_str()); delete c; return BSL_EINVAL; }
     *out = c; return 0;
@@ -464,8 +476,13 @@ uint32_t orc_myrand(uint32_t index, uint32_t seed) { return myrand(index, seed);
 static inline u32 rd_index(const bsl_batch *b, u32 i) { return b->index ? b->index[i] : b->first_index + i; }
 static inline u32 rd_raw(const bsl_batch *b, u32 i, u32 len) { return b->raw_len ? b->raw_len[i] : len; }
 
+// keep = 1: the aligner objects live as long as the context (the stand-alone CLI maps one read per call);
+// keep = 0 (default): every call starts with fresh objects, which is what one bsl_align_se / bsl_align_pe call does
+void orc_keep_state(orc_ctx *c, int keep) { c->C.keep_state = keep != 0; }
+
 int orc_align_se(orc_ctx *c, const bsl_batch *b, bsl_hit *out, bsl_hit *all, uint64_t all_cap, uint64_t *n_all) {
     Context &C = c->C; std::vector<bsl_hit> allv; bool want_all = C.P.report_repeat_hits == 2 && all;
+    if (!C.keep_state) memset(C.carry, 0, sizeof C.carry);
     for (u32 i = 0; i < b->n; i++) {
         const u8 *seq = b->bases + b->offsets[i]; u32 len = (u32)(b->offsets[i + 1] - b->offsets[i]);
         ReadState rs; C.st.reads++;
@@ -481,6 +498,7 @@ int orc_align_pe(orc_ctx *c, const bsl_batch *a, const bsl_batch *b, bsl_hit *oa
                  bsl_hit *all_a, bsl_hit *all_b, uint64_t all_cap, uint64_t *n_all) {
     Context &C = c->C; if (a->n != b->n) return BSL_EINVAL;
     std::vector<bsl_hit> va, vb; bool want_all = C.P.report_repeat_hits == 2 && all_a && all_b;
+    if (!C.keep_state) memset(C.carry, 0, sizeof C.carry);
     for (u32 i = 0; i < a->n; i++) {
         const u8 *sa = a->bases + a->offsets[i], *sb = b->bases + b->offsets[i];
         u32 la = (u32)(a->offsets[i + 1] - a->offsets[i]), lb = (u32)(b->offsets[i + 1] - b->offsets[i]);
@@ -506,7 +524,10 @@ int orc_align_pe(orc_ctx *c, const bsl_batch *a, const bsl_batch *b, bsl_hit *oa
                     ha.all_first = hb.all_first = x.insert; va.push_back(ha); vb.push_back(hb); } }
             reported = true; break;
         }
-        if (!reported) { report_single(A, oa[i], nullptr); report_single(B, ob[i], nullptr); }
+        if (!reported) {                                                                 // pairs.cpp:232-305: -r 2 lists every hit of a multi-hit mate
+            report_single(A, oa[i], want_all ? &va : nullptr); vb.resize(va.size());
+            report_single(B, ob[i], want_all ? &vb : nullptr); va.resize(vb.size());
+        }
     }
     if (n_all) *n_all = va.size();
     if (want_all) { u64 k = std::min<u64>(va.size(), all_cap); memcpy(all_a, va.data(), k * sizeof(bsl_hit)); memcpy(all_b, vb.data(), k * sizeof(bsl_hit)); }
@@ -655,6 +676,7 @@ int main(int argc, char **argv) {
     if (O.M.size() < 2) { fprintf(stderr, "\n-M option is required\n"); return 1; }
     P.from_base = O.M[0]; strncpy(P.to_bases, O.M.c_str() + 2, 6);
     orc_ctx *ctx; if (orc_ctx_create(&ctx, &P)) return 1; Context &C = ctx->C;
+    orc_keep_state(ctx, 1);                                                     // one read (pair) per call below: the aligner objects must outlive the calls
     { Rule chk; if (!make_rule(O.M, chk)) { fprintf(stderr, "%s\n", chk.err.c_str()); return 1; } }
     // FASTA: name = first token after '>', sequence tokens concatenated (refbase.cpp:17-61)
     std::ifstream fd(O.d.c_str()); if (!fd) { fprintf(stderr, "\nfailed to open reference file (check -d option): %s\n", O.d.c_str()); return 1; }
@@ -691,7 +713,7 @@ int main(int argc, char **argv) {
         } else {
             u64 offb[2] = {0, rb.seq.size()}; bsl_batch bb = ba; ba.readset = 1; bb.readset = 2;
             ba.bases = (const u8 *)ra.seq.data(); offs[1] = ra.seq.size(); bb.bases = (const u8 *)rb.seq.data(); bb.offsets = offb;
-            bsl_hit ha, hb; bsl_pair pr; std::vector<bsl_hit> alla(1100), allb(1100); u64 nall = 0;
+            bsl_hit ha, hb; bsl_pair pr; std::vector<bsl_hit> alla(2 * 1001 * 16 * 2), allb(alla.size()); u64 nall = 0;
             orc_align_pe(ctx, &ba, &bb, &ha, &hb, &pr, alla.data(), allb.data(), alla.size(), &nall);
             fix_names(ra.name, rb.name);
             bool reported = false;
@@ -705,9 +727,11 @@ int main(int argc, char **argv) {
                 u32 ca = ha.read_chain, cb = hb.read_chain;
                 if (ma <= 0) { if (O.unmap) out_unpair(os, O, C, ra, 0, 0, cb, ma, 0, ha, mb1, hb); }
                 else if (ma == 1 || P.report_repeat_hits == 1) out_unpair(os, O, C, ra, 0, ca, cb, ma, ha.nm, ha, mb1, hb);
+                else if (P.report_repeat_hits == 2) { for (int k = 0; k < ma; k++) { const bsl_hit &x = alla[ha.all_first + k]; out_unpair(os, O, C, ra, 0, x.read_chain, cb, ma, ha.nm, x, mb1, hb); } }   // pairs.cpp:270-274
                 else if (P.report_repeat_hits == 0 && O.unmap) out_unpair(os, O, C, ra, 0, 0, cb, 0, 0, ha, mb1, hb);
                 if (mb <= 0) { if (O.unmap) out_unpair(os, O, C, rb, 1, 0, ca, mb, 0, hb, ma1, ha); }
                 else if (mb == 1 || P.report_repeat_hits == 1) out_unpair(os, O, C, rb, 1, cb, ca, mb, hb.nm, hb, ma1, ha);
+                else if (P.report_repeat_hits == 2) { for (int k = 0; k < mb; k++) { const bsl_hit &x = allb[hb.all_first + k]; out_unpair(os, O, C, rb, 1, x.read_chain, cb, mb, hb.nm, x, ma1, ha); } }   // pairs.cpp:293-297 (chain_b is cb there, not ca)
                 else if (P.report_repeat_hits == 0 && O.unmap) out_unpair(os, O, C, rb, 1, 0, ca, 0, 0, hb, ma1, ha);
             }
         }
