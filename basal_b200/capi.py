@@ -29,7 +29,7 @@ class Params(C.Structure):
 
 class Batch(C.Structure):
     _fields_ = [("n", C.c_uint32), ("readset", C.c_uint32), ("bases", C.c_void_p), ("offsets", C.c_void_p),
-                ("index", C.c_void_p), ("first_index", C.c_uint32), ("reserved", C.c_uint32), ("raw_len", C.c_void_p)]
+                ("index", C.c_void_p), ("first_index", C.c_uint32), ("n_context", C.c_uint32), ("raw_len", C.c_void_p)]
 
 
 HIT_DTYPE = np.dtype([("loc", "<u4"), ("chr", "<u4"), ("n_hits", "<u4"), ("n_chain0", "<u4"), ("gap_size", "<i4"),
@@ -137,7 +137,8 @@ class ReadBatch:
     """Host-side batch: concatenated ASCII bases + offsets (bsl_batch)."""
 
     def __init__(self, bases: np.ndarray, offsets: np.ndarray, readset: int = 0, first_index: int = 0,
-                 index: Optional[np.ndarray] = None, raw_len: Optional[np.ndarray] = None):
+                 index: Optional[np.ndarray] = None, raw_len: Optional[np.ndarray] = None, n_context: int = 0):
+        self.n_context = n_context          # the first n_context reads only re-establish the carried aligner state (bsl_batch::n_context)
         self.bases = _as_u8(bases)
         self.offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         self.n = len(self.offsets) - 1
@@ -151,15 +152,15 @@ class ReadBatch:
         return cls(reads.reshape(-1), np.arange(n + 1, dtype=np.uint64) * L, readset, first_index)
 
     @classmethod
-    def from_strings(cls, seqs, readset: int = 0, first_index: int = 0) -> "ReadBatch":
+    def from_strings(cls, seqs, readset: int = 0, first_index: int = 0, n_context: int = 0) -> "ReadBatch":
         lens = np.array([len(s) for s in seqs], dtype=np.uint64)
         off = np.zeros(len(seqs) + 1, dtype=np.uint64); off[1:] = np.cumsum(lens)
         cat = np.frombuffer("".join(seqs).encode(), dtype=np.uint8) if seqs else np.zeros(0, np.uint8)
-        return cls(cat, off, readset, first_index)
+        return cls(cat, off, readset, first_index, n_context=n_context)
 
     def struct(self) -> Batch:
         b = Batch()
-        b.n, b.readset, b.first_index = self.n, self.readset, self.first_index
+        b.n, b.readset, b.first_index, b.n_context = self.n, self.readset, self.first_index, self.n_context
         b.bases = self.bases.ctypes.data if self.bases.size else None
         b.offsets = self.offsets.ctypes.data
         b.index = None if self.index is None else self.index.ctypes.data

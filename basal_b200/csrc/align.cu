@@ -49,6 +49,10 @@ struct KArgs {
     u32 readset_a, readset_b;
     const u8 *bases; const u64 *off; const u32 *index; const u16 *rawlen; u32 first_index_a, first_index_b; u64 bases_b_shift;
     u32 has_index, has_rawlen;
+    u32 n_ctx;                     // the first n_ctx reads of a batch (and of its mate batch) are context: scheduled, never mapped
+    u32 carry;                     // the batch holds reads with an empty start-offset range: their schedules are made by prepare_deferred
+    u8 *st0arr;                    // [slot*2+chain] start offset chosen by ReorderSeed for reads that have a range (carry mode)
+    u32 *defer; u32 *stale;        // slots left to prepare_deferred; [slot*2+chain][16] seed hashes inherited beyond the end of the read
     u64 off_base_a, off_base_b;    // value of offsets[first] of the sub-range (offsets are passed as given)
     u64 all_off;                   // all-hits records already produced by earlier sub-ranges of this call
     u32 Wb;                        // words per plane in this batch
@@ -94,6 +98,9 @@ __device__ __forceinline__ u64 l2_policy_keep() { u64 p; asm volatile("createpol
 __device__ __forceinline__ u64 l2_policy_stream() { u64 p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
 __device__ __forceinline__ u32 ldg_u8_hint(const u8 *p, u64 pol) { u32 v; asm volatile("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v; }
 __device__ __forceinline__ uint2 ldg_v2_hint(const void *p, u64 pol) { uint2 v; asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol)); return v; }
+__device__ __forceinline__ u32 ldg_u32_stream(const u32 *p, u64 pol) { u32 v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol)); return v; }
+__device__ __forceinline__ uint4 ldg_v4_stream(const void *p, u64 pol) { uint4 v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol)); return v; }
+__device__ __forceinline__ u64 ldg_u64_stream(const u64 *p, u64 pol) { u64 v; asm volatile("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol)); return v; }
 
 // ------------------------------------------------------------------------------------------------
 // prepare_reads : FilterReads (align.cpp:548-563), read planes (ConvertBinaySeq / ConvertBinarySeq, align.cpp:79-226)
@@ -102,13 +109,13 @@ __device__ __forceinline__ uint2 ldg_v2_hint(const void *p, u64 pol) { uint2 v; 
 //       word; four bases at a time are turned into 2-bit codes / ACGT flags / convert-to codes in registers (one PRMT
 //       looks up the expected letter, one the code) and packed with a multiply; the words go to global memory (2-bit
 //       streams, 1-bit streams) and to the warp's shared slice;
-//   A2. (same lanes) the 1-bit streams of the read taken backwards are bit-reversed funnel shifts of the forward ones;
+//       the 1-bit streams of the read taken backwards are bit-reversed funnel shifts of the forward ones, fetched by shuffle;
 //   B.  (lane per read) per seed segment j: seed hashes and bucket sizes of the read offsets j*s .. j*s + I + ii - 1 (every
 //       offset prof[j][i] + v - i the schedule can touch), eight gathers from the one-byte size table in flight, then
 //       CountSeeds(j, v) for every start v <= ii from those sizes;
 //   C.  (lane per read) ReorderSeed / AdjustSeedStartArray / the (count, segment) sort, literally, as look-ups in the
 //       CountSeeds table of step B.
-// Shared memory per lane: 2 WQ + 2 Wb + wd + nseg (ii + 1) words, odd stride so that per-lane rows sit in different banks.
+// Shared memory per lane: WQ + Wb + 1 + wd + nseg (ii + 1) words, odd stride so that per-lane rows sit in different banks.
 // ------------------------------------------------------------------------------------------------
 #define PR_WARPS 4
 #define BASES_PAD 64        // bytes in front of and behind the batch's bases in device memory: load32 may touch up to 39 bytes either side
@@ -143,7 +150,50 @@ __device__ __forceinline__ void load32(const u8 *p, u32 (&w)[8]) {
     for (int j = 0; j < 8; j++) w[j] = __funnelshift_r(y[j], y[j + 1], sh);
 }
 
-__global__ void __launch_bounds__(PR_WARPS * 32) prepare_reads(const __grid_constant__ KArgs A, u32 WQ, u32 WDM, u32 CSZ) {
+// CountSeeds(j, v) (align.cpp:526-540) for every start v <= vmax, from the bucket sizes (bit 31 = the seed holds a non-ACGT
+// base) of the read offsets j*s + d held in cwj[d]
+__device__ __forceinline__ void count_seeds_row(const u32 *cwj, const u16 *profj, u32 j, u32 s, u32 I, u32 vmax, u32 *csj) {
+    for (u32 v = 0; v <= vmax; v++) {
+        u32 total = 0, k = 0;
+        for (u32 i = 0; i < I; i++) {
+            const u32 e = cwj[profj[i] + v - i - j * s];
+            if (e >> 31) k = 12;
+            total += (e & 0x7fffffffu) << k;
+        }
+        csj[v] = total == 0 ? 9999999u : total;
+    }
+}
+// ReorderSeed / AdjustSeedStartArray / the (count, segment) sort (align.cpp:468-524), literally, as look-ups in the CountSeeds
+// table cs[j * ncol + v]. A read with an empty start-offset range (ii == 0) starts from `carried` (align.cpp:476-480 never
+// assigns xseed_start_offset then). keys: nseg scratch words or null. Returns the 16 schedule bytes (byte t = segment of
+// rank t | its start << 4).
+__device__ __forceinline__ uint4 schedule_from_table(const u32 *cs, u32 *keys, u32 ncol, u32 nseg, u32 ii, u32 carried, u32 &st0_out) {
+    u32 st0 = carried, best = 0xffffffffu;
+    for (u32 v = 0; v < ii; v++) { u32 tt = 0; for (u32 j = 0; j < nseg; j++) tt += cs[j * ncol + v]; if (tt < best) { best = tt; st0 = v; } }
+    st0_out = st0;
+    u64 stp = 0;                                                       // start[j] in 4 bits each
+    for (u32 j = 0; j < nseg; j++) stp |= (u64)st0 << (4 * j);
+    for (u32 t = 0; t < nseg; t++) {                                   // AdjustSeedStartArray
+        const u32 ptr = (t & 1) ? nseg - 1 - t / 2 : t / 2;
+        const u32 lo_ = ptr == 0 ? 0 : (u32)(stp >> (4 * (ptr - 1))) & 15u, hi_ = ptr == nseg - 1 ? ii : (u32)(stp >> (4 * (ptr + 1))) & 15u;
+        u32 pick = lo_, b = 0xffffffffu;
+        for (u32 x = lo_; x <= hi_; x++) { const u32 tt = cs[ptr * ncol + x]; if (tt < b) { b = tt; pick = x; } }
+        stp = (stp & ~(15ull << (4 * ptr))) | ((u64)pick << (4 * ptr));
+    }
+    if (keys) for (u32 j = 0; j < nseg; j++) keys[j] = cs[j * ncol + ((u32)(stp >> (4 * j)) & 15u)];
+    u32 sb[4] = {0, 0, 0, 0};
+    for (u32 j = 0; j < nseg; j++) {
+        const u32 stj = (u32)(stp >> (4 * j)) & 15u;
+        const int kj = (int)cs[j * ncol + stj]; u32 rank = 0;          // pair<int,int> order: (count, segment)
+        if (keys) for (u32 y = 0; y < nseg; y++) { const int ky = (int)keys[y]; rank += (ky < kj || (ky == kj && y < j)) ? 1u : 0u; }
+        else for (u32 y = 0; y < nseg; y++) { const int ky = (int)cs[y * ncol + ((u32)(stp >> (4 * y)) & 15u)]; rank += (ky < kj || (ky == kj && y < j)) ? 1u : 0u; }
+        const u32 v = (j | (stj << 4)) << ((rank & 3u) * 8);
+        if ((rank >> 2) == 0) sb[0] |= v; else if ((rank >> 2) == 1) sb[1] |= v; else if ((rank >> 2) == 2) sb[2] |= v; else sb[3] |= v;
+    }
+    return make_uint4(sb[0], sb[1], sb[2], sb[3]);
+}
+
+__global__ void __launch_bounds__(PR_WARPS * 32, 6) prepare_reads(const __grid_constant__ KArgs A, u32 WQ, u32 WDM, u32 CSZ) {
     extern __shared__ u32 psm[];
     __shared__ u16 s_prof[16][16];
     const DevTables *T = A.tab;
@@ -151,14 +201,16 @@ __global__ void __launch_bounds__(PR_WARPS * 32) prepare_reads(const __grid_cons
     for (u32 x = threadIdx.x; x < 256; x += blockDim.x) s_prof[x >> 4][x & 15u] = T->prof[x >> 4][x & 15u];
     __syncthreads();
     const u32 Wb = A.Wb, W2 = 2 * Wb, I = A.I, s = A.s;
-    const u32 RS = (2 * WQ + 2 * Wb + WDM + CSZ) | 1u;                              // words per lane row
+    const u32 RS = (WQ + Wb + 1 + WDM + CSZ) | 1u;                                  // words per lane row: 2-bit codes, ACGT bits, one segment of bucket sizes, CountSeeds table
     u32 *wsm = psm + (size_t)wid * 32 * RS;
     u32 *row = wsm + lane * RS;
-    u32 *sq = row, *sn = row + WQ, *cw = row + 2 * WQ + 2 * Wb, *cs = cw + WDM;
+    u32 *sq = row, *smk = row + WQ, *cw = smk + Wb + 1, *cs = cw + WDM;
     const u32 tabq[2] = {T->tab_code[0], T->tab_code[1]}, tabc[2] = {T->tab_conv[0], T->tab_conv[1]};
-    const u32 shs = 32 - 2 * s, full = (s == 16) ? 0x55555555u : (0x55555555u >> shs);
+    const u32 shs = 32 - 2 * s, nfull = (1u << s) - 1u;
     const u32 flipm = A.di.flip ? 0xffffffffu : 0u;
     const u64 keep = l2_policy_keep();
+    const u32 rpt = 32u / Wb;                                                       // reads per trip of step A: the words of a read stay in one trip
+    const u32 a_rl = lane / Wb, a_wv = lane - a_rl * Wb;
     for (u32 slot0 = (blockIdx.x * PR_WARPS + wid) * 32u; slot0 < A.n_slots; slot0 += gridDim.x * PR_WARPS * 32u) {
         const u32 slot = slot0 + lane;
         const bool valid = slot < A.n_slots;
@@ -174,7 +226,6 @@ __global__ void __launch_bounds__(PR_WARPS * 32) prepare_reads(const __grid_cons
             index = A.has_index ? A.index[slot] : (mate_b ? A.first_index_b : A.first_index_a) + r;
         }
         const u32 L = Lraw > BSL_MAX_READLEN ? BSL_MAX_READLEN : Lraw;
-        const u32 W = (L + 31) >> 5;
         u32 flags = 0;
         if (valid) {
             if ((A.chains == 1) || ((A.chains <= 1) == (readset < 2))) flags |= SF_CHAIN0;                       // align.cpp:83-84
@@ -186,22 +237,22 @@ __global__ void __launch_bounds__(PR_WARPS * 32) prepare_reads(const __grid_cons
             for (u32 x = lane; x < nz; x += 32) cz[x] = 0;
             if (valid) { A.stat[slot] = make_uint2(0u, 0u); A.minlvl[slot] = 255; }
         }
-        u32 B = 0, nseg = 0; bool filtered = false, ns_known = false;
+        u32 B = 0, nseg = 0; bool filtered = false, ns_known = false, deferred = false;
         const u32 ii = (L + 1 >= I) ? (L + 1 - I) % s : 0;
         for (u32 c = 0; c < 2; c++) {
             const bool en = valid && (flags & (c ? SF_CHAIN1 : SF_CHAIN0)) && !filtered;
             if (!__any_sync(0xffffffffu, en)) continue;
-            // ---- A: one plane word (32 bases) of one read per lane and trip
+            // ---- A: one plane word (32 bases) of one read per lane; rpt reads per trip
             const u32 tqb = tab_bytes(tabq[c]), tcb = tab_bytes(tabc[c]);
-            for (u32 idx = lane; idx < 32 * Wb; idx += 32) {
-                const u32 rl = idx / Wb, wv = idx - rl * Wb;
+            for (u32 r0 = 0; r0 < 32; r0 += rpt) {
+                const u32 rl = min(r0 + a_rl, 31u), wv = a_wv;
+                const bool mine = a_rl < rpt && r0 + a_rl < 32u;
                 const u32 Lr = __shfl_sync(0xffffffffu, L, rl);
                 const u32 b0l = __shfl_sync(0xffffffffu, (u32)b0, rl), b0h = __shfl_sync(0xffffffffu, (u32)(b0 >> 32), rl);
-                const bool enr = __shfl_sync(0xffffffffu, (u32)en, rl) != 0;
-                if (!enr) continue;
+                const bool enr = (__shfl_sync(0xffffffffu, (u32)en, rl) != 0) && mine;
                 const u8 *src = A.bases + (((u64)b0h << 32) | b0l);
                 const u32 p0 = wv * 32;
-                const u32 nbase = Lr > p0 ? min(32u, Lr - p0) : 0u;
+                const u32 nbase = (enr && Lr > p0) ? min(32u, Lr - p0) : 0u;
                 u32 qh = 0, ql = 0, nh = 0, nl = 0, ch = 0, cl = 0, lo = 0, mk = 0;
                 if (nbase) {
                     // chain 0: bases p0 .. p0+31 in order; chain 1: the reverse complement, i.e. bytes Lr-1-p0 down to Lr-32-p0
@@ -223,6 +274,20 @@ __global__ void __launch_bounds__(PR_WARPS * 32) prepare_reads(const __grid_cons
                         lo = (lo << 4) | pack4x1(k4.cq & 0x01010101u); mk = (mk << 4) | pack4x1(k4.r1);
                     }
                 }
+                // the two 1-bit streams of the read taken backwards (what screen_bits compares with a forward-plane sector when the
+                // candidate lies on the reverse strand): reversed word wv = forward bases s0+31 down to s0, from the lanes that hold
+                // forward words s0 >> 5 and (s0 >> 5) + 1 of the same read; the low bits carry the complement flip already
+                u32 rlo, rmk;
+                {
+                    const int s0 = (int)Lr - 32 - 32 * (int)wv, w0 = s0 >> 5; const u32 sf = (u32)s0 & 31u;
+                    const u32 lb_ = lane - wv;                                           // lane of word 0 of this read
+                    const u32 la = __shfl_sync(0xffffffffu, lo, (lb_ + (u32)max(w0, 0)) & 31u), lb = __shfl_sync(0xffffffffu, lo, (lb_ + (u32)min(w0 + 1, (int)Wb - 1)) & 31u);
+                    const u32 ma = __shfl_sync(0xffffffffu, mk, (lb_ + (u32)max(w0, 0)) & 31u), mb = __shfl_sync(0xffffffffu, mk, (lb_ + (u32)min(w0 + 1, (int)Wb - 1)) & 31u);
+                    const bool oka = w0 >= 0, okb = w0 + 1 >= 0 && w0 + 1 < (int)Wb;
+                    rlo = s0 > -32 ? __funnelshift_r(oka ? __brev(la) : 0u, okb ? __brev(lb) : 0u, sf) : 0u;
+                    rmk = s0 > -32 ? __funnelshift_r(oka ? __brev(ma) : 0u, okb ? __brev(mb) : 0u, sf) : 0u;
+                }
+                if (!enr) continue;
                 const u32 slr = slot0 + rl;
                 u32 *dst = (u32 *)(A.planes + ((u64)slr * 2 + c) * 3 * Wb);           // streams: logical 32-bit words, see KArgs::planes
                 __stcs((uint2 *)(dst + 2 * wv), make_uint2(qh, ql));
@@ -230,34 +295,15 @@ __global__ void __launch_bounds__(PR_WARPS * 32) prepare_reads(const __grid_cons
                 __stcs((uint2 *)(dst + 2 * W2 + 2 * wv), make_uint2(ch, cl));
                 u32 *b1 = A.bits1 + ((u64)slr * 2 + c) * 2 * W2;
                 __stcs((uint2 *)(b1 + 2 * wv), make_uint2(lo, mk));
-                u32 *r_ = wsm + rl * RS;
-                r_[2 * wv] = qh; r_[2 * wv + 1] = ql; r_[WQ + 2 * wv] = nh; r_[WQ + 2 * wv + 1] = nl;
-                r_[2 * WQ + wv] = lo; r_[2 * WQ + Wb + wv] = mk;
-            }
-            sq[W2] = 0; sq[W2 + 1] = 0; sq[W2 + 2] = 0; sn[W2] = 0; sn[W2 + 1] = 0; sn[W2 + 2] = 0;
-            __syncwarp();
-            // ---- A2: the same two 1-bit streams for the read taken backwards (what screen_bits compares with a forward-plane
-            //      sector when the candidate lies on the reverse strand); the low bits carry the complement flip already
-            for (u32 idx = lane; idx < 32 * Wb; idx += 32) {
-                const u32 rl = idx / Wb, wv = idx - rl * Wb;
-                const u32 Lr = __shfl_sync(0xffffffffu, L, rl);
-                const bool enr = __shfl_sync(0xffffffffu, (u32)en, rl) != 0;
-                if (!enr) continue;
-                const u32 *blo = wsm + rl * RS + 2 * WQ, *bmk = blo + Wb;
-                const int s0 = (int)Lr - 32 - 32 * (int)wv;                            // reversed word wv = forward bases s0+31 down to s0
-                u32 rlo = 0, rmk = 0;
-                if (s0 > -32) {
-                    const int w0 = s0 >> 5; const u32 sf = (u32)s0 & 31u;
-                    const u32 la = w0 >= 0 ? __brev(blo[w0]) : 0u, lb = (w0 + 1 < (int)Wb) ? __brev(blo[w0 + 1]) : 0u;
-                    const u32 ma = w0 >= 0 ? __brev(bmk[w0]) : 0u, mb = (w0 + 1 < (int)Wb) ? __brev(bmk[w0 + 1]) : 0u;
-                    rlo = __funnelshift_r(la, lb, sf); rmk = __funnelshift_r(ma, mb, sf);
-                }
-                u32 *b1 = A.bits1 + ((u64)(slot0 + rl) * 2 + c) * 2 * W2;
                 __stcs((uint2 *)(b1 + W2 + 2 * wv), make_uint2(rlo ^ flipm, rmk));
+                u32 *r_ = wsm + rl * RS;
+                r_[2 * wv] = qh; r_[2 * wv + 1] = ql; r_[WQ + wv] = mk;
             }
+            sq[W2] = 0; sq[W2 + 1] = 0; sq[W2 + 2] = 0; smk[Wb] = 0;
+            __syncwarp();
             if (en && !ns_known) {
                 ns_known = true;
-                u32 acgt = 0; for (u32 j = 0; j < 2 * W; j++) acgt += __popc(sn[j]);
+                u32 acgt = 0; for (u32 j = 0; j < Wb; j++) acgt += __popc(smk[j]);
                 const u32 ns = L - acgt;
                 filtered = (L == 0) || (L < A.min_read_size) || (ns > A.max_ns) || (Lraw > BSL_MAX_READLEN);     // align.cpp:559-560
                 if (!filtered) {
@@ -266,64 +312,115 @@ __global__ void __launch_bounds__(PR_WARPS * 32) prepare_reads(const __grid_cons
                     nseg = (L + 1 >= I + s) ? min((L + 1 - I) / s, B + 1) : 0;                                    // align.cpp:450
                 }
             }
-            if (en && !filtered && nseg > 0) {
+            if (en && !filtered && nseg > 0 && A.carry && ii == 0) deferred = true;          // inherits its start offset: prepare_deferred
+            else if (en && !filtered && nseg > 0) {
                 const u32 vmax = ii, wd = I + vmax, ncol = vmax + 1;
-                // ---- B: per segment, bucket sizes (bit 31 = the seed holds a non-ACGT base) of offsets j*s + d, d < wd, then
-                //      CountSeeds(j, v) (align.cpp:526-540) for every start v <= vmax
+                // ---- B: per segment, bucket sizes (bit 31 = the seed holds a non-ACGT base) of offsets j*s + d, d < wd, eight gathers
+                //      from the one-byte size table in flight, then CountSeeds(j, v) (align.cpp:526-540) for every start v <= vmax
+                auto seed_at = [&](u32 p, u32 &flag) -> u32 {
+                    const u32 w = p >> 4, o = (p & 15u) * 2, wm = p >> 5, om = p & 31u;
+                    const u32 xq = __funnelshift_l(sq[w + 1], sq[w], o) >> shs, xm = __funnelshift_l(smk[wm + 1], smk[wm], om) >> (32 - s);
+                    flag = xm != nfull ? 0x80000000u : 0u;
+                    return bsl_xt(xq);
+                };
                 for (u32 j = 0; j < nseg; j++) {
                     for (u32 d0 = 0; d0 < wd; d0 += 8) {
-                        u32 kmer[8], fl[8], c8[8];
+                        u32 c8[8], flb = 0;
 #pragma unroll
                         for (u32 u = 0; u < 8; u++) {
-                            const u32 p = j * s + min(d0 + u, wd - 1), w = p >> 4, o = (p & 15u) * 2;
-                            const u32 xq = __funnelshift_l(sq[w + 1], sq[w], o) >> shs, xn = __funnelshift_l(sn[w + 1], sn[w], o) >> shs;
-                            kmer[u] = bsl_xt(xq); fl[u] = xn != full ? 0x80000000u : 0u;
-                            c8[u] = ldg_u8_hint(A.di.cnt8 + kmer[u], keep);
+                            u32 fl; const u32 k = seed_at(j * s + min(d0 + u, wd - 1), fl);
+                            c8[u] = ldg_u8_hint(A.di.cnt8 + k, keep); flb |= (fl >> 31) << u;
                         }
 #pragma unroll
-                        for (u32 u = 0; u < 8; u++) {
-                            if (d0 + u < wd) { const u32 m = c8[u] == 0xFFu ? __ldg(A.di.bucket + 2 * kmer[u] + 2) - __ldg(A.di.bucket + 2 * kmer[u]) : c8[u]; cw[d0 + u] = (m & 0x7fffffffu) | fl[u]; }
-                        }
+                        for (u32 u = 0; u < 8; u++) if (d0 + u < wd) cw[d0 + u] = c8[u] | (((flb >> u) & 1u) << 31);
                     }
-                    for (u32 v = 0; v <= vmax; v++) {
-                        u32 total = 0, k = 0;
-                        for (u32 i = 0; i < I; i++) {
-                            const u32 e = cw[s_prof[j][i] + v - i - j * s];
-                            if (e >> 31) k = 12;
-                            total += (e & 0x7fffffffu) << k;
-                        }
-                        cs[j * ncol + v] = total == 0 ? 9999999u : total;
+                    for (u32 d = 0; d < wd; d++) if ((cw[d] & 0xFFu) == 0xFFu) {      // saturated: the exact size from the bucket table (rare)
+                        u32 fl; const u32 k = seed_at(j * s + d, fl);
+                        cw[d] = ((__ldg(A.di.bucket + 2 * k + 2) - __ldg(A.di.bucket + 2 * k)) & 0x7fffffffu) | fl;
                     }
+                    count_seeds_row(cw, s_prof[j], j, s, I, vmax, cs + j * ncol);
                 }
-                // ---- C: ReorderSeed (align.cpp:468-498): first minimum of the column sums
-                u32 st0 = 0, best = 0xffffffffu;
-                for (u32 v = 0; v < ii; v++) { u32 tt = 0; for (u32 j = 0; j < nseg; j++) tt += cs[j * ncol + v]; if (tt < best) { best = tt; st0 = v; } }
-                u64 stp = 0;                                                       // start[j] in 4 bits each
-                for (u32 j = 0; j < nseg; j++) stp |= (u64)st0 << (4 * j);
-                for (u32 t = 0; t < nseg; t++) {                                   // AdjustSeedStartArray (align.cpp:500-524)
-                    const u32 ptr = (t & 1) ? nseg - 1 - t / 2 : t / 2;
-                    const u32 lo_ = ptr == 0 ? 0 : (u32)(stp >> (4 * (ptr - 1))) & 15u, hi_ = ptr == nseg - 1 ? ii : (u32)(stp >> (4 * (ptr + 1))) & 15u;
-                    u32 pick = lo_, b = 0xffffffffu;
-                    for (u32 x = lo_; x <= hi_; x++) { const u32 tt = cs[ptr * ncol + x]; if (tt < b) { b = tt; pick = x; } }
-                    stp = (stp & ~(15ull << (4 * ptr))) | ((u64)pick << (4 * ptr));
-                }
-                u32 sb[4] = {0, 0, 0, 0};                                          // sched byte t = segment of rank t | its start << 4
-                for (u32 j = 0; j < nseg; j++) {
-                    const u32 stj = (u32)(stp >> (4 * j)) & 15u;
-                    const int kj = (int)cs[j * ncol + stj]; u32 rank = 0;          // pair<int,int> order: (count, segment)
-                    for (u32 y = 0; y < nseg; y++) { const int ky = (int)cs[y * ncol + ((u32)(stp >> (4 * y)) & 15u)]; rank += (ky < kj || (ky == kj && y < j)) ? 1u : 0u; }
-                    const u32 v = (j | (stj << 4)) << ((rank & 3u) * 8);
-                    if ((rank >> 2) == 0) sb[0] |= v; else if ((rank >> 2) == 1) sb[1] |= v; else if ((rank >> 2) == 2) sb[2] |= v; else sb[3] |= v;
-                }
-                *(uint4 *)(A.sched + ((u64)slot * 2 + c) * 16) = make_uint4(sb[0], sb[1], sb[2], sb[3]);
+                // ---- C: the schedule
+                u32 st0;
+                const uint4 sbytes = schedule_from_table(cs, nseg <= WDM ? cw : nullptr, ncol, nseg, ii, 0u, st0);
+                if (A.carry) A.st0arr[(u64)slot * 2 + c] = (u8)st0;
+                *(uint4 *)(A.sched + ((u64)slot * 2 + c) * 16) = sbytes;
             }
             __syncwarp();
         }
         if (valid) {
             if (filtered) flags |= SF_FILTERED;
+            if ((A.pe && slot >= A.n_a ? slot - A.n_a : slot) < A.n_ctx) flags |= SF_CONTEXT;
             SlotMeta m; m.rnd = bsl_rand(index, A.randseed); m.len = (u16)L; m.B = (u8)B; m.nseg = (u8)nseg; m.flags = (u8)flags; m.thr = (u8)B; m.nhit = 0; m.item = slot;
             A.meta[slot] = m;
+            if (deferred) A.defer[atomicAdd(&A.ctr->defer_n, 1u)] = slot;
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// prepare_deferred : the seed schedule of reads whose start-offset range is empty ((len - I + 1) % s == 0). The reference
+// never assigns xseed_start_offset for them (align.cpp:476-480), so they keep the value of the last read of the same
+// aligner object and chain that had a range, AdjustSeedStartArray then moves their segments up to that offset, and seed
+// positions beyond len - s still hold the hashes / non-ACGT flags of the last read long enough to have written them
+// (xseed_array / xseedreg_array are never cleared, align.cpp:79-150). One aligner object sees the reads of one mate in
+// batch order (-p 1 semantics; fresh, zeroed objects per call). Runs after prepare_reads: lane per deferred read.
+// ------------------------------------------------------------------------------------------------
+#define PD_WARPS 2
+__global__ void __launch_bounds__(PD_WARPS * 32) prepare_deferred(const __grid_constant__ KArgs A, u32 WDM, u32 CSZ) {
+    extern __shared__ u32 dsm[];
+    __shared__ u16 s_prof[16][16];
+    const DevTables *T = A.tab;
+    for (u32 x = threadIdx.x; x < 256; x += blockDim.x) s_prof[x >> 4][x & 15u] = T->prof[x >> 4][x & 15u];
+    __syncthreads();
+    const u32 I = A.I, s = A.s, Wb = A.Wb, W2 = 2 * Wb, shs = 64 - 2 * s, nfull = (1u << s) - 1u;
+    const u32 RS = (WDM + CSZ) | 1u;
+    u32 *cw = dsm + (size_t)threadIdx.x * RS, *cs = cw + WDM;
+    const u32 n_def = A.ctr->defer_n;
+    // seed hash (bit 31: the seed holds a non-ACGT base) at offset p of the read in `slot`; offsets beyond the end of the read
+    // belong to the nearest earlier unfiltered read of the same mate that is long enough, or to nobody (zeroed memory)
+    auto seed_of = [&](u32 slot, u32 c, u32 L, u32 base, u32 p) -> u32 {
+        u32 src = slot;
+        if (p + s > L) {
+            src = 0xffffffffu;
+            for (u32 t = slot; t-- > base;) { const SlotMeta d = A.meta[t]; if (!(d.flags & SF_FILTERED) && (u32)d.len >= p + s) { src = t; break; } }
+            if (src == 0xffffffffu) return 0u;
+        }
+        const u64 *pl = A.planes + ((u64)src * 2 + c) * 3 * Wb;
+        const u32 *b1 = A.bits1 + ((u64)src * 2 + c) * 2 * W2;                   // {low bits, ACGT mask} per 32 bases
+        const u32 wm = p >> 5, om = p & 31u;
+        const u32 m0 = b1[2 * wm + 1], m1 = wm + 1 < Wb ? b1[2 * wm + 3] : 0u;
+        const u32 xm = __funnelshift_l(m1, m0, om) >> (32 - s);
+        return bsl_xt((u32)(stream_extract(pl, p) >> shs)) | (xm != nfull ? 0x80000000u : 0u);
+    };
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n_def; k += gridDim.x * blockDim.x) {
+        const u32 slot = A.defer[k];
+        const SlotMeta m = A.meta[slot];
+        const u32 L = m.len, nseg = m.nseg, base = (A.pe && slot >= A.n_a) ? A.n_a : 0u;
+        for (u32 c = 0; c < 2; c++) {
+            if (!(m.flags & (c ? SF_CHAIN1 : SF_CHAIN0))) continue;
+            u32 carried = 0;                                           // xseed_start_offset as the previous reads left it
+            for (u32 t = slot; t-- > base;) {
+                const SlotMeta d = A.meta[t];
+                if (d.flags & SF_FILTERED) continue;
+                const u32 Ld = d.len;
+                if (Ld + 1 >= I && (Ld + 1 - I) % s != 0) { carried = A.st0arr[(u64)t * 2 + c]; break; }
+            }
+            const u32 vmax = carried, wd = I + vmax, ncol = vmax + 1;
+            for (u32 j = 0; j < nseg; j++) {
+                for (u32 d = 0; d < wd; d++) {
+                    const u32 e = seed_of(slot, c, L, base, j * s + d), kmer = e & 0x7fffffffu;
+                    u32 cnt = A.di.cnt8[kmer]; if (cnt == 0xFFu) cnt = A.di.bucket[2 * kmer + 2] - A.di.bucket[2 * kmer];
+                    cw[d] = (cnt & 0x7fffffffu) | (e & 0x80000000u);
+                }
+                count_seeds_row(cw, s_prof[j], j, s, I, vmax, cs + j * ncol);
+            }
+            u32 st0;
+            const uint4 sbytes = schedule_from_table(cs, nullptr, ncol, nseg, 0u, carried, st0);
+            *(uint4 *)(A.sched + ((u64)slot * 2 + c) * 16) = sbytes;
+            for (u32 x = 0; x < 16; x++) A.stale[((u64)slot * 2 + c) * 16 + x] = x < vmax ? (seed_of(slot, c, L, base, L - s + 1 + x) & 0x7fffffffu) : 0u;
+        }
+        A.meta[slot].flags = (u8)(m.flags | SF_STALE);
     }
 }
 
@@ -333,12 +430,12 @@ __global__ void build_lists(const __grid_constant__ KArgs A, u32 *se_list, u32 *
     if (!A.pe) {
         if (i >= A.n_slots) return;
         SlotMeta m = A.meta[i];
-        if (!(m.flags & SF_FILTERED) && m.nseg > 0) { u32 pos = atomicAdd(&A.ctr->rc[0].active, 1u); se_list[pos] = i; }
+        if (!(m.flags & (SF_FILTERED | SF_CONTEXT)) && m.nseg > 0) { u32 pos = atomicAdd(&A.ctr->rc[0].active, 1u); se_list[pos] = i; }
         return;
     }
     if (i >= A.n_a) return;
     SlotMeta ma = A.meta[i], mb = A.meta[i + A.n_a];
-    bool oka = !(ma.flags & SF_FILTERED), okb = !(mb.flags & SF_FILTERED);
+    bool oka = !(ma.flags & (SF_FILTERED | SF_CONTEXT)), okb = !(mb.flags & (SF_FILTERED | SF_CONTEXT));
     if (oka && okb) { u32 pos = atomicAdd(&A.ctr->rc[20].active, 1u); pe_list[pos] = i; }
     else {
         if (oka && ma.nseg > 0) { u32 pos = atomicAdd(&A.ctr->rc[0].active, 1u); se_list[pos] = i; }
@@ -391,6 +488,12 @@ __global__ void __launch_bounds__(LK_THREADS) seed_lookup(const __grid_constant_
         }
         // ---- pass 1: bucket sizes
         u32 tot = 0, nne = 0, j = 0, stj = 0; const u64 *pq = nullptr;
+        // seed hash at read offset h (xseeds, align.cpp:487-490); offsets beyond the end of the read exist only for reads whose
+        // schedule was made by prepare_deferred, and hold the hashes an earlier read left there
+        auto kmer_at = [&](u32 h) -> u32 {
+            if ((m.flags & SF_STALE) && h + A.s > (u32)m.len) return A.stale[((u64)slot * 2 + c) * 16 + (h + A.s - (u32)m.len - 1u)];
+            return bsl_xt((u32)(stream_extract(pq, h) >> shs));
+        };
         u32 ke0[4], ke1[4], ke2[4];                          // the look-ups of the first four phases stay in registers for pass 2
 #pragma unroll
         for (u32 i = 0; i < 4; i++) { ke0[i] = 0; ke1[i] = 0; ke2[i] = 0; }
@@ -401,7 +504,7 @@ __global__ void __launch_bounds__(LK_THREADS) seed_lookup(const __grid_constant_
             for (u32 i = 0; i < 4; i++) {
                 if (i < A.I) {
                     const u32 h = T->prof[j][i] + stj - i;
-                    const u32 kmer = bsl_xt((u32)(stream_extract(pq, h) >> shs));
+                    const u32 kmer = kmer_at(h);
                     ke0[i] = __ldg(A.di.bucket + 2 * kmer); ke1[i] = __ldg(A.di.bucket + 2 * kmer + 1); ke2[i] = __ldg(A.di.bucket + 2 * kmer + 2);
                 }
             }
@@ -409,7 +512,7 @@ __global__ void __launch_bounds__(LK_THREADS) seed_lookup(const __grid_constant_
             for (u32 i = 0; i < 4; i++) { const u32 pm = ke2[i] - ke0[i]; if (i < A.I && pm != 0 && pm <= A.di.maxk) { tot += pm; nne++; } }
             for (u32 i = 4; i < A.I; i++) {
                 const u32 h = T->prof[j][i] + stj - i;
-                const u32 kmer = bsl_xt((u32)(stream_extract(pq, h) >> shs));
+                const u32 kmer = kmer_at(h);
                 const u32 pm = A.di.bucket[2 * kmer + 2] - A.di.bucket[2 * kmer];
                 if (pm != 0 && pm <= A.di.maxk) { tot += pm; nne++; }
             }
@@ -456,7 +559,7 @@ __global__ void __launch_bounds__(LK_THREADS) seed_lookup(const __grid_constant_
                 const u32 h = T->prof[j][i] + stj - i;
                 u32 e0, e1, e2;
                 if (i < 4) { e0 = i == 0 ? ke0[0] : i == 1 ? ke0[1] : i == 2 ? ke0[2] : ke0[3]; e1 = i == 0 ? ke1[0] : i == 1 ? ke1[1] : i == 2 ? ke1[2] : ke1[3]; e2 = i == 0 ? ke2[0] : i == 1 ? ke2[1] : i == 2 ? ke2[2] : ke2[3]; }
-                else { const u32 kmer = bsl_xt((u32)(stream_extract(pq, h) >> shs)); e0 = A.di.bucket[2 * kmer]; e1 = A.di.bucket[2 * kmer + 1]; e2 = A.di.bucket[2 * kmer + 2]; }
+                else { const u32 kmer = kmer_at(h); e0 = A.di.bucket[2 * kmer]; e1 = A.di.bucket[2 * kmer + 1]; e2 = A.di.bucket[2 * kmer + 2]; }
                 const u32 pm = e2 - e0;
                 if (pm != 0 && pm <= A.di.maxk) {
                     // walk positions on the reverse strand: [x1, x2) (inv = 0) or all but [x1, x2) (inv = 1), see ItemHdr
@@ -715,7 +818,7 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
 // words straight from global memory (three independent loads per word, nothing staged). Passing candidates get their
 // bitmap bit and a mark record for reduce_fast.
 template <bool SINGLE>
-__device__ __forceinline__ void drain_exact(const KArgs &A, const uint4 sv, bool have) {
+__device__ __forceinline__ void drain_exact(const KArgs &A, const uint4 sv, bool have, u64 strm) {
     if (!have) return;
     const u32 y = sv.z, sig = IH_INV(y), slot = IH_SLOT(y), chain = IH_CHAIN(y), L = sv.w, g = sv.y;
     const u32 Wb = A.Wb, W = (L + 31u) >> 5;
@@ -723,13 +826,13 @@ __device__ __forceinline__ void drain_exact(const KArgs &A, const uint4 sv, bool
     const u64 *P = A.di.plane[sig] + (g >> 5);
     const u32 off = (g & 31u) * 2;
     u32 snp = 0;
-    u64 prev = __ldg(P);
+    u64 prev = ldg_u64_stream(P, strm);
 #pragma unroll 3
     for (u32 i = 0; i < W; i++) {
-        const u64 next = __ldg(P + i + 1);
+        const u64 next = ldg_u64_stream(P + i + 1, strm);
         const u64 r = off ? (prev << off) | (next >> (64 - off)) : prev;
-        const u64 q = swap32(__ldg(S + i)), n = swap32(__ldg(S + Wb + i));
-        u64 cm = 0; if (!SINGLE) cm = swap32(__ldg(S + 2 * Wb + i));
+        const u64 q = swap32(ldg_u64_stream(S + i, strm)), n = swap32(ldg_u64_stream(S + Wb + i, strm));
+        u64 cm = 0; if (!SINGLE) cm = swap32(ldg_u64_stream(S + 2 * Wb + i, strm));
         snp += __popcll(bsl_pairs(bsl_diff<SINGLE>(q, cm, r)) & n);
         prev = next;
     }
@@ -757,6 +860,7 @@ __global__ void __launch_bounds__(SC_WARPS * 32, 5) screen_candidates(const __gr
     u64 *S64 = (u64 *)S0;
     uint4 *Q = s_q[wid];
     u32 qn = 0;
+    const u64 strm = l2_policy_stream();
     for (u32 grp = blockIdx.x * SC_WARPS + wid; grp < n_groups; grp += gridDim.x * SC_WARPS) {
         const u32 gbeg = grp << 5, gend = min(gbeg + 32u, n_cands);
         const u32 first = __ldg(A.chunk_first + grp);
@@ -824,10 +928,10 @@ __global__ void __launch_bounds__(SC_WARPS * 32, 5) screen_candidates(const __gr
             if (pass) Q[qn + __popc(bal & ((1u << lane) - 1u))] = survivor(gbeg + lane, g, hy, sig, L);
             qn += __popc(bal);
             __syncwarp();
-            if (qn >= 32u) { qn -= 32u; drain_exact<SINGLE>(A, Q[qn + lane], true); __syncwarp(); }
+            if (qn >= 32u) { qn -= 32u; drain_exact<SINGLE>(A, Q[qn + lane], true, strm); __syncwarp(); }
         }
     }
-    if (qn) drain_exact<SINGLE>(A, Q[min(lane, qn - 1u)], lane < qn);
+    if (qn) drain_exact<SINGLE>(A, Q[min(lane, qn - 1u)], lane < qn, strm);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -843,20 +947,21 @@ __global__ void __launch_bounds__(SC_WARPS * 32, 5) screen_candidates(const __gr
 // that cross a sequence boundary are not screened on that strand: they go straight to the exact count.
 //
 // A warp owns groups of 32 consecutive flat candidates (lane per candidate) and never waits for another warp. Its
-// groups move through a software pipeline, one stage per visit, so that every global load has a whole visit (or more)
-// to arrive before it is used:
+// groups move through a software pipeline, one stage per visit; a visit runs C, S, B2, B1, P, F in that order, each for
+// a group one further ahead, so every global load is consumed at the code position that issued it one visit earlier:
 //   F  chunk_first of the group four visits ahead            (which items overlap the group)
 //   P  item headers + loc entries of the group three ahead   (16-byte ItemHdr per lane, 4-byte flat_loc per lane)
 //   B1 resolve each lane's item (one popcount over the "an item starts here" mask, four shuffles), strand, window start;
 //      reverse-strand lanes issue their strand-table look-up (ctab)
 //   B2 mirror reverse-strand windows, pick the sector, issue the 256-bit gather (and the nflag word)
 //   S  cp.async the items' 1-bit streams (16 Wb bytes per item: {low bits, ACGT mask} words forward, then reversed)
-//      into the warp's shared slice — issued after the previous group's compare has left the slice
+//      into the warp's shared slice, consecutive lanes copying consecutive 16-byte chunks — issued right after the
+//      previous group's compare has left the slice
 //   C  XOR / mask / popcount of <= 7 read words against funnel-shifted sector words; survivors join the warp's queue,
 //      32 waiting survivors are counted exactly (drain_exact), one per lane
 // ------------------------------------------------------------------------------------------------
 #define SB_WARPS 8
-__device__ __forceinline__ void cp_async16(u32 smem_addr, const void *gptr) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(smem_addr), "l"(gptr)); }
+__device__ __forceinline__ void cp_async16(u32 smem_addr, const void *gptr, u64 pol) { asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" :: "r"(smem_addr), "l"(gptr), "l"(pol)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void ldg256_keep(const u32 *p, u32 (&r)[8], u64 pol) {      // one 32-byte sector of the one-bit plane, L2 evict-last
@@ -865,144 +970,147 @@ __device__ __forceinline__ void ldg256_keep(const u32 *p, u32 (&r)[8], u64 pol) 
     r[0] = (u32)a; r[1] = (u32)(a >> 32); r[2] = (u32)b; r[3] = (u32)(b >> 32); r[4] = (u32)c; r[5] = (u32)(c >> 32); r[6] = (u32)d; r[7] = (u32)(d >> 32);
 }
 
-__global__ void __launch_bounds__(SB_WARPS * 32, 4) screen_bits(const __grid_constant__ KArgs A, u32 ci, u32 item_bytes) {
+__global__ void __launch_bounds__(SB_WARPS * 32, 4) screen_bits(const __grid_constant__ KArgs A, u32 ci, u32 item_bytes, u32 rcp_wb) {
     extern __shared__ __align__(16) unsigned char sbm[];                       // per warp: 32 staged items x item_bytes
     __shared__ uint4 s_q[SB_WARPS][SC_QCAP];
     constexpr u32 FULL = 0xffffffffu;
     const RoundCtr *rc = A.ctr->rc + ci;
     const unsigned long long al = min(rc->alloc, ~rc->limit_inv);
     const u32 n_cands = (u32)(al & ALLOC_MASK), n_items = (u32)(al >> ALLOC_SHIFT);
-    const int n_groups = (int)((n_cands + 31u) >> 5);
+    const u32 n_groups = (n_cands + 31u) >> 5;
     const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
-    const int stride = (int)(gridDim.x * SB_WARPS), g0 = (int)(blockIdx.x * SB_WARPS + wid);
+    const u32 stride = gridDim.x * SB_WARPS, g0 = blockIdx.x * SB_WARPS + wid;
     if (g0 >= n_groups) return;
     const u32 Wb = A.Wb, RB = 16u * Wb;                                        // bytes of one (slot, chain) record of bits1
     unsigned char *S0 = sbm + (size_t)wid * 32u * item_bytes;
     const u32 S0a = (u32)__cvta_generic_to_shared(S0);
     const unsigned char *bits = (const unsigned char *)A.bits1;
-    const u64 keep = l2_policy_keep();
+    const u64 keep = l2_policy_keep(), strm = l2_policy_stream();
     uint4 *Q = s_q[wid];
     u32 qn = 0;
-    auto group_of = [&](int k) -> int { return k < 0 ? -1 : g0 + k * stride; };
-    auto is_group = [&](int g) -> bool { return g >= 0 && g < n_groups; };
 
-    // ---- pipeline registers
-    u32 fP = 0, lP = 0;                                                        // F -> P
-    uint4 hB = make_uint4(FULL, 0, 0, 0); u32 clB = 0;                         // P -> B1
-    u32 g2 = 0, y2 = 0, m2 = 0, rec2 = FULL; uint2 ce2 = make_uint2(0u, 0u);   // B1 -> B2 (m: L | it << 9 | act << 14 | n_it << 15)
+    // ---- pipeline registers (every stage consumes what the same stage position issued one visit earlier)
+    u32 fP = 0, lP = 0;                                                        // F -> P   chunk_first pair
+    uint4 hB = make_uint4(FULL, 0, 0, 0); u32 clB = 0;                         // P -> B1  item header of this lane, loc entry of this lane's candidate
+    u32 g2 = 0, y2 = 0, m2 = 0, rec2 = FULL; uint2 ce2 = make_uint2(0u, 0u);   // B1 -> B2 / S   (m: L | staged offset << 9 | act << 23; y: ItemHdr::y with the strand in the inv bit)
     u32 R[8], nfl = 0, cx = 0, gC = 0, yC = 0, mC = 0;                         // B2 -> C  (cx: dlt+8 | sft << 5 | nW << 10 | screened << 14 | (sec & 31) << 15)
 #pragma unroll
     for (int j = 0; j < 8; j++) R[j] = 0;
-    { const int g = g0; fP = __ldg(A.chunk_first + g); lP = g + 1 < n_groups ? __ldg(A.chunk_first + g + 1) : n_items - 1u; }      // F of the first group
 
-    for (int v = -3;; v++) {
-        const int GC = group_of(v), GB2 = group_of(v + 1), GB1 = group_of(v + 2), GP = group_of(v + 3), GF = group_of(v + 4);
-        if (v >= 0 && GC >= n_groups) break;
-        // ---- B2 (group v+1): sector choice and gather
-        u32 Rn[8], nfl_n = 0, cx_n = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) Rn[j] = 0;
-        if (is_group(GB2)) {
-            const u32 L = m2 & 511u, sig = IH_INV(y2), g = g2; const bool act = (m2 >> 14) & 1u;
-            u32 p0 = g; bool screen = act; uint2 ce = ce2;
-            if (act && sig) {
-                if (ce.y == 0u) {                                                // a sequence boundary inside the 65 536-coordinate block
-                    u32 lo = 0, hi = A.di.nseq;
-                    while (lo + 1 < hi) { const u32 mid = (lo + hi) >> 1; if (g >= __ldg(A.di.anchor + mid)) lo = mid; else hi = mid; }
-                    const u32 a0 = __ldg(A.di.anchor + lo), P = __ldg(A.di.rcoff + lo);
-                    ce = make_uint2(2u * a0 + P - 1u, a0 + P);
-                    if (g < a0) screen = false;                                  // in the leading margin
-                }
-                if ((u64)g + L > (u64)ce.y) screen = false;                      // crosses into the next sequence
-                p0 = ce.x - g - L + 1u;                                          // forward coordinate of the window's lowest base
-            }
-            // the sector: read word i (32 bases; of the reversed read on the rc strand) lines up with plane words pw+i, pw+i+1;
-            // the sector that starts o words before pw covers i in [0, 6-o], the next one [8-o, 14-o]
-            const u32 pw = p0 >> 5, o = pw & 7u, nW = (L + 31u) >> 5, sft = p0 & 31u;
-            const u32 c0 = min(7u - o, nW), hi1 = min(14u - o, nW - 1u);
-            const u32 c1 = hi1 + o >= 8u ? hi1 + o - 7u : 0u;
-            const u32 k = c1 > c0 ? 1u : 0u;
-            const u32 dlt8 = k ? 16u - o : 8u - o;                               // (read word of sector word x) - x + 8
-            const u32 sec = (pw >> 3) + k;
-            if (screen) {
-                ldg256_keep(A.di.bit1 + (size_t)sec * 8, Rn, keep);
-                if (sig) nfl_n = __ldg(A.di.nflag + (sec >> 5));
-            }
-            cx_n = dlt8 | (sft << 5) | (nW << 10) | ((screen ? 1u : 0u) << 14) | ((sec & 31u) << 15);
+    // everything but the screening plane passes through once: evict-first, so that it does not push the plane out of L2
+    auto stage_F = [&](u32 G) { fP = ldg_u32_stream(A.chunk_first + G, strm); lP = G + 1 < n_groups ? ldg_u32_stream(A.chunk_first + G + 1, strm) : n_items - 1u; };
+    auto stage_P = [&](u32 G) {
+        hB = make_uint4(FULL, 0, 0, 0); clB = 0;
+        if (fP + lane <= lP) hB = ldg_v4_stream(A.hdr + fP + lane, strm);
+        const u32 c = (G << 5) + lane;
+        if (c < n_cands) clB = ldg_u32_stream(A.flat_loc + c, strm);
+    };
+    // B1: item of every candidate, strand, window start; reverse-strand lanes issue their strand-table look-up
+    auto stage_B1 = [&](u32 G) {
+        const u32 gbeg = G << 5, gend = min(gbeg + 32u, n_cands);
+        const bool act = gbeg + lane < gend;
+        const bool mine = hB.x != FULL && (lane == 0 || hB.x < gend);
+        const u32 pos = (mine && hB.x > gbeg) ? hB.x - gbeg : 0u;
+        const u32 mask = __reduce_or_sync(FULL, mine ? 1u << pos : 0u);
+        const u32 it = __popc(mask & (FULL >> (31u - lane))) - 1u;               // my candidate's item = lane `it`
+        const u32 ibase = __shfl_sync(FULL, hB.x, it), hy = __shfl_sync(FULL, hB.y, it), hz = __shfl_sync(FULL, hB.z, it), hw = __shfl_sync(FULL, hB.w, it);
+        const u32 sig = ih_strand(gbeg + lane - ibase, hy, hz, hw);              // forward-strand entries come first (align.cpp:296)
+        g2 = clB - IH_H(hw);                                                     // _hit.loc (align.cpp:297)
+        y2 = (hy & ~(1u << 27)) | (sig << 27);
+        m2 = IH_L(hz) | ((it * item_bytes + (sig ? 8u * Wb : 0u)) << 9) | ((act ? 1u : 0u) << 23);
+        ce2 = make_uint2(0u, 0u);
+        if (act && sig) ce2 = __ldg(A.di.ctab + (g2 >> BSL_CTAB_SHIFT));
+        rec2 = mine ? IH_SLOT(hB.y) * 2 + IH_CHAIN(hB.y) : FULL;
+        if (lane == 0) A.bitmap[G] = 0u;                                         // bits are set by drain_exact
+    };
+    // S: the items' 1-bit streams into the warp's slice, 16-byte chunks, consecutive lanes take consecutive chunks
+    auto stage_S = [&]() {
+        const u32 n_it = __popc(__ballot_sync(FULL, rec2 != FULL)), nch = n_it * Wb;
+        for (u32 c0 = 0; c0 < nch; c0 += 32) {
+            const u32 c = c0 + lane, item = min(__umulhi(c, rcp_wb), n_it - 1u), part = c - item * Wb;
+            const u32 rec = __shfl_sync(FULL, rec2, item);
+            if (c < nch) cp_async16(S0a + item * item_bytes + 16u * part, bits + (size_t)rec * RB + 16u * part, strm);
         }
-        // ---- C (group v): compare
-        if (is_group(GC)) {
-            cp_async_wait_all();
-            __syncwarp();
-            const bool act = (mC >> 14) & 1u; const u32 it = (mC >> 9) & 31u, sig = IH_INV(yC);
-            bool pass = false;
-            if (act) {
-                if (!((cx >> 14) & 1u) || (sig && ((nfl >> ((cx >> 15) & 31u)) & 1u))) pass = true;     // not screened on this strand: the exact count decides
-                else {
-                    const uint2 *Sr = (const uint2 *)(S0 + (size_t)it * item_bytes + (sig ? 8u * Wb : 0u));   // {low bits, ACGT mask} per 32 bases
-                    const u32 sft = (cx >> 5) & 31u, nW = (cx >> 10) & 15u, d8 = cx & 31u;
-                    u32 low = 0;
-#pragma unroll
-                    for (int x = 0; x < 7; x++) {
-                        const u32 i = (u32)x + d8 - 8u;
-                        if (i < nW) { const uint2 lm = Sr[i]; low += __popc((lm.x ^ __funnelshift_l(R[x + 1], R[x], sft)) & lm.y); }
-                    }
-                    pass = low <= IH_THR(yC);
-                }
+        cp_async_commit();
+    };
+    // B2: mirror reverse-strand windows, choose the sector, issue the gather
+    auto stage_B2 = [&]() {
+        const u32 L = m2 & 511u, sig = IH_INV(y2), g = g2; const bool act = (m2 >> 23) & 1u;
+        u32 p0 = g; bool screen = act; uint2 ce = ce2;
+        if (act && sig) {
+            if (ce.y == 0u) {                                                    // a sequence boundary inside the 65 536-coordinate block
+                u32 lo = 0, hi = A.di.nseq;
+                while (lo + 1 < hi) { const u32 mid = (lo + hi) >> 1; if (g >= __ldg(A.di.anchor + mid)) lo = mid; else hi = mid; }
+                const u32 a0 = __ldg(A.di.anchor + lo), P = __ldg(A.di.rcoff + lo);
+                ce = make_uint2(2u * a0 + P - 1u, a0 + P);
+                if (g < a0) screen = false;                                      // in the leading margin
             }
-            const u32 bal = __ballot_sync(FULL, pass);
-            if (bal) {
-                if (pass) Q[qn + __popc(bal & ((1u << lane) - 1u))] = make_uint4(((u32)GC << 5) + lane, gC, yC, mC & 511u);
-                qn += __popc(bal);
-                __syncwarp();
-                if (qn >= 32u) { qn -= 32u; drain_exact<true>(A, Q[qn + lane], true); }
-            }
+            if ((u64)g + L > (u64)ce.y) screen = false;                          // crosses into the next sequence
+            p0 = ce.x - g - L + 1u;                                              // forward coordinate of the window's lowest base
         }
-        // ---- S (group v+1): its items' 1-bit streams into the slice the compare above has just left
+        // the sector: read word i (32 bases; of the reversed read on the rc strand) lines up with plane words pw+i, pw+i+1;
+        // the sector that starts o words before pw covers i in [0, 6-o], the next one [8-o, 14-o]
+        const u32 pw = p0 >> 5, o = pw & 7u, nW = (L + 31u) >> 5, sft = p0 & 31u;
+        const u32 c0 = min(7u - o, nW), hi1 = min(14u - o, nW - 1u);
+        const u32 c1 = hi1 + o >= 8u ? hi1 + o - 7u : 0u;
+        const u32 k = c1 > c0 ? 1u : 0u;
+        const u32 dlt8 = k ? 16u - o : 8u - o;                                   // (read word of sector word x) - x + 8
+        const u32 sec = (pw >> 3) + k;
+        nfl = 0;
+        if (screen) {
+            ldg256_keep(A.di.bit1 + (size_t)sec * 8, R, keep);
+            if (sig) nfl = __ldg(A.di.nflag + (sec >> 5));
+        }
+        cx = dlt8 | (sft << 5) | (nW << 10) | ((screen ? 1u : 0u) << 14) | ((sec & 31u) << 15);
+        gC = g2; yC = y2; mC = m2;
+    };
+    // C: XOR / mask / popcount against the staged streams; survivors join the queue
+    auto stage_C = [&](u32 G) {
+        cp_async_wait_all();
         __syncwarp();
-        if (is_group(GB2)) {
-            if (rec2 != FULL) {
-                const unsigned char *src = bits + (size_t)rec2 * RB; const u32 dst = S0a + lane * item_bytes;
-                for (u32 part = 0; part < Wb; part++) cp_async16(dst + 16u * part, src + 16u * part);
-            }
-            cp_async_commit();
-        }
-        // ---- B1 (group v+2): item of every candidate, strand, window start; strand-table look-up
-        u32 g1 = 0, y1 = 0, m1 = 0, rec1 = FULL; uint2 ce1 = make_uint2(0u, 0u);
-        if (is_group(GB1)) {
-            const u32 gbeg = (u32)GB1 << 5, gend = min(gbeg + 32u, n_cands);
-            const bool act = gbeg + lane < gend;
-            const bool mine = hB.x != FULL && (lane == 0 || hB.x < gend);
-            const u32 pos = (mine && hB.x > gbeg) ? hB.x - gbeg : 0u;
-            const u32 mask = __reduce_or_sync(FULL, mine ? 1u << pos : 0u);
-            const u32 it = __popc(mask & (FULL >> (31u - lane))) - 1u;           // my candidate's item = lane `it`
-            const u32 ibase = __shfl_sync(FULL, hB.x, it), hy = __shfl_sync(FULL, hB.y, it), hz = __shfl_sync(FULL, hB.z, it), hw = __shfl_sync(FULL, hB.w, it);
-            const u32 sig = ih_strand(gbeg + lane - ibase, hy, hz, hw);          // forward-strand entries come first (align.cpp:296)
-            g1 = clB - IH_H(hw);                                                 // _hit.loc (align.cpp:297)
-            y1 = (hy & ~(1u << 27)) | (sig << 27);
-            m1 = IH_L(hz) | (it << 9) | ((act ? 1u : 0u) << 14) | ((u32)__popc(mask) << 15);
-            if (act && sig) ce1 = __ldg(A.di.ctab + (g1 >> BSL_CTAB_SHIFT));
-            if (mine) rec1 = IH_SLOT(hB.y) * 2 + IH_CHAIN(hB.y);
-            if (lane == 0) A.bitmap[GB1] = 0u;                                   // bits are set by drain_exact
-        }
-        // ---- P (group v+3): headers and loc entries
-        uint4 hN = make_uint4(FULL, 0, 0, 0); u32 clN = 0;
-        if (is_group(GP)) {
-            if (fP + lane <= lP) hN = __ldg((const uint4 *)(A.hdr + fP + lane));
-            const u32 c = ((u32)GP << 5) + lane;
-            if (c < n_cands) clN = __ldg(A.flat_loc + c);
-        }
-        // ---- F (group v+4)
-        if (is_group(GF)) { fP = __ldg(A.chunk_first + GF); lP = GF + 1 < n_groups ? __ldg(A.chunk_first + GF + 1) : n_items - 1u; }
-        // ---- rotate
+        const bool act = (mC >> 23) & 1u; const u32 sig = IH_INV(yC);
+        bool pass = false;
+        if (act) {
+            if (!((cx >> 14) & 1u) || (sig && ((nfl >> ((cx >> 15) & 31u)) & 1u))) pass = true;     // not screened on this strand: the exact count decides
+            else {
+                const uint2 *Sr = (const uint2 *)(S0 + ((mC >> 9) & 0x3FFFu));       // {low bits, ACGT mask} per 32 bases, forward or reversed
+                const u32 sft = (cx >> 5) & 31u, nW = (cx >> 10) & 15u, d8 = cx & 31u;
+                u32 low = 0;
 #pragma unroll
-        for (int j = 0; j < 8; j++) R[j] = Rn[j];
-        nfl = nfl_n; cx = cx_n; gC = g2; yC = y2; mC = m2;
-        g2 = g1; y2 = y1; m2 = m1; rec2 = rec1; ce2 = ce1;
-        hB = hN; clB = clN;
+                for (int x = 0; x < 7; x++) {
+                    const u32 i = (u32)x + d8 - 8u;
+                    if (i < nW) { const uint2 lm = Sr[i]; low += __popc((lm.x ^ __funnelshift_l(R[x + 1], R[x], sft)) & lm.y); }
+                }
+                pass = low <= IH_THR(yC);
+            }
+        }
+        const u32 bal = __ballot_sync(FULL, pass);
+        if (bal) {
+            if (pass) {
+                Q[qn + __popc(bal & ((1u << lane) - 1u))] = make_uint4((G << 5) + lane, gC, yC, mC & 511u);
+            }
+            qn += __popc(bal);
+            __syncwarp();
+            if (qn >= 32u) { qn -= 32u; drain_exact<true>(A, Q[qn + lane], true, strm); }
+        }
+        __syncwarp();                                                            // every lane is done with the slice
+    };
+
+    // ---- fill the pipeline: group k of this warp is G_k = g0 + k * stride
+    const u32 G1 = g0 + stride, G2 = G1 + stride, G3 = G2 + stride;
+    stage_F(g0);
+    stage_P(g0); if (G1 < n_groups) stage_F(G1);
+    stage_B1(g0); if (G1 < n_groups) { stage_P(G1); if (G2 < n_groups) stage_F(G2); }
+    stage_S(); stage_B2(); if (G1 < n_groups) { stage_B1(G1); if (G2 < n_groups) { stage_P(G2); if (G3 < n_groups) stage_F(G3); } }
+    // ---- steady state: C(G), then S / B2 of the next group, B1 of the one after, P, F
+    for (u32 G = g0; G < n_groups; G += stride) {
+        stage_C(G);
+        const u32 Ga = G + stride, Gb = Ga + stride, Gc = Gb + stride, Gd = Gc + stride;
+        if (Ga >= n_groups) break;
+        stage_S(); stage_B2();
+        if (Gb < n_groups) { stage_B1(Gb); if (Gc < n_groups) { stage_P(Gc); if (Gd < n_groups) stage_F(Gd); } }
     }
-    __syncwarp();
-    if (qn) drain_exact<true>(A, Q[min(lane, qn - 1u)], lane < qn);
+    if (qn) drain_exact<true>(A, Q[min(lane, qn - 1u)], lane < qn, strm);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1694,7 +1802,7 @@ __global__ void finalize_reads(const __grid_constant__ KArgs A, const u32 *only_
     if (!live) return;
     if (m.flags & SF_DONE) return;                               // already written by pair_round
     bsl_hit o; memset(&o, 0, sizeof o); o.read_len = m.len; o.max_snp = m.B;
-    if (m.flags & SF_FILTERED) { o.status = BSL_ST_FILTERED; A.out[slot] = o; return; }
+    if (m.flags & (SF_FILTERED | SF_CONTEXT)) { o.status = BSL_ST_FILTERED; A.out[slot] = o; return; }
     o.status = BSL_ST_UNMAPPED;
     if (m.nhit == 0) { A.out[slot] = o; return; }
     const SlotCounts cn = A.cnt[slot];
@@ -1706,10 +1814,13 @@ __global__ void finalize_reads(const __grid_constant__ KArgs A, const u32 *only_
         u32 seen = 0;
         for (u32 i = 0; i < m.nhit; i++) if (tag_is(h[i].tag, chain, l)) { if (seen == want) { fill_record(o, h[i], chain, l); break; } seen++; }
         o.n_hits = nn; o.n_chain0 = n0; o.status = nn == 1 ? BSL_ST_UNIQUE : BSL_ST_MULTI;
-        if (A.report == 2 && !A.pe && A.all_a && nn > 1) {
+        if (A.report == 2 && A.all_a && nn > 1) {
+            // -r 2: every hit of the level, chain 0 list then chain 1 list (align.cpp:604-607; for a mate that ends unpaired
+            // pairs.cpp:270-274, 293-297). Mate #2 of a pair lists into the second array; both share one index space.
+            bsl_hit *dst = (A.pe && slot >= A.n_a) ? A.all_b : A.all_a;
             u64 base = atomicAdd(&A.ctr->all_n, (unsigned long long)nn); o.all_first = (u32)(base + A.all_off); u64 w = base;
             for (u32 c = 0; c < 2; c++) for (u32 i = 0; i < m.nhit; i++) if (tag_is(h[i].tag, c, l)) {
-                if (w < A.all_cap) { bsl_hit r = o; fill_record(r, h[i], c, l); A.all_a[w] = r; } w++; }
+                if (w < A.all_cap) { bsl_hit r = o; fill_record(r, h[i], c, l); dst[w] = r; } w++; }
         }
         break;
     }
@@ -1773,6 +1884,7 @@ void bsl_lane_free(Lane &ln) {
     cudaFree(ln.d_bits1); cudaFree(ln.d_hdr); cudaFree(ln.d_chunk_first); cudaFree(ln.d_bitmap); cudaFree(ln.d_flat_loc);
     cudaFree(ln.d_planes); cudaFree(ln.d_hits); cudaFree(ln.d_heavy_hits); cudaFree(ln.d_list[0]); cudaFree(ln.d_list[1]); cudaFree(ln.d_heavy_list);
     cudaFree(ln.d_pe_list[0]); cudaFree(ln.d_pe_list[1]); cudaFree(ln.d_out); cudaFree(ln.d_pair); cudaFree(ln.d_all[0]); cudaFree(ln.d_all[1]); cudaFree(ln.d_ctr);
+    cudaFree(ln.d_st0); cudaFree(ln.d_defer); cudaFree(ln.d_stale);
     if (ln.h_ctr) cudaFreeHost(ln.h_ctr);
     for (auto &e : ln.ev) if (e) cudaEventDestroy(e);
     for (auto &e : ln.evk) if (e) cudaEventDestroy(e);
@@ -1818,17 +1930,50 @@ static int ensure_lane(bsl_ctx *ctx, Lane &ln) {
 // longest read of a sub-range; dims (optional) = shared-memory row sizes of prepare_reads over the read lengths present:
 // dims[0] = most read offsets per seed segment the schedule can touch, I + (L - I + 1) % s; dims[1] = largest CountSeeds table,
 // segments x ((L - I + 1) % s + 1) with segments <= (L - I + 1) / s (align.cpp:450, 476-480)
-static u32 max_len_of(const bsl_batch *b, u32 first, u32 n, const bsl_params *P = nullptr, u32 *dims = nullptr) {
+static u32 max_len_of(const bsl_batch *b, u32 first, u32 n, const bsl_params *P = nullptr, u32 *dims = nullptr, bool *empty_range = nullptr) {
     u32 mx = 0, last = 0xffffffffu;
     for (u32 i = first; i < first + n; i++) {
         const u64 l = b->offsets[i + 1] - b->offsets[i];
         if (l > mx) mx = (u32)std::min<u64>(l, 0xffffffffu);
-        if (P && dims && (u32)l != last) {
+        if (P && (u32)l != last) {
             last = (u32)l; const u32 L = (u32)std::min<u64>(l, BSL_MAX_READLEN), I = P->index_interval, s = P->seed_size;
-            if (L + 1 >= I + s) { const u32 ii = (L + 1 - I) % s; dims[0] = std::max(dims[0], I + ii); dims[1] = std::max(dims[1], std::min<u32>((L + 1 - I) / s, 16) * (ii + 1)); }
+            if (L + 1 >= I + s) {
+                const u32 ii = (L + 1 - I) % s;
+                if (dims) { dims[0] = std::max(dims[0], I + ii); dims[1] = std::max(dims[1], std::min<u32>((L + 1 - I) / s, 16) * (ii + 1)); }
+                if (ii == 0 && empty_range) *empty_range = true;          // SURVEY trap 3: this read inherits its start offset
+            }
         }
     }
     return mx;
+}
+
+// ---- carried aligner state (SURVEY trap 3) across the sub-ranges of one call: which reads of [0, upto) re-create, when
+// they precede read `upto`, the state a single aligner object would have there — per mate the last unfiltered read with
+// a start-offset range, and every unfiltered read longer than all unfiltered reads after it (its seed hashes are still
+// visible beyond the end of a shorter read). Ascending indices.
+static void carry_context(const bsl_params &P, const bsl_batch *a, const bsl_batch *b, u32 upto, std::vector<u32> &idx) {
+    idx.clear();
+    const u32 I = P.index_interval, s = P.seed_size; const int nm = b ? 2 : 1;
+    u32 maxlen[2] = {0, 0}; bool have_def[2] = {false, b == nullptr};
+    auto defining = [&](u32 L) { return L + 1 >= I && (L + 1 - I) % s != 0; };
+    auto filtered = [&](const bsl_batch *q, u32 i, u32 L) {
+        if (L == 0 || L < P.min_read_size || L > BSL_MAX_READLEN) return true;
+        const u8 *p = q->bases + q->offsets[i]; u32 ns = 0;
+        for (u32 k = 0; k < L; k++) { const u8 c = p[k] & 0xDFu; ns += !(c == 'A' || c == 'C' || c == 'G' || c == 'T'); }
+        return ns > P.max_ns;
+    };
+    for (u32 i = upto; i-- > 0;) {
+        bool want = false, settled = true;
+        for (int m = 0; m < nm; m++) {
+            const bsl_batch *q = m ? b : a; const u32 L = (u32)std::min<u64>(q->offsets[i + 1] - q->offsets[i], 0xffffu);
+            const bool cand = L > maxlen[m] || (!have_def[m] && defining(L));
+            if (cand && !filtered(q, i, L)) { if (L > maxlen[m]) maxlen[m] = L; if (defining(L)) have_def[m] = true; want = true; }
+            if (!have_def[m] || maxlen[m] < BSL_MAX_READLEN) settled = false;
+        }
+        if (want) idx.push_back(i);
+        if (settled) break;
+    }
+    std::reverse(idx.begin(), idx.end());
 }
 
 // Opt-in shared-memory sizes are per device: done once per context (under its first lane's lock or any later one: idempotent).
@@ -1836,6 +1981,7 @@ static int configure_kernels(bsl_ctx *ctx) {
     std::lock_guard<std::mutex> g(ctx->stats_mu);
     if (ctx->kernels_configured) return 0;
     CUDA_TRY(cudaFuncSetAttribute(prepare_reads, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(prepare_deferred, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(screen_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(pair_round_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairWideSmem)));
     CUDA_TRY(cudaFuncSetAttribute(reduce_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -1851,7 +1997,7 @@ static int configure_kernels(bsl_ctx *ctx) {
 // One sub-range [first, first+n_a) of the caller's batch on one lane. Sub-ranges keep the number of items a search
 // round can produce below MAX_ITEMS_PER_ROUND and bound the device memory of a call.
 static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_batch *b, u32 first, u32 n_a, bsl_hit *out_a, bsl_hit *out_b, bsl_pair *out_pair,
-                       bsl_hit *all_a, bsl_hit *all_b, u64 all_cap, u64 all_off, u64 *all_made, int resident, bsl_stats *acc) {
+                       bsl_hit *all_a, bsl_hit *all_b, u64 all_cap, u64 all_off, u64 *all_made, int resident, bsl_stats *acc, bool carry) {
     int rc = 0;
     const bool pe = b != nullptr; const u32 n_slots = pe ? 2 * n_a : n_a;
     cudaStream_t st = ln.stream;
@@ -1861,6 +2007,11 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     const u64 bases_a = a->offsets[first + n_a] - off0_a, bases_b = pe ? b->offsets[first + n_a] - off0_b : 0;
     u32 pdims[2] = {P.index_interval, 1};
     u32 Lmax = max_len_of(a, first, n_a, &P, pdims); if (pe) Lmax = std::max(Lmax, max_len_of(b, first, n_a, &P, pdims));
+    if (carry) {            // st0 per (slot, chain), the deferred list, and 16 inherited seed hashes per (slot, chain)
+        size_t c1 = ln.cap_st0; if ((rc = grow(ctx, &ln.d_st0, &c1, (size_t)n_slots * 2 + 16))) return rc; ln.cap_st0 = c1;
+        c1 = ln.cap_defer; if ((rc = grow(ctx, &ln.d_defer, &c1, (size_t)n_slots + 16))) return rc; ln.cap_defer = c1;
+        c1 = ln.cap_stale; if ((rc = grow(ctx, &ln.d_stale, &c1, (size_t)n_slots * 32 + 16))) return rc; ln.cap_stale = c1;
+    }
     if (Lmax > BSL_MAX_READLEN) Lmax = BSL_MAX_READLEN;       // longer reads are flagged filtered by prepare_reads; the CLI truncates like the reference
     const u32 Wb = std::max(1u, (Lmax + 31) / 32);
     const u32 cap = 32;
@@ -1926,6 +2077,7 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     A.bases = ln.d_bases + BASES_PAD; A.off = ln.d_off; A.index = ln.d_index; A.rawlen = ln.d_rawlen; A.first_index_a = a->first_index + first; A.first_index_b = pe ? b->first_index + first : 0;
     A.off_base_a = off0_a; A.off_base_b = off0_b; A.all_off = all_off;
     A.bases_b_shift = bases_a; A.has_index = (a->index != nullptr) && (!pe || b->index != nullptr); A.has_rawlen = (a->raw_len != nullptr) && (!pe || b->raw_len != nullptr);
+    A.n_ctx = first == 0 ? std::min(a->n_context, n_a) : 0; A.carry = carry ? 1u : 0u; A.st0arr = ln.d_st0; A.defer = ln.d_defer; A.stale = ln.d_stale;
     A.Wb = Wb; A.planes = ln.d_planes; A.bits1 = ln.d_bits1; A.sched = ln.d_sched; A.meta = ln.d_meta; A.cnt = ln.d_cnt; A.stat = ln.d_stat; A.minlvl = ln.d_minlvl;
     A.hits = ln.d_hits; A.cap = cap_main; A.ctr = ln.d_ctr;
     A.hdr = ln.d_hdr; A.cap_items = (u32)std::min<u64>(want_items - 16, 0xffffffffu); A.cap_cands = (u32)want_cands;
@@ -1953,13 +2105,19 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     const int sms = ctx->sm_count;
     CUDA_TRY(cudaEventRecord(ln.ev[1], st));
     {
-        // prepare_reads keeps 2 WQ + 2 Wb + wd + nseg (ii + 1) words per read in shared memory (<= 200 KB per CTA for any -s / -I / length)
+        // prepare_reads keeps WQ + Wb + 1 + wd + nseg (ii + 1) words per read in shared memory (<= 200 KB per CTA for any -s / -I / length)
         const u32 WQ = 2 * Wb + 3;
-        const size_t smem_p = (size_t)PR_WARPS * 32 * ((2 * WQ + 2 * Wb + pdims[0] + pdims[1]) | 1u) * 4;
+        const size_t smem_p = (size_t)PR_WARPS * 32 * ((WQ + Wb + 1 + pdims[0] + pdims[1]) | 1u) * 4;
         if (smem_p > 200 * 1024) { set_error(ctx, "seed schedule does not fit the shared memory of prepare_reads"); return BSL_ELIMIT; }
         const u32 groups = (n_slots + 31) / 32;
+        if (carry) CUDA_TRY(cudaMemsetAsync(ln.d_st0, 0, (size_t)n_slots * 2, st));
         prepare_reads<<<std::min<u32>((groups + PR_WARPS - 1) / PR_WARPS, (u32)sms * 16), PR_WARPS * 32, smem_p, st>>>(A, WQ, pdims[0], pdims[1]);
         launches++;
+        if (carry) {        // reads with an empty start-offset range: schedule from the state the earlier reads of the batch leave behind
+            const u32 wdm = P.index_interval + P.seed_size, csz = 16 * P.seed_size;
+            prepare_deferred<<<sms * 4, PD_WARPS * 32, (size_t)PD_WARPS * 32 * ((wdm + csz) | 1u) * 4, st>>>(A, wdm, csz);
+            launches++;
+        }
     }
     build_lists<<<(std::max(n_slots, n_a) + 255) / 256, 256, 0, st>>>(A, ln.d_list[0], ln.d_pe_list[0]); launches++;
     CUDA_TRY(cudaGetLastError());
@@ -2000,12 +2158,13 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     const int grid_s = sms * ctx->occ_screen;
     // 1-bit screen (single-conversion rules)
     const bool use_bits = ctx->di.has_bit1 != 0;
-    const u32 item_bytes = 16 * Wb + 16;                                  // staged item: {low bits, ACGT mask} x Wb forward, x Wb reversed (+16: bank spread)
+    const u32 item_bytes = 16 * Wb + ((Wb & 1u) ? 0u : 16u);              // staged item: {low bits, ACGT mask} x Wb forward, x Wb reversed; stride = 4 x odd words spreads the items over the banks
+    const u32 rcp_wb = (u32)((0x100000000ull + Wb - 1) / Wb);
     const size_t smem_b = (size_t)SB_WARPS * 32 * item_bytes;
     if (!ctx->occ_bits || ctx->occ_bits_wb != Wb) { int occ = 0; cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, screen_bits, SB_WARPS * 32, smem_b); ctx->occ_bits = (oe == cudaSuccess && occ > 0) ? occ : 1; ctx->occ_bits_wb = Wb; }
     const int grid_b = sms * ctx->occ_bits;
     auto launch_verify = [&](KArgs &K, u32 ci) {
-        if (!G && use_bits) { screen_bits<<<grid_b, SB_WARPS * 32, smem_b, st>>>(K, ci, item_bytes); return; }
+        if (!G && use_bits) { screen_bits<<<grid_b, SB_WARPS * 32, smem_b, st>>>(K, ci, item_bytes, rcp_wb); return; }
         if (!G) {
             if (ctx->rule.single) screen_candidates<true><<<grid_s, SC_WARPS * 32, smem_s, st>>>(K, ci, stage_items, rcp_dw);
             else screen_candidates<false><<<grid_s, SC_WARPS * 32, smem_s, st>>>(K, ci, stage_items, rcp_dw);
@@ -2143,10 +2302,40 @@ int bsl_align_impl(bsl_ctx *ctx, const bsl_batch *a, const bsl_batch *b, bsl_hit
     if (resident && n > sub) { set_error(ctx, "bsl_align_rerun: the batch was split into sub-ranges and is not resident"); return BSL_ESTATE; }
     bsl_stats acc; memset(&acc, 0, sizeof acc);
     u64 all_off = 0;
+    bool carry = false;                                             // any read with an empty start-offset range in this call?
+    max_len_of(a, 0, n, &P, nullptr, &carry); if (pe) max_len_of(b, 0, n, &P, nullptr, &carry);
     for (u32 first = 0; first < n; first += sub) {
         const u32 cnt = std::min(sub, n - first);
         u64 made = 0;
-        rc = align_range(ctx, ln, a, b, first, cnt, out_a, out_b, out_pair, all_a, all_b, all_cap, all_off, &made, resident, &acc);
+        std::vector<u32> cidx;
+        if (carry && first > 0) carry_context(P, a, b, first, cidx);
+        if (cidx.empty()) rc = align_range(ctx, ln, a, b, first, cnt, out_a, out_b, out_pair, all_a, all_b, all_cap, all_off, &made, resident, &acc, carry);
+        else {
+            // a later sub-range in carry mode: the reads that define its inherited state go in front of it as context
+            if (resident) { set_error(ctx, "bsl_align_rerun: the batch was split into sub-ranges and is not resident"); return BSL_ESTATE; }
+            const u32 nc = (u32)cidx.size(), nt = nc + cnt;
+            struct Tmp { std::vector<u8> bases; std::vector<u64> off; std::vector<u32> index; std::vector<u16> raw; bsl_batch q; std::vector<bsl_hit> out; } t[2];
+            std::vector<bsl_pair> tpair(pe ? nt : 0);
+            for (int m = 0; m < (pe ? 2 : 1); m++) {
+                const bsl_batch *q = m ? b : a; Tmp &T = t[m];
+                T.off.resize((size_t)nt + 1); T.index.resize(nt); if (q->raw_len) T.raw.resize(nt);
+                u64 tot = 0; for (u32 k = 0; k < nt; k++) { const u32 i = k < nc ? cidx[k] : first + (k - nc); tot += q->offsets[i + 1] - q->offsets[i]; }
+                T.bases.resize(tot + 1); u64 pos = 0;
+                for (u32 k = 0; k < nt; k++) {
+                    const u32 i = k < nc ? cidx[k] : first + (k - nc); const u64 l = q->offsets[i + 1] - q->offsets[i];
+                    T.off[k] = pos; memcpy(T.bases.data() + pos, q->bases + q->offsets[i], l); pos += l;
+                    T.index[k] = q->index ? q->index[i] : q->first_index + i; if (q->raw_len) T.raw[k] = q->raw_len[i];
+                }
+                T.off[nt] = pos; T.out.resize(nt);
+                T.q = *q; T.q.n = nt; T.q.bases = T.bases.data(); T.q.offsets = T.off.data(); T.q.index = T.index.data(); T.q.raw_len = q->raw_len ? T.raw.data() : nullptr; T.q.n_context = nc;
+            }
+            rc = align_range(ctx, ln, &t[0].q, pe ? &t[1].q : nullptr, 0, nt, t[0].out.data(), pe ? t[1].out.data() : nullptr, pe ? tpair.data() : nullptr,
+                             all_a, all_b, all_cap, all_off, &made, 0, &acc, true);
+            if (rc == 0) {
+                memcpy(out_a + first, t[0].out.data() + nc, (size_t)cnt * sizeof(bsl_hit));
+                if (pe) { memcpy(out_b + first, t[1].out.data() + nc, (size_t)cnt * sizeof(bsl_hit)); memcpy(out_pair + first, tpair.data() + nc, (size_t)cnt * sizeof(bsl_pair)); }
+            }
+        }
         if (rc) return rc;
         all_off += made;
     }

@@ -116,6 +116,8 @@ struct __align__(16) SlotMeta {
 #define SF_OVERFLOW 8u
 #define SF_DONE 16u
 #define SF_ABORT0 32u   // level-0 list reached -w
+#define SF_CONTEXT 64u  // context read (bsl_batch::n_context): scheduled, never mapped
+#define SF_STALE 128u   // its schedule reaches beyond the end of the read: those seed hashes come from KArgs::stale
 
 struct SlotCounts { u16 c[2][16]; };   // hits per read chain and mismatch level
 
@@ -155,6 +157,7 @@ struct DevCounters {
     unsigned long long seed_lookups, candidates, hits_added, heavy, all_n;
     RoundCtr rc[40];
     u32 overflow_n;
+    u32 defer_n;                // reads whose seed schedule is left to prepare_deferred
 };
 
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error(ctx, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); return (e_ == cudaErrorMemoryAllocation) ? BSL_ENOMEM : BSL_ECUDA; } } while (0)

@@ -6,11 +6,15 @@
 // external `samtools view -bS -` like the reference, main.cpp:505).  The mapping itself happens on the GPU(s):
 // this file only parses text, trims reads, batches them and prints result records.
 //
-//   reader thread  ->  batches of reads  ->  worker threads (bsl_align_se/pe on a GPU, then SAM text)
-//                                        ->  writer (input order)
+//   splitter thread per input file -> text blocks of whole records -> worker threads (tokenise, pack into pinned memory,
+//   bsl_align_se/pe on a GPU, SAM text) -> output in input order (parallel pwrite into reserved byte ranges)
 //
 // Reads shard across GPUs by batch; every GPU holds a replica of the index; results are merged
 // in input order, so the output does not depend on the number of GPUs.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -20,9 +24,12 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cerrno>
 #include <cstring>
 #include <ctime>
+#include <deque>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -216,7 +223,9 @@ static bool load_reference(const std::string &path, Reference &R) {
         if (s[i] == '>') { i++; while (i < n && isspace((unsigned char)s[i])) i++; size_t j = i; while (j < n && !isspace((unsigned char)s[j])) j++;
             R.names.emplace_back(s + i, j - i); R.off.push_back(R.cat.size()); R.len.push_back(0); continue; }
         if (R.names.empty()) continue;
-        for (; i < n; i++) if (!isspace((unsigned char)s[i])) { R.cat.push_back((u8)s[i]); R.len.back()++; }
+        const size_t before = R.cat.size(); R.cat.resize(before + (n - i)); u8 *d = R.cat.data() + before; size_t k = 0;
+        for (; i < n; i++) if (!isspace((unsigned char)s[i])) d[k++] = (u8)s[i];
+        R.cat.resize(before + k); R.len.back() += (u32)k;
     }
     in.close();
     // sequences with no bases end the reference's loading loop (refbase.cpp:192: `while(LoadNextSeq(...))`)
@@ -225,98 +234,204 @@ static bool load_reference(const std::string &path, Reference &R) {
     return true;
 }
 
-struct ReadRec { std::string name, seq, qual; u32 raw_len = 0; };
+// ---- read input: every source (plain / gzip'd FASTA or FASTQ, unaligned BAM) is cut by ONE splitter thread per file into
+//      text blocks of whole records; the worker threads tokenise the blocks (ReadClass::LoadBatchReads, reads.cpp:42-111).
+//      A plain file is memory-mapped and its blocks are views of the mapping; compressed input is inflated by the
+//      splitter thread into owned buffers (BAM records are rewritten as FASTQ text there).
+struct TextBlock { const char *p = nullptr; size_t n = 0; u32 records = 0; std::shared_ptr<std::vector<char>> keep; };
 
-struct ReadFile {
-    GzReader in; int format = -1;   // 0 fasta, 1 fastq, 3 bam (unaligned reads in a BAM file, reads.cpp:85-108)
+struct ReadSource {
+    int format = -1;                // 0 fasta, 1 fastq, 3 bam (unaligned reads in a BAM file, reads.cpp:85-108)
     int mate = 0;                   // BAM input of a paired run: both -a and -b name the same interleaved file; file #1 takes
                                     // records 0, 2, 4, ... and file #2 records 1, 3, 5, ... (reads.cpp:88,107)
-    std::vector<char> rec;
-    bool open(const std::string &p) {
-        if (!in.open(p)) return false;
-        in.fill(); size_t i = 0;
+    bool fastq() const { return format != 0; }          // BAM records are handed on as FASTQ text
+    const char *format_name() const { return format == 3 ? "BAM" : format == 1 ? "FASTQ" : "FASTA"; }
+    // plain file
+    const char *map = nullptr; size_t map_len = 0, map_pos = 0;
+    // streamed input
+    GzReader in; bool streamed = false; std::vector<char> rec; std::vector<char> pending;     // pending: bytes of the block being built
+    u32 max_readlen = 480;
+
+    bool open(const std::string &path, u32 max_len) {
+        max_readlen = max_len;
+        int fd = ::open(path.c_str(), O_RDONLY); if (fd < 0) return false;
+        struct stat st; if (fstat(fd, &st) != 0) { ::close(fd); return false; }
+        unsigned char magic[4] = {0, 0, 0, 0}; const ssize_t got = pread(fd, magic, 4, 0);
+        const bool gz = got >= 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+        if (!gz && S_ISREG(st.st_mode) && st.st_size > 0) {
+            void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m != MAP_FAILED) { madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL); map = (const char *)m; map_len = (size_t)st.st_size; }
+        }
+        ::close(fd);
+        if (map) {
+            size_t i = 0; while (i < map_len && isspace((unsigned char)map[i])) i++;
+            format = (i < map_len && map[i] == '>') ? 0 : (i < map_len && map[i] == '@') ? 1 : -1;
+            return true;
+        }
+        streamed = true;
+        if (!in.open(path)) return false;
+        in.fill();
         if (in.len >= 4 && memcmp(in.buf.data(), "BAM\1", 4) == 0) {                 // zlib has already undone the BGZF layer
             format = -1; int32_t l_text = 0, n_ref = 0;
             if (!in.bytes(nullptr, 4) || !in.bytes(&l_text, 4) || l_text < 0 || !in.bytes(nullptr, (size_t)l_text) || !in.bytes(&n_ref, 4) || n_ref < 0) return true;
             for (int32_t k = 0; k < n_ref; k++) { int32_t l_name = 0; if (!in.bytes(&l_name, 4) || l_name < 0 || !in.bytes(nullptr, (size_t)l_name + 4)) return true; }
             format = 3; return true;
         }
-        while (i < in.len && isspace((unsigned char)in.buf[i])) i++;
-        if (i < in.len && in.buf[i] == '>') format = 0; else if (i < in.len && in.buf[i] == '@') format = 1; else format = -1;
+        size_t i = 0; while (i < in.len && isspace((unsigned char)in.buf[i])) i++;
+        format = (i < in.len && in.buf[i] == '>') ? 0 : (i < in.len && in.buf[i] == '@') ? 1 : -1;
         return true;
     }
-    const char *format_name() const { return format == 3 ? "BAM" : format == 1 ? "FASTQ" : "FASTA"; }
-    bool bam_record(ReadRec *r, const Options &O) {                                   // one alignment record; r == null skips it
+    // one BAM alignment record appended to `out` as FASTQ text; out == null skips it
+    bool bam_record(std::vector<char> *out) {
         int32_t bs = 0; if (!in.bytes(&bs, 4) || bs < 32) return false;
         rec.resize((size_t)bs); if (!in.bytes(rec.data(), (size_t)bs)) return false;
-        if (!r) return true;
+        if (!out) return true;
         const unsigned char *b = (const unsigned char *)rec.data();
         const u32 l_name = b[8], n_cig = (u32)b[12] | ((u32)b[13] << 8); u32 l_seq; memcpy(&l_seq, b + 16, 4);
         const size_t o_name = 32, o_seq = o_name + l_name + 4ull * n_cig, o_qual = o_seq + (l_seq + 1) / 2;
         if (o_qual + l_seq > (size_t)bs || l_name == 0) return false;
-        r->name.assign((const char *)b + o_name, strnlen((const char *)b + o_name, l_name));
-        const u32 n = std::min<u32>(l_seq, (u32)O.max_readlen);                           // reads.cpp:93
-        r->seq.resize(n); r->qual.resize(n);
-        for (u32 i = 0; i < n; i++) {
-            r->seq[i] = "=ACMGRSVTWYHKDBN"[(b[o_seq + i / 2] >> ((i & 1) ? 0 : 4)) & 15];  // bam_nt16_rev_table (reads.cpp:103)
-            r->qual[i] = (char)(b[o_qual + i] + 33);
-        }
+        const size_t nl = strnlen((const char *)b + o_name, l_name);
+        const u32 n = std::min<u32>(l_seq, max_readlen);                                  // reads.cpp:93
+        const size_t at = out->size(); out->resize(at + nl + 2 * (size_t)n + 6); char *d = out->data() + at;
+        *d++ = '@'; memcpy(d, b + o_name, nl); d += nl; *d++ = '\n';
+        for (u32 i = 0; i < n; i++) *d++ = "=ACMGRSVTWYHKDBN"[(b[o_seq + i / 2] >> ((i & 1) ? 0 : 4)) & 15];   // bam_nt16_rev_table (reads.cpp:103)
+        *d++ = '\n'; *d++ = '+'; *d++ = '\n';
+        for (u32 i = 0; i < n; i++) *d++ = (char)(b[o_qual + i] + 33);
+        *d++ = '\n';
         return true;
     }
-    // ReadClass::LoadBatchReads (reads.cpp:42-84), line oriented
-    bool next(ReadRec &r, const Options &O) {
-        if (format == 3) {
-            if (mate == 2 && !bam_record(nullptr, O)) return false;
-            if (!bam_record(&r, O)) return false;
-            if (mate == 1 && !bam_record(nullptr, O)) return false;
+    // The lines of one record: the header is the next non-empty line, then 1 (FASTA) or 3 (FASTQ) more lines, whatever they
+    // hold. Returns the end of the record inside [p, e), or null when the input ends first.
+    const char *skip_record(const char *p, const char *e, bool at_eof) const {
+        const int more = format == 0 ? 1 : 3;
+        for (;;) {                                                      // header: skip empty lines (also "\r\n" ones)
+            if (p >= e) return nullptr;
+            const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p));
+            const char *le = nl ? nl : e; if (!nl && !at_eof) return nullptr;
+            size_t n = (size_t)(le - p); if (n && p[n - 1] == '\r') n--;
+            p = nl ? nl + 1 : e;
+            if (n) break;
+        }
+        for (int k = 0; k < more; k++) {
+            if (p >= e) return nullptr;
+            const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p));
+            if (!nl) { if (!at_eof) return nullptr; p = e; continue; }
+            p = nl + 1;
+        }
+        return p;
+    }
+    // the next `want` records (fewer at the end of the input); false when nothing is left
+    bool next(TextBlock &b, u32 want) {
+        b = TextBlock();
+        if (map) {
+            const char *p0 = map + map_pos, *e = map + map_len, *p = p0; u32 k = 0;
+            while (k < want) { const char *q = skip_record(p, e, true); if (!q) break; p = q; k++; }
+            if (!k) return false;
+            b.p = p0; b.n = (size_t)(p - p0); b.records = k; map_pos += b.n;
             return true;
         }
-        const char *s; size_t n;
-        do { if (!in.line(s, n)) return false; } while (n == 0);
-        size_t i = 1; while (i < n && isspace((unsigned char)s[i])) i++; size_t j = i; while (j < n && !isspace((unsigned char)s[j])) j++;
-        r.name.assign(s + i, j - i);
-        if (!in.line(s, n)) return false;
-        while (n && isspace((unsigned char)s[n - 1])) n--;
-        r.seq.assign(s, n);
-        if (format == 1) { if (!in.line(s, n)) return false; if (!in.line(s, n)) return false; while (n && isspace((unsigned char)s[n - 1])) n--; r.qual.assign(s, n); }
-        else r.qual.assign(r.seq.size(), (char)(O.zero_qual + O.default_qual));
-        if (r.seq.size() > O.max_readlen) { r.seq.erase(O.max_readlen); if (r.qual.size() > O.max_readlen) r.qual.erase(O.max_readlen); }
+        auto buf = std::make_shared<std::vector<char>>(); buf->swap(pending); u32 k = 0; size_t scanned = 0;
+        if (format == 3) {
+            buf->reserve((size_t)want * 360);
+            while (k < want) {
+                if (mate == 2 && !bam_record(nullptr)) break;
+                if (!bam_record(buf.get())) break;
+                k++;
+                if (mate == 1 && !bam_record(nullptr)) break;
+            }
+            scanned = buf->size();
+        } else {
+            for (;;) {
+                const char *base = buf->data();
+                while (k < want) { const char *q = skip_record(base + scanned, base + buf->size(), in.eof && in.pos >= in.len); if (!q) break; scanned = (size_t)(q - base); k++; }
+                if (k >= want || (in.eof && in.pos >= in.len)) break;
+                if (in.pos >= in.len && !in.fill()) continue;                // eof is set now: one more round takes an unterminated last line
+                buf->insert(buf->end(), in.buf.data() + in.pos, in.buf.data() + in.len); in.pos = in.len;
+            }
+            pending.assign(buf->begin() + (long)scanned, buf->end()); buf->resize(scanned);
+        }
+        if (!k) return false;
+        b.keep = buf; b.p = buf->data(); b.n = scanned; b.records = k;
         return true;
     }
 };
 
+// a read as the workers see it: views into a TextBlock (or into the arena of its batch)
+struct ReadView { const char *name = nullptr, *seq = nullptr, *qual = nullptr; u32 name_len = 0, len = 0, raw_len = 0; bool too_short = false; };
+
+// tokenise one block (reads.cpp:53-84): name = first token after the '@' / '>' character, the rest of the line is dropped
+static void parse_block(const TextBlock &b, bool fastq, u32 max_readlen, const char *fasta_qual, std::vector<ReadView> &out) {
+    out.clear(); out.reserve(b.records);
+    const char *p = b.p, *e = b.p + b.n;
+    auto line = [&](const char *&s, size_t &n) -> bool {
+        if (p >= e) return false;
+        const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p)); const char *le = nl ? nl : e;
+        s = p; n = (size_t)(le - p); if (n && s[n - 1] == '\r') n--; p = nl ? nl + 1 : e; return true;
+    };
+    for (u32 k = 0; k < b.records; k++) {
+        const char *s; size_t n; ReadView r;
+        do { if (!line(s, n)) return; } while (n == 0);
+        size_t i = 1; while (i < n && isspace((unsigned char)s[i])) i++; size_t j = i; while (j < n && !isspace((unsigned char)s[j])) j++;
+        r.name = s + i; r.name_len = (u32)(j - i);
+        if (!line(s, n)) return;
+        while (n && isspace((unsigned char)s[n - 1])) n--;
+        r.seq = s; size_t ls = n, lq;
+        if (fastq) { if (!line(s, n) || !line(s, n)) return; while (n && isspace((unsigned char)s[n - 1])) n--; r.qual = s; lq = n; }
+        else { r.qual = fasta_qual; lq = std::min<size_t>(ls, 480); }
+        if (ls > max_readlen) { ls = max_readlen; if (lq > max_readlen) lq = max_readlen; }
+        // a quality string of another length than the sequence is replaced by the default one in TrimLowQual (align.cpp:53); until
+        // then only its length matters
+        r.len = (u32)ls; r.raw_len = (u32)lq;                       // raw_len carries the quality length until trim_read
+        out.push_back(r);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ trimming (align.cpp:51-76, 418-435)
-static void trim_read(ReadRec &r, const Options &O, bool &too_short) {
-    too_short = false;
-    r.raw_len = (u32)r.seq.size();
-    bool cut = false;
-    for (size_t a = 0; a < O.adapters.size() && !cut; a++) {                                          // TrimAdapter
+// Works on views: trimming only ever shortens a read. `arena` receives rewritten quality strings (non-default -z, or a
+// quality string whose length differs from the sequence's).
+static void trim_read(ReadView &r, const Options &O, std::deque<std::string> &arena, const char *fasta_qual) {
+    r.too_short = false;
+    u32 qlen = r.raw_len; r.raw_len = r.len;
+    for (size_t a = 0, cut = 0; a < O.adapters.size() && !cut; a++) {                                    // TrimAdapter
         const std::string &ad = O.adapters[a];
-        for (u32 pos = O.P.seed_size + O.P.index_interval - 1; (size_t)pos + 4 < r.seq.size() && r.seq.size() >= 4; pos++) {
+        for (u32 pos = O.P.seed_size + O.P.index_interval - 1; (size_t)pos + 4 < r.len && r.len >= 4; pos++) {
             u32 m0 = 0, k = 0;
-            for (; k < ad.size() && k < 15 && pos + k < r.seq.size(); k++) if ((m0 += (ad[k] != r.seq[pos + k])) > 4) break;
-            if (k >= m0 * 5 && k > 3) { r.seq.erase(pos); if (r.qual.size() > pos) r.qual.erase(pos); cut = true; break; }
+            for (; k < ad.size() && k < 15 && pos + k < r.len; k++) if ((m0 += (ad[k] != r.seq[pos + k])) > 4) break;
+            if (k >= m0 * 5 && k > 3) { r.len = pos; if (qlen > pos) qlen = pos; cut = 1; break; }
         }
     }
     // TrimLowQual
-    if (r.seq.size() != r.qual.size()) r.qual.assign(r.seq.size(), (char)(O.zero_qual + O.default_qual));
+    if (r.len != qlen) { r.qual = fasta_qual; qlen = r.len; }                                             // string(seq.size(), zero_qual + default_qual)
     u8 qual_thres = (u8)(O.zero_qual + O.qual_threshold);
-    if (O.zero_qual != '!') { for (char &c : r.qual) c = (char)(c - (O.zero_qual - '!')); qual_thres = (u8)(qual_thres - (O.zero_qual - '!')); }
+    if (O.zero_qual != '!') {
+        arena.emplace_back(r.qual, qlen); std::string &q = arena.back();
+        for (char &c : q) c = (char)(c - (O.zero_qual - '!'));
+        r.qual = q.data(); qual_thres = (u8)(qual_thres - (O.zero_qual - '!'));
+    }
     if (O.qual_threshold == 0) return;
-    size_t i = r.qual.size();
+    size_t i = qlen;
     while (i > 0 && !((u8)r.qual[i - 1] > qual_thres)) i--;
-    if (i < O.P.seed_size + O.P.index_interval - 1) { too_short = true; return; }
-    r.qual.erase(i); r.seq.erase(i);
+    if (i < O.P.seed_size + O.P.index_interval - 1) { r.too_short = true; return; }
+    r.len = (u32)i;
 }
 
 // ------------------------------------------------------------------------------------------------ SAM text
-static const char kRev[256] = {0};
 static inline char rev_char(char c) {
     switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A';
                  case 'a': return 't'; case 'c': return 'g'; case 'g': return 'c'; case 't': return 'a'; default: return 'N'; }
 }
-static void append_seq(std::string &os, const std::string &s, bool rev) { if (!rev) { os += s; return; } size_t n = os.size(); os.resize(n + s.size()); for (size_t i = 0; i < s.size(); i++) os[n + i] = rev_char(s[s.size() - 1 - i]); }
-static void append_qual(std::string &os, const std::string &s, bool rev) { if (!rev) { os += s; return; } os.append(s.rbegin(), s.rend()); }
+struct RevTable { char t[256]; RevTable() { for (int i = 0; i < 256; i++) t[i] = rev_char((char)i); } };
+static const RevTable kRevTab;
+static void append_seq(std::string &os, const ReadView &r, bool rev) {
+    if (!rev) { os.append(r.seq, r.len); return; }
+    const size_t n = os.size(); os.resize(n + r.len); char *d = &os[n];
+    for (u32 i = 0; i < r.len; i++) d[i] = kRevTab.t[(u8)r.seq[r.len - 1 - i]];
+}
+static void append_qual(std::string &os, const ReadView &r, bool rev) {
+    if (!rev) { os.append(r.qual, r.len); return; }
+    const size_t n = os.size(); os.resize(n + r.len); char *d = &os[n];
+    for (u32 i = 0; i < r.len; i++) d[i] = r.qual[r.len - 1 - i];
+}
 static void append_u(std::string &os, u64 v) { char b[24]; int n = 0; do { b[n++] = (char)('0' + v % 10); v /= 10; } while (v); while (n) os.push_back(b[--n]); }
 static void append_i(std::string &os, long long v) { if (v < 0) { os.push_back('-'); append_u(os, (u64)(-v)); } else append_u(os, (u64)v); }
 
@@ -340,140 +455,255 @@ struct Formatter {
         m[m.size() - 1] += 32; m[m.size() - 2] += 32;
         os += "\tXR:Z:"; os += m;
     }
-    void unaligned(std::string &os, const ReadRec &r, int flag) const {
-        os += r.name; os.push_back('\t'); append_i(os, flag); os += "\t*\t0\t0\t*\t*\t0\t0\t"; os += r.seq; os.push_back('\t'); os += r.qual; os.push_back('\n');
+    static void name(std::string &os, const ReadView &r) { os.append(r.name, r.name_len); }
+    void unaligned(std::string &os, const ReadView &r, int flag) const {
+        name(os, r); os.push_back('\t'); append_i(os, flag); os += "\t*\t0\t0\t*\t*\t0\t0\t"; os.append(r.seq, r.len); os.push_back('\t'); os.append(r.qual, r.len); os.push_back('\n');
     }
     // s_OutHit (align.cpp:616-669): n<0 filtered, n==0 unmapped, else hit count
-    void single(std::string &os, const ReadRec &r, u32 readset, const bsl_hit &h, int n) const {
+    void single(std::string &os, const ReadView &r, u32 readset, const bsl_hit &h, int n) const {
         int flag = 0x40 * (int)readset;
         if (n <= 0) { if (!O.unmap) return; unaligned(os, r, flag | (n < 0 ? 0x204 : 0x4)); return; }
         bool rev = (h.read_chain ^ (h.chr & 1)) != 0;
         if (n > 1) flag |= 0x100;
         if (rev) flag |= 0x10;
-        os += r.name; os.push_back('\t'); append_i(os, flag); os.push_back('\t'); os += R.names[h.chr >> 1]; os.push_back('\t'); append_u(os, h.loc + 1);
-        os += "\t255\t"; append_cigar(os, h); os += "\t*\t0\t0\t"; append_seq(os, r.seq, rev); os.push_back('\t'); append_qual(os, r.qual, rev);
+        name(os, r); os.push_back('\t'); append_i(os, flag); os.push_back('\t'); os += R.names[h.chr >> 1]; os.push_back('\t'); append_u(os, h.loc + 1);
+        os += "\t255\t"; append_cigar(os, h); os += "\t*\t0\t0\t"; append_seq(os, r, rev); os.push_back('\t'); append_qual(os, r, rev);
         os += "\tNM:i:"; append_i(os, h.nm);
         if (O.outref) xr(os, h);
         os += "\tZS:Z:"; os.push_back("+-"[h.chr & 1]); os.push_back("+-"[h.read_chain]); os.push_back('\n');
     }
     // s_OutHitPair (pairs.cpp:307-416)
-    void pair(std::string &os, const ReadRec &ra, const ReadRec &rb, const bsl_hit &a, const bsl_hit &b, u32 chain, u32 insert, int n) const {
+    void pair(std::string &os, const ReadView &ra, const ReadView &rb, const bsl_hit &a, const bsl_hit &b, u32 chain, u32 insert, int n) const {
         for (int side = 0; side < 2; side++) {
-            const bsl_hit &me = side ? b : a, &mate = side ? a : b; const ReadRec &r = side ? rb : ra;
+            const bsl_hit &me = side ? b : a, &mate = side ? a : b; const ReadView &r = side ? rb : ra;
             u32 ch = side ? !chain : chain; bool rev = (ch ^ (me.chr & 1)) != 0;
             int flag = 0x3; if (n > 1) flag |= 0x100; long long ins;
             if (rev) { flag |= 0x10; ins = -(long long)(int)insert; } else { flag |= 0x20; ins = (int)insert; }
             flag |= 0x40 * (side + 1);
-            os += r.name; os.push_back('\t'); append_i(os, flag); os.push_back('\t'); os += R.names[me.chr >> 1]; os.push_back('\t'); append_u(os, me.loc + 1);
+            name(os, r); os.push_back('\t'); append_i(os, flag); os.push_back('\t'); os += R.names[me.chr >> 1]; os.push_back('\t'); append_u(os, me.loc + 1);
             os += "\t255\t"; append_cigar(os, me); os += "\t=\t"; append_u(os, mate.loc + 1); os.push_back('\t'); append_i(os, ins); os.push_back('\t');
-            append_seq(os, r.seq, rev); os.push_back('\t'); append_qual(os, r.qual, rev); os += "\tNM:i:"; append_i(os, me.nm);
+            append_seq(os, r, rev); os.push_back('\t'); append_qual(os, r, rev); os += "\tNM:i:"; append_i(os, me.nm);
             if (O.outref) xr(os, me);
             os += "\tZS:Z:"; os.push_back("+-"[me.chr & 1]); os.push_back("+-"[ch]); os.push_back('\n');
         }
     }
     // s_OutHitUnpair (pairs.cpp:418-485)
-    void unpair(std::string &os, const ReadRec &r, int side, u32 chain_a, u32 chain_b, int ma, u32 na, const bsl_hit &ha, int mb, const bsl_hit &hb) const {
+    void unpair(std::string &os, const ReadView &r, int side, u32 chain_a, u32 chain_b, int ma, u32 na, const bsl_hit &ha, int mb, const bsl_hit &hb) const {
         int flag = 1 | (0x40 * (side + 1)); bool rev = (chain_a ^ (ha.chr & 1)) != 0;
         if (ma <= 0) {
-            if (ma < 0) flag |= 0x204; if (ma == 0) flag |= 0x4;
+            if (ma < 0) flag |= 0x204;
+            if (ma == 0) flag |= 0x4;
             if (mb <= 0) { unaligned(os, r, flag | 0x8); return; }
             if (chain_b ^ (hb.chr & 1)) flag |= 0x20;
-            os += r.name; os.push_back('\t'); append_i(os, flag); os += "\t*\t0\t0\t*\t"; os += R.names[hb.chr >> 1]; os.push_back('\t'); append_u(os, hb.loc + 1);
-            os += "\t0\t"; os += r.seq; os.push_back('\t'); os += r.qual; os.push_back('\n'); return;
+            name(os, r); os.push_back('\t'); append_i(os, flag); os += "\t*\t0\t0\t*\t"; os += R.names[hb.chr >> 1]; os.push_back('\t'); append_u(os, hb.loc + 1);
+            os += "\t0\t"; os.append(r.seq, r.len); os.push_back('\t'); os.append(r.qual, r.len); os.push_back('\n'); return;
         }
-        if (ma > 1) flag |= 0x100; if (rev) flag |= 0x10;
+        if (ma > 1) flag |= 0x100;
+        if (rev) flag |= 0x10;
         if (mb <= 0) flag |= 0x8; else if (chain_b ^ (hb.chr & 1)) flag |= 0x20;
-        os += r.name; os.push_back('\t'); append_i(os, flag); os.push_back('\t'); os += R.names[ha.chr >> 1]; os.push_back('\t'); append_u(os, ha.loc + 1);
+        name(os, r); os.push_back('\t'); append_i(os, flag); os.push_back('\t'); os += R.names[ha.chr >> 1]; os.push_back('\t'); append_u(os, ha.loc + 1);
         os += "\t255\t"; append_cigar(os, ha);
         if (mb <= 0) os += "\t*\t0\t0\t"; else { os.push_back('\t'); os += R.names[hb.chr >> 1]; os.push_back('\t'); append_u(os, hb.loc + 1); os += "\t0\t"; }
-        append_seq(os, r.seq, rev); os.push_back('\t'); append_qual(os, r.qual, rev); os += "\tNM:i:"; append_i(os, na);
+        append_seq(os, r, rev); os.push_back('\t'); append_qual(os, r, rev); os += "\tNM:i:"; append_i(os, na);
         if (O.outref) xr(os, ha);
         os += "\tZS:Z:"; os.push_back("+-"[ha.chr & 1]); os.push_back("+-"[chain_a]); os.push_back('\n');
     }
 };
 
-// FixPairReadName (pairs.cpp:487-507)
-static void fix_pair_names(std::string &a, std::string &b) {
-    if (a == b) return;
-    int d = -1; size_t i, n = std::min(a.size(), b.size());
-    for (i = 0; i < n; i++) { if (a[i] != b[i]) break; else if (isdigit((unsigned char)a[i])) d = (int)i; }
-    if (i > 0) { if (d < 0) d = (int)i - 1; a.erase(d + 1); b.erase(d + 1); }
-    else { fprintf(stderr, "Error: Paired reads name not match:\n%s\n%s\n", a.c_str(), b.c_str()); exit(1); }
+// FixPairReadName (pairs.cpp:487-507): both names are cut after the last digit of their common prefix
+static void fix_pair_names(ReadView &a, ReadView &b) {
+    if (a.name_len == b.name_len && memcmp(a.name, b.name, a.name_len) == 0) return;
+    int d = -1; size_t i, n = std::min(a.name_len, b.name_len);
+    for (i = 0; i < n; i++) { if (a.name[i] != b.name[i]) break; else if (isdigit((unsigned char)a.name[i])) d = (int)i; }
+    if (i > 0) { if (d < 0) d = (int)i - 1; a.name_len = std::min<u32>(a.name_len, (u32)d + 1); b.name_len = std::min<u32>(b.name_len, (u32)d + 1); }
+    else { fprintf(stderr, "Error: Paired reads name not match:\n%.*s\n%.*s\n", (int)a.name_len, a.name, (int)b.name_len, b.name); exit(1); }
 }
 
 // ------------------------------------------------------------------------------------------------ pipeline
-struct Batch {
-    u64 ticket = 0; u32 first_index = 0;
-    std::vector<ReadRec> a, b;
-    std::string text;
+//   splitter thread per input file  ->  queue of text blocks (whole records)
+//   worker threads: take block k of every file (ticket k), tokenise + trim + pack the bases into pinned memory,
+//                   bsl_align_se / bsl_align_pe on their GPU, SAM text (or BGZF blocks) into their own buffer
+//   output: tickets reserve their byte range in input order, the bytes are written by the workers in parallel (pwrite);
+//           a pipe / stdout is written in ticket order
+struct BlockQueue {
+    std::mutex mu; std::condition_variable cv_put, cv_get; std::deque<TextBlock> q; bool done = false; size_t cap = 8;
+    void put(TextBlock &&b) { std::unique_lock<std::mutex> g(mu); cv_put.wait(g, [&] { return q.size() < cap; }); q.push_back(std::move(b)); cv_get.notify_one(); }
+    void finish() { std::lock_guard<std::mutex> g(mu); done = true; cv_get.notify_all(); }
+    bool get(TextBlock &b) { std::unique_lock<std::mutex> g(mu); cv_get.wait(g, [&] { return !q.empty() || done; }); if (q.empty()) return false; b = std::move(q.front()); q.pop_front(); cv_put.notify_one(); return true; }
+};
+
+struct OutSink {
+    int fd = -1; bool seekable = false; FILE *pipe = nullptr;
+    std::mutex mu; std::condition_variable cv; u64 next_ticket = 0; u64 offset = 0;
+    static bool write_all(int fd, const char *p, size_t n) { while (n) { ssize_t k = ::write(fd, p, n); if (k < 0) { if (errno == EINTR) continue; return false; } p += k; n -= (size_t)k; } return true; }
+    static bool pwrite_all(int fd, const char *p, size_t n, u64 off) { while (n) { ssize_t k = ::pwrite(fd, p, n, (off_t)off); if (k < 0) { if (errno == EINTR) continue; return false; } p += k; n -= (size_t)k; off += (u64)k; } return true; }
+    bool head(const std::string &s) { if (s.empty()) return true; if (seekable) { const bool ok = pwrite_all(fd, s.data(), s.size(), offset); offset += s.size(); return ok; } return write_all(fd, s.data(), s.size()); }
+    // the bytes of ticket t; blocks until every earlier ticket has reserved its range (seekable) or has been written (pipe)
+    bool submit(u64 t, const char *p, size_t n) {
+        std::unique_lock<std::mutex> g(mu);
+        cv.wait(g, [&] { return next_ticket == t; });
+        bool ok = true;
+        if (seekable) { const u64 off = offset; offset += n; next_ticket++; g.unlock(); cv.notify_all(); ok = pwrite_all(fd, p, n, off); }
+        else { ok = write_all(fd, p, n); next_ticket++; g.unlock(); cv.notify_all(); }
+        return ok;
+    }
+    void skip(u64 t) { std::unique_lock<std::mutex> g(mu); cv.wait(g, [&] { return next_ticket == t; }); next_ticket++; g.unlock(); cv.notify_all(); }
 };
 
 struct Counters { u64 al = 0, un = 0, mu = 0, pal = 0, pun = 0, pmu = 0, aal = 0, aun = 0, amu = 0, bal = 0, bun = 0, bmu = 0; };
 
+// Earlier reads a batch must be preceded by so that the aligner state the reference carries from read to read
+// (xseed_start_offset, xseed_array: align.cpp:476-480, 79-150; SURVEY trap 3) is what a -p 1 run of the reference would
+// have: per mate, the last unfiltered read with a non-empty start-offset range, and every unfiltered read longer than all
+// unfiltered reads after it (the reads whose seed hashes are still visible beyond the end of a shorter read).
+struct CtxPair { std::string a, b; u32 raw_a = 0, raw_b = 0; bool short_a = false, short_b = false; };
+typedef std::vector<CtxPair> Tail;
+
 struct Pipeline {
     const Options &O; const Reference &R; const TextRule &T; bool pe;
     std::vector<bsl_ctx *> ctx;
-    ReadFile fa, fb;
-    std::mutex in_mu, out_mu; std::condition_variable out_cv;
-    u64 next_ticket = 0, next_write = 0; u32 next_index; bool input_done = false;
-    std::map<u64, std::string> done;
-    FILE *out = nullptr;
+    ReadSource fa, fb; BlockQueue qa, qb;
+    std::mutex in_mu; u64 next_ticket = 0; u32 next_index; u64 reads_left;
+    OutSink sink;
     bool bam_native = false; bam::Refs refs;          // -o x.bam without an external samtools
-    Counters total; u64 reads_seen = 0;
+    Counters total; std::mutex total_mu;
     std::atomic<int> failed{0};
-    size_t batch_reads;
+    u32 batch_reads; std::string fasta_qual;
+    // tails: tail[k] = context for batch k+1, published by the worker of batch k
+    std::mutex tail_mu; std::condition_variable tail_cv; std::map<u64, std::shared_ptr<Tail>> tails;
 
     Pipeline(const Options &o, const Reference &r, const TextRule &t) : O(o), R(r), T(t), pe(!o.b.empty()), next_index(o.read_start - 1) {
-        const char *e = getenv("BASAL_BATCH"); batch_reads = e ? (size_t)atol(e) : (size_t)(pe ? 262144 : 524288);
+        const char *e = getenv("BASAL_BATCH"); batch_reads = e ? (u32)std::max(1l, atol(e)) : (pe ? 131072u : 262144u);
+        reads_left = O.read_end > O.read_start - 1 ? (u64)O.read_end - (O.read_start - 1) : 0;
+        fasta_qual.assign(512, (char)(O.zero_qual + O.default_qual));
     }
+
+    void splitter(ReadSource &src, BlockQueue &q) {
+        u64 skip = O.read_start - 1, left = reads_left;                        // InitIndex (reads.cpp:13-40) / -E
+        TextBlock b;
+        while (skip) { const u32 k = (u32)std::min<u64>(skip, 1u << 20); if (!src.next(b, k)) { q.finish(); return; } skip -= b.records; if (b.records < k) { q.finish(); return; } }
+        while (left && !failed) { const u32 k = (u32)std::min<u64>(left, batch_reads); if (!src.next(b, k)) break; left -= b.records; q.put(std::move(b)); }
+        q.finish();
+    }
+
+    struct Batch {
+        u64 ticket = 0; u32 first_index = 0, n = 0; TextBlock ba, bb;
+        std::vector<ReadView> a, b; std::deque<std::string> arena; std::string text, blk;
+    };
+    // per-worker staging in pinned memory (bsl_host_alloc), grown on demand and reused from batch to batch
+    struct Staging {
+        u8 *bases[2] = {nullptr, nullptr}; size_t cap_bases[2] = {0, 0};
+        bsl_hit *hits[2] = {nullptr, nullptr}; bsl_pair *pairs = nullptr; size_t cap_recs = 0;
+        std::vector<u64> off[2]; std::vector<u16> raw[2];
+        bool need(int m, size_t bytes) { if (bytes <= cap_bases[m]) return true; bsl_host_free(bases[m]); cap_bases[m] = bytes + bytes / 4 + 4096; bases[m] = (u8 *)bsl_host_alloc(cap_bases[m]); return bases[m] != nullptr; }
+        bool need_recs(size_t n, bool pe) { if (n <= cap_recs) return true; for (int m = 0; m < 2; m++) bsl_host_free(hits[m]); bsl_host_free(pairs); cap_recs = n + n / 4 + 64;
+            hits[0] = (bsl_hit *)bsl_host_alloc(cap_recs * sizeof(bsl_hit)); hits[1] = pe ? (bsl_hit *)bsl_host_alloc(cap_recs * sizeof(bsl_hit)) : nullptr; pairs = pe ? (bsl_pair *)bsl_host_alloc(cap_recs * sizeof(bsl_pair)) : nullptr;
+            return hits[0] && (!pe || (hits[1] && pairs)); }
+        ~Staging() { for (int m = 0; m < 2; m++) { bsl_host_free(bases[m]); bsl_host_free(hits[m]); } bsl_host_free(pairs); }
+    };
 
     bool load(Batch &B) {
         std::lock_guard<std::mutex> g(in_mu);
-        if (input_done) return false;
-        B.ticket = next_ticket; B.first_index = next_index; B.a.clear(); B.b.clear();
-        ReadRec ra, rb;
-        while (B.a.size() < batch_reads && next_index < O.read_end) {
-            if (!fa.next(ra, O)) { input_done = true; break; }
-            if (pe) { if (!fb.next(rb, O)) { input_done = true; break; } B.b.push_back(rb); }
-            B.a.push_back(ra); next_index++;
-        }
-        if (next_index >= O.read_end) input_done = true;
-        if (B.a.empty()) return false;
-        next_ticket++; reads_seen += B.a.size();
+        if (!qa.get(B.ba)) return false;
+        if (pe && !qb.get(B.bb)) return false;
+        B.n = pe ? std::min(B.ba.records, B.bb.records) : B.ba.records;
+        if (!B.n) return false;
+        B.ticket = next_ticket++; B.first_index = next_index; next_index += B.n;
         return true;
     }
 
     static int mate_count(const bsl_hit &h) { return h.status == BSL_ST_FILTERED ? -1 : (h.status == BSL_ST_UNMAPPED ? 0 : (int)h.n_hits); }
 
-    void process(Batch &B, bsl_ctx *c, Counters &cn) {
-        const size_t n = B.a.size(); Formatter F(O, R, T);
-        std::vector<u8> short_a(n, 0), short_b(pe ? n : 0, 0);
-        auto pack = [&](std::vector<ReadRec> &v, std::vector<u8> &too_short, std::vector<u8> &bases, std::vector<u64> &off, std::vector<u16> &raw) {
-            off.resize(n + 1); raw.resize(n); size_t tot = 0;
-            for (size_t i = 0; i < n; i++) { bool ts; trim_read(v[i], O, ts); too_short[i] = ts; tot += v[i].seq.size(); }
-            bases.resize(tot + 1); size_t p = 0;
-            for (size_t i = 0; i < n; i++) { off[i] = p; const std::string &s = too_short[i] ? std::string() : v[i].seq; memcpy(bases.data() + p, s.data(), s.size()); p += s.size(); raw[i] = (u16)v[i].raw_len; }
-            off[n] = p;
+    // ---- carried aligner state across batches (SURVEY trap 3)
+    bool defining(u32 len) const { return len + 1 >= O.P.index_interval && (len + 1 - O.P.index_interval) % O.P.seed_size != 0; }
+    bool filtered(const char *s, u32 len, bool too_short) const {                 // FilterReads (align.cpp:557-560)
+        if (too_short || len == 0 || len < O.P.min_read_size) return true;
+        u32 ns = 0; for (u32 i = 0; i < len; i++) { const char c = (char)(s[i] & 0xDF); ns += !(c == 'A' || c == 'C' || c == 'G' || c == 'T'); }
+        return ns > O.P.max_ns;
+    }
+    std::shared_ptr<Tail> wait_tail(u64 ticket) {                                // the context in front of batch `ticket`
+        if (ticket == 0) return std::make_shared<Tail>();
+        std::unique_lock<std::mutex> g(tail_mu);
+        tail_cv.wait(g, [&] { return tails.count(ticket - 1) != 0 || failed; });
+        auto it = tails.find(ticket - 1); return it == tails.end() ? std::make_shared<Tail>() : it->second;
+    }
+    void publish_tail(Batch &B) {
+        // walk back through this batch, then through the context it was given, until both mates have their last defining
+        // read and nothing longer can follow
+        std::shared_ptr<Tail> prev;                                             // fetched only if this batch does not settle it
+        u32 maxlen[2] = {0, 0}; bool have_def[2] = {false, !pe};
+        u32 top = 0; for (u32 i = 0; i < B.n; i++) { top = std::max(top, B.a[i].len); if (pe) top = std::max(top, B.b[i].len); }
+        std::vector<CtxPair> picked;                                            // newest first
+        auto consider = [&](const char *sa, u32 la, u32 ra, bool ta, const char *sb, u32 lb, u32 rb, bool tb) {
+            bool want = false;
+            for (int m = 0; m < (pe ? 2 : 1); m++) {
+                const char *s = m ? sb : sa; const u32 l = m ? lb : la; const bool ts = m ? tb : ta;
+                const bool cand = l > maxlen[m] || (!have_def[m] && defining(l));
+                if (!cand || filtered(s, l, ts)) continue;
+                if (l > maxlen[m]) maxlen[m] = l;
+                if (defining(l)) have_def[m] = true;
+                want = true;
+            }
+            if (want) { CtxPair c; c.a.assign(sa, la); c.raw_a = ra; c.short_a = ta; if (pe) { c.b.assign(sb, lb); c.raw_b = rb; c.short_b = tb; } picked.push_back(std::move(c)); }
         };
-        std::vector<u8> ba, bb; std::vector<u64> oa, ob; std::vector<u16> rwa, rwb;
-        pack(B.a, short_a, ba, oa, rwa);
-        if (pe) { pack(B.b, short_b, bb, ob, rwb); for (size_t i = 0; i < n; i++) fix_pair_names(B.a[i].name, B.b[i].name); }
-        bsl_batch qa; memset(&qa, 0, sizeof qa); qa.n = (u32)n; qa.readset = pe ? 1 : 0; qa.bases = ba.data(); qa.offsets = oa.data(); qa.first_index = B.first_index; qa.raw_len = rwa.data();
-        std::vector<bsl_hit> ha(n), hb(pe ? n : 0); std::vector<bsl_pair> hp(pe ? n : 0);
+        auto settled = [&](u32 cap) { for (int m = 0; m < (pe ? 2 : 1); m++) if (!have_def[m] || maxlen[m] < cap) return false; return true; };
+        for (u32 i = B.n; i-- > 0 && !settled(480);) {
+            const ReadView &a = B.a[i]; const ReadView *b = pe ? &B.b[i] : nullptr;
+            consider(a.seq, a.too_short ? 0 : a.len, a.raw_len, a.too_short, b ? b->seq : nullptr, b ? (b->too_short ? 0 : b->len) : 0, b ? b->raw_len : 0, b ? b->too_short : false);
+            if (i == 0 || settled(480)) break;
+            if (settled(top) && i + 1 < B.n) { /* nothing in this batch can add to the skyline any more; older context may */ break; }
+        }
+        if (!settled(480)) {
+            prev = wait_tail(B.ticket);
+            for (size_t i = prev->size(); i-- > 0 && !settled(480);) { const CtxPair &c = (*prev)[i]; consider(c.a.data(), (u32)c.a.size(), c.raw_a, c.short_a, c.b.data(), (u32)c.b.size(), c.raw_b, c.short_b); }
+        }
+        auto t = std::make_shared<Tail>(picked.rbegin(), picked.rend());
+        { std::lock_guard<std::mutex> g(tail_mu); tails[B.ticket] = t; if (B.ticket >= 2) tails.erase(B.ticket - 2); }
+        tail_cv.notify_all();
+    }
+
+    bool process(Batch &B, Staging &S, bsl_ctx *c, Counters &cn) {
+        const u32 n = B.n; Formatter F(O, R, T);
+        B.arena.clear();
+        parse_block(B.ba, fa.fastq(), O.max_readlen, fasta_qual.data(), B.a);
+        if (pe) parse_block(B.bb, fb.fastq(), O.max_readlen, fasta_qual.data(), B.b);
+        if (B.a.size() < n || (pe && B.b.size() < n)) { fprintf(stderr, "\ninternal error: block holds fewer records than counted\n"); return false; }
+        bool need_ctx = false;
+        for (int m = 0; m < (pe ? 2 : 1); m++) for (ReadView &r : (m ? B.b : B.a)) { trim_read(r, O, B.arena, fasta_qual.data()); if (!r.too_short && r.len >= O.P.min_read_size && !defining(r.len)) need_ctx = true; }
+        if (pe) for (u32 i = 0; i < n; i++) fix_pair_names(B.a[i], B.b[i]);
+        // ---- context reads in front of the batch (only when a read of this batch can inherit state at all)
+        std::shared_ptr<Tail> tin; u32 nctx = 0;
+        if (need_ctx) { tin = wait_tail(B.ticket); nctx = (u32)tin->size(); }
+        publish_tail(B);
+        // ---- pack: bases of (context +) batch, back to back, into pinned memory
+        const u32 nt = nctx + n;
+        for (int m = 0; m < (pe ? 2 : 1); m++) {
+            std::vector<ReadView> &v = m ? B.b : B.a;
+            size_t tot = 0; for (u32 k = 0; k < nctx; k++) tot += m ? (*tin)[k].b.size() : (*tin)[k].a.size();
+            for (u32 i = 0; i < n; i++) tot += v[i].too_short ? 0 : v[i].len;
+            if (!S.need(m, tot + 64)) { fprintf(stderr, "\npinned host allocation failed\n"); return false; }
+            S.off[m].resize((size_t)nt + 1); S.raw[m].resize(nt); size_t p = 0; u8 *dst = S.bases[m];
+            for (u32 k = 0; k < nctx; k++) { const CtxPair &cp = (*tin)[k]; const std::string &s = m ? cp.b : cp.a; S.off[m][k] = p; memcpy(dst + p, s.data(), s.size()); p += s.size(); S.raw[m][k] = (u16)(m ? cp.raw_b : cp.raw_a); }
+            for (u32 i = 0; i < n; i++) { S.off[m][nctx + i] = p; if (!v[i].too_short) { memcpy(dst + p, v[i].seq, v[i].len); p += v[i].len; } S.raw[m][nctx + i] = (u16)v[i].raw_len; }
+            S.off[m][nt] = p;
+        }
+        if (!S.need_recs(nt, pe)) { fprintf(stderr, "\npinned host allocation failed\n"); return false; }
+        bsl_batch qa; memset(&qa, 0, sizeof qa); qa.n = nt; qa.readset = pe ? 1 : 0; qa.bases = S.bases[0]; qa.offsets = S.off[0].data(); qa.first_index = B.first_index - nctx; qa.raw_len = S.raw[0].data(); qa.n_context = nctx;
         const bool all = O.P.report_repeat_hits == 2;
-        std::vector<bsl_hit> alla, allb; u64 n_all = 0; u64 all_cap = all ? std::max<u64>(n * 8, 1u << 20) : 0;
+        std::vector<bsl_hit> alla, allb; u64 n_all = 0; u64 all_cap = all ? std::max<u64>((u64)nt * 8, 1u << 20) : 0;
         int rc;
         for (;;) {
             if (all) { alla.resize(all_cap); if (pe) allb.resize(all_cap); }
-            if (!pe) rc = bsl_align_se(c, &qa, ha.data(), all ? alla.data() : nullptr, all_cap, &n_all);
-            else { bsl_batch qb = qa; qb.readset = 2; qb.bases = bb.data(); qb.offsets = ob.data(); qb.raw_len = rwb.data();
-                rc = bsl_align_pe(c, &qa, &qb, ha.data(), hb.data(), hp.data(), all ? alla.data() : nullptr, all ? allb.data() : nullptr, all_cap, &n_all); }
+            if (!pe) rc = bsl_align_se(c, &qa, S.hits[0], all ? alla.data() : nullptr, all_cap, &n_all);
+            else { bsl_batch qb = qa; qb.readset = 2; qb.bases = S.bases[1]; qb.offsets = S.off[1].data(); qb.raw_len = S.raw[1].data();
+                rc = bsl_align_pe(c, &qa, &qb, S.hits[0], S.hits[1], S.pairs, all ? alla.data() : nullptr, all ? allb.data() : nullptr, all_cap, &n_all); }
             if (rc == 0 && all && n_all > all_cap) { all_cap = n_all + 16; continue; }      // grow the all-hits buffer and redo the batch
             break;
         }
-        if (rc != 0) { fprintf(stderr, "GPU alignment failed (%d): %s\n", rc, bsl_last_error(c)); failed = 1; return; }
-        std::string &os = B.text; os.clear(); os.reserve(n * (pe ? 900 : 400));
-        for (size_t i = 0; i < n; i++) {
+        if (rc != 0) { fprintf(stderr, "GPU alignment failed (%d): %s\n", rc, bsl_last_error(c)); return false; }
+        const bsl_hit *ha = S.hits[0] + nctx, *hb = pe ? S.hits[1] + nctx : nullptr; const bsl_pair *hp = pe ? S.pairs + nctx : nullptr;
+        std::string &os = B.text; os.clear(); os.reserve((size_t)n * (pe ? 900 : 420));
+        for (u32 i = 0; i < n; i++) {
             if (!pe) {                                                                        // StringAlign (align.cpp:583-612)
                 const bsl_hit &h = ha[i];
                 if (h.status == BSL_ST_FILTERED) F.single(os, B.a[i], 0, h, -1);
@@ -501,35 +731,31 @@ struct Pipeline {
             if (ma <= 0) { if (O.unmap) F.unpair(os, B.a[i], 0, 0, cb, ma, 0, a, mb1, b); }
             else if (ma == 1) { cn.aal++; cn.aun++; F.unpair(os, B.a[i], 0, ca, cb, 1, a.nm, a, mb1, b); }
             else { cn.amu++;
-                if (O.P.report_repeat_hits >= 1) { cn.aal++; F.unpair(os, B.a[i], 0, ca, cb, ma, a.nm, a, mb1, b); }   // -r 2 lists every hit in the reference; the GPU build reports the pick
+                if (O.P.report_repeat_hits == 1) { cn.aal++; F.unpair(os, B.a[i], 0, ca, cb, ma, a.nm, a, mb1, b); }
+                else if (O.P.report_repeat_hits == 2) { cn.aal++; for (int k = 0; k < ma; k++) { const bsl_hit &x = alla[a.all_first + k]; F.unpair(os, B.a[i], 0, x.read_chain, cb, ma, a.nm, x, mb1, b); } }   // pairs.cpp:270-274
                 else if (O.unmap) F.unpair(os, B.a[i], 0, 0, cb, 0, 0, a, mb1, b); }
             if (mb <= 0) { if (O.unmap) F.unpair(os, B.b[i], 1, 0, ca, mb, 0, b, ma1, a); }
             else if (mb == 1) { cn.bal++; cn.bun++; F.unpair(os, B.b[i], 1, cb, ca, 1, b.nm, b, ma1, a); }
             else { cn.bmu++;
-                if (O.P.report_repeat_hits >= 1) { cn.bal++; F.unpair(os, B.b[i], 1, cb, ca, mb, b.nm, b, ma1, a); }
+                if (O.P.report_repeat_hits == 1) { cn.bal++; F.unpair(os, B.b[i], 1, cb, ca, mb, b.nm, b, ma1, a); }
+                else if (O.P.report_repeat_hits == 2) { cn.bal++; for (int k = 0; k < mb; k++) { const bsl_hit &x = allb[b.all_first + k]; F.unpair(os, B.b[i], 1, x.read_chain, cb, mb, b.nm, x, ma1, a); } }   // pairs.cpp:293-297 (passes cb, not ca)
                 else if (O.unmap) F.unpair(os, B.b[i], 1, 0, ca, 0, 0, b, ma1, a); }
         }
-    }
-
-    void emit(Batch &B) {
-        std::unique_lock<std::mutex> g(out_mu);
-        done[B.ticket] = std::move(B.text);
-        while (!done.empty() && done.begin()->first == next_write) {
-            const std::string &s = done.begin()->second;
-            if (!s.empty()) fwrite(s.data(), 1, s.size(), out);
-            done.erase(done.begin()); next_write++;
-            if (O.verbose >= 2) fprintf(stderr, "[BASAL @%s] batch %llu finished. %ld secs passed\n", now_str(), (unsigned long long)next_write, secs_passed());
-        }
+        return true;
     }
 
     void worker(int wid) {
-        bsl_ctx *c = ctx[wid % ctx.size()]; Counters cn; Batch B;
+        bsl_ctx *c = ctx[wid % ctx.size()]; Counters cn; Batch B; Staging S;
         while (!failed && load(B)) {
-            process(B, c, cn);
-            if (bam_native) { std::string blk; if (!bam::text_to_blocks(B.text, refs, blk)) { fprintf(stderr, "\ninternal error: malformed SAM record in BAM conversion\n"); failed = 1; } B.text.swap(blk); }
-            emit(B);
+            bool ok = process(B, S, c, cn);
+            const std::string *out = &B.text;
+            if (ok && bam_native) { B.blk.clear(); if (!bam::text_to_blocks(B.text, refs, B.blk)) { fprintf(stderr, "\ninternal error: malformed SAM record in BAM conversion\n"); ok = false; } out = &B.blk; }
+            if (!ok) { failed = 1; tail_cv.notify_all(); sink.skip(B.ticket); break; }
+            if (!sink.submit(B.ticket, out->data(), out->size())) { fprintf(stderr, "\nwrite failed: %s\n", strerror(errno)); failed = 1; break; }
+            if (O.verbose >= 2) fprintf(stderr, "[BASAL @%s] batch %llu finished. %ld secs passed\n", now_str(), (unsigned long long)B.ticket + 1, secs_passed());
         }
-        std::lock_guard<std::mutex> g(out_mu);
+        if (failed) { qa.finish(); qb.finish(); TextBlock d; while (qa.get(d)) {} while (qb.get(d)) {} }      // unblock the splitters
+        std::lock_guard<std::mutex> g(total_mu);
         total.al += cn.al; total.un += cn.un; total.mu += cn.mu; total.pal += cn.pal; total.pun += cn.pun; total.pmu += cn.pmu;
         total.aal += cn.aal; total.aun += cn.aun; total.amu += cn.amu; total.bal += cn.bal; total.bun += cn.bun; total.bmu += cn.bmu;
     }
@@ -538,10 +764,12 @@ struct Pipeline {
 static void check_input(const std::string &path, const char *msg) {
     FILE *f = fopen(path.c_str(), "rb"); if (!f) { fprintf(stderr, "\n%s%s\n", msg, path.c_str()); exit(1); } fclose(f);
 }
+static double wall() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
 
 int main(int argc, char **argv) {
     if (argc == 1) usage();
     g_t0 = time(nullptr);
+    const double t_start = wall();
     Options O;
     int bad = parse_options(argc, argv, O);
     if (bad) { fprintf(stderr, "unknown option: %s\n", argv[bad]); exit(bad); }
@@ -557,22 +785,30 @@ int main(int argc, char **argv) {
     if (!load_reference(O.d, R)) { fprintf(stderr, "\nfailed to open reference file (check -d option): %s\n", O.d.c_str()); exit(1); }
     if (R.names.empty()) { fprintf(stderr, "\t(format: unknown)\nreference must be in FASTA format.\n"); exit(1); }
     if (O.verbose >= 1) fprintf(stderr, " \t(format: FASTA)\n[BASAL @%s] %zu reference seqs loaded, total size %llu bp. %ld secs passed\n", now_str(), R.names.size(), (unsigned long long)R.total, secs_passed());
+    const double t_ref = wall();
+    const bool pe = !O.b.empty();
 
     // ---- $BASAL_PARSE_ONLY: run the read loader alone (no GPU) and print what it parsed as FASTQ, mates interleaved:
-    //      the CPU test hook of the host loader (FASTA / FASTQ / gz / BAM input, -L)
+    //      the CPU test hook of the host loader (FASTA / FASTQ / gz / BAM input, -L, -B / -E, block boundaries)
     if (getenv("BASAL_PARSE_ONLY")) {
-        ReadFile fa, fb; const bool pe2 = !O.b.empty();
-        if (!fa.open(O.a) || fa.format < 0 || (pe2 && (!fb.open(O.b) || fb.format != fa.format))) { fprintf(stderr, "\t(format: unknown)\nUnknown input format.\n"); return 1; }
-        if (pe2) { fa.mate = 1; fb.mate = 2; }
-        fprintf(stderr, "format: %s\n", fa.format_name());
+        Pipeline P(O, R, T);
+        if (!P.fa.open(O.a, O.max_readlen) || P.fa.format < 0 || (pe && (!P.fb.open(O.b, O.max_readlen) || P.fb.format != P.fa.format))) { fprintf(stderr, "\t(format: unknown)\nUnknown input format.\n"); return 1; }
+        if (pe) { P.fa.mate = 1; P.fb.mate = 2; }
+        fprintf(stderr, "format: %s\n", P.fa.format_name());
         const bool count_only = strcmp(getenv("BASAL_PARSE_ONLY"), "count") == 0;      // loader throughput without the printing
-        ReadRec ra, rb; std::string o; u64 n_rec = 0, n_base = 0;
-        while (fa.next(ra, O)) {
-            n_rec++; n_base += ra.seq.size();
-            if (!count_only) o += "@" + ra.name + "\n" + ra.seq + "\n+\n" + ra.qual + "\n";
-            if (pe2) { if (!fb.next(rb, O)) break; n_rec++; n_base += rb.seq.size(); if (!count_only) o += "@" + rb.name + "\n" + rb.seq + "\n+\n" + rb.qual + "\n"; }
+        std::thread ta([&] { P.splitter(P.fa, P.qa); }), tb; if (pe) tb = std::thread([&] { P.splitter(P.fb, P.qb); });
+        Pipeline::Batch B; std::string o; u64 n_rec = 0, n_base = 0;
+        while (P.load(B)) {
+            parse_block(B.ba, P.fa.fastq(), O.max_readlen, P.fasta_qual.data(), B.a); if (pe) parse_block(B.bb, P.fb.fastq(), O.max_readlen, P.fasta_qual.data(), B.b);
+            for (u32 i = 0; i < B.n; i++) for (int m = 0; m < (pe ? 2 : 1); m++) {
+                const ReadView &r = m ? B.b[i] : B.a[i]; n_rec++; n_base += r.len;
+                if (count_only) continue;
+                const u32 ql = std::min(r.raw_len, r.len);                                  // raw_len = quality length before trim_read
+                o.push_back('@'); o.append(r.name, r.name_len); o.push_back('\n'); o.append(r.seq, r.len); o += "\n+\n"; o.append(r.qual, ql); o.push_back('\n');
+            }
             if (o.size() > (1u << 20)) { fwrite(o.data(), 1, o.size(), stdout); o.clear(); }
         }
+        ta.join(); if (pe) tb.join();
         fwrite(o.data(), 1, o.size(), stdout);
         fprintf(stderr, "parsed %llu reads, %llu bases\n", (unsigned long long)n_rec, (unsigned long long)n_base);
         return 0;
@@ -595,6 +831,7 @@ int main(int argc, char **argv) {
         P.ctx = cs;
     }
     if (O.verbose >= 1) fprintf(stderr, "[BASAL @%s] create seed table. %ld secs passed\n", now_str(), secs_passed());
+    const double t_index = wall();
 
     // ---- RunProcess (main.cpp:409-614)
     if (O.o.size() > 4) { if (O.o.compare(O.o.size() - 4, 4, ".sam") == 0) O.out_sam = 1; else if (O.o.compare(O.o.size() - 4, 4, ".bam") == 0) O.out_sam = 2; }
@@ -604,30 +841,30 @@ int main(int argc, char **argv) {
         fprintf(stderr, "\tquality cutoff: %d \tbase quality char: '%c' \tmax Ns: %u\n", O.qual_threshold, O.zero_qual, O.P.max_ns);
         fprintf(stderr, "\twildcard mapping approach \tseed size: %u \tindex interval: %u\n", O.P.seed_size, O.P.index_interval);
     }
-    const bool pe = !O.b.empty();
-    if (O.verbose >= 1) fprintf(stderr, "[BASAL @%s] %s alignment(%zu GPU(s), %d host threads),\n", now_str(), pe ? "Pair-end" : "Single-end", P.ctx.size(), std::max(O.procs, 1));
+    const int nw = std::max<int>(std::max(O.procs, 1), (int)P.ctx.size() * 3);                 // three lanes per GPU context
+    if (O.verbose >= 1) fprintf(stderr, "[BASAL @%s] %s alignment(%zu GPU(s), %d host threads),\n", now_str(), pe ? "Pair-end" : "Single-end", P.ctx.size(), nw);
     check_input(O.a, pe ? "failed to open read file #1 (check -a option): " : "failed to open read file (check -a option): ");
-    if (!P.fa.open(O.a) || P.fa.format < 0) { fprintf(stderr, "\t(format: unknown)\nUnknown input format.\n"); exit(1); }
+    if (!P.fa.open(O.a, O.max_readlen) || P.fa.format < 0) { fprintf(stderr, "\t(format: unknown)\nUnknown input format.\n"); exit(1); }
     if (pe) P.fa.mate = 1;
     if (O.verbose >= 1) fprintf(stderr, "\tInput read file%s: %s \t(format: %s)\n", pe ? " #1" : "", O.a.c_str(), P.fa.format_name());
     if (pe) {
         check_input(O.b, "failed to open read file #2 (check -b option): ");
-        if (!P.fb.open(O.b) || P.fb.format < 0) { fprintf(stderr, "\t(format: unknown)\nUnknown input format.\n"); exit(1); }
+        if (!P.fb.open(O.b, O.max_readlen) || P.fb.format < 0) { fprintf(stderr, "\t(format: unknown)\nUnknown input format.\n"); exit(1); }
         if (P.fb.format != P.fa.format) { fprintf(stderr, "Input read file #1 and #2 should be in same format.\n"); exit(1); }
         P.fb.mate = 2;
         if (O.verbose >= 1) fprintf(stderr, "\tInput read file #2: %s \t(format: %s)\n", O.b.c_str(), P.fb.format_name());
     }
-    { ReadRec skip; for (u32 i = 1; i < O.read_start; i++) { P.fa.next(skip, O); if (pe) P.fb.next(skip, O); } }     // InitIndex (reads.cpp:13-40)
-    bool piped = false;
-    if (O.to_stdout) { P.out = stdout; if (O.verbose >= 1) fprintf(stderr, "\tOutput: STDOUT\t (format: SAM)\n"); }
+    FILE *piped = nullptr;
+    if (O.to_stdout) { P.sink.fd = 1; if (O.verbose >= 1) fprintf(stderr, "\tOutput: STDOUT\t (format: SAM)\n"); }
     else {
         if (O.verbose >= 1 || pe) fprintf(stderr, "\tOutput file: %s\t (format: SAM%s)\n", O.o.c_str(), O.out_sam == 2 ? ", automatically convert to BAM" : "");
-        FILE *probe = fopen(O.o.c_str(), "wb"); if (!probe) { fprintf(stderr, "\nfailed to open output file (check -o option): %s\n", O.o.c_str()); exit(1); } fclose(probe);
-        if (O.out_sam == 2 && getenv("BASAL_SAMTOOLS")) { std::string cmd = "samtools view -bS - >" + O.o; P.out = popen(cmd.c_str(), "w"); piped = P.out != nullptr; }   // main.cpp:505
-        if (!P.out) P.out = fopen(O.o.c_str(), "wb");
+        const int fd = ::open(O.o.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (fd < 0) { fprintf(stderr, "\nfailed to open output file (check -o option): %s\n", O.o.c_str()); exit(1); }
+        if (O.out_sam == 2 && getenv("BASAL_SAMTOOLS")) { ::close(fd); std::string cmd = "samtools view -bS - >" + O.o; piped = popen(cmd.c_str(), "w"); if (piped) P.sink.fd = fileno(piped); }   // main.cpp:505
+        if (!piped) { P.sink.fd = piped ? P.sink.fd : (O.out_sam == 2 && getenv("BASAL_SAMTOOLS") ? ::open(O.o.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644) : fd);
+            struct stat st; P.sink.seekable = fstat(P.sink.fd, &st) == 0 && S_ISREG(st.st_mode); }
         if (O.out_sam == 2 && !piped) { P.bam_native = true; for (size_t i = 0; i < R.names.size(); i++) P.refs.add(R.names[i], R.len[i]); }
     }
-    static char obuf[8 << 20]; setvbuf(P.out, obuf, _IOFBF, sizeof obuf);
     {
         std::string h;
         if (O.header) {                                                                                  // main.cpp:516-526
@@ -635,20 +872,28 @@ int main(int argc, char **argv) {
             for (size_t i = 0; i < R.names.size(); i++) { h += "@SQ\tSN:" + R.names[i] + "\tLN:"; append_u(h, R.len[i]); h.push_back('\n'); }
             h += std::string("@PG\tID:BASAL\tVN:") + kVersion + "\tCL:\"" + O.cmdline + "\"\n";
         }
-        if (P.bam_native) { const std::string raw = bam::header_bytes(h, P.refs); std::string blk; bam::bgzf_append(raw.data(), raw.size(), blk); fwrite(blk.data(), 1, blk.size(), P.out); }
-        else if (!h.empty()) fwrite(h.data(), 1, h.size(), P.out);
+        if (P.bam_native) { const std::string raw = bam::header_bytes(h, P.refs); std::string blk; bam::bgzf_append(raw.data(), raw.size(), blk); P.sink.head(blk); }
+        else P.sink.head(h);
     }
+    const double t_map0 = wall();
     {
-        int nw = std::max<int>(O.procs, (int)P.ctx.size() * 3);                 // three lanes per GPU context
+        P.qa.cap = P.qb.cap = (size_t)nw + 2;
+        std::thread ta([&] { P.splitter(P.fa, P.qa); }), tb; if (pe) tb = std::thread([&] { P.splitter(P.fb, P.qb); });
         std::vector<std::thread> th; for (int w = 0; w < nw; w++) th.emplace_back([&, w]() { P.worker(w); });
         for (auto &t : th) t.join();
+        P.qa.finish(); P.qb.finish(); { TextBlock d; while (P.qa.get(d)) {} while (P.qb.get(d)) {} }
+        ta.join(); if (pe) tb.join();
     }
-    if (P.bam_native) { std::string e; bam::bgzf_eof(e); fwrite(e.data(), 1, e.size(), P.out); }
-    if (piped) pclose(P.out); else if (P.out != stdout) fclose(P.out); else fflush(stdout);
+    if (P.bam_native) { std::string e; bam::bgzf_eof(e); P.sink.head(e); }
+    if (piped) pclose(piped); else if (P.sink.fd != 1) ::close(P.sink.fd);
+    const double t_map1 = wall();
     for (bsl_ctx *c : P.ctx) bsl_ctx_destroy(c);
     if (P.failed) return 2;
+    const double tot = (double)(P.next_index - (O.read_start - 1));
+    if (getenv("BASAL_TIMING"))                                          // machine-readable phase clocks (bench.py: cli_e2e)
+        fprintf(stderr, "[timing] load_ref_s=%.4f index_s=%.4f map_s=%.4f total_s=%.4f reads=%.0f gpus=%zu threads=%d\n", t_ref - t_start, t_index - t_ref, t_map1 - t_map0, wall() - t_start, tot * (pe ? 2 : 1), P.ctx.size(), nw);
     if (O.verbose >= 1) {                                                                                // main.cpp:536-552, 606-612
-        const double tot = (double)(P.next_index - (O.read_start - 1)); const Counters &c = P.total; const char *sup = O.P.report_repeat_hits == 0 ? "suppressed " : "";
+        const Counters &c = P.total; const char *sup = O.P.report_repeat_hits == 0 ? "suppressed " : "";
         if (pe) {
             fprintf(stderr, "[BASAL @%s] total read pairs: %.0f \ttotal time consumed:  %ld secs\n", now_str(), tot, secs_passed());
             fprintf(stderr, "\taligned pairs: %llu (%.1f%%), unique pairs: %llu (%.1f%%), %snon-unique pairs: %llu (%.1f%%)\n", (unsigned long long)c.pal, 100.0 * c.pal / tot, (unsigned long long)c.pun, 100.0 * c.pun / tot, sup, (unsigned long long)c.pmu, 100.0 * c.pmu / tot);

@@ -38,6 +38,7 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import synth  # noqa: E402
 
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "basal")
+GPU_BIN = os.path.join(ROOT, "basal_b200", "bin", "basal")
 CONFIG_ID = int(os.environ.get("BENCH_CONFIG", "2"))
 SCALE = float(os.environ.get("BENCH_SCALE", "1.0"))            # <1 only for smoke-testing the script itself
 STEP_PAIRS = int(os.environ.get("BENCH_STEP_PAIRS", "1000000"))
@@ -119,8 +120,8 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------------ reference arm / cpu baseline
 
-def run_reference_sample(cfg, chrs, pairs: int, workdir: str, threads: int, index_time: float | None = None):
-    """Run the reference binary on `pairs` simulated pairs. Returns (reads, align_seconds, index_seconds)."""
+def write_sample(cfg, chrs, pairs: int, workdir: str):
+    """ref.fa + FASTQ file(s) of `pairs` simulated reads / pairs of the workload (default simulator seed). Returns (n, args)."""
     os.makedirs(workdir, exist_ok=True)
     ref = os.path.join(workdir, "ref.fa")
     if not os.path.exists(ref):
@@ -134,7 +135,15 @@ def run_reference_sample(cfg, chrs, pairs: int, workdir: str, threads: int, inde
         if m2 is not None:
             synth.write_fastq(fb, m2, idx, "/2", append=not first)
         idx += len(m1); first = False
-    base = [REF_BIN, "-a", fa] + (["-b", fb] if cfg.paired else []) + ["-d", ref, "-M", cfg.rule] + list(cfg.flags) + ["-S", "7", "-p", str(threads)]
+    args = ["-a", fa] + (["-b", fb] if cfg.paired else []) + ["-d", ref, "-M", cfg.rule] + list(cfg.flags) + ["-S", "7"]
+    return idx, args
+
+
+def run_reference_sample(cfg, chrs, pairs: int, workdir: str, threads: int, index_time: float | None = None, have_files=None):
+    """Run the reference binary on `pairs` simulated pairs. Returns (reads, align_seconds, index_seconds); its SAM stays in
+    workdir/ref_out.sam."""
+    idx, args = have_files if have_files else write_sample(cfg, chrs, pairs, workdir)
+    base = [REF_BIN] + args + ["-p", str(threads)]
 
     def timed(extra):
         t0 = time.perf_counter()
@@ -145,6 +154,42 @@ def run_reference_sample(cfg, chrs, pairs: int, workdir: str, threads: int, inde
     total = timed([])
     reads = idx * (2 if cfg.paired else 1)
     return reads, max(total - index_time, 1e-3), index_time
+
+
+def run_gpu_cli(args, workdir: str, gpus: int = 1):
+    """The drop-in `basal` binary of this repo on the same files. Returns (map_seconds, index_seconds, total_seconds):
+    the binary's own phase clocks ($BASAL_TIMING), mapping = first batch load to last byte written."""
+    env = dict(os.environ); env["BASAL_TIMING"] = "1"; env["BASAL_GPUS"] = str(gpus)
+    t0 = time.perf_counter()
+    p = subprocess.run([GPU_BIN] + args + ["-p", str(os.cpu_count() or 1), "-o", os.path.join(workdir, "gpu_out.sam")], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env)
+    total = time.perf_counter() - t0
+    t_map = t_idx = None
+    for line in p.stderr.decode(errors="replace").splitlines():
+        if line.startswith("[timing]"):
+            kv = dict(x.split("=") for x in line.split()[1:])
+            t_map = float(kv["map_s"]); t_idx = float(kv["load_ref_s"]) + float(kv["index_s"])
+    if t_map is None:
+        raise RuntimeError("basal did not print its [timing] line")
+    return t_map, t_idx, total
+
+
+def compare_sam(workdir: str):
+    """Record-by-record diff of ref_out.sam (reference binary) and gpu_out.sam (this repo's binary): every line except the
+    @PG header must be byte-identical; batch completion order differs with -p > 1 (SURVEY trap 1), so records are compared as
+    sorted multisets. Returns (records, mismatching lines)."""
+    env = dict(os.environ); env["LC_ALL"] = "C"
+    outs = []
+    for name in ("ref_out.sam", "gpu_out.sam"):
+        o = os.path.join(workdir, name + ".sorted")
+        with open(o, "wb") as fh:
+            g = subprocess.Popen(["grep", "-v", "^@PG", os.path.join(workdir, name)], stdout=subprocess.PIPE)
+            subprocess.run(["sort", "-S", "2G", "--parallel=8"], stdin=g.stdout, stdout=fh, env=env, check=True)
+            g.wait()
+        outs.append(o)
+    n = int(subprocess.run(["wc", "-l", outs[0]], capture_output=True, text=True).stdout.split()[0])
+    d = subprocess.run(["comm", "-3", outs[0], outs[1]], capture_output=True, env=env)
+    bad = [l for l in d.stdout.decode(errors="replace").splitlines() if l.strip()]
+    return n, len(bad), bad[:4]
 
 
 def reference_arm(args):
@@ -339,6 +384,7 @@ def gpu_arm(args):
                      "ms_pack_per_step": pack_ms / args.steps, "ms_pair_per_step": pair_ms / args.steps,
                      "wall_ms_per_step": 1000.0 * t_wall / args.steps},
     }
+    parity_failed = False
     if rank == 0:
         if world == 1 and os.environ.get("BENCH_SKIP_CPU", "0") != "1" and os.path.exists(REF_BIN):
             threads = os.cpu_count() or 1
@@ -348,17 +394,37 @@ def gpu_arm(args):
                 if SCALE < 0.1:
                     sample = max(1000, int(sample * SCALE * 10))
                 log(f"cpu_baseline: reference binary, {sample} pairs, -p {threads}")
-                r, t, ti = run_reference_sample(cfg, chrs, sample, work, threads)
+                files = write_sample(cfg, chrs, sample, work)
+                r, t, ti = run_reference_sample(cfg, chrs, sample, work, threads, have_files=files)
                 line["cpu_baseline"] = {"value": r / t, "unit": UNIT, "cores": threads, "kind": "reference",
                                         "sample": f"{sample} pairs of the same workload, wall-clock minus index-only run ({ti:.1f}s index, {t:.1f}s align)"}
             except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": threads, "kind": "reference", "sample": f"failed: {e}"}
+                files = None
+            # ---- parity beside the number: the drop-in binary of this repo maps the very same files on the GPU and its SAM is
+            #      compared record by record with what the reference binary just printed; the same run is `cli_e2e`
+            #      (reads/s of the whole process path: FASTQ text in, SAM text out, index build excluded)
+            try:
+                if files is not None and os.path.exists(GPU_BIN):
+                    t_map, t_idx, t_tot = run_gpu_cli(files[1], work)
+                    n_rec, n_bad, examples = compare_sam(work)
+                    line["parity_check"] = {"reads": r, "sam_records": n_rec, "mismatches": n_bad, "against": "oracle/_ref/basal (unmodified reference) on the same FASTQ files, full-size reference, sorted record-by-record diff"}
+                    line["cli_e2e"] = {"value": r / t_map, "unit": UNIT, "reads": r, "map_s": t_map, "index_s": t_idx, "process_s": t_tot, "host_threads": threads,
+                                       "note": "basal_b200/bin/basal: plain FASTQ in, SAM out on local disk; mapping phase = first batch load to last byte written (the binary's own clock); reference binary on the same files is cpu_baseline"}
+                    if n_bad:
+                        log("PARITY MISMATCH:", examples)
+                        parity_failed = True
+            except Exception as e:
+                line["parity_check"] = {"reads": 0, "mismatches": None, "error": str(e)[-300:]}
+                parity_failed = True
             finally:
                 shutil.rmtree(work, ignore_errors=True)
         print(json.dumps(line))
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
+    if parity_failed:
+        sys.exit(3)
 
 
 def _flag_kwargs(cfg):

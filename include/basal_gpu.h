@@ -72,7 +72,12 @@ typedef struct bsl_batch {
     const uint64_t *offsets;     /* n+1 byte offsets into bases                                        */
     const uint32_t *index;       /* ReadInf::index per read (0-based input order) or NULL              */
     uint32_t        first_index; /* used when index==NULL: read i has index first_index+i              */
-    uint32_t        reserved;
+    uint32_t        n_context;   /* the first n_context reads are CONTEXT: reads that came earlier in the input
+                                    and only re-establish the state the reference's aligner object carries from
+                                    read to read (xseed_start_offset / xseed_array, align.cpp:476-480, 79-150);
+                                    they are packed and scheduled, never mapped; their records are undefined.
+                                    Every call starts with fresh aligner objects (zeroed state), reads are taken
+                                    in batch order like one SingleAlign / PairAlign object would take them.   */
     const uint16_t *raw_len;     /* length before adapter trimming (align.cpp:420) or NULL = length    */
 } bsl_batch;
 

@@ -485,7 +485,12 @@ int orc_align_se(orc_ctx *c, const bsl_batch *b, bsl_hit *out, bsl_hit *all, uin
     if (!C.keep_state) memset(C.carry, 0, sizeof C.carry);
     for (u32 i = 0; i < b->n; i++) {
         const u8 *seq = b->bases + b->offsets[i]; u32 len = (u32)(b->offsets[i + 1] - b->offsets[i]);
-        ReadState rs; C.st.reads++;
+        ReadState rs;
+        if (i < b->n_context) {                                             // context read: leaves its state behind, is not mapped
+            prepare(rs, C, seq, len, rd_raw(b, i, len), rd_index(b, i), b->readset);
+            memset(&out[i], 0, sizeof out[i]); out[i].status = BSL_ST_FILTERED; continue;
+        }
+        C.st.reads++;
         if (prepare(rs, C, seq, len, rd_raw(b, i, len), rd_index(b, i), b->readset)) run_single(rs, C.st);
         report_single(rs, out[i], want_all ? &allv : nullptr);
     }
@@ -502,10 +507,14 @@ int orc_align_pe(orc_ctx *c, const bsl_batch *a, const bsl_batch *b, bsl_hit *oa
     for (u32 i = 0; i < a->n; i++) {
         const u8 *sa = a->bases + a->offsets[i], *sb = b->bases + b->offsets[i];
         u32 la = (u32)(a->offsets[i + 1] - a->offsets[i]), lb = (u32)(b->offsets[i + 1] - b->offsets[i]);
-        ReadState A, B; C.st.reads += 2;
+        ReadState A, B;
         bool okA = prepare(A, C, sa, la, rd_raw(a, i, la), rd_index(a, i), a->readset);
         bool okB = prepare(B, C, sb, lb, rd_raw(b, i, lb), rd_index(b, i), b->readset);
         memset(&op[i], 0, sizeof op[i]);
+        if (i < a->n_context) {                                             // context pair: leaves its state behind, is not mapped
+            memset(&oa[i], 0, sizeof oa[i]); memset(&ob[i], 0, sizeof ob[i]); oa[i].status = ob[i].status = BSL_ST_FILTERED; continue;
+        }
+        C.st.reads += 2;
         std::vector<PairRec> ph[2 * MAXSNPS + 1]; int paired = 0;
         if (okA && okB) paired = run_pair(A, B, ph, C.P, C.st);
         else { if (okA) run_single(A, C.st); if (okB) run_single(B, C.st); }

@@ -152,24 +152,38 @@ CASES = [
     # strands and filters on pairs (SURVEY §8c iv, vii)
     ("ag_pe_n2", "A:G", True, 100, 300, 0.9, False, ["-S", "13", "-n", "2", "-u"]),
     ("ag_pe_f0", "A:G", True, 100, 300, 0.9, False, ["-S", "7", "-f", "0", "-u"]),
-    # KNOWN GAP (cases.json "known_gap"): with -r 2 the reference lists EVERY hit of an unpaired multi-hit mate
-    # (pairs.cpp:232-305); the oracle and the CUDA path report the -S pick only. Pairs under -r 2 are listed in full.
+    # -r 2 on pairs: every pair of the best level, and EVERY hit of an unpaired multi-hit mate (pairs.cpp:232-305)
     ("ag_pe_r2", "A:G", True, 100, 300, 0.9, False, ["-S", "7", "-f", "0", "-u", "-r", "2"]),
+    # mixed read lengths (SURVEY trap 3): reads with (L - I + 1) % s == 0 (99, 83, 67, 51 at -s 16 -I 4) inherit the start
+    # offset and the stale seed hashes of earlier reads of the same aligner object (align.cpp:476-480, 79-150); the
+    # reference ran with -p 1, where that is deterministic
+    ("ct_se_mixed", "C:T", False, 100, 500, 0.9, False, ["-S", "7", "-u"], [100, 99, 98, 83, 90, 67, 51, 100, 99]),
+    ("ag_pe_mixed", "A:G", True, 100, 400, 0.9, False, ["-S", "7", "-u", "-n", "1"], [100, 99, 97, 83, 99, 67, 96]),
+    ("ct_se_mixed_s12", "C:T", False, 100, 400, 0.9, True, ["-S", "5", "-s", "12", "-I", "3", "-g", "1", "-u"], [100, 98, 86, 74, 93, 62, 100]),
 ]
-KNOWN_GAPS = {"ag_pe_r2"}
 
 
 def main():
     if not os.path.exists(REF_BIN):
         sys.exit("oracle/_ref/basal is missing: make -f oracle/Makefile.ref")
     meta = {}
-    for ci, (name, rule, paired, L, n, conv, indel, args) in enumerate(CASES):
+    only = set(sys.argv[1:])                     # optional: regenerate just the named cases
+    if only:
+        meta = json.load(open(os.path.join(HERE, "cases.json")))
+    for ci, case in enumerate(CASES):
+        name, rule, paired, L, n, conv, indel, args = case[:8]
+        lengths = case[8] if len(case) > 8 else None
+        if only and name not in only:
+            continue
         rng = np.random.default_rng(100 + ci)
         d = os.path.join(HERE, name)
         os.makedirs(d, exist_ok=True)
         seqs = make_ref(np.random.default_rng(42))
         write_fa(os.path.join(d, "ref.fa"), seqs)
         r1, r2 = simulate(rng, seqs, rule, n, L, paired, conv, indel)
+        if lengths:                              # cut read i to a length from the list (mates independently)
+            r1 = [r[:lengths[int(rng.integers(0, len(lengths)))]] for r in r1]
+            r2 = [r[:lengths[int(rng.integers(0, len(lengths)))]] for r in r2]
         if paired:
             write_fq(os.path.join(d, "reads_1.fq"), r1, "/1"); write_fq(os.path.join(d, "reads_2.fq"), r2, "/2")
             inp = ["-a", "reads_1.fq", "-b", "reads_2.fq"]
@@ -184,8 +198,6 @@ def main():
                     out.write(line)
         os.unlink(os.path.join(d, "out.sam"))
         meta[name] = {"args": full, "paired": paired}
-        if name in KNOWN_GAPS:
-            meta[name]["known_gap"] = True
         print(name, sum(1 for _ in open(os.path.join(d, "expected.sam"))), "lines")
     with open(os.path.join(HERE, "cases.json"), "w") as fh:
         json.dump(meta, fh, indent=1, sort_keys=True)

@@ -115,3 +115,40 @@ def test_loader_paired_bam_is_one_interleaved_file(tmp_path):
     fq, _ = parsed(tmp, "-a", "reads_1.fq", "-b", "reads_2.fq", "-d", "ref.fa")
     bam, err = parsed(tmp, "-a", "pairs.bam", "-b", "pairs.bam", "-d", "ref.fa")
     assert "format: BAM" in err and fq == bam and fq.count("\n") > 2000
+
+
+def test_loader_block_boundaries_and_read_window(tmp_path):
+    """The splitter cuts the input into blocks of whole records; any block size, -B / -E windows, blank lines, CRLF line
+    ends and a missing final newline must give the same reads (reads.cpp:13-40, 42-84)."""
+    import shutil
+    tmp = str(tmp_path)
+    g = os.path.join(helpers.GOLDEN, "ag_pe")
+    for f in ("ref.fa", "reads_1.fq", "reads_2.fq"):
+        shutil.copy(os.path.join(g, f), tmp)
+
+    def run_parse(args, batch):
+        env = dict(os.environ, BASAL_PARSE_ONLY="1", BASAL_BATCH=str(batch))
+        r = subprocess.run([helpers.GPU_BIN] + args + ["-M", "C:T", "-S", "7"], capture_output=True, timeout=60, env=env, cwd=tmp)
+        assert r.returncode == 0, r.stderr.decode()
+        out = r.stdout.decode().split("\n")
+        return "\n".join(out[next(i for i, l in enumerate(out) if l.startswith("@")):])
+    base = ["-a", "reads_1.fq", "-b", "reads_2.fq", "-d", "ref.fa"]
+    whole = run_parse(base, 1 << 20)
+    assert whole.count("\n") == 4 * 600
+    for batch in (1, 7, 64, 299, 300):
+        assert run_parse(base, batch) == whole
+    recs = whole.strip().split("\n")
+    win = run_parse(base + ["-B", "11", "-E", "25"], 4)                      # pairs 11..25
+    assert win.strip().split("\n") == recs[8 * 10: 8 * 25]
+    # blank lines before headers, CRLF line ends, no newline at the end of the file
+    src = open(os.path.join(tmp, "reads_1.fq")).read().rstrip("\n").split("\n")
+    messy = []
+    for i in range(0, len(src), 4):
+        messy += ([""] if (i // 4) % 3 == 0 else []) + [src[i] + "\r", src[i + 1] + "\r", src[i + 2], src[i + 3] + "\r"]
+    open(os.path.join(tmp, "messy.fq"), "w").write("\n".join(messy))
+    clean = run_parse(["-a", "reads_1.fq", "-d", "ref.fa"], 50)
+    assert run_parse(["-a", "messy.fq", "-d", "ref.fa"], 13) == clean
+    import gzip
+    with gzip.open(os.path.join(tmp, "messy.fq.gz"), "wb") as fh:
+        fh.write("\n".join(messy).encode())
+    assert run_parse(["-a", "messy.fq.gz", "-d", "ref.fa"], 17) == clean

@@ -150,3 +150,58 @@ def test_capacity_paths_match_oracle(env, pe, monkeypatch):
         gs, os_ = gpu.stats(), orc.stats()
         assert gs.seed_lookups == os_.seed_lookups and gs.candidates == os_.candidates
     gpu.close(); orc.close()
+
+
+# ------------------------------------------------------------------ mixed read lengths: carried aligner state (SURVEY trap 3)
+
+def _mixed(matrix, rng, lengths):
+    """Cut every read of a fixed-length matrix to a length drawn from `lengths`; returns the reads as strings."""
+    return [bytes(row[: int(rng.choice(lengths))]).decode() for row in matrix]
+
+
+@pytest.mark.parametrize("pe,env", [(False, {}), (True, {}), (False, {"BSL_SUB_BATCH": "1500"}), (True, {"BSL_SUB_BATCH": "1200"})])
+def test_mixed_lengths_match_oracle(pe, env, monkeypatch):
+    """Reads whose start-offset range is empty ((L - I + 1) % s == 0: 99, 83, 67, 51 / 147, 131 at the defaults) inherit the
+    start offset and the stale seed hashes of earlier reads of the same aligner object (align.cpp:476-480, 79-150). The
+    oracle keeps that state like a -p 1 run of the reference (tools/fuzz_mixed.py pins it against the binary); the CUDA
+    path must give the same records AND the same look-up / candidate counts, also when the call is cut into sub-ranges."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(11)
+    if pe:
+        cfg, chrs, m1, m2 = helpers.small_case(2, 0.001, limit=6000)
+        lengths = [150, 147, 149, 131, 148, 115, 150, 99, 140]
+    else:
+        cfg, chrs, m1, m2 = helpers.small_case(1, 0.01, limit=8000)
+        lengths = [100, 99, 98, 83, 97, 67, 96, 51, 100]
+    params = helpers.flags_to_params(cfg, {"n": 1} if pe else {})
+    gpu, orc = _build_both(cfg, chrs, params)
+    a = capi.ReadBatch.from_strings(_mixed(m1, rng, lengths), readset=1 if pe else 0)
+    if pe:
+        b = capi.ReadBatch.from_strings(_mixed(m2, rng, lengths), readset=2)
+        ga, gb, gp = gpu.align_pe(a, b); wa, wb, wp = orc.align_pe(a, b)
+        helpers.assert_records_equal(gp, wp, "pair records", fields=["n_pairs", "insert", "chain", "na", "nb"])
+        helpers.assert_records_equal(ga, wa, "mate 1 records"); helpers.assert_records_equal(gb, wb, "mate 2 records")
+    else:
+        helpers.assert_records_equal(gpu.align_se(a), orc.align_se(a), "SE records")
+    gs, os_ = gpu.stats(), orc.stats()
+    assert gs.seed_lookups == os_.seed_lookups and gs.candidates == os_.candidates
+    gpu.close(); orc.close()
+
+
+def test_context_reads_restore_the_carried_state():
+    """bsl_batch::n_context: mapping reads [k, n) with the right earlier reads in front as context gives the records the
+    whole batch gives for them (how the CLI keeps -p 1 semantics across its batches)."""
+    rng = np.random.default_rng(12)
+    cfg, chrs, m1, _ = helpers.small_case(1, 0.01, limit=3000)
+    reads = _mixed(m1, rng, [100, 99, 98, 83, 97, 67, 96, 100])
+    params = helpers.flags_to_params(cfg, {})
+    gpu, orc = _build_both(cfg, chrs, params)
+    whole = gpu.align_se(capi.ReadBatch.from_strings(reads))
+    k = 1700
+    ctx = reads[:k]                                   # (a superset of) the reads that matter; all of them as context
+    part = gpu.align_se(capi.ReadBatch.from_strings(ctx + reads[k:], first_index=0, n_context=k))
+    helpers.assert_records_equal(part[k:], whole[k:], "records after a context prefix")
+    want = orc.align_se(capi.ReadBatch.from_strings(ctx + reads[k:], first_index=0, n_context=k))
+    helpers.assert_records_equal(part[k:], want[k:], "records after a context prefix, oracle")
+    gpu.close(); orc.close()

@@ -17,8 +17,7 @@ def _oracle_sam(args, cwd, out):
     return helpers.run_cli(helpers.ORACLE_BIN, args, cwd, out)
 
 
-@pytest.mark.parametrize("name", [pytest.param(n, marks=pytest.mark.xfail(strict=True, reason="known gap: -r 2 lists every hit of an unpaired multi-hit mate in the reference (pairs.cpp:232-305); oracle and CUDA path report the pick"))
-                                  if CASES[n].get("known_gap") else n for n in sorted(CASES)])
+@pytest.mark.parametrize("name", sorted(CASES))
 def test_oracle_matches_golden(name, tmp_path):
     d = os.path.join(helpers.GOLDEN, name)
     got = _oracle_sam(CASES[name]["args"], d, str(tmp_path / "orc.sam"))
