@@ -59,6 +59,8 @@ struct KArgs {
     u32 *bits1;                    // [slot*2+chain][2*Wb]: low code bit per base, then ACGT mask per base (32 bases per word, first base in the top bit)
     u64 *planes; u8 *sched; SlotMeta *meta; SlotCounts *cnt; uint2 *stat; u8 *minlvl;   // stat: executed seed look-ups / candidates per slot
     DevHit *hits; u32 cap;         // hit pool and per-slot capacity
+    DevHit *bighits; u32 big_cap, big_blocks;   // large blocks for the few reads whose list outgrows `cap` (repeat families): handed out by add_hit
+    u32 *wide_list;                // pairs routed to pair_round_wide
     DevCounters *ctr;
     // per-round scratch
     ItemHdr *hdr; u32 cap_items; u32 cap_cands;
@@ -83,6 +85,11 @@ __device__ __forceinline__ u64 plane_extract(const u64 *pl, u32 p) {     // 32 b
 // as a u32 array are in logical order (u32 j = bases 16j..16j+15, first base in the top bits), which is what
 // verify_candidates stages. Plane order per (slot, chain): bases, N-mask reduced to 01 per ACGT base, convert-to mask.
 __device__ __forceinline__ u64 swap32(u64 x) { return (x << 32) | (x >> 32); }
+// hit list of a slot and its capacity
+__device__ __forceinline__ DevHit *slot_hits(const KArgs &A, u32 item, u32 &cap) {
+    if (item & SLOT_BIG) { cap = A.big_cap; return A.bighits + (u64)(item & ~SLOT_BIG) * A.big_cap; }
+    cap = A.cap; return A.hits + (u64)item * A.cap;
+}
 __device__ __forceinline__ u64 stream_extract(const u64 *pl, u32 p) {    // plane_extract over a stream in global memory
     u32 w = p >> 5, o = (p & 31u) * 2;
     u64 x = swap32(pl[w]) << o;
@@ -435,12 +442,11 @@ __global__ void build_lists(const __grid_constant__ KArgs A, u32 *se_list, u32 *
     }
     if (i >= A.n_a) return;
     SlotMeta ma = A.meta[i], mb = A.meta[i + A.n_a];
-    bool oka = !(ma.flags & (SF_FILTERED | SF_CONTEXT)), okb = !(mb.flags & (SF_FILTERED | SF_CONTEXT));
-    if (oka && okb) { u32 pos = atomicAdd(&A.ctr->rc[20].active, 1u); pe_list[pos] = i; }
-    else {
-        if (oka && ma.nseg > 0) { u32 pos = atomicAdd(&A.ctr->rc[0].active, 1u); se_list[pos] = i; }
-        if (okb && mb.nseg > 0) { u32 pos = atomicAdd(&A.ctr->rc[0].active, 1u); se_list[pos] = i + A.n_a; }
-    }
+    // a pair with one filtered mate stays in the pair list: seed_lookup<PE> gives its lone mate SingleAlign's stop rule and
+    // pair_round leaves its hit lists alone, so the paired rounds also do what the reference's `_sa.RunAlign` does (pairs.cpp:197-201)
+    if ((ma.flags | mb.flags) & SF_CONTEXT) return;
+    const bool oka = !(ma.flags & SF_FILTERED), okb = !(mb.flags & SF_FILTERED);
+    if (oka || okb) { u32 pos = atomicAdd(&A.ctr->rc[20].active, 1u); pe_list[pos] = i; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -467,15 +473,20 @@ __global__ void __launch_bounds__(LK_THREADS) seed_lookup(const __grid_constant_
         const u32 k = k0 + threadIdx.x;
         const bool act = k < n_thr;
         const u32 entry = k >> SH, c = k & 1u, mate = PE ? (k >> 1) & 1u : 0u;
-        u32 slot = 0; SlotMeta m; m.flags = 0; m.nseg = 0; m.rnd = 0; m.len = 0; m.thr = 0;
+        u32 slot = 0, mlvl = 255; SlotMeta m; m.flags = 0; m.nseg = 0; m.rnd = 0; m.len = 0; m.thr = 0;
         bool search = false, keep = false;
         if (act) {
             slot = list_in[entry] + mate * A.n_a;
             m = A.meta[slot];
             bool cont = !(m.flags & (SF_OVERFLOW | SF_FILTERED));
             if (!PE) cont = cont && round < m.nseg && A.minlvl[slot] >= round;          // stop rule of RunAlign (align.cpp:459-463)
+            mlvl = A.minlvl[slot];
             search = cont && round < m.nseg && (m.flags & (c ? SF_CHAIN1 : SF_CHAIN0));
             keep = !PE && c == 0 && cont;
+        }
+        if (PE) {                                                                       // the mate's threads are two lanes away
+            const u32 mate_flags = __shfl_xor_sync(0xffffffffu, (u32)m.flags, 2);
+            if (act && (mate_flags & SF_FILTERED) && mlvl < round) search = false;          // lone mate: RunAlign's stop rule (align.cpp:459-463)
         }
         if (!PE) {                                                                      // compact the list of reads searched in this round
             const u32 bal = __ballot_sync(0xffffffffu, keep);
@@ -1127,7 +1138,8 @@ __global__ void __launch_bounds__(256) reduce_fast(const __grid_constant__ KArgs
         const u32 c = A.slot_flag[slot];
         if (c == 0 || c > MK_CAP) continue;
         SlotMeta m = A.meta[slot];
-        if (m.nhit + c >= A.w || m.nhit + c > A.cap) continue;            // a level could reach -w, or the list could overflow
+        u32 hcap; DevHit *hits = slot_hits(A, m.item, hcap);
+        if (m.nhit + c >= A.w || m.nhit + c > hcap) continue;             // a level could reach -w, or the list could outgrow its storage
         uint4 e[MK_CAP];
 #pragma unroll
         for (u32 i = 0; i < MK_CAP; i++) e[i] = i < c ? A.marks[(size_t)slot * MK_CAP + i] : make_uint4(0xffffffffu, 0, 0, 0);
@@ -1135,7 +1147,6 @@ __global__ void __launch_bounds__(256) reduce_fast(const __grid_constant__ KArgs
         for (u32 i = 1; i < MK_CAP; i++)                                    // discovery order = flat candidate index
 #pragma unroll
             for (u32 j = i; j > 0; j--) if (e[j].x < e[j - 1].x) { const uint4 tmp = e[j]; e[j] = e[j - 1]; e[j - 1] = tmp; }
-        DevHit *hits = A.hits + (u64)m.item * A.cap;
         u32 nhit = m.nhit, minl = A.minlvl[slot];
         const u32 L = m.len;
 #pragma unroll
@@ -1171,7 +1182,7 @@ __global__ void __launch_bounds__(256) reduce_fast(const __grid_constant__ KArgs
 
 struct WarpCtx {
     // warp-uniform running state of one read (one SingleAlign object)
-    u32 L, W, thr, nhit, chain, cap; u32 mycnt;     // mycnt: lane c*16+l holds hits[c][l]
+    u32 L, W, thr, nhit, chain, cap, item; u32 mycnt;     // mycnt: lane c*16+l holds hits[c][l]
     DevHit *hits; bool overflow;
     u64 *keys; u32 kcap;                            // shared-memory copy of the dedup keys of hits[0 .. min(nhit, kcap))
 };
@@ -1288,7 +1299,16 @@ __device__ int add_hit(const KArgs &A, WarpCtx &S, u32 lane, u32 level, u32 g, u
     for (u32 i = lane; i < nk; i += 32) dup |= S.keys[i] == key;
     for (u32 i = nk + lane; i < S.nhit; i += 32) { DevHit hh = S.hits[i]; if (hh.loc == x && HIT_GAPPED(hh.tag) == gapped && (HIT_CHR2(hh.tag) >> 1) == lo) dup = true; }
     if (__any_sync(0xffffffffu, dup)) return 0;
-    if (S.nhit >= S.cap) { S.overflow = true; return 1; }
+    if (S.nhit >= S.cap) {
+        // the list outgrew its storage: move it into a large block (no re-run); only when none is left does the read take the large-capacity pass
+        u32 blk = 0xffffffffu;
+        if (!(S.item & SLOT_BIG) && A.bighits && A.big_cap > S.cap) { if (lane == 0) blk = atomicAdd(&A.ctr->big_n, 1u); blk = __shfl_sync(0xffffffffu, blk, 0); }
+        if (blk >= A.big_blocks) { S.overflow = true; return 1; }
+        DevHit *nh = A.bighits + (u64)blk * A.big_cap;
+        for (u32 i = lane; i < S.nhit; i += 32) nh[i] = S.hits[i];
+        __syncwarp();
+        S.hits = nh; S.cap = A.big_cap; S.item = SLOT_BIG | blk;
+    }
     if (lane == 0) {
         DevHit hh; hh.loc = x; hh.tag = (lo * 2 + sig) | (level << 20) | (S.chain << 24) | (gapped << 25); hh.gap = (u32)sh; hh.gp = gp; S.hits[S.nhit] = hh;
         if (S.nhit < S.kcap) S.keys[S.nhit] = key;
@@ -1301,8 +1321,13 @@ __device__ int add_hit(const KArgs &A, WarpCtx &S, u32 lane, u32 level, u32 g, u
     return 0;
 }
 
+// long_pass = 0: every listed slot, 32 per grab; slots with many marked candidates or a long hit list (reads from repeat
+// families: their replay is long and serial) are only collected in KArgs::flag_list. long_pass = 1: those, one per grab, so that
+// they spread over all warps instead of queueing behind each other in one.
+#define RR_LONG_MARKS 48u
+#define RR_LONG_HITS 64u
 template <bool SINGLE>
-__global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_constant__ KArgs A, u32 round, u32 ci, u32 NW, u32 NWS, const u32 *list, u32 list_ci, u32 as_pe) {
+__global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_constant__ KArgs A, u32 round, u32 ci, u32 NW, u32 NWS, const u32 *list, u32 list_ci, u32 as_pe, u32 long_pass) {
     extern __shared__ u64 smem[];
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     u64 *win_all = smem + (size_t)wid * (32 * NWS + 48 + RR_KEYS);
@@ -1312,24 +1337,28 @@ __global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_co
     const u32 n_cands_rc = (u32)(al_rc & ALLOC_MASK), n_items_rc = (u32)(al_rc >> ALLOC_SHIFT);
     // every slot searched in this round: SE = the compacted list seed_lookup wrote, PE = both mates of every listed pair;
     // a warp takes 32 of them at a time and replays those verify_candidates flagged
-    const u32 n_entries = A.ctr->rc[list_ci].active << (as_pe ? 1 : 0);
-    const u32 batch = min(32u, max(1u, n_entries / (gridDim.x * ROUND_WARPS * 4)));      // few entries (the large-capacity pass): one per grab, for balance
+    const u32 n_entries = long_pass ? rc->long_n : A.ctr->rc[list_ci].active << (as_pe ? 1 : 0);
+    const u32 batch = long_pass ? 1u : min(32u, max(1u, n_entries / (gridDim.x * ROUND_WARPS * 4)));      // few entries: one per grab, for balance
     const u32 G = A.gap;
     unsigned long long st_hits = 0;
     for (;;) {
         u32 k0 = 0;
-        if (lane == 0) k0 = atomicAdd(&rc->work, batch);
+        if (lane == 0) k0 = atomicAdd(long_pass ? &rc->long_work : &rc->work, batch);
         k0 = __shfl_sync(0xffffffffu, k0, 0);
         if (k0 >= n_entries) break;
         u32 my_slot = 0; bool flagged = false;
-        if (lane < batch && k0 + lane < n_entries) { const u32 kk = k0 + lane; my_slot = as_pe ? list[kk >> 1] + (kk & 1u) * A.n_a : list[kk]; flagged = A.slot_flag[my_slot] != 0u; }
+        if (lane < batch && k0 + lane < n_entries) {
+            const u32 kk = k0 + lane; my_slot = long_pass ? A.flag_list[kk] : (as_pe ? list[kk >> 1] + (kk & 1u) * A.n_a : list[kk]);
+            const u32 nmark = A.slot_flag[my_slot]; flagged = nmark != 0u;
+            if (flagged && !long_pass && (nmark >= RR_LONG_MARKS || A.meta[my_slot].nhit >= RR_LONG_HITS)) { A.flag_list[atomicAdd(&rc->long_n, 1u)] = my_slot; flagged = false; }
+        }
         u32 todo = __ballot_sync(0xffffffffu, flagged);
       while (todo) {
         const u32 src_lane = __ffs(todo) - 1; todo &= todo - 1;
         const u32 slot = __shfl_sync(0xffffffffu, my_slot, src_lane);
         SlotMeta m = A.meta[slot];
-        WarpCtx S; S.L = m.len; S.W = (S.L + 31) >> 5; S.thr = m.thr; S.nhit = m.nhit; S.cap = A.cap; S.overflow = false;
-        S.hits = A.hits + (u64)m.item * A.cap;
+        WarpCtx S; S.L = m.len; S.W = (S.L + 31) >> 5; S.thr = m.thr; S.nhit = m.nhit; S.overflow = false; S.item = m.item;
+        S.hits = slot_hits(A, m.item, S.cap);
         S.mycnt = ((const u16 *)&A.cnt[slot])[lane];
         S.keys = keys; S.kcap = RR_KEYS;
         __syncwarp();
@@ -1424,7 +1453,7 @@ __global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_co
         if (lane == 0) {
             u32 fl = m.flags;
             if (S.overflow) { fl |= SF_OVERFLOW; atomicAdd(&A.ctr->overflow_n, 1u); }
-            SlotMeta *mp = A.meta + slot; mp->thr = (u8)S.thr; mp->nhit = (u16)S.nhit; mp->flags = (u8)fl;
+            SlotMeta *mp = A.meta + slot; mp->thr = (u8)S.thr; mp->nhit = (u16)S.nhit; mp->flags = (u8)fl; if (S.item != m.item) mp->item = S.item;
             if (un_lookups | un_cand) { uint2 ss = A.stat[slot]; ss.x -= un_lookups; ss.y -= un_cand; A.stat[slot] = ss; }
             const u32 lv = (nz | (nz >> 16)) & 0xffffu;
             A.minlvl[slot] = lv ? (u8)(__ffs(lv) - 1) : (u8)255;
@@ -1506,6 +1535,7 @@ __device__ void fill_record(bsl_hit &o, const DevHit &h, u32 chain, u32 level) {
 }
 
 #define PR_LOCAL 4u
+#define PR_WIDE_HITS 12u     // a pair with a longer hit list goes to pair_round_wide
 __global__ void pair_round(const __grid_constant__ KArgs A, u32 round, const u32 *list_in, u32 *list_out, u32 ci) {
     RoundCtr *rc = A.ctr->rc + ci;
     const u32 n_items = rc->active;
@@ -1517,7 +1547,12 @@ __global__ void pair_round(const __grid_constant__ KArgs A, u32 round, const u32
             if (!(mb.flags & SF_OVERFLOW)) { A.meta[sb].flags = mb.flags | SF_OVERFLOW; }
             continue;
         }
-        DevHit *ha = A.hits + (u64)ma.item * A.cap, *hb = A.hits + (u64)mb.item * A.cap;
+        if ((ma.flags | mb.flags) & SF_FILTERED) {                 // a lone mate (the other one was filtered) runs SingleAlign::RunAlign in the reference
+            if (round < max((u32)ma.B, (u32)mb.B)) { u32 pos = atomicAdd(&rc[1].active, 1u); list_out[pos] = p; }      // (pairs.cpp:197-201): no SortHits4PE, no pairs
+            continue;
+        }
+        if (((ma.item | mb.item) & SLOT_BIG) || ma.nhit > PR_WIDE_HITS || mb.nhit > PR_WIDE_HITS) { A.wide_list[atomicAdd(&rc->wide, 1u)] = p; continue; }      // long lists: warp per pair
+        u32 capa, capb; DevHit *ha = slot_hits(A, ma.item, capa), *hb = slot_hits(A, mb.item, capb);
         const u32 nA = ma.nhit, nB = mb.nhit, Ba = ma.B, Bb = mb.B, La = ma.len, Lb = mb.len;
         const u32 i = round;
         u32 total = 0, best = 0xffffffffu, best_cnt = 0;
@@ -1692,11 +1727,11 @@ __device__ u32 pw_get_pairs(const KArgs &A, PairWideSmem &sm, u32 lane, const De
     return npair;
 }
 
-__global__ void __launch_bounds__(32) pair_round_wide(const __grid_constant__ KArgs A, u32 round, const u32 *list_in, u32 *list_out, u32 ci) {
+__global__ void __launch_bounds__(32) pair_round_wide(const __grid_constant__ KArgs A, u32 round, const u32 *list_in, u32 *list_out, u32 ci, u32 from_wide) {
     extern __shared__ __align__(16) unsigned char pw_raw[];
     PairWideSmem &sm = *reinterpret_cast<PairWideSmem *>(pw_raw);
     RoundCtr *rc = A.ctr->rc + ci;
-    const u32 n_items = rc->active, lane = threadIdx.x;
+    const u32 n_items = from_wide ? rc->wide : rc->active, lane = threadIdx.x;      // from_wide: the pairs pair_round of this round left in KArgs::wide_list
     for (u32 k = blockIdx.x; k < n_items; k += gridDim.x) {
         const u32 p = list_in[k]; const u32 sa = p, sb = p + A.n_a;
         const SlotMeta ma = A.meta[sa], mb = A.meta[sb];
@@ -1705,7 +1740,11 @@ __global__ void __launch_bounds__(32) pair_round_wide(const __grid_constant__ KA
             if (lane == 0) { if (!(ma.flags & SF_OVERFLOW)) A.meta[sa].flags = ma.flags | SF_OVERFLOW; if (!(mb.flags & SF_OVERFLOW)) A.meta[sb].flags = mb.flags | SF_OVERFLOW; }
             continue;
         }
-        DevHit *ha = A.hits + (u64)ma.item * A.cap, *hb = A.hits + (u64)mb.item * A.cap;
+        if ((ma.flags | mb.flags) & SF_FILTERED) {                 // lone mate: see pair_round
+            if (lane == 0 && round < max((u32)ma.B, (u32)mb.B)) { const u32 pos = atomicAdd(&rc[1].active, 1u); list_out[pos] = p; }
+            continue;
+        }
+        u32 capa, capb; DevHit *ha = slot_hits(A, ma.item, capa), *hb = slot_hits(A, mb.item, capb);
         const u32 nA = ma.nhit, nB = mb.nhit, Ba = ma.B, Bb = mb.B, La = ma.len, Lb = mb.len;
         const u32 i = round;
         u32 total = 0, best = 0xffffffffu, best_cnt = 0;
@@ -1806,7 +1845,7 @@ __global__ void finalize_reads(const __grid_constant__ KArgs A, const u32 *only_
     o.status = BSL_ST_UNMAPPED;
     if (m.nhit == 0) { A.out[slot] = o; return; }
     const SlotCounts cn = A.cnt[slot];
-    const DevHit *h = A.hits + (u64)m.item * A.cap;
+    u32 hcap; const DevHit *h = slot_hits(A, m.item, hcap);
     for (u32 l = 0; l <= m.B; l++) {
         u32 n0 = cn.c[0][l], nn = n0 + cn.c[1][l];
         if (!nn) continue;
@@ -1852,12 +1891,8 @@ __global__ void reset_heavy(const __grid_constant__ KArgs A, const u32 *heavy_li
     }
     if (!A.pe) { u32 pos = atomicAdd(&A.ctr->rc[0].active, 1u); se_list[pos] = i; return; }
     SlotMeta ma = A.meta[i], mb = A.meta[i + A.n_a];
-    bool oka = !(ma.flags & SF_FILTERED), okb = !(mb.flags & SF_FILTERED);
-    if (oka && okb) { u32 pos = atomicAdd(&A.ctr->rc[20].active, 1u); pe_list[pos] = i; }
-    else {
-        if (oka && ma.nseg > 0) { u32 pos = atomicAdd(&A.ctr->rc[0].active, 1u); se_list[pos] = i; }
-        if (okb && mb.nseg > 0) { u32 pos = atomicAdd(&A.ctr->rc[0].active, 1u); se_list[pos] = i + A.n_a; }
-    }
+    const bool oka = !(ma.flags & SF_FILTERED), okb = !(mb.flags & SF_FILTERED);
+    if (oka || okb) { u32 pos = atomicAdd(&A.ctr->rc[20].active, 1u); pe_list[pos] = i; }
 }
 
 __global__ void expand_pairs_to_slots(const u32 *heavy_list, u32 first, u32 count, u32 n_a, u32 pe, u32 *slots) {
@@ -1884,7 +1919,7 @@ void bsl_lane_free(Lane &ln) {
     cudaFree(ln.d_bits1); cudaFree(ln.d_hdr); cudaFree(ln.d_chunk_first); cudaFree(ln.d_bitmap); cudaFree(ln.d_flat_loc);
     cudaFree(ln.d_planes); cudaFree(ln.d_hits); cudaFree(ln.d_heavy_hits); cudaFree(ln.d_list[0]); cudaFree(ln.d_list[1]); cudaFree(ln.d_heavy_list);
     cudaFree(ln.d_pe_list[0]); cudaFree(ln.d_pe_list[1]); cudaFree(ln.d_out); cudaFree(ln.d_pair); cudaFree(ln.d_all[0]); cudaFree(ln.d_all[1]); cudaFree(ln.d_ctr);
-    cudaFree(ln.d_st0); cudaFree(ln.d_defer); cudaFree(ln.d_stale);
+    cudaFree(ln.d_st0); cudaFree(ln.d_defer); cudaFree(ln.d_stale); cudaFree(ln.d_bighits); cudaFree(ln.d_wide_list);
     if (ln.h_ctr) cudaFreeHost(ln.h_ctr);
     for (auto &e : ln.ev) if (e) cudaEventDestroy(e);
     for (auto &e : ln.evk) if (e) cudaEventDestroy(e);
@@ -2041,6 +2076,12 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     c0 = ln.cap_words; if ((rc = grow(ctx, &ln.d_planes, &c0, (size_t)n_slots * 6 * Wb + 16))) return rc; ln.cap_words = c0;
     c0 = ln.cap_bits1; if ((rc = grow(ctx, &ln.d_bits1, &c0, (size_t)n_slots * 8 * Wb + 16))) return rc; ln.cap_bits1 = c0;
     c0 = ln.cap_hits; if ((rc = grow(ctx, &ln.d_hits, &c0, (size_t)n_slots * cap_main))) return rc; ln.cap_hits = c0;
+    // large blocks for lists that outgrow cap_main (reads from repeat families: every level may fill up to -w): room for about
+    // 1.5 % of the slots, at most 1 GB; a read that finds none left is re-run on the large-capacity pass
+    const u32 big_cap = std::min<u32>(16 * P.max_num_hits + 32, 65535u);
+    const u32 big_blocks = (u32)std::min<u64>(std::max<u64>(n_slots / 64, 256), std::max<u64>((1ull << 30) / ((u64)big_cap * sizeof(DevHit)), 16));
+    c0 = ln.cap_bighits; if ((rc = grow(ctx, &ln.d_bighits, &c0, (size_t)big_blocks * big_cap))) return rc; ln.cap_bighits = c0;
+    c0 = ln.cap_wide; if ((rc = grow(ctx, &ln.d_wide_list, &c0, (size_t)n_a + 16))) return rc; ln.cap_wide = c0;
     // per-round scratch: flat candidate space (1 bit per candidate) and item headers
     const u32 nch = P.chains == 1 ? 2 : 1;
     const u64 worst_slot = 2ull * P.index_interval * std::max<u32>(ctx->di.maxk, 1);      // candidates one read can have in one round
@@ -2080,6 +2121,7 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     A.n_ctx = first == 0 ? std::min(a->n_context, n_a) : 0; A.carry = carry ? 1u : 0u; A.st0arr = ln.d_st0; A.defer = ln.d_defer; A.stale = ln.d_stale;
     A.Wb = Wb; A.planes = ln.d_planes; A.bits1 = ln.d_bits1; A.sched = ln.d_sched; A.meta = ln.d_meta; A.cnt = ln.d_cnt; A.stat = ln.d_stat; A.minlvl = ln.d_minlvl;
     A.hits = ln.d_hits; A.cap = cap_main; A.ctr = ln.d_ctr;
+    A.bighits = ln.d_bighits; A.big_cap = big_cap; A.big_blocks = big_blocks; A.wide_list = ln.d_wide_list;
     A.hdr = ln.d_hdr; A.cap_items = (u32)std::min<u64>(want_items - 16, 0xffffffffu); A.cap_cands = (u32)want_cands;
     A.slot_item = ln.d_slot_item; A.marks = ln.d_marks; A.slot_flag = ln.d_slot_flag; A.flag_list = ln.d_flag_list; A.chunk_first = ln.d_chunk_first; A.bitmap = ln.d_bitmap; A.flat_loc = ln.d_flat_loc;
     A.out = ln.d_out; A.pair_out = ln.d_pair; A.all_a = want_all ? ln.d_all[0] : nullptr; A.all_b = want_all ? ln.d_all[1] : nullptr; A.all_cap = want_all ? sub_cap : 0;
@@ -2185,23 +2227,29 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
         {
             const u32 *rl = as_pe ? lin : lout; const u32 rci = as_pe ? ci : ci + 1;
             if (!G) { reduce_fast<<<sms * 8, 256, 0, st>>>(K, rl, rci, as_pe ? 1u : 0u); launches++; }
-            if (ctx->rule.single) reduce_round<true><<<grid_r, ROUND_WARPS * 32, smem_r, st>>>(K, r, ci, NW, NWS, rl, rci, as_pe ? 1u : 0u);
-            else reduce_round<false><<<grid_r, ROUND_WARPS * 32, smem_r, st>>>(K, r, ci, NW, NWS, rl, rci, as_pe ? 1u : 0u);
+            for (u32 lp = 0; lp < 2; lp++) {
+                if (ctx->rule.single) reduce_round<true><<<grid_r, ROUND_WARPS * 32, smem_r, st>>>(K, r, ci, NW, NWS, rl, rci, as_pe ? 1u : 0u, lp);
+                else reduce_round<false><<<grid_r, ROUND_WARPS * 32, smem_r, st>>>(K, r, ci, NW, NWS, rl, rci, as_pe ? 1u : 0u, lp);
+            }
         }
         ev_end();
-        launches += 3;
+        launches += 4;
     };
     auto run_passes = [&](KArgs &K) -> int {
         // SE rounds (stop rule evaluated by the next round's seed_lookup)
-        KArgs Kse = K; Kse.pe = 0;
-        for (u32 r = 0; r < rounds_se; r++) search(Kse, false, r, ln.d_list[r & 1], ln.d_list[(r + 1) & 1], r);
-        if (K.pe) {
+        if (!K.pe) for (u32 r = 0; r < rounds_se; r++) search(K, false, r, ln.d_list[r & 1], ln.d_list[(r + 1) & 1], r);
+        else {
+            // paired rounds; pairs with a filtered mate ride along (their lone mate follows SingleAlign's stop rule, see seed_lookup)
             for (u32 r = 0; r <= BSL_MAXSNPS; r++) {
                 if (r < rounds_se) search(K, true, r, ln.d_pe_list[r & 1], nullptr, 20 + r);
                 ev_begin('p');
-                if (K.hits == ln.d_heavy_hits) pair_round_wide<<<sms * 4, 32, sizeof(PairWideSmem), st>>>(K, r, ln.d_pe_list[r & 1], ln.d_pe_list[(r + 1) & 1], 20 + r);
-                else pair_round<<<sms * 8, 128, 0, st>>>(K, r, ln.d_pe_list[r & 1], ln.d_pe_list[(r + 1) & 1], 20 + r);
-                ev_end(); launches++;
+                if (K.hits == ln.d_heavy_hits) { pair_round_wide<<<sms * 4, 32, sizeof(PairWideSmem), st>>>(K, r, ln.d_pe_list[r & 1], ln.d_pe_list[(r + 1) & 1], 20 + r, 0u); launches++; }
+                else {
+                    pair_round<<<sms * 8, 128, 0, st>>>(K, r, ln.d_pe_list[r & 1], ln.d_pe_list[(r + 1) & 1], 20 + r);
+                    pair_round_wide<<<sms * 4, 32, sizeof(PairWideSmem), st>>>(K, r, K.wide_list, ln.d_pe_list[(r + 1) & 1], 20 + r, 1u);      // the pairs with long lists
+                    launches += 2;
+                }
+                ev_end();
             }
         }
         cudaError_t e = cudaGetLastError();
@@ -2213,6 +2261,18 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     CUDA_TRY(cudaEventRecord(ln.ev[3], st));
     finalize_reads<<<(n_slots + 255) / 256, 256, 0, st>>>(A, nullptr, 0); launches++;
     CUDA_TRY(cudaMemcpyAsync(ln.h_ctr, ln.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(ln.ev[4], st));
+    // ---- D2H: the records leave right behind the kernels; only a call that needs the large-capacity pass (rare: a read found no
+    //      large block left, or the candidate space of a round ran out) synchronises twice and copies them again
+    auto copy_out = [&]() -> int {
+        if (resident) return 0;
+        CUDA_TRY(cudaMemcpyAsync(out_a + first, ln.d_out, (size_t)n_a * sizeof(bsl_hit), cudaMemcpyDeviceToHost, st));
+        if (pe) { CUDA_TRY(cudaMemcpyAsync(out_b + first, ln.d_out + n_a, (size_t)n_a * sizeof(bsl_hit), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(out_pair + first, ln.d_pair, (size_t)n_a * sizeof(bsl_pair), cudaMemcpyDeviceToHost, st)); }
+        return 0;
+    };
+    if ((rc = copy_out())) return rc;
+    CUDA_TRY(cudaEventRecord(ln.ev[5], st));
     CUDA_TRY(cudaStreamSynchronize(st));
     DevCounters c1 = *ln.h_ctr;
     u64 heavy_total = 0;
@@ -2243,16 +2303,11 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
             CUDA_TRY(cudaGetLastError());
         }
         CUDA_TRY(cudaMemcpyAsync(ln.h_ctr, ln.d_ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaEventRecord(ln.ev[4], st));
+        if ((rc = copy_out())) return rc;
+        CUDA_TRY(cudaEventRecord(ln.ev[5], st));
+        CUDA_TRY(cudaStreamSynchronize(st));
     }
-    CUDA_TRY(cudaEventRecord(ln.ev[4], st));
-    // ---- D2H
-    if (!resident) {
-    CUDA_TRY(cudaMemcpyAsync(out_a + first, ln.d_out, (size_t)n_a * sizeof(bsl_hit), cudaMemcpyDeviceToHost, st));
-    if (pe) { CUDA_TRY(cudaMemcpyAsync(out_b + first, ln.d_out + n_a, (size_t)n_a * sizeof(bsl_hit), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(out_pair + first, ln.d_pair, (size_t)n_a * sizeof(bsl_pair), cudaMemcpyDeviceToHost, st)); }
-    }
-    CUDA_TRY(cudaEventRecord(ln.ev[5], st));
-    CUDA_TRY(cudaStreamSynchronize(st));
     DevCounters c2 = *ln.h_ctr;
     if (want_all && !resident) {
         u64 na_ = std::min<u64>(c2.all_n, sub_cap);

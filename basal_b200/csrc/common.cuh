@@ -108,8 +108,9 @@ struct __align__(16) SlotMeta {
     u8  flags;      // bit0 chain0 enabled, bit1 chain1 enabled, bit2 filtered, bit3 overflow (needs heavy pass), bit4 done
     u8  thr;        // current snp_thres
     u16 nhit;       // hits stored
-    u32 item;       // position of this slot's hit storage (index into the hit pool, in units of cap)
+    u32 item;       // this slot's hit storage: index into the hit pool in units of cap, or SLOT_BIG | index of a large block
 };
+#define SLOT_BIG 0x80000000u
 #define SF_CHAIN0 1u
 #define SF_CHAIN1 2u
 #define SF_FILTERED 4u
@@ -151,13 +152,15 @@ struct RoundCtr {
     u32 active;                 // length of the list this round consumes
     u32 flagged;                // reads with at least one marked candidate
     u32 work;                   // work-stealing cursor of reduce_round
-    u32 pad;
+    u32 wide;                   // pairs of this round left to pair_round_wide (a mate's hit list lives in a large block)
+    u32 long_n, long_work;      // reads with many marked candidates / long hit lists: replayed by a second reduce_round launch, one read per grab
 };
 struct DevCounters {
     unsigned long long seed_lookups, candidates, hits_added, heavy, all_n;
     RoundCtr rc[40];
     u32 overflow_n;
     u32 defer_n;                // reads whose seed schedule is left to prepare_deferred
+    u32 big_n;                  // large hit-list blocks handed out
 };
 
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_error(ctx, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); return (e_ == cudaErrorMemoryAllocation) ? BSL_ENOMEM : BSL_ECUDA; } } while (0)

@@ -27,6 +27,7 @@ struct Lane {
     u8 *d_minlvl = nullptr; uint2 *d_slot_item = nullptr; u32 *d_slot_flag = nullptr; u32 *d_flag_list = nullptr; uint4 *d_marks = nullptr;
     ItemHdr *d_hdr = nullptr; u32 *d_chunk_first = nullptr; u32 *d_bitmap = nullptr; u32 *d_flat_loc = nullptr;      // per-round flat candidate space
     DevCounters *d_ctr = nullptr;
+    DevHit *d_bighits = nullptr; size_t cap_bighits = 0; u32 *d_wide_list = nullptr; size_t cap_wide = 0;   // large hit-list blocks, pairs for pair_round_wide
     u8 *d_st0 = nullptr; u32 *d_defer = nullptr; u32 *d_stale = nullptr; size_t cap_st0 = 0, cap_defer = 0, cap_stale = 0;   // carried seed-start state (mixed read lengths only)
     // pinned staging
     DevCounters *h_ctr = nullptr;

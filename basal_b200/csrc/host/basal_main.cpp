@@ -533,21 +533,44 @@ struct BlockQueue {
 };
 
 struct OutSink {
-    int fd = -1; bool seekable = false; FILE *pipe = nullptr;
+    int fd = -1; bool seekable = false;
     std::mutex mu; std::condition_variable cv; u64 next_ticket = 0; u64 offset = 0;
+    // A regular file grows in 1 GB windows that are mapped once (MAP_SHARED) and never moved: a ticket reserves its byte range in
+    // input order, then the worker copies its bytes into the mapping — in parallel with the other workers (write(2) / pwrite(2)
+    // on one file serialise on the inode lock). A file system that cannot map falls back to pwrite.
+    static constexpr u64 kWin = 1ull << 30;
+    std::vector<char *> wins; bool can_map = true;
     static bool write_all(int fd, const char *p, size_t n) { while (n) { ssize_t k = ::write(fd, p, n); if (k < 0) { if (errno == EINTR) continue; return false; } p += k; n -= (size_t)k; } return true; }
     static bool pwrite_all(int fd, const char *p, size_t n, u64 off) { while (n) { ssize_t k = ::pwrite(fd, p, n, (off_t)off); if (k < 0) { if (errno == EINTR) continue; return false; } p += k; n -= (size_t)k; off += (u64)k; } return true; }
-    bool head(const std::string &s) { if (s.empty()) return true; if (seekable) { const bool ok = pwrite_all(fd, s.data(), s.size(), offset); offset += s.size(); return ok; } return write_all(fd, s.data(), s.size()); }
-    // the bytes of ticket t; blocks until every earlier ticket has reserved its range (seekable) or has been written (pipe)
+    bool map_upto(u64 end) {                                             // caller holds mu
+        while (can_map && (u64)wins.size() * kWin < end) {
+            const u64 at = (u64)wins.size() * kWin;
+            if (ftruncate(fd, (off_t)(at + kWin)) != 0) { can_map = false; break; }
+            void *m = mmap(nullptr, kWin, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)at);
+            if (m == MAP_FAILED) { can_map = false; break; }
+            wins.push_back((char *)m);
+        }
+        return can_map;
+    }
+    void copy_in(const char *p, size_t n, u64 off) { while (n) { const u64 w = off / kWin, o = off % kWin; const size_t k = (size_t)std::min<u64>(n, kWin - o); memcpy(wins[w] + o, p, k); p += k; n -= k; off += k; } }
+    bool put(const char *p, size_t n, u64 off, bool mapped) { if (mapped) { copy_in(p, n, off); return true; } return pwrite_all(fd, p, n, off); }
+    bool head(const std::string &s) {
+        if (s.empty()) return true;
+        if (!seekable) return write_all(fd, s.data(), s.size());
+        std::unique_lock<std::mutex> g(mu); const u64 off = offset; offset += s.size(); const bool mapped = map_upto(offset); g.unlock();
+        return put(s.data(), s.size(), off, mapped);
+    }
+    // the bytes of ticket t; blocks until every earlier ticket has reserved its range (regular file) or has been written (pipe)
     bool submit(u64 t, const char *p, size_t n) {
         std::unique_lock<std::mutex> g(mu);
         cv.wait(g, [&] { return next_ticket == t; });
         bool ok = true;
-        if (seekable) { const u64 off = offset; offset += n; next_ticket++; g.unlock(); cv.notify_all(); ok = pwrite_all(fd, p, n, off); }
+        if (seekable) { const u64 off = offset; offset += n; const bool mapped = map_upto(offset); next_ticket++; g.unlock(); cv.notify_all(); ok = put(p, n, off, mapped); }
         else { ok = write_all(fd, p, n); next_ticket++; g.unlock(); cv.notify_all(); }
         return ok;
     }
     void skip(u64 t) { std::unique_lock<std::mutex> g(mu); cv.wait(g, [&] { return next_ticket == t; }); next_ticket++; g.unlock(); cv.notify_all(); }
+    void finish() { for (char *w : wins) munmap(w, kWin); if (!wins.empty()) { if (ftruncate(fd, (off_t)offset) != 0) perror("ftruncate"); } wins.clear(); }
 };
 
 struct Counters { u64 al = 0, un = 0, mu = 0, pal = 0, pun = 0, pmu = 0, aal = 0, aun = 0, amu = 0, bal = 0, bun = 0, bmu = 0; };
@@ -601,6 +624,23 @@ struct Pipeline {
             return hits[0] && (!pe || (hits[1] && pairs)); }
         ~Staging() { for (int m = 0; m < 2; m++) { bsl_host_free(bases[m]); bsl_host_free(hits[m]); } bsl_host_free(pairs); }
     };
+
+    // a pool of staging sets (one per worker + 2), allocated by a background thread while the index is built and the first
+    // batches are parsed: pinned memory is expensive to allocate
+    std::vector<std::unique_ptr<Staging>> pool; std::vector<Staging *> pool_free; std::mutex pool_mu; std::condition_variable pool_cv;
+    void make_pool(size_t n_sets) {
+        const size_t guess = (size_t)batch_reads * 168 + 4096;                    // 150-bp reads fit without a second allocation
+        for (size_t k = 0; k < n_sets; k++) {
+            std::unique_ptr<Staging> s(new Staging());
+            s->need(0, guess); if (pe) s->need(1, guess); s->need_recs(batch_reads + 64, pe);
+            std::lock_guard<std::mutex> g(pool_mu); pool_free.push_back(s.get()); pool.push_back(std::move(s)); pool_cv.notify_one();
+        }
+    }
+    Staging *acquire() { std::unique_lock<std::mutex> g(pool_mu); pool_cv.wait(g, [&] { return !pool_free.empty(); }); Staging *s = pool_free.back(); pool_free.pop_back(); return s; }
+    void release(Staging *s) { std::lock_guard<std::mutex> g(pool_mu); pool_free.push_back(s); pool_cv.notify_one(); }
+    // phase clocks (seconds summed over the workers), printed with $BASAL_TIMING
+    std::atomic<long long> ns_parse{0}, ns_wait_stage{0}, ns_pack{0}, ns_gpu{0}, ns_format{0}, ns_out{0};
+    static long long now_ns() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (long long)ts.tv_sec * 1000000000ll + ts.tv_nsec; }
 
     bool load(Batch &B) {
         std::lock_guard<std::mutex> g(in_mu);
@@ -662,8 +702,15 @@ struct Pipeline {
         tail_cv.notify_all();
     }
 
-    bool process(Batch &B, Staging &S, bsl_ctx *c, Counters &cn) {
+    bool process(Batch &B, bsl_ctx *c, Counters &cn) {
+        Staging *Sp = nullptr;
+        const bool ok = process_with(B, Sp, c, cn);
+        if (Sp) release(Sp);
+        return ok;
+    }
+    bool process_with(Batch &B, Staging *&Sp, bsl_ctx *c, Counters &cn) {
         const u32 n = B.n; Formatter F(O, R, T);
+        long long t0 = now_ns(), t1;
         B.arena.clear();
         parse_block(B.ba, fa.fastq(), O.max_readlen, fasta_qual.data(), B.a);
         if (pe) parse_block(B.bb, fb.fastq(), O.max_readlen, fasta_qual.data(), B.b);
@@ -675,6 +722,9 @@ struct Pipeline {
         std::shared_ptr<Tail> tin; u32 nctx = 0;
         if (need_ctx) { tin = wait_tail(B.ticket); nctx = (u32)tin->size(); }
         publish_tail(B);
+        t1 = now_ns(); ns_parse += t1 - t0; t0 = t1;
+        Sp = acquire(); Staging &S = *Sp;
+        t1 = now_ns(); ns_wait_stage += t1 - t0; t0 = t1;
         // ---- pack: bases of (context +) batch, back to back, into pinned memory
         const u32 nt = nctx + n;
         for (int m = 0; m < (pe ? 2 : 1); m++) {
@@ -691,6 +741,7 @@ struct Pipeline {
         bsl_batch qa; memset(&qa, 0, sizeof qa); qa.n = nt; qa.readset = pe ? 1 : 0; qa.bases = S.bases[0]; qa.offsets = S.off[0].data(); qa.first_index = B.first_index - nctx; qa.raw_len = S.raw[0].data(); qa.n_context = nctx;
         const bool all = O.P.report_repeat_hits == 2;
         std::vector<bsl_hit> alla, allb; u64 n_all = 0; u64 all_cap = all ? std::max<u64>((u64)nt * 8, 1u << 20) : 0;
+        t1 = now_ns(); ns_pack += t1 - t0; t0 = t1;
         int rc;
         for (;;) {
             if (all) { alla.resize(all_cap); if (pe) allb.resize(all_cap); }
@@ -701,6 +752,7 @@ struct Pipeline {
             break;
         }
         if (rc != 0) { fprintf(stderr, "GPU alignment failed (%d): %s\n", rc, bsl_last_error(c)); return false; }
+        t1 = now_ns(); ns_gpu += t1 - t0; t0 = t1;
         const bsl_hit *ha = S.hits[0] + nctx, *hb = pe ? S.hits[1] + nctx : nullptr; const bsl_pair *hp = pe ? S.pairs + nctx : nullptr;
         std::string &os = B.text; os.clear(); os.reserve((size_t)n * (pe ? 900 : 420));
         for (u32 i = 0; i < n; i++) {
@@ -741,17 +793,20 @@ struct Pipeline {
                 else if (O.P.report_repeat_hits == 2) { cn.bal++; for (int k = 0; k < mb; k++) { const bsl_hit &x = allb[b.all_first + k]; F.unpair(os, B.b[i], 1, x.read_chain, cb, mb, b.nm, x, ma1, a); } }   // pairs.cpp:293-297 (passes cb, not ca)
                 else if (O.unmap) F.unpair(os, B.b[i], 1, 0, ca, 0, 0, b, ma1, a); }
         }
+        ns_format += now_ns() - t0;
         return true;
     }
 
     void worker(int wid) {
-        bsl_ctx *c = ctx[wid % ctx.size()]; Counters cn; Batch B; Staging S;
+        bsl_ctx *c = ctx[wid % ctx.size()]; Counters cn; Batch B;
         while (!failed && load(B)) {
-            bool ok = process(B, S, c, cn);
+            bool ok = process(B, c, cn);
+            const long long tw = now_ns();
             const std::string *out = &B.text;
             if (ok && bam_native) { B.blk.clear(); if (!bam::text_to_blocks(B.text, refs, B.blk)) { fprintf(stderr, "\ninternal error: malformed SAM record in BAM conversion\n"); ok = false; } out = &B.blk; }
             if (!ok) { failed = 1; tail_cv.notify_all(); sink.skip(B.ticket); break; }
             if (!sink.submit(B.ticket, out->data(), out->size())) { fprintf(stderr, "\nwrite failed: %s\n", strerror(errno)); failed = 1; break; }
+            ns_out += now_ns() - tw;
             if (O.verbose >= 2) fprintf(stderr, "[BASAL @%s] batch %llu finished. %ld secs passed\n", now_str(), (unsigned long long)B.ticket + 1, secs_passed());
         }
         if (failed) { qa.finish(); qb.finish(); TextBlock d; while (qa.get(d)) {} while (qb.get(d)) {} }      // unblock the splitters
@@ -817,6 +872,15 @@ int main(int argc, char **argv) {
     // ---- GPUs: every visible device holds a replica of the index
     int ngpu = 1; { const char *e = getenv("BASAL_GPUS"); if (e) ngpu = std::max(1, atoi(e)); else { const char *v = getenv("BASAL_ALL_GPUS"); if (v && atoi(v)) ngpu = 64; } }
     Pipeline P(O, R, T);
+    // a short input is cut into more, smaller batches so that every worker gets some (the default suits long runs)
+    if (!getenv("BASAL_BATCH")) {
+        struct stat st; if (stat(O.a.c_str(), &st) == 0 && S_ISREG(st.st_mode)) {
+            const u64 est = (u64)st.st_size / 330 + 1;                           // ~reads in a plain 150-bp FASTQ file; only a heuristic
+            const u64 want = est / (4ull * std::max(O.procs, 3)) + 1;
+            P.batch_reads = (u32)std::min<u64>(P.batch_reads, std::max<u64>(want, 16384));
+        }
+    }
+    std::thread pool_thread;
     {
         std::vector<std::thread> th; std::vector<int> rcs; std::vector<bsl_ctx *> cs;
         for (int g = 0; g < ngpu; g++) {
@@ -825,6 +889,7 @@ int main(int argc, char **argv) {
             cs.push_back(c);
         }
         rcs.assign(cs.size(), 0);
+        pool_thread = std::thread([&P, &O, n = cs.size()]() { P.make_pool((size_t)std::max<int>(std::max(O.procs, 1), (int)n * 3) + 2); });   // pinned staging (one set per worker) while the GPUs build their index
         for (size_t g = 0; g < cs.size(); g++) th.emplace_back([&, g]() { rcs[g] = bsl_index_build(cs[g], R.cat.data(), R.off.data(), R.len.data(), (u32)R.len.size()); });
         for (auto &t : th) t.join();
         for (size_t g = 0; g < cs.size(); g++) if (rcs[g] != 0) { fprintf(stderr, "index build failed on GPU %zu (%d): %s\n", g, rcs[g], bsl_last_error(cs[g])); exit(1); }
@@ -858,10 +923,10 @@ int main(int argc, char **argv) {
     if (O.to_stdout) { P.sink.fd = 1; if (O.verbose >= 1) fprintf(stderr, "\tOutput: STDOUT\t (format: SAM)\n"); }
     else {
         if (O.verbose >= 1 || pe) fprintf(stderr, "\tOutput file: %s\t (format: SAM%s)\n", O.o.c_str(), O.out_sam == 2 ? ", automatically convert to BAM" : "");
-        const int fd = ::open(O.o.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        const int fd = ::open(O.o.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);
         if (fd < 0) { fprintf(stderr, "\nfailed to open output file (check -o option): %s\n", O.o.c_str()); exit(1); }
         if (O.out_sam == 2 && getenv("BASAL_SAMTOOLS")) { ::close(fd); std::string cmd = "samtools view -bS - >" + O.o; piped = popen(cmd.c_str(), "w"); if (piped) P.sink.fd = fileno(piped); }   // main.cpp:505
-        if (!piped) { P.sink.fd = piped ? P.sink.fd : (O.out_sam == 2 && getenv("BASAL_SAMTOOLS") ? ::open(O.o.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644) : fd);
+        if (!piped) { P.sink.fd = piped ? P.sink.fd : (O.out_sam == 2 && getenv("BASAL_SAMTOOLS") ? ::open(O.o.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644) : fd);
             struct stat st; P.sink.seekable = fstat(P.sink.fd, &st) == 0 && S_ISREG(st.st_mode); }
         if (O.out_sam == 2 && !piped) { P.bam_native = true; for (size_t i = 0; i < R.names.size(); i++) P.refs.add(R.names[i], R.len[i]); }
     }
@@ -884,14 +949,18 @@ int main(int argc, char **argv) {
         P.qa.finish(); P.qb.finish(); { TextBlock d; while (P.qa.get(d)) {} while (P.qb.get(d)) {} }
         ta.join(); if (pe) tb.join();
     }
+    pool_thread.join();
     if (P.bam_native) { std::string e; bam::bgzf_eof(e); P.sink.head(e); }
+    P.sink.finish();
     if (piped) pclose(piped); else if (P.sink.fd != 1) ::close(P.sink.fd);
     const double t_map1 = wall();
     for (bsl_ctx *c : P.ctx) bsl_ctx_destroy(c);
     if (P.failed) return 2;
     const double tot = (double)(P.next_index - (O.read_start - 1));
     if (getenv("BASAL_TIMING"))                                          // machine-readable phase clocks (bench.py: cli_e2e)
-        fprintf(stderr, "[timing] load_ref_s=%.4f index_s=%.4f map_s=%.4f total_s=%.4f reads=%.0f gpus=%zu threads=%d\n", t_ref - t_start, t_index - t_ref, t_map1 - t_map0, wall() - t_start, tot * (pe ? 2 : 1), P.ctx.size(), nw);
+        fprintf(stderr, "[timing] load_ref_s=%.4f index_s=%.4f map_s=%.4f total_s=%.4f reads=%.0f gpus=%zu threads=%d batch=%u parse_s=%.3f stage_wait_s=%.3f pack_s=%.3f gpu_s=%.3f format_s=%.3f out_s=%.3f\n",
+                t_ref - t_start, t_index - t_ref, t_map1 - t_map0, wall() - t_start, tot * (pe ? 2 : 1), P.ctx.size(), nw, P.batch_reads,
+                1e-9 * P.ns_parse, 1e-9 * P.ns_wait_stage, 1e-9 * P.ns_pack, 1e-9 * P.ns_gpu, 1e-9 * P.ns_format, 1e-9 * P.ns_out);
     if (O.verbose >= 1) {                                                                                // main.cpp:536-552, 606-612
         const Counters &c = P.total; const char *sup = O.P.report_repeat_hits == 0 ? "suppressed " : "";
         if (pe) {
