@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "ctx.hpp"
+#include "stdsort.cuh"
 
 namespace {
 
@@ -828,15 +829,69 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
 // whole CountMismatch / CountMismatch_new (align.h:118-131 / 199-239) over the 2-bit window, reference words and read
 // words straight from global memory (three independent loads per word, nothing staged). Passing candidates get their
 // bitmap bit and a mark record for reduce_fast.
-template <bool SINGLE>
+template <bool SINGLE, bool GAP = false>
 __device__ __forceinline__ void drain_exact(const KArgs &A, const uint4 sv, bool have, u64 strm) {
     if (!have) return;
-    const u32 y = sv.z, sig = IH_INV(y), slot = IH_SLOT(y), chain = IH_CHAIN(y), L = sv.w, g = sv.y;
+    const u32 y = sv.z, sig = IH_INV(y), slot = IH_SLOT(y), chain = IH_CHAIN(y), L = sv.w & 511u, g = sv.y;
+    const u32 hs = GAP ? min((sv.w >> 9) + A.s, L) : 0u;                           // GAP: sv.w = L | h << 9; prefix [0, h + s) of GapAlign's first test
     const u32 Wb = A.Wb, W = (L + 31u) >> 5;
     const u64 *S = A.planes + ((u64)slot * 2 + chain) * 3 * Wb;                    // streams: bases, 01 per ACGT base, convert-to mask
     const u64 *P = A.di.plane[sig] + (g >> 5);
     const u32 off = (g & 31u) * 2;
-    u32 snp = 0;
+    u32 snp = 0, pre = 0;
+    const u32 thr = IH_THR(y);
+    if (GAP && W <= 6u) {
+        // -g, reads up to 192 bases: the window (one word before it, two behind) and the read words stay in registers, so that
+        // gap_possible — a necessary condition of GapAlign finding anything, see reduce_round — is decided here and random
+        // candidates that merely pass GapAlign's first test never reach reduce_round
+        u64 win[9], q[6], cm[6];
+#pragma unroll
+        for (int k = 0; k < 9; k++) win[k] = (u32)k < W + 3u ? ldg_u64_stream(P - 1 + k, strm) : 0ULL;
+        const u32 lastb = L & 31u; const u64 endmask = lastb ? (~0ULL << (64 - 2 * lastb)) : ~0ULL;
+        // read word i against the window at shift sh (first base of the alignment = window base 32 + (g & 31) + sh)
+        auto ref_at = [&](int sh, int i) -> u64 {
+            const u32 pos = 32u + (g & 31u) + (u32)sh, w0 = pos >> 5, o = (pos & 31u) * 2;      // w0 in {0, 1, 2}
+            const u64 a = w0 == 0 ? win[i] : (w0 == 1 ? win[i + 1] : win[i + 2]), b = w0 == 0 ? win[i + 1] : (w0 == 1 ? win[i + 2] : (i + 3 < 9 ? win[i + 3] : 0ULL));
+            return o ? (a << o) | (b >> (64 - o)) : a;
+        };
+        u64 d0[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            q[i] = cm[i] = d0[i] = 0;
+            if ((u32)i < W) {
+                q[i] = swap32(ldg_u64_stream(S + i, strm)); const u64 n = swap32(ldg_u64_stream(S + Wb + i, strm));
+                if (!SINGLE) cm[i] = swap32(ldg_u64_stream(S + 2 * Wb + i, strm));
+                u64 d = bsl_pairs(bsl_diff<SINGLE>(q[i], cm[i], ref_at(0, i)));
+                snp += __popcll(d & n);
+                if ((u32)i == W - 1) d &= endmask;
+                d0[i] = d;
+                const u32 np = hs > 32u * i ? min(hs - 32u * i, 32u) : 0u;
+                if (np) pre += __popcll(d & (~0ULL << (64 - 2 * np)));
+            }
+        }
+        bool mark = snp <= thr;
+        if (!mark && thr >= 2 && pre < thr - 1) {                                  // GapAlign's first test passes (align.cpp:353-360): can it find a gap at all?
+            const u32 G = A.gap, M = L >> 1, start = G + M - 1;
+            u32 a = 0;
+#pragma unroll
+            for (int i = 0; i < 6; i++) if (32u * i < M && (u32)i < W) { const u32 n = min(M - 32u * i, 32u); a += __popcll(d0[i] & (~0ULL << (64 - 2 * n))); }
+            mark = a <= thr - 2;
+            for (u32 tt = 1; tt <= 2 * G && !mark; tt++) {
+                const u32 t = (tt + 1) >> 1; const int sh = (tt & 1) ? -(int)t : (int)t;
+                if (thr < 1 + t) break;
+                u32 b = 0;
+#pragma unroll
+                for (int i = 0; i < 6; i++) if ((u32)i >= (start >> 5) && (u32)i < W) {
+                    u64 d = bsl_pairs(bsl_diff<SINGLE>(q[i], cm[i], ref_at(sh, i))); if ((u32)i == W - 1) d &= endmask;
+                    const u32 n0 = start > 32u * i ? start - 32u * i : 0u;
+                    b += __popcll(n0 ? d & (~0ULL >> (2 * n0)) : d);
+                }
+                mark = b <= thr - 2;
+            }
+        }
+        if (mark) { atomicOr(&A.bitmap[sv.x >> 5], 1u << (sv.x & 31u)); atomicAdd(&A.slot_flag[slot], 1u); }
+        return;
+    }
     u64 prev = ldg_u64_stream(P, strm);
 #pragma unroll 3
     for (u32 i = 0; i < W; i++) {
@@ -844,13 +899,18 @@ __device__ __forceinline__ void drain_exact(const KArgs &A, const uint4 sv, bool
         const u64 r = off ? (prev << off) | (next >> (64 - off)) : prev;
         const u64 q = swap32(ldg_u64_stream(S + i, strm)), n = swap32(ldg_u64_stream(S + Wb + i, strm));
         u64 cm = 0; if (!SINGLE) cm = swap32(ldg_u64_stream(S + 2 * Wb + i, strm));
-        snp += __popcll(bsl_pairs(bsl_diff<SINGLE>(q, cm, r)) & n);
+        const u64 d = bsl_pairs(bsl_diff<SINGLE>(q, cm, r));
+        snp += __popcll(d & n);
+        if (GAP) {                                                                 // mismatches among the first h + s bases, without the N mask (MismatchPattern0, align.h:133-168)
+            const u32 np = hs > 32 * i ? min(hs - 32 * i, 32u) : 0u;
+            if (np) pre += __popcll(d & (~0ULL << (64 - 2 * np)));
+        }
         prev = next;
     }
-    if (snp <= IH_THR(y)) {
+    if (snp <= thr || (GAP && thr >= 2 && pre < thr - 1)) {                        // ungapped hit, or GapAlign's first test passes (align.cpp:353-360)
         atomicOr(&A.bitmap[sv.x >> 5], 1u << (sv.x & 31u));
         const u32 pos = atomicAdd(&A.slot_flag[slot], 1u);
-        if (pos < MK_CAP) A.marks[(size_t)slot * MK_CAP + pos] = make_uint4(sv.x, g, snp | (sig << 8) | (chain << 9), 0u);
+        if (!GAP && pos < MK_CAP) A.marks[(size_t)slot * MK_CAP + pos] = make_uint4(sv.x, g, snp | (sig << 8) | (chain << 9), 0u);
     }
 }
 // queue entry of a survivor
@@ -981,7 +1041,11 @@ __device__ __forceinline__ void ldg256_keep(const u32 *p, u32 (&r)[8], u64 pol) 
     r[0] = (u32)a; r[1] = (u32)(a >> 32); r[2] = (u32)b; r[3] = (u32)(b >> 32); r[4] = (u32)c; r[5] = (u32)(c >> 32); r[6] = (u32)d; r[7] = (u32)(d >> 32);
 }
 
-__global__ void __launch_bounds__(SB_WARPS * 32, 4) screen_bits(const __grid_constant__ KArgs A, u32 ci, u32 item_bytes, u32 rcp_wb) {
+// SINGLE: one substitution base (CountMismatch) or an empty substitution set like "T:-" (CountMismatch_new compares exactly).
+// GAP (-g > 0): a candidate also survives when the low-bit mismatches among its first h + s bases stay below thr - 1, a lower bound
+// of what GapAlign's first test counts (align.cpp:353-360); the exact count then decides both tests.
+template <bool SINGLE, bool GAP>
+__global__ void __launch_bounds__(SB_WARPS * 32, GAP ? 2 : 4) screen_bits(const __grid_constant__ KArgs A, u32 ci, u32 item_bytes, u32 rcp_wb) {
     extern __shared__ __align__(16) unsigned char sbm[];                       // per warp: 32 staged items x item_bytes
     __shared__ uint4 s_q[SB_WARPS][SC_QCAP];
     constexpr u32 FULL = 0xffffffffu;
@@ -1003,8 +1067,8 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 4) screen_bits(const __grid_con
     // ---- pipeline registers (every stage consumes what the same stage position issued one visit earlier)
     u32 fP = 0, lP = 0;                                                        // F -> P   chunk_first pair
     uint4 hB = make_uint4(FULL, 0, 0, 0); u32 clB = 0;                         // P -> B1  item header of this lane, loc entry of this lane's candidate
-    u32 g2 = 0, y2 = 0, m2 = 0, rec2 = FULL; uint2 ce2 = make_uint2(0u, 0u);   // B1 -> B2 / S   (m: L | staged offset << 9 | act << 23; y: ItemHdr::y with the strand in the inv bit)
-    u32 R[8], nfl = 0, cx = 0, gC = 0, yC = 0, mC = 0;                         // B2 -> C  (cx: dlt+8 | sft << 5 | nW << 10 | screened << 14 | (sec & 31) << 15)
+    u32 g2 = 0, y2 = 0, m2 = 0, rec2 = FULL, h2 = 0; uint2 ce2 = make_uint2(0u, 0u);   // B1 -> B2 / S   (m: L | staged offset << 9 | act << 23; y: ItemHdr::y with the strand in the inv bit)
+    u32 R[8], nfl = 0, cx = 0, gC = 0, yC = 0, mC = 0;                         // B2 -> C  (cx: dlt+8 | sft << 5 | nW << 10 | screened << 14 | (sec & 31) << 15 | h << 20)
 #pragma unroll
     for (int j = 0; j < 8; j++) R[j] = 0;
 
@@ -1026,7 +1090,7 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 4) screen_bits(const __grid_con
         const u32 it = __popc(mask & (FULL >> (31u - lane))) - 1u;               // my candidate's item = lane `it`
         const u32 ibase = __shfl_sync(FULL, hB.x, it), hy = __shfl_sync(FULL, hB.y, it), hz = __shfl_sync(FULL, hB.z, it), hw = __shfl_sync(FULL, hB.w, it);
         const u32 sig = ih_strand(gbeg + lane - ibase, hy, hz, hw);              // forward-strand entries come first (align.cpp:296)
-        g2 = clB - IH_H(hw);                                                     // _hit.loc (align.cpp:297)
+        g2 = clB - IH_H(hw); h2 = IH_H(hw);                                      // _hit.loc (align.cpp:297)
         y2 = (hy & ~(1u << 27)) | (sig << 27);
         m2 = IH_L(hz) | ((it * item_bytes + (sig ? 8u * Wb : 0u)) << 9) | ((act ? 1u : 0u) << 23);
         ce2 = make_uint2(0u, 0u);
@@ -1072,7 +1136,7 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 4) screen_bits(const __grid_con
             ldg256_keep(A.di.bit1 + (size_t)sec * 8, R, keep);
             if (sig) nfl = __ldg(A.di.nflag + (sec >> 5));
         }
-        cx = dlt8 | (sft << 5) | (nW << 10) | ((screen ? 1u : 0u) << 14) | ((sec & 31u) << 15);
+        cx = dlt8 | (sft << 5) | (nW << 10) | ((screen ? 1u : 0u) << 14) | ((sec & 31u) << 15) | (h2 << 20);
         gC = g2; yC = y2; mC = m2;
     };
     // C: XOR / mask / popcount against the staged streams; survivors join the queue
@@ -1086,23 +1150,35 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 4) screen_bits(const __grid_con
             else {
                 const uint2 *Sr = (const uint2 *)(S0 + ((mC >> 9) & 0x3FFFu));       // {low bits, ACGT mask} per 32 bases, forward or reversed
                 const u32 sft = (cx >> 5) & 31u, nW = (cx >> 10) & 15u, d8 = cx & 31u;
-                u32 low = 0;
+                u32 low = 0, lowp = 0;
+                // GAP: the first h + s bases of the read; in the reversed stream (reverse strand) they are the LAST h + s positions
+                const u32 L = mC & 511u, hs = GAP ? min((cx >> 20) + A.s, L) : 0u;
 #pragma unroll
                 for (int x = 0; x < 7; x++) {
                     const u32 i = (u32)x + d8 - 8u;
-                    if (i < nW) { const uint2 lm = Sr[i]; low += __popc((lm.x ^ __funnelshift_l(R[x + 1], R[x], sft)) & lm.y); }
+                    if (i < nW) {
+                        const uint2 lm = Sr[i]; const u32 dm = (lm.x ^ __funnelshift_l(R[x + 1], R[x], sft)) & lm.y;
+                        low += __popc(dm);
+                        if (GAP) {
+                            u32 pm;
+                            if (!sig) { const u32 np = hs > 32u * i ? min(hs - 32u * i, 32u) : 0u; pm = np ? (0xffffffffu << (32u - np)) : 0u; }
+                            else { const u32 z0 = L - hs, sk = z0 > 32u * i ? min(z0 - 32u * i, 32u) : 0u; pm = sk >= 32u ? 0u : (0xffffffffu >> sk); }
+                            lowp += __popc(dm & pm);
+                        }
+                    }
                 }
-                pass = low <= IH_THR(yC);
+                const u32 thr = IH_THR(yC);
+                pass = low <= thr || (GAP && thr >= 2 && lowp < thr - 1);
             }
         }
         const u32 bal = __ballot_sync(FULL, pass);
         if (bal) {
             if (pass) {
-                Q[qn + __popc(bal & ((1u << lane) - 1u))] = make_uint4((G << 5) + lane, gC, yC, mC & 511u);
+                Q[qn + __popc(bal & ((1u << lane) - 1u))] = make_uint4((G << 5) + lane, gC, yC, (mC & 511u) | (GAP ? (cx >> 20) << 9 : 0u));
             }
             qn += __popc(bal);
             __syncwarp();
-            if (qn >= 32u) { qn -= 32u; drain_exact<true>(A, Q[qn + lane], true, strm); }
+            if (qn >= 32u) { qn -= 32u; drain_exact<SINGLE, GAP>(A, Q[qn + lane], true, strm); }
         }
         __syncwarp();                                                            // every lane is done with the slice
     };
@@ -1121,7 +1197,7 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 4) screen_bits(const __grid_con
         stage_S(); stage_B2();
         if (Gb < n_groups) { stage_B1(Gb); if (Gc < n_groups) { stage_P(Gc); if (Gd < n_groups) stage_F(Gd); } }
     }
-    if (qn) drain_exact<true>(A, Q[min(lane, qn - 1u)], lane < qn, strm);
+    if (qn) drain_exact<SINGLE, GAP>(A, Q[min(lane, qn - 1u)], lane < qn, strm);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1198,52 +1274,89 @@ __device__ __forceinline__ u64 ref_word(const u64 *win, u32 NW, u32 rel, u32 i) 
     return x;
 }
 
-// GapAlign (align.cpp:348-410) over MismatchPattern0/1 (align.h:133-196, 241-327). Returns GAP_NONE or
-// level | (shift+4)<<8 | gap_pos<<16
+// GapAlign (align.cpp:348-410) over MismatchPattern0/1 (align.h:133-196, 241-327): the result is GAP_NONE or
+// level | (shift+4)<<8 | gap_pos<<16.
+// ---- GapAlign for ONE candidate by the whole warp (a thread-serial search costs the same issue slots with one lane active).
+// The two half-warps take two shifts at a time: lane k of a half holds the k-th mismatch position of its list
+// (MismatchPattern0 from the left at shift 0, MismatchPattern1 from the right at the half's shift), found by a prefix sum over the
+// per-word mismatch masks and __fns; the (i, j) search of align.cpp:370-405 becomes lane i counting the PR entries below what it
+// needs. The reference's answer, including which of several admissible gaps wins (lowest tt, then i, then j).
+__device__ __forceinline__ u32 compress_even(u64 x) {                      // bit k of the result = bit 2k of x
+    x &= 0x5555555555555555ULL;
+    x = (x | (x >> 1)) & 0x3333333333333333ULL; x = (x | (x >> 2)) & 0x0f0f0f0f0f0f0f0fULL; x = (x | (x >> 4)) & 0x00ff00ff00ff00ffULL;
+    x = (x | (x >> 8)) & 0x0000ffff0000ffffULL; x = (x | (x >> 16)) & 0x00000000ffffffffULL;
+    return (u32)x;
+}
+// mismatches of read word w against the window at offset relx, one bit per base, first base in the top bit; no N mask (align.h:133-196)
 template <bool SINGLE>
-__device__ u32 gap_search(const u64 *win, u32 NW, u32 rel, const u64 *q, const u64 *cm, u32 L, u32 W, u64 endmask,
-                          u32 thr, u32 h, u32 s, u32 G) {
-    if (thr < 2) return GAP_NONE;
-    u16 P0[16], PR[16];
-    const u32 want = thr - 1;
-    u32 n0 = 0, ret0 = L;
-    for (u32 i = 0; i < W && n0 < want; i++) {
-        u64 d = bsl_diff<SINGLE>(q[i], cm[i], ref_word(win, NW, rel, i)); if (i == W - 1) d &= endmask;
-        u64 x = bsl_pairs(d);
-        while (x && n0 < want) { u32 b = __clzll((long long)x) >> 1; u32 pos = 32 * i + b; P0[n0++] = (u16)pos; if (n0 == want) ret0 = pos; x &= ~(0x4000000000000000ULL >> (2 * b)); }
+__device__ __forceinline__ u32 mm_word(const u64 *win, u32 NW, u32 relx, const u64 *q, const u64 *cm, u32 w, u32 W, u64 endmask) {
+    if (w >= W) return 0u;
+    u64 d = bsl_pairs(bsl_diff<SINGLE>(q[w], cm[w], ref_word(win, NW, relx, w))); if (w == W - 1) d &= endmask;
+    return compress_even(d);
+}
+// half-warp: lane hl holds `bits` of slot hl (slots and the bits inside them in list order, lowest bit first); returns true and the
+// (slot, bit) of the k-th set bit, k = hl
+__device__ __forceinline__ bool kth_bit(u32 bits, u32 hl, u32 nslots, u32 &slot, u32 &bit) {
+    const u32 cnt = __popc(bits); u32 incl = cnt;
+    for (u32 o = 1; o < 16; o <<= 1) { const u32 v = __shfl_up_sync(0xffffffffu, incl, o, 16); if (hl >= o) incl += v; }
+    bool found = false; u32 excl = 0; slot = 0;
+    for (u32 w = 0; w < nslots; w++) {
+        const u32 iw = __shfl_sync(0xffffffffu, incl, w, 16), cw_ = __shfl_sync(0xffffffffu, cnt, w, 16);
+        if (!found && iw > hl) { found = true; slot = w; excl = iw - cw_; }
     }
-    for (u32 k = n0; k < want; k++) P0[k] = (u16)L;
+    const u32 sb = __shfl_sync(0xffffffffu, bits, slot, 16);
+    bit = found ? __fns(sb, 0u, (int)(hl - excl + 1u)) : 0u;
+    return found;
+}
+template <bool SINGLE>
+__device__ u32 gap_search_warp(const u64 *win, u32 NW, u32 rel, const u64 *q, const u64 *cm, u32 L, u32 W, u64 endmask,
+                               u32 thr, u32 h, u32 s, u32 G, u32 lane) {
+    if (thr < 2) return GAP_NONE;
+    const u32 want = thr - 1, hl = lane & 15u, half = lane >> 4;
+    // P0: the first `want` mismatch positions from the left at shift 0 (lane k: position k, or L)
+    u32 slot, bit;
+    const bool f0 = kth_bit(__brev(mm_word<SINGLE>(win, NW, rel, q, cm, hl, W, endmask)), hl, W, slot, bit);
+    const u32 P0k = (f0 && hl < want) ? 32u * slot + bit : L;
+    const u32 ret0 = __shfl_sync(0xffffffffu, P0k, want - 1u, 16);           // the last collected position, or L when fewer were found
     if (ret0 < h + s) return GAP_NONE;
-    for (u32 tt = 1; tt <= 2 * G; tt++) {
-        const u32 t = (tt + 1) >> 1; const int sh = (tt & 1) ? -(int)t : (int)t; const int sh1 = sh < 0 ? sh : 0;
-        if (thr < 1 + t) break;
-        u32 n1 = 0; const u32 rel1 = (u32)((int)rel + sh);
-        for (int i = (int)W - 1; i >= 0 && n1 < want; i--) {
-            u64 d = bsl_diff<SINGLE>(q[i], cm[i], ref_word(win, NW, rel1, (u32)i)); if (i == (int)W - 1) d &= endmask;
-            u64 x = bsl_pairs(d);
-            while (x && n1 < want) { u32 b = (u32)(__ffsll((long long)x) - 1) >> 1; u32 pos = 32 * (u32)i + 31 - b; PR[n1++] = (u16)(L - 1 - pos); x &= x - 1; }
-        }
-        for (u32 k = n1; k < want; k++) PR[k] = (u16)L;
-        const u32 rl = L - t - 1;
-        // first (i, j) in the reference's loop order with 6 <= P0[i] < rl, 6 <= PR[j] < rl, P0[i] + PR[j] - sh1 >= L.
-        // Both lists ascend, so for growing i the first admissible j only moves down: a two-pointer walk replaces the
-        // quadratic scan (the j the inner loop would stop at = first j with PR[j] >= max(6, L + sh1 - P0[i])).
-        u32 jj = 0; bool started = false;
-        for (u32 i = 0; i < thr - t; i++) {
-            u32 gp = P0[i];
-            if (gp < 6 || gp >= rl) continue;
-            const int nd = (int)L + sh1 - (int)gp; const u32 need = nd > 6 ? (u32)nd : 6u;
-            if (!started) { while (jj < want && PR[jj] < need) jj++; started = true; }
-            else while (jj > 0 && PR[jj - 1] >= need) jj--;
-            if (jj < thr - t - i && jj < want) {
-                const u32 m2 = PR[jj];
-                if (m2 < rl) {
-                    int clip = (int)gp + 6 - (int)L - sh1;
-                    if (clip > 0) gp -= (u32)clip;
-                    return (i + jj + t) | ((u32)(sh + 4) << 8) | (gp << 16);
-                }
+    // a gap sits at one of the first thr - t mismatch positions P0[i] with 6 <= P0[i] < L - t - 1 (align.cpp:372-376): none there, nothing to find
+    const u32 real = __ballot_sync(0xffffffffu, hl + 2u <= thr && P0k >= 6u && P0k + 2u < L) & 0xffffu;
+    if (!real) return GAP_NONE;
+    const u32 gpmax = __shfl_sync(0xffffffffu, P0k, 31u - (u32)__clz(real), 16);    // the largest of them (P0 ascends)
+    for (u32 tt0 = 1; tt0 <= 2 * G; tt0 += 2) {
+        const u32 tt = tt0 + half, t = (tt + 1) >> 1; const int sh = (tt & 1) ? -(int)t : (int)t, sh1 = sh < 0 ? sh : 0;
+        const bool active = tt <= 2 * G && thr >= 1 + t;                     // `if (thr < 1 + t) break;`
+        // PR: the first `want` mismatch positions from the right at this shift, counted from the read's last base
+        const u32 wr = W - 1u - hl;                                          // words right to left (hl < W)
+        const u32 c = (active && hl < W) ? mm_word<SINGLE>(win, NW, (u32)((int)rel + sh), q, cm, wr, W, endmask) : 0u;
+        // the right part must reach back to the gap: PR[j] >= L + min(sh, 0) - P0[i] for some j < thr - t - i, i.e. at most thr - t - 1 mismatches
+        // among the last L + min(sh, 0) - P0[i] bases; cheapest to satisfy with the largest P0[i]. Count them before building the list.
+        {
+            const int xs = (int)L + sh1 - (int)gpmax;                        // bases counted from the read's end
+            u32 cntx = 0;
+            if (xs > 0 && hl < W) {
+                const int lo_base = (int)L - xs, wb = 32 * (int)wr;          // bases >= lo_base of word wr
+                const int skip = lo_base - wb;                               // leading bases of the word to ignore
+                cntx = skip <= 0 ? __popc(c) : (skip >= 32 ? 0u : __popc(c & (0xffffffffu >> skip)));
             }
+            for (u32 o = 8; o; o >>= 1) cntx += __shfl_xor_sync(0xffffffffu, cntx, o, 16);
+            const bool hopeless = !active || cntx + t + 1u > thr;            // needs j <= thr - t - 1 - i mismatches skipped, so count <= thr - t - 1
+            const u32 hb = __ballot_sync(0xffffffffu, hopeless);
+            if ((hb & 0xffffu) && (hb >> 16)) continue;                      // both shifts of this trip
         }
+        const bool f1 = kth_bit(c, hl, W, slot, bit);                        // lowest bit of a word = its last base
+        const u32 PRk = (f1 && hl < want) ? L - 1u - (32u * (W - 1u - slot) + 31u - bit) : L;
+        const u32 rl = L - t - 1u, i = hl, gp = P0k;
+        const bool vg = active && i < thr - t && gp >= 6u && gp < rl;
+        const int nd = (int)L + sh1 - (int)gp; const u32 need = nd > 6 ? (u32)nd : 6u;
+        u32 jj = 0;
+        for (u32 j = 0; j < want; j++) jj += __shfl_sync(0xffffffffu, PRk, j, 16) < need ? 1u : 0u;      // PR ascends: the first admissible j
+        const u32 pj = __shfl_sync(0xffffffffu, PRk, min(jj, 15u), 16);
+        const bool ok = vg && jj < thr - t - i && jj < want && pj < rl;
+        u32 g2 = gp; { const int clip = (int)gp + 6 - (int)L - sh1; if (clip > 0) g2 -= (u32)clip; }
+        const u32 res = (i + jj + t) | ((u32)(sh + 4) << 8) | (g2 << 16);
+        const u32 bal = __ballot_sync(0xffffffffu, ok);
+        if (bal) { const u32 src = (bal & 0xffffu) ? (u32)__ffs(bal & 0xffffu) - 1u : 16u + (u32)__ffs(bal >> 16) - 1u; return __shfl_sync(0xffffffffu, res, src); }
     }
     return GAP_NONE;
 }
@@ -1327,7 +1440,7 @@ __device__ int add_hit(const KArgs &A, WarpCtx &S, u32 lane, u32 level, u32 g, u
 #define RR_LONG_MARKS 48u
 #define RR_LONG_HITS 64u
 template <bool SINGLE>
-__global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_constant__ KArgs A, u32 round, u32 ci, u32 NW, u32 NWS, const u32 *list, u32 list_ci, u32 as_pe, u32 long_pass) {
+__global__ void __launch_bounds__(ROUND_WARPS * 32, 3) reduce_round(const __grid_constant__ KArgs A, u32 round, u32 ci, u32 NW, u32 NWS, const u32 *list, u32 list_ci, u32 as_pe, u32 long_pass) {
     extern __shared__ u64 smem[];
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     u64 *win_all = smem + (size_t)wid * (32 * NWS + 48 + RR_KEYS);
@@ -1411,18 +1524,18 @@ __global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_co
                     const u64 *P = A.di.plane[sig] + word0;
                     for (u32 w = 0; w < NW; w++) win[w] = __ldg(P + w);
                 }
-                u32 snp = 0xffffu, gres = GAP_NONE; bool gscr = false;
+                u32 snp = 0xffffu; bool gscr = false;
                 if (valid) {
                     snp = 0;
                     for (u32 i = 0; i < W; i++) {                              // CountMismatch / CountMismatch_new
                         const u64 d = bsl_diff<SINGLE>(pq[i], pc[i], ref_word(win, NW, rel, i));
                         snp += __popcll(bsl_pairs(d) & pn[i]);
                     }
-                    if (G) { gscr = gap_possible<SINGLE>(win, NW, rel, pq, pc, L, W, endmask, S.thr, G); if (gscr) gres = gap_search<SINGLE>(win, NW, rel, pq, pc, L, W, endmask, S.thr, ch, A.s, G); }
+                    if (G) gscr = gap_possible<SINGLE>(win, NW, rel, pq, pc, L, W, endmask, S.thr, G);        // necessary for GapAlign to find anything
                 }
                 // ---- in-order reduction (AddHit semantics need the discovery order)
                 const u32 thr0 = S.thr;
-                const bool cand = valid && (snp <= thr0 || gres != GAP_NONE);
+                const bool cand = valid && (snp <= thr0 || gscr);
                 const u32 myseq = cand ? seq_of(A, g) : 0u;                       // every lane finds the sequence of its own candidate
                 u32 pending = __ballot_sync(0xffffffffu, cand);
                 while (pending) {
@@ -1431,9 +1544,9 @@ __global__ void __launch_bounds__(ROUND_WARPS * 32) reduce_round(const __grid_co
                     const u32 cseq = __shfl_sync(0xffffffffu, myseq, l);
                     bool ab = false;
                     if (csnp <= S.thr) ab = add_hit(A, S, lane, csnp, cg, cseq, csig, 0, 0);
-                    if (G && !ab) {
-                        if (S.thr != thr0 && lane == l && gscr) gres = gap_search<SINGLE>(win, NW, rel, pq, pc, L, W, endmask, S.thr, ch, A.s, G);
-                        const u32 cres = __shfl_sync(0xffffffffu, gres, l);
+                    if (G && !ab && __shfl_sync(0xffffffffu, (u32)gscr, l)) {       // GapAlign with the threshold as AddHit has left it (align.cpp:311-312)
+                        const u32 cres = gap_search_warp<SINGLE>(win_all + l * NWS, NW, __shfl_sync(0xffffffffu, rel, l), pq, pc, L, W, endmask, S.thr,
+                                                                 __shfl_sync(0xffffffffu, ch, l), A.s, G, lane);
                         if (cres != GAP_NONE) ab = add_hit(A, S, lane, cres & 255u, cg, cseq, csig, (int)((cres >> 8) & 255u) - 4, cres >> 16);
                     }
                     if (ab) {                    // SnpAlign returns here: later phases / the other chain are never looked up
@@ -1639,18 +1752,36 @@ __device__ u32 pw_compact(const DevHit *h, u32 n, u32 chain, u32 level, u16 *idx
     return c;
 }
 
+// SortHits4PE's std::sort over one (chain, level) list. Up to 16 elements libstdc++ runs a plain insertion sort (stable), and a
+// list without equal (chr, loc) keys has only one sorted order: both are the stable rank sort below. A longer list that holds
+// equal keys (a gapped and an ungapped hit at the same place) comes out of introsort in an order of its own, which stdsort()
+// reproduces step by step (SURVEY trap 10).
 __device__ void pw_sort_level(DevHit *h, u32 n, u32 chain, u32 level, PairWideSmem &sm, u32 lane) {
     const u32 c = pw_compact(h, n, chain, level, sm.ia, lane);
     if (c <= 1) return;
     for (u32 x = lane; x < c; x += 32) sm.stage[x] = h[sm.ia[x]];
     __syncwarp();
-    for (u32 x = lane; x < c; x += 32) {
-        const DevHit me = sm.stage[x]; const u64 kx = ((u64)HIT_CHR2(me.tag) << 32) | me.loc;
-        u32 rank = 0;
-        for (u32 f = 0; f < c; f++) { const u64 kf = ((u64)HIT_CHR2(sm.stage[f].tag) << 32) | sm.stage[f].loc; rank += (kf < kx || (kf == kx && f < x)) ? 1u : 0u; }
-        h[sm.ia[rank]] = me;
+    bool twins = false;
+    for (u32 x0 = 0; x0 < c; x0 += 32) {
+        const u32 x = x0 + lane; u32 rank = 0; DevHit me; me.loc = 0; me.tag = 0; me.gap = 0; me.gp = 0; bool eq = false;
+        if (x < c) {
+            me = sm.stage[x]; const u64 kx = ((u64)HIT_CHR2(me.tag) << 32) | me.loc;
+            for (u32 f = 0; f < c; f++) { const u64 kf = ((u64)HIT_CHR2(sm.stage[f].tag) << 32) | sm.stage[f].loc; rank += (kf < kx || (kf == kx && f < x)) ? 1u : 0u; eq |= kf == kx && f != x; }
+        }
+        twins |= __any_sync(0xffffffffu, eq);
+        if (x < c && (c <= 16 || !twins)) h[sm.ia[rank]] = me;              // provisional when a later tile finds twins: rewritten below
     }
     __syncwarp();
+    if (c > 16 && twins) {
+        u16 *p = sm.ib;
+        if (lane == 0) {
+            for (u32 x = 0; x < c; x++) p[x] = (u16)x;
+            stdsort(p, (int)c, [&](u16 a, u16 b) { const DevHit &A_ = sm.stage[a], &B_ = sm.stage[b]; const u32 ca = HIT_CHR2(A_.tag), cb = HIT_CHR2(B_.tag); return ca < cb || (ca == cb && A_.loc < B_.loc); });
+        }
+        __syncwarp();
+        for (u32 x = lane; x < c; x += 32) h[sm.ia[x]] = sm.stage[p[x]];
+        __syncwarp();
+    }
 }
 
 __device__ __forceinline__ bool pw_valid(const KArgs &A, u32 chain, u32 chra, u32 aloc, u32 bloc, u32 La, u32 Lb, u32 &ins) {
@@ -2017,7 +2148,10 @@ static int configure_kernels(bsl_ctx *ctx) {
     if (ctx->kernels_configured) return 0;
     CUDA_TRY(cudaFuncSetAttribute(prepare_reads, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(prepare_deferred, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(screen_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(screen_bits<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(screen_bits<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(screen_bits<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(screen_bits<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(pair_round_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairWideSmem)));
     CUDA_TRY(cudaFuncSetAttribute(reduce_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(reduce_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -2203,10 +2337,19 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     const u32 item_bytes = 16 * Wb + ((Wb & 1u) ? 0u : 16u);              // staged item: {low bits, ACGT mask} x Wb forward, x Wb reversed; stride = 4 x odd words spreads the items over the banks
     const u32 rcp_wb = (u32)((0x100000000ull + Wb - 1) / Wb);
     const size_t smem_b = (size_t)SB_WARPS * 32 * item_bytes;
-    if (!ctx->occ_bits || ctx->occ_bits_wb != Wb) { int occ = 0; cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, screen_bits, SB_WARPS * 32, smem_b); ctx->occ_bits = (oe == cudaSuccess && occ > 0) ? occ : 1; ctx->occ_bits_wb = Wb; }
+    if (!ctx->occ_bits || ctx->occ_bits_wb != Wb) {
+        int occ = 0; cudaError_t oe;
+        if (G) oe = ctx->rule.single ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, screen_bits<true, true>, SB_WARPS * 32, smem_b) : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, screen_bits<false, true>, SB_WARPS * 32, smem_b);
+        else oe = ctx->rule.single ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, screen_bits<true, false>, SB_WARPS * 32, smem_b) : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, screen_bits<false, false>, SB_WARPS * 32, smem_b);
+        ctx->occ_bits = (oe == cudaSuccess && occ > 0) ? occ : 1; ctx->occ_bits_wb = Wb;
+    }
     const int grid_b = sms * ctx->occ_bits;
     auto launch_verify = [&](KArgs &K, u32 ci) {
-        if (!G && use_bits) { screen_bits<<<grid_b, SB_WARPS * 32, smem_b, st>>>(K, ci, item_bytes, rcp_wb); return; }
+        if (use_bits) {                                      // single-conversion and '-'-only rules, with or without -g
+            if (ctx->rule.single) { if (G) screen_bits<true, true><<<grid_b, SB_WARPS * 32, smem_b, st>>>(K, ci, item_bytes, rcp_wb); else screen_bits<true, false><<<grid_b, SB_WARPS * 32, smem_b, st>>>(K, ci, item_bytes, rcp_wb); }
+            else { if (G) screen_bits<false, true><<<grid_b, SB_WARPS * 32, smem_b, st>>>(K, ci, item_bytes, rcp_wb); else screen_bits<false, false><<<grid_b, SB_WARPS * 32, smem_b, st>>>(K, ci, item_bytes, rcp_wb); }
+            return;
+        }
         if (!G) {
             if (ctx->rule.single) screen_candidates<true><<<grid_s, SC_WARPS * 32, smem_s, st>>>(K, ci, stage_items, rcp_dw);
             else screen_candidates<false><<<grid_s, SC_WARPS * 32, smem_s, st>>>(K, ci, stage_items, rcp_dw);

@@ -535,10 +535,10 @@ struct BlockQueue {
 struct OutSink {
     int fd = -1; bool seekable = false;
     std::mutex mu; std::condition_variable cv; u64 next_ticket = 0; u64 offset = 0;
-    // A regular file grows in 1 GB windows that are mapped once (MAP_SHARED) and never moved: a ticket reserves its byte range in
+    // A regular file grows in 256 MB windows that are mapped once (MAP_SHARED) and never moved: a ticket reserves its byte range in
     // input order, then the worker copies its bytes into the mapping — in parallel with the other workers (write(2) / pwrite(2)
     // on one file serialise on the inode lock). A file system that cannot map falls back to pwrite.
-    static constexpr u64 kWin = 1ull << 30;
+    static constexpr u64 kWin = 256ull << 20;
     std::vector<char *> wins; bool can_map = true;
     static bool write_all(int fd, const char *p, size_t n) { while (n) { ssize_t k = ::write(fd, p, n); if (k < 0) { if (errno == EINTR) continue; return false; } p += k; n -= (size_t)k; } return true; }
     static bool pwrite_all(int fd, const char *p, size_t n, u64 off) { while (n) { ssize_t k = ::pwrite(fd, p, n, (off_t)off); if (k < 0) { if (errno == EINTR) continue; return false; } p += k; n -= (size_t)k; off += (u64)k; } return true; }
@@ -549,6 +549,9 @@ struct OutSink {
             void *m = mmap(nullptr, kWin, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)at);
             if (m == MAP_FAILED) { can_map = false; break; }
             wins.push_back((char *)m);
+#ifdef MADV_POPULATE_WRITE
+            if (wins.size() > 1) std::thread([m]() { madvise(m, kWin, MADV_POPULATE_WRITE); }).detach();   // a long output: fault the window in ahead of the workers' copies
+#endif
         }
         return can_map;
     }

@@ -297,7 +297,10 @@ int bsl_index_build_impl(bsl_ctx *ctx, const u8 *cat, const u64 *off, const u32 
         const u8 *cd = ctx->rule.code, *rd = ctx->rule.rcode;
         const u32 f = (cd['A'] ^ rd['A']) & 1u;
         const bool uniform = ((cd['C'] ^ rd['C']) & 1u) == f && ((cd['G'] ^ rd['G']) & 1u) == f && ((cd['T'] ^ rd['T']) & 1u) == f;
-        di.flip = f; di.has_bit1 = (ctx->rule.single && uniform) ? 1u : 0u;
+        // also rules whose substitution set is empty ("T:-"): CountMismatch_new (align.h:199-239) then compares every read base exactly,
+        // so differing low bits are a mismatch there as well
+        const bool dash_only = strcmp(ctx->P.to_bases, "-") == 0;
+        di.flip = f; di.has_bit1 = ((ctx->rule.single || dash_only) && uniform) ? 1u : 0u;
     }
     di.plane[0] = d_fwd; di.plane[1] = d_rc; di.bucket = d_bucket; di.cnt8 = d_cnt8; di.loc = d_loc;
     di.anchor = d_anchor; di.seqlen = d_len; di.rcoff = d_rcoff; di.nseq = n; di.K = K; di.maxk = maxk; di.n_words = n_words; di.n_entries = ne;

@@ -455,7 +455,7 @@ def gpu_arm(args):
     line["config"]["host_cores_per_rank"] = cores
     ctx.close()
     # ---- 8 GPUs: BASELINE configs[4] (-M C:T PE 2x150 bp, 3.1 Gb human-scale reference, sharded over the box) rides along in the same line
-    if world >= 8 and CONFIG_ID == 2 and SCALE >= 1.0 and os.environ.get("BENCH_NO_C5", "0") != "1":
+    if (world >= 8 or os.environ.get("BENCH_C5", "0") == "1") and CONFIG_ID == 2 and SCALE >= 1.0 and os.environ.get("BENCH_NO_C5", "0") != "1":
         try:
             del chrs
             cfg5 = synth.baseline_config(5, SCALE)

@@ -50,6 +50,8 @@ CASES = [
     (4, ["-S", "7"]),
     (4, ["-S", "7", "-n", "1", "-R", "-u"]),
     (5, ["-S", "7", "-u"]),
+    (1, ["-S", "7", "-z", "64", "-q", "3", "-u"]),          # -z: quality base other than '!' (qualities are rewritten, align.cpp:56-60)
+    (4, ["-S", "7", "-g", "0", "-u"]),
 ]
 
 

@@ -65,6 +65,8 @@ SE_CASES = [
     (1, 0.01, {"g": 2, "n": 1}),            # gapped single conversion, all four strands
     (3, 0.002, {"w": 3}),                   # -w feedback
     (4, 0.002, {"n": 2, "w": 2}),
+    (4, 0.002, {"g": 0, "n": 1}),           # '-'-only rule without gaps: one-bit screen + CountMismatch_new exact count
+    (1, 0.01, {"g": 3, "w": 3}),            # single conversion with gaps: one-bit screen with the prefix bound of GapAlign's first test
 ]
 
 
