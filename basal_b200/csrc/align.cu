@@ -331,7 +331,31 @@ __global__ void __launch_bounds__(PR_WARPS * 32, 6) prepare_reads(const __grid_c
                     flag = xm != nfull ? 0x80000000u : 0u;
                     return bsl_xt(xq);
                 };
-                for (u32 j = 0; j < nseg; j++) {
+                if (wd <= 8) {
+                    // the usual case (I + ii <= 8): one batch of eight gathers per segment; the batch of segment j+1 is issued before
+                    // the sizes of segment j are consumed, so its latency hides behind CountSeeds
+                    u32 ca[8], fa = 0;
+                    auto issue = [&](u32 j, u32 (&c8)[8], u32 &flb) {
+                        flb = 0;
+#pragma unroll
+                        for (u32 u = 0; u < 8; u++) { u32 fl; const u32 k = seed_at(j * s + min(u, wd - 1), fl); c8[u] = ldg_u8_hint(A.di.cnt8 + k, keep); flb |= (fl >> 31) << u; }
+                    };
+                    issue(0, ca, fa);
+                    for (u32 j = 0; j < nseg; j++) {
+                        u32 cb[8], fb = 0;
+                        if (j + 1 < nseg) issue(j + 1, cb, fb);
+#pragma unroll
+                        for (u32 u = 0; u < 8; u++) if (u < wd) cw[u] = ca[u] | (((fa >> u) & 1u) << 31);
+                        for (u32 d = 0; d < wd; d++) if ((cw[d] & 0xFFu) == 0xFFu) {      // saturated: the exact size from the bucket table (rare)
+                            u32 fl; const u32 k = seed_at(j * s + d, fl);
+                            cw[d] = ((__ldg(A.di.bucket + 2 * k + 2) - __ldg(A.di.bucket + 2 * k)) & 0x7fffffffu) | fl;
+                        }
+                        count_seeds_row(cw, s_prof[j], j, s, I, vmax, cs + j * ncol);
+#pragma unroll
+                        for (u32 u = 0; u < 8; u++) ca[u] = cb[u];
+                        fa = fb;
+                    }
+                } else for (u32 j = 0; j < nseg; j++) {
                     for (u32 d0 = 0; d0 < wd; d0 += 8) {
                         u32 c8[8], flb = 0;
 #pragma unroll
@@ -2165,8 +2189,16 @@ static int configure_kernels(bsl_ctx *ctx) {
 
 // One sub-range [first, first+n_a) of the caller's batch on one lane. Sub-ranges keep the number of items a search
 // round can produce below MAX_ITEMS_PER_ROUND and bound the device memory of a call.
+struct LenScan { u32 Lmax = 0; u32 dims[2] = {0, 1}; bool empty_range = false; };       // one pass over the read lengths of a (sub-)range
+static LenScan scan_lengths(const bsl_batch *a, const bsl_batch *b, u32 first, u32 n, const bsl_params &P) {
+    LenScan r; r.dims[0] = P.index_interval;
+    r.Lmax = max_len_of(a, first, n, &P, r.dims, &r.empty_range);
+    if (b) r.Lmax = std::max(r.Lmax, max_len_of(b, first, n, &P, r.dims, &r.empty_range));
+    return r;
+}
+
 static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_batch *b, u32 first, u32 n_a, bsl_hit *out_a, bsl_hit *out_b, bsl_pair *out_pair,
-                       bsl_hit *all_a, bsl_hit *all_b, u64 all_cap, u64 all_off, u64 *all_made, int resident, bsl_stats *acc, bool carry) {
+                       bsl_hit *all_a, bsl_hit *all_b, u64 all_cap, u64 all_off, u64 *all_made, int resident, bsl_stats *acc, bool carry, const LenScan *scan = nullptr) {
     int rc = 0;
     const bool pe = b != nullptr; const u32 n_slots = pe ? 2 * n_a : n_a;
     cudaStream_t st = ln.stream;
@@ -2174,8 +2206,9 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
 
     const u64 off0_a = a->offsets[first], off0_b = pe ? b->offsets[first] : 0;
     const u64 bases_a = a->offsets[first + n_a] - off0_a, bases_b = pe ? b->offsets[first + n_a] - off0_b : 0;
-    u32 pdims[2] = {P.index_interval, 1};
-    u32 Lmax = max_len_of(a, first, n_a, &P, pdims); if (pe) Lmax = std::max(Lmax, max_len_of(b, first, n_a, &P, pdims));
+    const LenScan ls = scan ? *scan : scan_lengths(a, b, first, n_a, P);
+    const u32 pdims[2] = {ls.dims[0], ls.dims[1]};
+    u32 Lmax = ls.Lmax;
     if (carry) {            // st0 per (slot, chain), the deferred list, and 16 inherited seed hashes per (slot, chain)
         size_t c1 = ln.cap_st0; if ((rc = grow(ctx, &ln.d_st0, &c1, (size_t)n_slots * 2 + 16))) return rc; ln.cap_st0 = c1;
         c1 = ln.cap_defer; if ((rc = grow(ctx, &ln.d_defer, &c1, (size_t)n_slots + 16))) return rc; ln.cap_defer = c1;
@@ -2500,14 +2533,14 @@ int bsl_align_impl(bsl_ctx *ctx, const bsl_batch *a, const bsl_batch *b, bsl_hit
     if (resident && n > sub) { set_error(ctx, "bsl_align_rerun: the batch was split into sub-ranges and is not resident"); return BSL_ESTATE; }
     bsl_stats acc; memset(&acc, 0, sizeof acc);
     u64 all_off = 0;
-    bool carry = false;                                             // any read with an empty start-offset range in this call?
-    max_len_of(a, 0, n, &P, nullptr, &carry); if (pe) max_len_of(b, 0, n, &P, nullptr, &carry);
+    const LenScan whole = scan_lengths(a, b, 0, n, P);                // one pass over the lengths; reused when the call is one sub-range
+    const bool carry = whole.empty_range;                           // any read with an empty start-offset range in this call?
     for (u32 first = 0; first < n; first += sub) {
         const u32 cnt = std::min(sub, n - first);
         u64 made = 0;
         std::vector<u32> cidx;
         if (carry && first > 0) carry_context(P, a, b, first, cidx);
-        if (cidx.empty()) rc = align_range(ctx, ln, a, b, first, cnt, out_a, out_b, out_pair, all_a, all_b, all_cap, all_off, &made, resident, &acc, carry);
+        if (cidx.empty()) rc = align_range(ctx, ln, a, b, first, cnt, out_a, out_b, out_pair, all_a, all_b, all_cap, all_off, &made, resident, &acc, carry, n <= sub ? &whole : nullptr);
         else {
             // a later sub-range in carry mode: the reads that define its inherited state go in front of it as context
             if (resident) { set_error(ctx, "bsl_align_rerun: the batch was split into sub-ranges and is not resident"); return BSL_ESTATE; }

@@ -403,8 +403,11 @@ def measure(capi, cfg, args, dist, rank, world, local, step_pairs, e2e_reps=3):
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp) and cfg.cid == 2:
         try:
+            import hashlib
             tj = json.load(open(tp))
-            traffic = tj.get("dram_bytes_per_launch")
+            src = hashlib.sha256(open(os.path.join(ROOT, "basal_b200", "csrc", "align.cu"), "rb").read()).hexdigest()
+            # only a capture of the kernels as they are now counts (tools/ncu_traffic.py records the source hash)
+            traffic = tj.get("dram_bytes_per_launch") if tj.get("kernel_source_sha256") == src else None
         except Exception:
             traffic = None
     out = {

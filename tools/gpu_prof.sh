@@ -2,7 +2,7 @@
 # ncu --set full captures of chosen kernels of one bench step (config 2).
 # usage: bash tools/gpu_prof.sh <tag> "<kernel-regex>:<skip>:<count> ..."   [bench first: set BENCH_FIRST=1]
 TAG=${1:-x}; shift
-SPECS=${1:-"screen_bits:9:2 reduce_round:9:1 prepare_reads2:1:1"}
+SPECS=${1:-"screen_bits:0:2 reduce_round:0:2 prepare_reads:1:1"}
 mkdir -p gpurun_out
 export BENCH_SKIP_CPU=1
 if [ -n "$BENCH_FIRST" ]; then
