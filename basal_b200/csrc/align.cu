@@ -161,6 +161,22 @@ __device__ __forceinline__ void load32(const u8 *p, u32 (&w)[8]) {
 // CountSeeds(j, v) (align.cpp:526-540) for every start v <= vmax, from the bucket sizes (bit 31 = the seed holds a non-ACGT
 // base) of the read offsets j*s + d held in cwj[d]
 __device__ __forceinline__ void count_seeds_row(const u32 *cwj, const u16 *profj, u32 j, u32 s, u32 I, u32 vmax, u32 *csj) {
+    if (I <= 4) {                                                      // the usual interval: the four offsets stay in registers
+        u32 d[4];
+#pragma unroll
+        for (u32 i = 0; i < 4; i++) d[i] = i < I ? profj[i] - i - j * s : 0u;
+        for (u32 v = 0; v <= vmax; v++) {
+            u32 total = 0, k = 0;
+#pragma unroll
+            for (u32 i = 0; i < 4; i++) if (i < I) {
+                const u32 e = cwj[d[i] + v];
+                if (e >> 31) k = 12;
+                total += (e & 0x7fffffffu) << k;
+            }
+            csj[v] = total == 0 ? 9999999u : total;
+        }
+        return;
+    }
     for (u32 v = 0; v <= vmax; v++) {
         u32 total = 0, k = 0;
         for (u32 i = 0; i < I; i++) {
@@ -335,20 +351,36 @@ __global__ void __launch_bounds__(PR_WARPS * 32, 6) prepare_reads(const __grid_c
                     // the usual case (I + ii <= 8): one batch of eight gathers per segment; the batch of segment j+1 is issued before
                     // the sizes of segment j are consumed, so its latency hides behind CountSeeds
                     u32 ca[8], fa = 0;
+                    // the s + 7 bases the eight seeds of a segment cover are read once; the hash of offset u + 1 follows from the one
+                    // of offset u (drop the leading base-3 digit, append one)
+                    u32 pw3 = 1; for (u32 x = 1; x < s; x++) pw3 *= 3u;
                     auto issue = [&](u32 j, u32 (&c8)[8], u32 &flb) {
+                        const u32 p0 = j * s, w = p0 >> 4, o = (p0 & 15u) * 2, wm = p0 >> 5, om = p0 & 31u;
+                        const u32 q0 = sq[w], q1 = sq[w + 1], q2 = sq[w + 2];
+                        u32 f0 = __funnelshift_l(q1, q0, o), f1 = __funnelshift_l(q2, q1, o);        // bases p0 .. p0+15, p0+16 .. p0+31
+                        f0 -= (f0 << 1) & f0 & 0xAAAAAAAAu; f1 -= (f1 << 1) & f1 & 0xAAAAAAAAu;      // digits: 11 -> 01 (the first step of XT)
+                        const u32 fin = s >= 16 ? f1 : __funnelshift_l(f1, f0, 2 * s);             // digits p0+s .. : what the window takes in
+                        const u32 zm = ~__funnelshift_l(smk[wm + 1], smk[wm], om);                 // a set bit = a non-ACGT base, from p0
+                        u32 h = bsl_xt(f0 >> shs);
                         flb = 0;
 #pragma unroll
-                        for (u32 u = 0; u < 8; u++) { u32 fl; const u32 k = seed_at(j * s + min(u, wd - 1), fl); c8[u] = ldg_u8_hint(A.di.cnt8 + k, keep); flb |= (fl >> 31) << u; }
+                        for (u32 u = 0; u < 8; u++) {
+                            if (u) h = (h - ((f0 >> (32 - 2 * u)) & 3u) * pw3) * 3u + ((fin >> (32 - 2 * u)) & 3u);
+                            c8[u] = 0;
+                            if (u < wd) c8[u] = ldg_u8_hint(A.di.cnt8 + h, keep);
+                            flb |= (((zm << u) >> (32 - s)) != 0u ? 1u : 0u) << u;
+                        }
                     };
                     issue(0, ca, fa);
                     for (u32 j = 0; j < nseg; j++) {
                         u32 cb[8], fb = 0;
                         if (j + 1 < nseg) issue(j + 1, cb, fb);
+                        bool sat = false;
 #pragma unroll
-                        for (u32 u = 0; u < 8; u++) if (u < wd) cw[u] = ca[u] | (((fa >> u) & 1u) << 31);
-                        for (u32 d = 0; d < wd; d++) if ((cw[d] & 0xFFu) == 0xFFu) {      // saturated: the exact size from the bucket table (rare)
+                        for (u32 u = 0; u < 8; u++) if (u < wd) { cw[u] = ca[u] | (((fa >> u) & 1u) << 31); sat |= ca[u] == 0xFFu; }
+                        if (sat) for (u32 d = 0; d < wd; d++) if ((cw[d] & 0xFFu) == 0xFFu) {      // saturated: the exact size from the bucket table
                             u32 fl; const u32 k = seed_at(j * s + d, fl);
-                            cw[d] = ((__ldg(A.di.bucket + 2 * k + 2) - __ldg(A.di.bucket + 2 * k)) & 0x7fffffffu) | fl;
+                            cw[d] = (__ldg(A.di.loc + A.di.rec_base + 8 * (size_t)k) & 0x7fffffffu) | fl;
                         }
                         count_seeds_row(cw, s_prof[j], j, s, I, vmax, cs + j * ncol);
 #pragma unroll
@@ -368,13 +400,14 @@ __global__ void __launch_bounds__(PR_WARPS * 32, 6) prepare_reads(const __grid_c
                     }
                     for (u32 d = 0; d < wd; d++) if ((cw[d] & 0xFFu) == 0xFFu) {      // saturated: the exact size from the bucket table (rare)
                         u32 fl; const u32 k = seed_at(j * s + d, fl);
-                        cw[d] = ((__ldg(A.di.bucket + 2 * k + 2) - __ldg(A.di.bucket + 2 * k)) & 0x7fffffffu) | fl;
+                        cw[d] = (__ldg(A.di.loc + A.di.rec_base + 8 * (size_t)k) & 0x7fffffffu) | fl;
                     }
                     count_seeds_row(cw, s_prof[j], j, s, I, vmax, cs + j * ncol);
                 }
                 // ---- C: the schedule
                 u32 st0;
-                const uint4 sbytes = schedule_from_table(cs, nseg <= WDM ? cw : nullptr, ncol, nseg, ii, 0u, st0);
+                // the sort keys go where the read's 2-bit words were (step A of the next chain writes them again)
+                const uint4 sbytes = schedule_from_table(cs, nseg <= WQ ? sq : (nseg <= WDM ? cw : nullptr), ncol, nseg, ii, 0u, st0);
                 if (A.carry) A.st0arr[(u64)slot * 2 + c] = (u8)st0;
                 *(uint4 *)(A.sched + ((u64)slot * 2 + c) * 16) = sbytes;
             }
@@ -419,11 +452,8 @@ __global__ void __launch_bounds__(PD_WARPS * 32) prepare_deferred(const __grid_c
             if (src == 0xffffffffu) return 0u;
         }
         const u64 *pl = A.planes + ((u64)src * 2 + c) * 3 * Wb;
-        const u32 *b1 = A.bits1 + ((u64)src * 2 + c) * 2 * W2;                   // {low bits, ACGT mask} per 32 bases
-        const u32 wm = p >> 5, om = p & 31u;
-        const u32 m0 = b1[2 * wm + 1], m1 = wm + 1 < Wb ? b1[2 * wm + 3] : 0u;
-        const u32 xm = __funnelshift_l(m1, m0, om) >> (32 - s);
-        return bsl_xt((u32)(stream_extract(pl, p) >> shs)) | (xm != nfull ? 0x80000000u : 0u);
+        const bool acgt = (stream_extract(pl + Wb, p) >> shs) == (0x5555555555555555ULL >> shs);       // second stream: 01 per ACGT base
+        return bsl_xt((u32)(stream_extract(pl, p) >> shs)) | (acgt ? 0u : 0x80000000u);
     };
     for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n_def; k += gridDim.x * blockDim.x) {
         const u32 slot = A.defer[k];
@@ -442,7 +472,7 @@ __global__ void __launch_bounds__(PD_WARPS * 32) prepare_deferred(const __grid_c
             for (u32 j = 0; j < nseg; j++) {
                 for (u32 d = 0; d < wd; d++) {
                     const u32 e = seed_of(slot, c, L, base, j * s + d), kmer = e & 0x7fffffffu;
-                    u32 cnt = A.di.cnt8[kmer]; if (cnt == 0xFFu) cnt = A.di.bucket[2 * kmer + 2] - A.di.bucket[2 * kmer];
+                    u32 cnt = A.di.cnt8[kmer]; if (cnt == 0xFFu) cnt = A.di.loc[A.di.rec_base + 8 * (size_t)kmer];
                     cw[d] = (cnt & 0x7fffffffu) | (e & 0x80000000u);
                 }
                 count_seeds_row(cw, s_prof[j], j, s, I, vmax, cs + j * ncol);
@@ -478,13 +508,14 @@ __global__ void build_lists(const __grid_constant__ KArgs A, u32 *se_list, u32 *
 // seed_lookup : the bucket look-ups of mode `round` (align.cpp:279-292) for every active (read, chain)
 // ------------------------------------------------------------------------------------------------
 #define LK_THREADS 256
+#define LK_BIG 64u            // a bucket with more entries is copied by the whole warp on its own
 #define CHUNK 256            // candidates per verify chunk
 #define ALLOC_SHIFT 40       // RoundCtr::alloc = items << 40 | candidates
 #define ALLOC_MASK ((1ULL << ALLOC_SHIFT) - 1)
 #define MAX_ITEMS_PER_ROUND ((1u << 24) - (1u << 16))
 
 template <bool PE>
-__global__ void __launch_bounds__(LK_THREADS) seed_lookup(const __grid_constant__ KArgs A, u32 round, const u32 *list_in, u32 *list_out, u32 ci) {
+__global__ void __launch_bounds__(LK_THREADS, 4) seed_lookup(const __grid_constant__ KArgs A, u32 round, const u32 *list_in, u32 *list_out, u32 ci) {
     __shared__ u32 s_wi[LK_THREADS / 32], s_wc[LK_THREADS / 32];
     __shared__ u32 s_ibase, s_cbase, s_ok;
     const DevTables *T = A.tab;
@@ -530,9 +561,12 @@ __global__ void __launch_bounds__(LK_THREADS) seed_lookup(const __grid_constant_
             if ((m.flags & SF_STALE) && h + A.s > (u32)m.len) return A.stale[((u64)slot * 2 + c) * 16 + (h + A.s - (u32)m.len - 1u)];
             return bsl_xt((u32)(stream_extract(pq, h) >> shs));
         };
-        u32 ke0[4], ke1[4], ke2[4];                          // the look-ups of the first four phases stay in registers for pass 2
+        // a look-up = the first two words of the k-mer's record (entries, forward-strand entries); where the entries are follows in
+        // pass 2. The look-ups of the first four phases stay in registers.
+        const u32 *rec = A.di.loc + A.di.rec_base;
+        u32 kpm[4], knf[4], kk[4];
 #pragma unroll
-        for (u32 i = 0; i < 4; i++) { ke0[i] = 0; ke1[i] = 0; ke2[i] = 0; }
+        for (u32 i = 0; i < 4; i++) { kpm[i] = 0; knf[i] = 0; kk[i] = 0; }
         if (search) {
             const u8 sc = A.sched[((u64)slot * 2 + c) * 16 + round]; j = sc & 15u; stj = sc >> 4;
             pq = A.planes + ((u64)slot * 2 + c) * 3 * A.Wb;
@@ -541,15 +575,15 @@ __global__ void __launch_bounds__(LK_THREADS) seed_lookup(const __grid_constant_
                 if (i < A.I) {
                     const u32 h = T->prof[j][i] + stj - i;
                     const u32 kmer = kmer_at(h);
-                    ke0[i] = __ldg(A.di.bucket + 2 * kmer); ke1[i] = __ldg(A.di.bucket + 2 * kmer + 1); ke2[i] = __ldg(A.di.bucket + 2 * kmer + 2);
+                    const uint2 r01 = __ldg((const uint2 *)(rec + 8 * (size_t)kmer)); kpm[i] = r01.x; knf[i] = r01.y; kk[i] = kmer;
                 }
             }
 #pragma unroll
-            for (u32 i = 0; i < 4; i++) { const u32 pm = ke2[i] - ke0[i]; if (i < A.I && pm != 0 && pm <= A.di.maxk) { tot += pm; nne++; } }
+            for (u32 i = 0; i < 4; i++) { const u32 pm = kpm[i]; if (i < A.I && pm != 0 && pm <= A.di.maxk) { tot += pm; nne++; } }
             for (u32 i = 4; i < A.I; i++) {
                 const u32 h = T->prof[j][i] + stj - i;
                 const u32 kmer = kmer_at(h);
-                const u32 pm = A.di.bucket[2 * kmer + 2] - A.di.bucket[2 * kmer];
+                const u32 pm = __ldg(rec + 8 * (size_t)kmer);
                 if (pm != 0 && pm <= A.di.maxk) { tot += pm; nne++; }
             }
         }
@@ -593,13 +627,14 @@ __global__ void __launch_bounds__(LK_THREADS) seed_lookup(const __grid_constant_
             u32 x_cb = 0, x_pm = 0, x_e0 = 0, x_rot = 0;
             if (search && ok && nne) {
                 const u32 h = T->prof[j][i] + stj - i;
-                u32 e0, e1, e2;
-                if (i < 4) { e0 = i == 0 ? ke0[0] : i == 1 ? ke0[1] : i == 2 ? ke0[2] : ke0[3]; e1 = i == 0 ? ke1[0] : i == 1 ? ke1[1] : i == 2 ? ke1[2] : ke1[3]; e2 = i == 0 ? ke2[0] : i == 1 ? ke2[1] : i == 2 ? ke2[2] : ke2[3]; }
-                else { const u32 kmer = kmer_at(h); e0 = A.di.bucket[2 * kmer]; e1 = A.di.bucket[2 * kmer + 1]; e2 = A.di.bucket[2 * kmer + 2]; }
-                const u32 pm = e2 - e0;
+                u32 pm, nf, kmer;
+                if (i < 4) { pm = i == 0 ? kpm[0] : i == 1 ? kpm[1] : i == 2 ? kpm[2] : kpm[3]; nf = i == 0 ? knf[0] : i == 1 ? knf[1] : i == 2 ? knf[2] : knf[3]; kmer = i == 0 ? kk[0] : i == 1 ? kk[1] : i == 2 ? kk[2] : kk[3]; }
+                else { kmer = kmer_at(h); const uint2 r01 = __ldg((const uint2 *)(rec + 8 * (size_t)kmer)); pm = r01.x; nf = r01.y; }
                 if (pm != 0 && pm <= A.di.maxk) {
+                    // where the entries are, as an index into loc[]: inside the record, or what the record's third word says
+                    const u32 e0 = pm <= BSL_REC_INLINE ? A.di.rec_base + 8u * kmer + 2u : __ldg(rec + 8 * (size_t)kmer + 2);
                     // walk positions on the reverse strand: [x1, x2) (inv = 0) or all but [x1, x2) (inv = 1), see ItemHdr
-                    const u32 nf = e1 - e0, rot = m.rnd % pm;
+                    const u32 rot = m.rnd % pm;
                     const u32 inv = rot < nf ? 0u : 1u, x1 = inv ? pm - rot : nf - rot, x2 = inv ? pm - rot + nf : pm - rot;
                     *(uint4 *)(A.hdr + it) = make_uint4(cb, slot | (c << 22) | ((u32)m.thr << 23) | (inv << 27) | (i << 28), x1 | ((u32)m.len << 23), x2 | (h << 23));
                     for (u32 cc = (cb + 31u) / 32u; (u64)cc * 32u < (u64)cb + pm; cc++) A.chunk_first[cc] = it;
@@ -607,22 +642,41 @@ __global__ void __launch_bounds__(LK_THREADS) seed_lookup(const __grid_constant_
                     cb += pm; it++;
                 }
             }
-            u32 todo = __ballot_sync(0xffffffffu, x_pm != 0);
-            while (todo) {                                   // 8 buckets per trip: their gathers are all in flight before the first store
-                u32 v[8], dst[8];
+            // ---- a large bucket (reads from repeat families) is copied by the whole warp, four loads in flight per lane
+            u32 bigm = __ballot_sync(0xffffffffu, x_pm > LK_BIG);
+            while (bigm) {
+                const u32 l = __ffs(bigm) - 1; bigm &= bigm - 1;
+                const u32 ycb = __shfl_sync(0xffffffffu, x_cb, l), ypm = __shfl_sync(0xffffffffu, x_pm, l);
+                const u32 ye0 = __shfl_sync(0xffffffffu, x_e0, l), yrot = __shfl_sync(0xffffffffu, x_rot, l);
+                for (u32 tt = lane; tt < ypm; tt += 128) {
+                    u32 vv[4];
 #pragma unroll
-                for (u32 b = 0; b < 8; b++) {
-                    dst[b] = 0xffffffffu;
-                    if (todo) {
-                        const u32 l = __ffs(todo) - 1; todo &= todo - 1;
-                        const u32 ycb = __shfl_sync(0xffffffffu, x_cb, l), ypm = __shfl_sync(0xffffffffu, x_pm, l);
-                        const u32 ye0 = __shfl_sync(0xffffffffu, x_e0, l), yrot = __shfl_sync(0xffffffffu, x_rot, l);
-                        if (lane < ypm) { u32 e = yrot + lane; if (e >= ypm) e -= ypm; v[b] = __ldg(A.di.loc + ye0 + e); dst[b] = ycb + lane; }
-                        for (u32 tt = lane + 32; tt < ypm; tt += 32) { u32 e = yrot + tt; if (e >= ypm) e -= ypm; A.flat_loc[ycb + tt] = __ldg(A.di.loc + ye0 + e); }
-                    }
+                    for (u32 q = 0; q < 4; q++) { const u32 t2 = tt + 32 * q; u32 e = yrot + t2; if (e >= ypm) e -= ypm; vv[q] = t2 < ypm ? __ldg(A.di.loc + ye0 + e) : 0u; }
+#pragma unroll
+                    for (u32 q = 0; q < 4; q++) { const u32 t2 = tt + 32 * q; if (t2 < ypm) A.flat_loc[ycb + t2] = vv[q]; }
+                }
+            }
+            // ---- the others (two or three entries on average): the entries of all lanes' buckets in one flat sequence, a lane per
+            //      entry — the owner of entry t is the first lane whose inclusive entry count exceeds t
+            const u32 fp = x_pm > LK_BIG ? 0u : x_pm;
+            u32 inc = fp;
+            for (u32 o = 1; o < 32; o <<= 1) { const u32 a = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += a; }
+            const u32 T_ = __shfl_sync(0xffffffffu, inc, 31);
+            for (u32 t0 = 0; t0 < T_; t0 += 64) {
+                u32 vv[2], dd[2];
+#pragma unroll
+                for (u32 q = 0; q < 2; q++) {
+                    const u32 t = t0 + 32 * q + lane;
+                    u32 ow = 0;
+#pragma unroll
+                    for (u32 o = 16; o; o >>= 1) { const u32 a = __shfl_sync(0xffffffffu, inc, ow + o - 1u); if (a <= t) ow += o; }
+                    const u32 ycb = __shfl_sync(0xffffffffu, x_cb, ow), ypm = __shfl_sync(0xffffffffu, fp, ow), yinc = __shfl_sync(0xffffffffu, inc, ow);
+                    const u32 ye0 = __shfl_sync(0xffffffffu, x_e0, ow), yrot = __shfl_sync(0xffffffffu, x_rot, ow);
+                    dd[q] = 0xffffffffu; vv[q] = 0;
+                    if (t < T_) { const u32 idx = t - (yinc - ypm); u32 e = yrot + idx; if (e >= ypm) e -= ypm; vv[q] = __ldg(A.di.loc + ye0 + e); dd[q] = ycb + idx; }
                 }
 #pragma unroll
-                for (u32 b = 0; b < 8; b++) if (dst[b] != 0xffffffffu) A.flat_loc[dst[b]] = v[b];
+                for (u32 q = 0; q < 2; q++) if (dd[q] != 0xffffffffu) A.flat_loc[dd[q]] = vv[q];
             }
         }
         __syncthreads();
@@ -1230,16 +1284,29 @@ __global__ void __launch_bounds__(SB_WARPS * 32, GAP ? 2 : 4) screen_bits(const 
 // hit list needs no window gather and no warp: sort the marks into discovery order (= flat index), int2hit + AddHit
 // each (align.cpp:319-346, align.h:329-347). Everything else (long lists, -w in reach, -g) is left to reduce_round.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) reduce_fast(const __grid_constant__ KArgs A, const u32 *list, u32 list_ci, u32 as_pe) {
+// Reads it leaves to reduce_round are collected in KArgs::flag_list: those with many marked candidates or a long hit list (reads from
+// repeat families: their replay is long and serial) from the front, the others from the back, so that reduce_round can start the
+// long ones first and hand every warp one read at a time. fast = 0 (-g): nothing is replayed here, the reads are only listed.
+#define RR_LONG_MARKS 48u
+#define RR_LONG_HITS 64u
+__global__ void __launch_bounds__(256) reduce_fast(const __grid_constant__ KArgs A, const u32 *list, u32 list_ci, u32 ci, u32 as_pe, u32 fast) {
     const u32 n_entries = A.ctr->rc[list_ci].active << (as_pe ? 1 : 0);
+    RoundCtr *rc = A.ctr->rc + ci;
+    const u32 lane = threadIdx.x & 31u;
     u32 added = 0;
-    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n_entries; k += gridDim.x * blockDim.x) {
-        const u32 slot = as_pe ? list[k >> 1] + (k & 1u) * A.n_a : list[k];
+    for (u32 kb = blockIdx.x * blockDim.x + threadIdx.x - lane; kb < n_entries; kb += gridDim.x * blockDim.x) {
+      const u32 k = kb + lane;
+      u32 cls = 0, slot = 0;                                                // 0: nothing left to do, 1: reduce_round, 2: reduce_round, long replay
+      if (k < n_entries) do {
+        slot = as_pe ? list[k >> 1] + (k & 1u) * A.n_a : list[k];
         const u32 c = A.slot_flag[slot];
-        if (c == 0 || c > MK_CAP) continue;
+        if (c == 0) break;
         SlotMeta m = A.meta[slot];
+        cls = (c >= RR_LONG_MARKS || m.nhit >= RR_LONG_HITS) ? 2u : 1u;
+        if (!fast || c > MK_CAP) break;
         u32 hcap; DevHit *hits = slot_hits(A, m.item, hcap);
-        if (m.nhit + c >= A.w || m.nhit + c > hcap) continue;             // a level could reach -w, or the list could outgrow its storage
+        if (m.nhit + c >= A.w || m.nhit + c > hcap) break;                // a level could reach -w, or the list could outgrow its storage
+        cls = 0;
         uint4 e[MK_CAP];
 #pragma unroll
         for (u32 i = 0; i < MK_CAP; i++) e[i] = i < c ? A.marks[(size_t)slot * MK_CAP + i] : make_uint4(0xffffffffu, 0, 0, 0);
@@ -1268,7 +1335,18 @@ __global__ void __launch_bounds__(256) reduce_fast(const __grid_constant__ KArgs
         }
         added += nhit - m.nhit;
         if (nhit != m.nhit) { A.meta[slot].nhit = (u16)nhit; A.minlvl[slot] = (u8)minl; }
-        A.slot_flag[slot] = 0;                                              // done: reduce_round skips it
+        A.slot_flag[slot] = 0;                                              // done
+      } while (0);
+      // ---- list what is left (one atomic per warp and list)
+      const u32 bl = __ballot_sync(0xffffffffu, cls == 2u), bn = __ballot_sync(0xffffffffu, cls == 1u);
+      if (bl | bn) {
+        u32 basel = 0, basen = 0;
+        if (lane == 0) { if (bl) basel = atomicAdd(&rc->long_n, (u32)__popc(bl)); if (bn) basen = atomicAdd(&rc->flagged, (u32)__popc(bn)); }
+        basel = __shfl_sync(0xffffffffu, basel, 0); basen = __shfl_sync(0xffffffffu, basen, 0);
+        const u32 below = (1u << lane) - 1u;
+        if (cls == 2u) A.flag_list[basel + __popc(bl & below)] = slot;
+        if (cls == 1u) A.flag_list[A.n_slots - 1u - (basen + __popc(bn & below))] = slot;
+      }
     }
     for (u32 o = 16; o; o >>= 1) added += __shfl_xor_sync(0xffffffffu, added, o);
     if ((threadIdx.x & 31u) == 0 && added) atomicAdd(&A.ctr->hits_added, (unsigned long long)added);
@@ -1458,13 +1536,11 @@ __device__ int add_hit(const KArgs &A, WarpCtx &S, u32 lane, u32 level, u32 g, u
     return 0;
 }
 
-// long_pass = 0: every listed slot, 32 per grab; slots with many marked candidates or a long hit list (reads from repeat
-// families: their replay is long and serial) are only collected in KArgs::flag_list. long_pass = 1: those, one per grab, so that
-// they spread over all warps instead of queueing behind each other in one.
-#define RR_LONG_MARKS 48u
-#define RR_LONG_HITS 64u
+// The reads reduce_fast listed in KArgs::flag_list: first the long replays (front of the list), one per grab, so that they start
+// early and spread over all warps; then the others (back of the list), RR_GRAB per grab.
+#define RR_GRAB 2u
 template <bool SINGLE>
-__global__ void __launch_bounds__(ROUND_WARPS * 32, 3) reduce_round(const __grid_constant__ KArgs A, u32 round, u32 ci, u32 NW, u32 NWS, const u32 *list, u32 list_ci, u32 as_pe, u32 long_pass) {
+__global__ void __launch_bounds__(ROUND_WARPS * 32, 3) reduce_round(const __grid_constant__ KArgs A, u32 round, u32 ci, u32 NW, u32 NWS) {
     extern __shared__ u64 smem[];
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     u64 *win_all = smem + (size_t)wid * (32 * NWS + 48 + RR_KEYS);
@@ -1472,22 +1548,19 @@ __global__ void __launch_bounds__(ROUND_WARPS * 32, 3) reduce_round(const __grid
     RoundCtr *rc = A.ctr->rc + ci;
     const unsigned long long al_rc = min(rc->alloc, ~rc->limit_inv);
     const u32 n_cands_rc = (u32)(al_rc & ALLOC_MASK), n_items_rc = (u32)(al_rc >> ALLOC_SHIFT);
-    // every slot searched in this round: SE = the compacted list seed_lookup wrote, PE = both mates of every listed pair;
-    // a warp takes 32 of them at a time and replays those verify_candidates flagged
-    const u32 n_entries = long_pass ? rc->long_n : A.ctr->rc[list_ci].active << (as_pe ? 1 : 0);
-    const u32 batch = long_pass ? 1u : min(32u, max(1u, n_entries / (gridDim.x * ROUND_WARPS * 4)));      // few entries: one per grab, for balance
+    const u32 n_long = rc->long_n, n_norm = rc->flagged;
     const u32 G = A.gap;
     unsigned long long st_hits = 0;
     for (;;) {
-        u32 k0 = 0;
-        if (lane == 0) k0 = atomicAdd(long_pass ? &rc->long_work : &rc->work, batch);
-        k0 = __shfl_sync(0xffffffffu, k0, 0);
-        if (k0 >= n_entries) break;
+        u32 v = 0;
+        if (lane == 0) v = atomicAdd(&rc->work, 1u);                       // grab number: n_long grabs of one long replay, then the others
+        v = __shfl_sync(0xffffffffu, v, 0);
         u32 my_slot = 0; bool flagged = false;
-        if (lane < batch && k0 + lane < n_entries) {
-            const u32 kk = k0 + lane; my_slot = long_pass ? A.flag_list[kk] : (as_pe ? list[kk >> 1] + (kk & 1u) * A.n_a : list[kk]);
-            const u32 nmark = A.slot_flag[my_slot]; flagged = nmark != 0u;
-            if (flagged && !long_pass && (nmark >= RR_LONG_MARKS || A.meta[my_slot].nhit >= RR_LONG_HITS)) { A.flag_list[atomicAdd(&rc->long_n, 1u)] = my_slot; flagged = false; }
+        if (v < n_long) { if (lane == 0) { my_slot = A.flag_list[v]; flagged = true; } }
+        else {
+            const u32 k0 = (v - n_long) * RR_GRAB;
+            if (k0 >= n_norm) break;
+            if (lane < RR_GRAB && k0 + lane < n_norm) { my_slot = A.flag_list[A.n_slots - 1u - (k0 + lane)]; flagged = true; }
         }
         u32 todo = __ballot_sync(0xffffffffu, flagged);
       while (todo) {
@@ -1530,10 +1603,29 @@ __global__ void __launch_bounds__(ROUND_WARPS * 32, 3) reduce_round(const __grid
                 pq[lane] = in ? swap32(src[lane]) : 0; pn[lane] = in ? swap32(src[A.Wb + lane]) : 0; pc[lane] = in ? swap32(src[2 * A.Wb + lane]) : 0;   // pn: 01 per ACGT base
             }
             __syncwarp();
-            for (u32 tile = 0; tile < total && !stop_all; tile += 32) {
-                const u32 idx = tile + lane; const u32 flat = cbase + idx;
-                const bool valid = idx < total && ((A.bitmap[flat >> 5] >> (flat & 31u)) & 1u);
-                if (!__any_sync(0xffffffffu, valid)) continue;
+            // ---- the marked candidates of the chain in discovery (= flat) order, 32 per trip: a lane takes one bitmap word of a
+            //      1024-candidate stretch, a prefix sum ranks the set bits, lane k of a trip finds the k-th of them
+            const u32 fend = cbase + total;
+            for (u32 wc = cbase >> 5; wc * 32u < fend && !stop_all; wc += 32) {
+              u32 mbits = 0;
+              {
+                const u32 f0 = (wc + lane) * 32u;
+                if (f0 < fend) {
+                    mbits = A.bitmap[wc + lane];
+                    if (f0 < cbase) mbits &= 0xffffffffu << (cbase - f0);
+                    if (f0 + 32u > fend) mbits &= 0xffffffffu >> (f0 + 32u - fend);
+                }
+              }
+              const u32 mcnt = __popc(mbits); u32 mincl = mcnt;
+              for (u32 o = 1; o < 32; o <<= 1) { const u32 v = __shfl_up_sync(0xffffffffu, mincl, o); if (lane >= o) mincl += v; }
+              const u32 nmk = __shfl_sync(0xffffffffu, mincl, 31);
+              for (u32 k0 = 0; k0 < nmk && !stop_all; k0 += 32) {
+                const u32 rank = k0 + lane; const bool valid = rank < nmk;
+                u32 wsel = 0;                                                   // words whose inclusive count is <= rank come before the one that holds it
+                for (u32 o = 16; o; o >>= 1) { const u32 v = __shfl_sync(0xffffffffu, mincl, wsel + o - 1u); if (v <= rank) wsel += o; }
+                const u32 wexcl = __shfl_sync(0xffffffffu, mincl - mcnt, wsel), wbits = __shfl_sync(0xffffffffu, mbits, wsel);
+                const u32 flat = (wc + wsel) * 32u + (valid ? __fns(wbits, 0u, (int)(rank - wexcl + 1u)) : 0u);
+                const u32 idx = valid ? flat - cbase : 0u;
                 u32 ph = 0;
                 for (u32 i = 1; i < ni; i++) { u32 o = __shfl_sync(0xffffffffu, poff, i); if (idx >= o) ph = i; }
                 const u32 t = idx - __shfl_sync(0xffffffffu, poff, ph);
@@ -1581,6 +1673,7 @@ __global__ void __launch_bounds__(ROUND_WARPS * 32, 3) reduce_round(const __grid
                         stop_all = true; break;
                     }
                 }
+              }
             }
         }
         st_hits += S.nhit - hits_before;
@@ -1673,22 +1766,30 @@ __device__ void fill_record(bsl_hit &o, const DevHit &h, u32 chain, u32 level) {
 
 #define PR_LOCAL 4u
 #define PR_WIDE_HITS 12u     // a pair with a longer hit list goes to pair_round_wide
-__global__ void pair_round(const __grid_constant__ KArgs A, u32 round, const u32 *list_in, u32 *list_out, u32 ci) {
+#define PW_CAP 2048u        // longest list the shared-memory path handles; longer ones take the serial path (lane 0)
+#define PW_CAP_SMALL 256u   // most long lists are shorter than this: their pairs run in a second instance with eight times the resident warps
+// Rounds [round, r_hi]: after the last search round no list changes any more, so the remaining rounds of a pair (levels up to its
+// budget) are replayed by the same thread in one launch.
+__global__ void pair_round(const __grid_constant__ KArgs A, u32 round0, u32 r_hi, const u32 *list_in, u32 *list_out, u32 ci) {
     RoundCtr *rc = A.ctr->rc + ci;
     const u32 n_items = rc->active;
-    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n_items; k += gridDim.x * blockDim.x) {
-        const u32 p = list_in[k]; const u32 sa = p, sb = p + A.n_a;
+    // one round of one pair; true = no pair yet and levels left: the pair stays listed
+    auto one = [&](const u32 p, const u32 round) -> bool {
+        const u32 sa = p, sb = p + A.n_a;
         SlotMeta ma = A.meta[sa], mb = A.meta[sb];
         if ((ma.flags | mb.flags) & SF_OVERFLOW) {                 // re-run the whole pair on the large-capacity path
             if (!(ma.flags & SF_OVERFLOW)) { A.meta[sa].flags = ma.flags | SF_OVERFLOW; }
             if (!(mb.flags & SF_OVERFLOW)) { A.meta[sb].flags = mb.flags | SF_OVERFLOW; }
-            continue;
+            return false;
         }
         if ((ma.flags | mb.flags) & SF_FILTERED) {                 // a lone mate (the other one was filtered) runs SingleAlign::RunAlign in the reference
-            if (round < max((u32)ma.B, (u32)mb.B)) { u32 pos = atomicAdd(&rc[1].active, 1u); list_out[pos] = p; }      // (pairs.cpp:197-201): no SortHits4PE, no pairs
-            continue;
+            return round < max((u32)ma.B, (u32)mb.B);                // (pairs.cpp:197-201): no SortHits4PE, no pairs
         }
-        if (((ma.item | mb.item) & SLOT_BIG) || ma.nhit > PR_WIDE_HITS || mb.nhit > PR_WIDE_HITS) { A.wide_list[atomicAdd(&rc->wide, 1u)] = p; continue; }      // long lists: warp per pair
+        if (((ma.item | mb.item) & SLOT_BIG) || ma.nhit > PR_WIDE_HITS || mb.nhit > PR_WIDE_HITS) {      // long lists: warp per pair
+            if (max((u32)ma.nhit, (u32)mb.nhit) <= PW_CAP_SMALL) A.wide_list[atomicAdd(&rc->wide, 1u)] = p;
+            else A.wide_list[A.n_a - 1u - atomicAdd(&rc->long_work, 1u)] = p;                            // RoundCtr::long_work: pairs with a list beyond PW_CAP_SMALL
+            return false;
+        }
         u32 capa, capb; DevHit *ha = slot_hits(A, ma.item, capa), *hb = slot_hits(A, mb.item, capb);
         const u32 nA = ma.nhit, nB = mb.nhit, Ba = ma.B, Bb = mb.B, La = ma.len, Lb = mb.len;
         const u32 i = round;
@@ -1720,14 +1821,10 @@ __global__ void pair_round(const __grid_constant__ KArgs A, u32 round, const u32
                 if (cj && i + j < best) { best = i + j; best_cnt = cj; }
             }
         }
-        if (total == 0) {
-            const u32 maxi = max(Ba, Bb);
-            if (round < maxi) { u32 pos = atomicAdd(&rc[1].active, 1u); list_out[pos] = p; }
-            continue;
-        }
+        if (total == 0) return round < max(Ba, Bb);
         // a pair exists: the search ends here (pairs.cpp:173)
         bsl_pair pr; memset(&pr, 0, sizeof pr); pr.n_pairs = best_cnt;
-        if (best_cnt > 1 && A.report == 0) { A.pair_out[p] = pr; continue; }       // suppressed; mates get reported unpaired by finalize
+        if (best_cnt > 1 && A.report == 0) { A.pair_out[p] = pr; return false; }   // suppressed; mates get reported unpaired by finalize
         const u32 target = best_cnt == 1 ? 0 : ma.rnd % best_cnt;
         PairPick pk; pk.found = 0;
         u64 all_base = 0;
@@ -1746,6 +1843,11 @@ __global__ void pair_round(const __grid_constant__ KArgs A, u32 round, const u32
         oa.status = ob.status = BSL_ST_PAIRED; oa.n_hits = ob.n_hits = best_cnt; oa.read_len = (u16)La; ob.read_len = (u16)Lb; oa.max_snp = (u8)Ba; ob.max_snp = (u8)Bb;
         A.out[sa] = oa; A.out[sb] = ob;
         A.meta[sa].flags = ma.flags | SF_DONE; A.meta[sb].flags = mb.flags | SF_DONE;
+        return false;
+    };
+    for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n_items; k += gridDim.x * blockDim.x) {
+        const u32 p = list_in[k];
+        for (u32 r = round0; one(p, r); r++) if (r >= r_hi) { list_out[atomicAdd(&rc[1].active, 1u)] = p; break; }
     }
 }
 
@@ -1756,18 +1858,22 @@ __global__ void pair_round(const __grid_constant__ KArgs A, u32 round, const u32
 // over the lanes; positions in the reference's enumeration order come from prefix sums, so the -w cut, the
 // -S pick and the -r 2 listing are the same pairs in the same order.
 // ------------------------------------------------------------------------------------------------
-#define PW_CAP 2048u        // longest sub-list the shared-memory path handles; longer ones take the serial path (lane 0)
-struct PairWideSmem {
-    union { DevHit stage[PW_CAP]; struct { u32 a_loc[PW_CAP], a_chr[PW_CAP], b_loc[PW_CAP], b_chr[PW_CAP]; } k; };
-    u16 ia[PW_CAP], ib[PW_CAP], wbs[PW_CAP], wbe[PW_CAP];
+template <u32 CAP>
+struct PairWideSmemT {
+    union { DevHit stage[CAP]; struct { u32 a_loc[CAP], a_chr[CAP], b_loc[CAP], b_chr[CAP]; } k; };
+    u16 ia[CAP], ib[CAP], wbs[CAP], wbe[CAP];
+    u8 cla[CAP], clb[CAP];                  // chain << 4 | level of every hit of mate a / b (SortHits4PE only permutes hits of equal chain and level)
+    u32 hist[2][32];                        // how many hits of mate a / b carry each (chain, level)
     PairPick pick;
 };
+typedef PairWideSmemT<PW_CAP> PairWideSmem;
+#define HIT_CL(tag) (((tag) >> 20) & 31u)
 
 // indices (in list order) of the hits of `h[0..n)` tagged (chain, level) -> idx[]; returns how many (lists longer than PW_CAP are cut: caller checks n first)
-__device__ u32 pw_compact(const DevHit *h, u32 n, u32 chain, u32 level, u16 *idx, u32 lane) {
-    u32 c = 0;
+__device__ u32 pw_compact(const u8 *cl, u32 n, u32 chain, u32 level, u16 *idx, u32 lane) {
+    u32 c = 0; const u32 want = (chain << 4) | level;
     for (u32 t = 0; t < n; t += 32) {
-        const u32 i = t + lane; const bool ok = i < n && tag_is(h[i].tag, chain, level);
+        const u32 i = t + lane; const bool ok = i < n && cl[i] == want;
         const u32 bal = __ballot_sync(0xffffffffu, ok);
         if (ok) idx[c + __popc(bal & ((1u << lane) - 1u))] = (u16)i;
         c += __popc(bal);
@@ -1780,9 +1886,10 @@ __device__ u32 pw_compact(const DevHit *h, u32 n, u32 chain, u32 level, u16 *idx
 // list without equal (chr, loc) keys has only one sorted order: both are the stable rank sort below. A longer list that holds
 // equal keys (a gapped and an ungapped hit at the same place) comes out of introsort in an order of its own, which stdsort()
 // reproduces step by step (SURVEY trap 10).
-__device__ void pw_sort_level(DevHit *h, u32 n, u32 chain, u32 level, PairWideSmem &sm, u32 lane) {
-    const u32 c = pw_compact(h, n, chain, level, sm.ia, lane);
-    if (c <= 1) return;
+template <class SM>
+__device__ void pw_sort_level(DevHit *h, const u8 *cl, const u32 *hist, u32 n, u32 chain, u32 level, SM &sm, u32 lane) {
+    if (hist[(chain << 4) | level] <= 1) return;
+    const u32 c = pw_compact(cl, n, chain, level, sm.ia, lane);
     for (u32 x = lane; x < c; x += 32) sm.stage[x] = h[sm.ia[x]];
     __syncwarp();
     bool twins = false;
@@ -1817,15 +1924,15 @@ __device__ __forceinline__ bool pw_valid(const KArgs &A, u32 chain, u32 chra, u3
 }
 
 // warp version of get_pairs; every argument and the return value are warp-uniform
-__device__ u32 pw_get_pairs(const KArgs &A, PairWideSmem &sm, u32 lane, const DevHit *ha, u32 nA, u32 Ba, u32 La, const DevHit *hb, u32 nB, u32 Bb, u32 Lb,
+template <class SM>
+__device__ u32 pw_get_pairs(const KArgs &A, SM &sm, u32 lane, const DevHit *ha, u32 nA, u32 Ba, u32 La, const DevHit *hb, u32 nB, u32 Bb, u32 Lb,
                             u32 na, u32 nb, u32 &cnt_level, int mode, u32 target, u64 all_base) {
     if (na > Ba || nb > Bb) return 0;
     u32 npair = 0;
     for (u32 chain = 0; chain < 2; chain++) {
-        const u32 cA = pw_compact(ha, nA, chain, na, sm.ia, lane);
-        if (cA == 0) continue;
-        const u32 cB = pw_compact(hb, nB, 1 - chain, nb, sm.ib, lane);
-        if (cB == 0) continue;
+        if (sm.hist[0][(chain << 4) | na] == 0 || sm.hist[1][((1 - chain) << 4) | nb] == 0) continue;
+        const u32 cA = pw_compact(sm.cla, nA, chain, na, sm.ia, lane);
+        const u32 cB = pw_compact(sm.clb, nB, 1 - chain, nb, sm.ib, lane);
         for (u32 x = lane; x < cA; x += 32) { const DevHit t = ha[sm.ia[x]]; sm.k.a_loc[x] = t.loc; sm.k.a_chr[x] = HIT_CHR2(t.tag); }
         for (u32 x = lane; x < cB; x += 32) { const DevHit t = hb[sm.ib[x]]; sm.k.b_loc[x] = t.loc; sm.k.b_chr[x] = HIT_CHR2(t.tag); }
         __syncwarp();
@@ -1882,31 +1989,41 @@ __device__ u32 pw_get_pairs(const KArgs &A, PairWideSmem &sm, u32 lane, const De
     return npair;
 }
 
-__global__ void __launch_bounds__(32) pair_round_wide(const __grid_constant__ KArgs A, u32 round, const u32 *list_in, u32 *list_out, u32 ci, u32 from_wide) {
+// from_wide = 0: every pair of list_in (large-capacity pass); 1: the pairs pair_round of this round left at the front of
+// KArgs::wide_list (no list longer than PW_CAP_SMALL); 2: those it left at the back
+template <u32 CAP>
+__global__ void __launch_bounds__(32) pair_round_wide(const __grid_constant__ KArgs A, u32 round0, u32 r_hi, const u32 *list_in, u32 *list_out, u32 ci, u32 from_wide) {
     extern __shared__ __align__(16) unsigned char pw_raw[];
-    PairWideSmem &sm = *reinterpret_cast<PairWideSmem *>(pw_raw);
+    typedef PairWideSmemT<CAP> SM;
+    SM &sm = *reinterpret_cast<SM *>(pw_raw);
     RoundCtr *rc = A.ctr->rc + ci;
-    const u32 n_items = from_wide ? rc->wide : rc->active, lane = threadIdx.x;      // from_wide: the pairs pair_round of this round left in KArgs::wide_list
-    for (u32 k = blockIdx.x; k < n_items; k += gridDim.x) {
-        const u32 p = list_in[k]; const u32 sa = p, sb = p + A.n_a;
+    const u32 n_items = from_wide == 1 ? rc->wide : (from_wide == 2 ? rc->long_work : rc->active), lane = threadIdx.x;
+    // one round of one pair (warp-uniform); true = no pair yet and levels left
+    auto one = [&](const u32 p, const u32 round) -> bool {
+        const u32 sa = p, sb = p + A.n_a;
         const SlotMeta ma = A.meta[sa], mb = A.meta[sb];
         __syncwarp();
         if ((ma.flags | mb.flags) & SF_OVERFLOW) {
             if (lane == 0) { if (!(ma.flags & SF_OVERFLOW)) A.meta[sa].flags = ma.flags | SF_OVERFLOW; if (!(mb.flags & SF_OVERFLOW)) A.meta[sb].flags = mb.flags | SF_OVERFLOW; }
-            continue;
+            return false;
         }
-        if ((ma.flags | mb.flags) & SF_FILTERED) {                 // lone mate: see pair_round
-            if (lane == 0 && round < max((u32)ma.B, (u32)mb.B)) { const u32 pos = atomicAdd(&rc[1].active, 1u); list_out[pos] = p; }
-            continue;
-        }
+        if ((ma.flags | mb.flags) & SF_FILTERED) return round < max((u32)ma.B, (u32)mb.B);      // lone mate: see pair_round
         u32 capa, capb; DevHit *ha = slot_hits(A, ma.item, capa), *hb = slot_hits(A, mb.item, capb);
         const u32 nA = ma.nhit, nB = mb.nhit, Ba = ma.B, Bb = mb.B, La = ma.len, Lb = mb.len;
         const u32 i = round;
         u32 total = 0, best = 0xffffffffu, best_cnt = 0;
-        const bool wide = nA <= PW_CAP && nB <= PW_CAP;
+        const bool wide = nA <= CAP && nB <= CAP;
         if (wide) {
-            if (i <= Ba) { pw_sort_level(ha, nA, 0, i, sm, lane); pw_sort_level(ha, nA, 1, i, sm, lane); }
-            if (i <= Bb) { pw_sort_level(hb, nB, 0, i, sm, lane); pw_sort_level(hb, nB, 1, i, sm, lane); }
+            // one pass over both lists: (chain, level) of every hit into shared memory, and how many of each there are — most
+            // (chain, level) combinations of a pair are empty and cost nothing below
+            __syncwarp();
+            sm.hist[0][lane] = 0; sm.hist[1][lane] = 0;
+            __syncwarp();
+            for (u32 x = lane; x < nA; x += 32) { const u32 cl = HIT_CL(ha[x].tag); sm.cla[x] = (u8)cl; atomicAdd(&sm.hist[0][cl], 1u); }
+            for (u32 x = lane; x < nB; x += 32) { const u32 cl = HIT_CL(hb[x].tag); sm.clb[x] = (u8)cl; atomicAdd(&sm.hist[1][cl], 1u); }
+            __syncwarp();
+            if (i <= Ba) { pw_sort_level(ha, sm.cla, sm.hist[0], nA, 0, i, sm, lane); pw_sort_level(ha, sm.cla, sm.hist[0], nA, 1, i, sm, lane); }
+            if (i <= Bb) { pw_sort_level(hb, sm.clb, sm.hist[1], nB, 0, i, sm, lane); pw_sort_level(hb, sm.clb, sm.hist[1], nB, 1, i, sm, lane); }
             if (nA && nB) {
                 u32 c = 0; total += pw_get_pairs(A, sm, lane, ha, nA, Ba, La, hb, nB, Bb, Lb, i, i, c, 0, 0, 0);
                 if (c) { best = 2 * i; best_cnt = c; }
@@ -1934,12 +2051,9 @@ __global__ void __launch_bounds__(32) pair_round_wide(const __grid_constant__ KA
             }
             total = __shfl_sync(0xffffffffu, total, 0); best = __shfl_sync(0xffffffffu, best, 0); best_cnt = __shfl_sync(0xffffffffu, best_cnt, 0);
         }
-        if (total == 0) {
-            if (lane == 0 && round < max(Ba, Bb)) { const u32 pos = atomicAdd(&rc[1].active, 1u); list_out[pos] = p; }
-            continue;
-        }
+        if (total == 0) return round < max(Ba, Bb);
         bsl_pair pr; memset(&pr, 0, sizeof pr); pr.n_pairs = best_cnt;
-        if (best_cnt > 1 && A.report == 0) { if (lane == 0) A.pair_out[p] = pr; continue; }
+        if (best_cnt > 1 && A.report == 0) { if (lane == 0) A.pair_out[p] = pr; return false; }
         const u32 target = best_cnt == 1 ? 0 : ma.rnd % best_cnt;
         u64 all_base = 0;
         if (A.report == 2 && A.all_a) {
@@ -1973,6 +2087,12 @@ __global__ void __launch_bounds__(32) pair_round_wide(const __grid_constant__ KA
             A.out[sa] = oa; A.out[sb] = ob;
             A.meta[sa].flags = ma.flags | SF_DONE; A.meta[sb].flags = mb.flags | SF_DONE;
         }
+        __syncwarp();
+        return false;
+    };
+    for (u32 k = blockIdx.x; k < n_items; k += gridDim.x) {
+        const u32 p = from_wide == 2 ? list_in[A.n_a - 1u - k] : list_in[k];
+        for (u32 r = round0; one(p, r); r++) if (r >= r_hi) { if (lane == 0) list_out[atomicAdd(&rc[1].active, 1u)] = p; break; }
         __syncwarp();
     }
 }
@@ -2176,7 +2296,7 @@ static int configure_kernels(bsl_ctx *ctx) {
     CUDA_TRY(cudaFuncSetAttribute(screen_bits<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(screen_bits<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(screen_bits<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(pair_round_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairWideSmem)));
+    CUDA_TRY(cudaFuncSetAttribute(pair_round_wide<PW_CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PairWideSmem)));
     CUDA_TRY(cudaFuncSetAttribute(reduce_round<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(reduce_round<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(verify_candidates<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
@@ -2367,7 +2487,7 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     const int grid_s = sms * ctx->occ_screen;
     // 1-bit screen (single-conversion rules)
     const bool use_bits = ctx->di.has_bit1 != 0;
-    const u32 item_bytes = 16 * Wb + ((Wb & 1u) ? 0u : 16u);              // staged item: {low bits, ACGT mask} x Wb forward, x Wb reversed; stride = 4 x odd words spreads the items over the banks
+    const u32 item_bytes = 16 * (Wb | 1u);                                // staged item: {low bits, ACGT mask} x Wb forward, x Wb reversed; stride = 4 x odd words spreads the items over the banks
     const u32 rcp_wb = (u32)((0x100000000ull + Wb - 1) / Wb);
     const size_t smem_b = (size_t)SB_WARPS * 32 * item_bytes;
     if (!ctx->occ_bits || ctx->occ_bits_wb != Wb) {
@@ -2402,11 +2522,9 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
         ev_begin('r');
         {
             const u32 *rl = as_pe ? lin : lout; const u32 rci = as_pe ? ci : ci + 1;
-            if (!G) { reduce_fast<<<sms * 8, 256, 0, st>>>(K, rl, rci, as_pe ? 1u : 0u); launches++; }
-            for (u32 lp = 0; lp < 2; lp++) {
-                if (ctx->rule.single) reduce_round<true><<<grid_r, ROUND_WARPS * 32, smem_r, st>>>(K, r, ci, NW, NWS, rl, rci, as_pe ? 1u : 0u, lp);
-                else reduce_round<false><<<grid_r, ROUND_WARPS * 32, smem_r, st>>>(K, r, ci, NW, NWS, rl, rci, as_pe ? 1u : 0u, lp);
-            }
+            reduce_fast<<<sms * 8, 256, 0, st>>>(K, rl, rci, ci, as_pe ? 1u : 0u, G ? 0u : 1u);      // -g: lists the reads, replays none
+            if (ctx->rule.single) reduce_round<true><<<grid_r, ROUND_WARPS * 32, smem_r, st>>>(K, r, ci, NW, NWS);
+            else reduce_round<false><<<grid_r, ROUND_WARPS * 32, smem_r, st>>>(K, r, ci, NW, NWS);
         }
         ev_end();
         launches += 4;
@@ -2418,14 +2536,19 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
             // paired rounds; pairs with a filtered mate ride along (their lone mate follows SingleAlign's stop rule, see seed_lookup)
             for (u32 r = 0; r <= BSL_MAXSNPS; r++) {
                 if (r < rounds_se) search(K, true, r, ln.d_pe_list[r & 1], nullptr, 20 + r);
+                // after the last search round nothing changes between the pairing rounds: one launch replays all that are left
+                const u32 r_hi = r + 1 >= rounds_se ? BSL_MAXSNPS : r;
                 ev_begin('p');
-                if (K.hits == ln.d_heavy_hits) { pair_round_wide<<<sms * 4, 32, sizeof(PairWideSmem), st>>>(K, r, ln.d_pe_list[r & 1], ln.d_pe_list[(r + 1) & 1], 20 + r, 0u); launches++; }
+                if (K.hits == ln.d_heavy_hits) { pair_round_wide<PW_CAP><<<sms * 4, 32, sizeof(PairWideSmem), st>>>(K, r, r_hi, ln.d_pe_list[r & 1], ln.d_pe_list[(r + 1) & 1], 20 + r, 0u); launches++; }
                 else {
-                    pair_round<<<sms * 8, 128, 0, st>>>(K, r, ln.d_pe_list[r & 1], ln.d_pe_list[(r + 1) & 1], 20 + r);
-                    pair_round_wide<<<sms * 4, 32, sizeof(PairWideSmem), st>>>(K, r, K.wide_list, ln.d_pe_list[(r + 1) & 1], 20 + r, 1u);      // the pairs with long lists
-                    launches += 2;
+                    pair_round<<<sms * 8, 128, 0, st>>>(K, r, r_hi, ln.d_pe_list[r & 1], ln.d_pe_list[(r + 1) & 1], 20 + r);
+                    // the pairs with long lists: first the few with a list beyond PW_CAP_SMALL (they take longest), then the rest
+                    pair_round_wide<PW_CAP><<<sms * 4, 32, sizeof(PairWideSmem), st>>>(K, r, r_hi, K.wide_list, ln.d_pe_list[(r + 1) & 1], 20 + r, 2u);
+                    pair_round_wide<PW_CAP_SMALL><<<sms * 24, 32, sizeof(PairWideSmemT<PW_CAP_SMALL>), st>>>(K, r, r_hi, K.wide_list, ln.d_pe_list[(r + 1) & 1], 20 + r, 1u);
+                    launches += 3;
                 }
                 ev_end();
+                if (r_hi != r) break;
             }
         }
         cudaError_t e = cudaGetLastError();

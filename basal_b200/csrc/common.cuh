@@ -71,7 +71,9 @@ struct DevIndex {
     const u64 *plane[2];     // forward / reverse-complement 2-bit planes with 400-word margins
     const u32 *bucket;       // [2K+1]: bucket[2k]=first entry of k-mer k, bucket[2k+1]=end of its forward-strand entries
     const u8 *cnt8;          // [K] saturating bucket sizes for seed selection (0xFF -> use bucket[]); 43 MB at -s 16: L2 resident
-    const u32 *loc;          // seed table entries (global coordinates), forward entries first per bucket
+    const u32 *loc;          // seed table entries (global coordinates), forward entries first per bucket; behind them, at rec_base, one
+                             // 8-word record per k-mer: {entries, forward-strand entries, the entries if <= BSL_REC_INLINE else the first one's index}
+    u32 rec_base;
     const u32 *anchor;       // [nseq+1] ref_anchor (refbase.cpp:222-226)
     const u32 *seqlen;       // [nseq]
     const u32 *rcoff;        // [nseq] RefTitle::rc_offset
@@ -87,6 +89,7 @@ struct DevIndex {
     u32 has_bit1;
 };
 #define BSL_CTAB_SHIFT 16
+#define BSL_REC_INLINE 6u
 
 // ---- per-read ("slot") device state -------------------------------------------------------
 // hit record: 16 bytes
@@ -150,10 +153,11 @@ struct RoundCtr {
     unsigned long long alloc;   // items<<40 | candidates allocated by seed_lookup
     unsigned long long limit_inv; // 0, or ~(allocation state at which the flat candidate space ran out)
     u32 active;                 // length of the list this round consumes
-    u32 flagged;                // reads with at least one marked candidate
-    u32 work;                   // work-stealing cursor of reduce_round
-    u32 wide;                   // pairs of this round left to pair_round_wide (a mate's hit list lives in a large block)
-    u32 long_n, long_work;      // reads with many marked candidates / long hit lists: replayed by a second reduce_round launch, one read per grab
+    u32 flagged;                // reads left to reduce_round, listed from the back of KArgs::flag_list
+    u32 work;                   // work-stealing cursor of reduce_round (grab number)
+    u32 wide;                   // pairs of this round left to pair_round_wide (a mate's hit list is long or lives in a large block), front of KArgs::wide_list
+    u32 long_n;                 // reads with many marked candidates / long hit lists, listed from the front of KArgs::flag_list: reduce_round starts them first, one per grab
+    u32 long_work;              // pairs with a list beyond PW_CAP_SMALL, back of KArgs::wide_list
 };
 struct DevCounters {
     unsigned long long seed_lookups, candidates, hits_added, heavy, all_n;

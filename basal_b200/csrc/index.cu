@@ -109,6 +109,19 @@ __global__ void bucket_counts(const u32 *__restrict__ bucket, u32 K, u32 *__rest
     cnt[k] = m; cnt8[k] = m >= 0xFFu ? (u8)0xFFu : (u8)m;
 }
 
+// One 32-byte record per k-mer for seed_lookup: {entries, forward-strand entries, then the entries themselves when there are at
+// most BSL_REC_INLINE of them, else the index of the first one in loc[]}. A look-up then costs one sector instead of one in
+// bucket[] plus one in loc[]; the records sit behind loc[] in the same allocation, so that "where the entries are" is one index.
+__global__ void bucket_records(const u32 *__restrict__ bucket, const u32 *__restrict__ loc, u32 K, u32 *__restrict__ rec) {
+    const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const u32 e0 = bucket[2 * k], pm = bucket[2 * k + 2] - e0, nf = bucket[2 * k + 1] - e0;
+    u32 w[6] = {e0, 0, 0, 0, 0, 0};
+    if (pm <= BSL_REC_INLINE) for (u32 i = 0; i < BSL_REC_INLINE; i++) w[i] = i < pm ? loc[e0 + i] : 0u;
+    uint4 *dst = (uint4 *)(rec + 8 * (size_t)k);
+    dst[0] = make_uint4(pm, nf, w[0], w[1]); dst[1] = make_uint4(w[2], w[3], w[4], w[5]);
+}
+
 __global__ void split_bucket(const u32 *__restrict__ bucket, u32 K, u32 *__restrict__ start, u32 *__restrict__ nfwd) {
     u32 k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > K) return;
@@ -227,13 +240,14 @@ int bsl_index_build_impl(bsl_ctx *ctx, const u8 *cat, const u64 *off, const u32 
         }
     }
     (void)ne_fwd;
-    if (ne >= (1ull << 32)) { set_error(ctx, "seed table would exceed 2^32 entries; use a larger -I"); return BSL_ELIMIT; }
     u32 K = 1; for (u32 i = 0; i < s; i++) K *= 3;
+    if (ne + 8ull * K + 64 >= (1ull << 32)) { set_error(ctx, "seed table would exceed 2^32 entries; use a larger -I"); return BSL_ELIMIT; }
 
     // ---- seeds -> sort -> table
+    const size_t rec_base = (ne + 32 + 7) / 8 * 8;                       // the bucket records follow loc[] (32-byte aligned)
     SeedBlock *d_sb = nullptr; u32 *d_keys = nullptr, *d_vals = nullptr, *d_keys2 = nullptr, *d_loc = nullptr, *d_bucket = nullptr; u8 *d_cnt8 = nullptr;
     if ((rc_ = dmalloc(ctx, &d_sb, sb.size())) || (rc_ = dmalloc(ctx, &d_keys, ne)) || (rc_ = dmalloc(ctx, &d_vals, ne)) ||
-        (rc_ = dmalloc(ctx, &d_keys2, ne)) || (rc_ = dmalloc(ctx, &d_loc, ne + 32)) || (rc_ = dmalloc(ctx, &d_bucket, 2 * (size_t)K + 2)) ||
+        (rc_ = dmalloc(ctx, &d_keys2, ne)) || (rc_ = dmalloc(ctx, &d_loc, rec_base + 8 * (size_t)K)) || (rc_ = dmalloc(ctx, &d_bucket, 2 * (size_t)K + 2)) ||
         (rc_ = dmalloc(ctx, &d_cnt8, (size_t)K + 16))) return rc_;
     if (!sb.empty()) CUDA_TRY(cudaMemcpy(d_sb, sb.data(), sb.size() * sizeof(SeedBlock), cudaMemcpyHostToDevice));
     if (ne) {
@@ -255,6 +269,8 @@ int bsl_index_build_impl(bsl_ctx *ctx, const u8 *cat, const u64 *off, const u32 
     u32 *d_cnt = nullptr, *d_cnt_sorted = d_keys2;          // reuse: keys2 has >= K entries only if ne >= K; allocate otherwise
     if ((rc_ = dmalloc(ctx, &d_cnt, K))) return rc_;
     bucket_counts<<<(K + 255) / 256, 256>>>(d_bucket, K, d_cnt, d_cnt8);
+    CUDA_TRY(cudaGetLastError());
+    bucket_records<<<(K + 255) / 256, 256>>>(d_bucket, d_loc, K, d_loc + rec_base);
     CUDA_TRY(cudaGetLastError());
     u32 *d_sorted = nullptr; if ((rc_ = dmalloc(ctx, &d_sorted, K))) return rc_;
     (void)d_cnt_sorted;
@@ -302,7 +318,7 @@ int bsl_index_build_impl(bsl_ctx *ctx, const u8 *cat, const u64 *off, const u32 
         const bool dash_only = strcmp(ctx->P.to_bases, "-") == 0;
         di.flip = f; di.has_bit1 = ((ctx->rule.single || dash_only) && uniform) ? 1u : 0u;
     }
-    di.plane[0] = d_fwd; di.plane[1] = d_rc; di.bucket = d_bucket; di.cnt8 = d_cnt8; di.loc = d_loc;
+    di.plane[0] = d_fwd; di.plane[1] = d_rc; di.bucket = d_bucket; di.cnt8 = d_cnt8; di.loc = d_loc; di.rec_base = (u32)rec_base;
     di.anchor = d_anchor; di.seqlen = d_len; di.rcoff = d_rcoff; di.nseq = n; di.K = K; di.maxk = maxk; di.n_words = n_words; di.n_entries = ne;
     memset(&ctx->info, 0, sizeof ctx->info);
     ctx->info.n_seq = n; ctx->info.n_kmers = K; ctx->info.sum_length = bases; ctx->info.n_words = n_words; ctx->info.n_entries = ne; ctx->info.max_kmer_num = maxk;
