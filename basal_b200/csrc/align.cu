@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(PR_WARPS * 32, 6) prepare_reads(const __grid_c
                 u32 *r_ = wsm + rl * RS;
                 r_[2 * wv] = qh; r_[2 * wv + 1] = ql; r_[WQ + wv] = mk;
             }
-            sq[W2] = 0; sq[W2 + 1] = 0; sq[W2 + 2] = 0; smk[Wb] = 0;
+            sq[W2] = 0; smk[Wb] = 0;
             __syncwarp();
             if (en && !ns_known) {
                 ns_known = true;
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(PR_WARPS * 32, 6) prepare_reads(const __grid_c
                     u32 pw3 = 1; for (u32 x = 1; x < s; x++) pw3 *= 3u;
                     auto issue = [&](u32 j, u32 (&c8)[8], u32 &flb) {
                         const u32 p0 = j * s, w = p0 >> 4, o = (p0 & 15u) * 2, wm = p0 >> 5, om = p0 & 31u;
-                        const u32 q0 = sq[w], q1 = sq[w + 1], q2 = sq[w + 2];
+                        const u32 q0 = sq[w], q1 = sq[w + 1], q2 = w + 2 <= W2 ? sq[w + 2] : 0u;
                         u32 f0 = __funnelshift_l(q1, q0, o), f1 = __funnelshift_l(q2, q1, o);        // bases p0 .. p0+15, p0+16 .. p0+31
                         f0 -= (f0 << 1) & f0 & 0xAAAAAAAAu; f1 -= (f1 << 1) & f1 & 0xAAAAAAAAu;      // digits: 11 -> 01 (the first step of XT)
                         const u32 fin = s >= 16 ? f1 : __funnelshift_l(f1, f0, 2 * s);             // digits p0+s .. : what the window takes in
@@ -2291,6 +2291,7 @@ static int configure_kernels(bsl_ctx *ctx) {
     std::lock_guard<std::mutex> g(ctx->stats_mu);
     if (ctx->kernels_configured) return 0;
     CUDA_TRY(cudaFuncSetAttribute(prepare_reads, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(prepare_reads, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUDA_TRY(cudaFuncSetAttribute(prepare_deferred, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(screen_bits<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(screen_bits<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -2435,7 +2436,7 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     CUDA_TRY(cudaEventRecord(ln.ev[1], st));
     {
         // prepare_reads keeps WQ + Wb + 1 + wd + nseg (ii + 1) words per read in shared memory (<= 200 KB per CTA for any -s / -I / length)
-        const u32 WQ = 2 * Wb + 3;
+        const u32 WQ = 2 * Wb + 1;
         const size_t smem_p = (size_t)PR_WARPS * 32 * ((WQ + Wb + 1 + pdims[0] + pdims[1]) | 1u) * 4;
         if (smem_p > 200 * 1024) { set_error(ctx, "seed schedule does not fit the shared memory of prepare_reads"); return BSL_ELIMIT; }
         const u32 groups = (n_slots + 31) / 32;
