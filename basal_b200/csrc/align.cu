@@ -349,12 +349,13 @@ __global__ void __launch_bounds__(PR_WARPS * 32, 6) prepare_reads(const __grid_c
                 };
                 if (wd <= 8) {
                     // the usual case (I + ii <= 8): one batch of eight gathers per segment; the batch of segment j+1 is issued before
-                    // the sizes of segment j are consumed, so its latency hides behind CountSeeds
-                    u32 ca[8], fa = 0;
+                    // the sizes of segment j are consumed, so its latency hides behind CountSeeds; a saturated size (0xFF: reads from repeat
+                    // families, but with 224 look-ups per warp and segment nearly every warp meets one) asks the k-mer's record for the
+                    // exact one, again one segment ahead of its use
                     // the s + 7 bases the eight seeds of a segment cover are read once; the hash of offset u + 1 follows from the one
                     // of offset u (drop the leading base-3 digit, append one)
                     u32 pw3 = 1; for (u32 x = 1; x < s; x++) pw3 *= 3u;
-                    auto issue = [&](u32 j, u32 (&c8)[8], u32 &flb) {
+                    auto hashes = [&](u32 j, u32 (&hk)[8], u32 &flb) {
                         const u32 p0 = j * s, w = p0 >> 4, o = (p0 & 15u) * 2, wm = p0 >> 5, om = p0 & 31u;
                         const u32 q0 = sq[w], q1 = sq[w + 1], q2 = w + 2 <= W2 ? sq[w + 2] : 0u;
                         u32 f0 = __funnelshift_l(q1, q0, o), f1 = __funnelshift_l(q2, q1, o);        // bases p0 .. p0+15, p0+16 .. p0+31
@@ -366,26 +367,69 @@ __global__ void __launch_bounds__(PR_WARPS * 32, 6) prepare_reads(const __grid_c
 #pragma unroll
                         for (u32 u = 0; u < 8; u++) {
                             if (u) h = (h - ((f0 >> (32 - 2 * u)) & 3u) * pw3) * 3u + ((fin >> (32 - 2 * u)) & 3u);
-                            c8[u] = 0;
-                            if (u < wd) c8[u] = ldg_u8_hint(A.di.cnt8 + h, keep);
+                            hk[u] = h;
                             flb |= (((zm << u) >> (32 - s)) != 0u ? 1u : 0u) << u;
                         }
                     };
-                    issue(0, ca, fa);
-                    for (u32 j = 0; j < nseg; j++) {
-                        u32 cb[8], fb = 0;
-                        if (j + 1 < nseg) issue(j + 1, cb, fb);
-                        bool sat = false;
+                    auto issue = [&](u32 j, u32 (&c8)[8], u32 &flb) {
+                        u32 hk[8]; hashes(j, hk, flb);
 #pragma unroll
-                        for (u32 u = 0; u < 8; u++) if (u < wd) { cw[u] = ca[u] | (((fa >> u) & 1u) << 31); sat |= ca[u] == 0xFFu; }
-                        if (sat) for (u32 d = 0; d < wd; d++) if ((cw[d] & 0xFFu) == 0xFFu) {      // saturated: the exact size from the bucket table
-                            u32 fl; const u32 k = seed_at(j * s + d, fl);
-                            cw[d] = (__ldg(A.di.loc + A.di.rec_base + 8 * (size_t)k) & 0x7fffffffu) | fl;
+                        for (u32 u = 0; u < 8; u++) { c8[u] = 0; if (u < wd) c8[u] = ldg_u8_hint(A.di.cnt8 + hk[u], keep); }
+                    };
+                    const u32 *rec = A.di.loc + A.di.rec_base;
+                    u32 r8[8], fr = 0;                           // one-byte sizes of the segment after the one being packed (in flight), its non-ACGT flags
+                    u32 ex[8];                                   // exact sizes of the saturated offsets of the segment to consume next (in flight)
+                    u32 cap0 = 0, cap1 = 0, fa = 0, sa = 0;      // the segment to consume: one-byte sizes (packed), flags, which offsets are saturated
+#pragma unroll
+                    for (u32 u = 0; u < 8; u++) ex[u] = 0;
+                    issue(0, r8, fr);
+                    // -I 4 with -s a multiple of 4 (the defaults): CountSeeds(j, v) reads offsets v, v+3, v+2, v+1 of the segment, in that order
+                    const bool quad = I == 4u && (s & 3u) == 0u;
+                    for (u32 j = 0; j <= nseg; j++) {
+                        // (a) segment j-1: its sizes are complete
+                        u32 fv[8];
+#pragma unroll
+                        for (u32 u = 0; u < 8; u++) {
+                            u32 v = ((u < 4 ? cap0 : cap1) >> (8u * (u & 3u))) & 0xFFu;
+                            if ((sa >> u) & 1u) v = ex[u] & 0x7fffffffu;
+                            fv[u] = u < wd ? v | (((fa >> u) & 1u) << 31) : 0u;
                         }
-                        count_seeds_row(cw, s_prof[j], j, s, I, vmax, cs + j * ncol);
+                        if (j > 0 && !quad) {
 #pragma unroll
-                        for (u32 u = 0; u < 8; u++) ca[u] = cb[u];
-                        fa = fb;
+                            for (u32 u = 0; u < 8; u++) if (u < wd) cw[u] = fv[u];
+                        }
+                        // (b) segment j: the one-byte sizes have arrived; exact sizes of the saturated ones requested
+                        u32 sb = 0, n0 = 0, n1 = 0; const u32 fn = fr;
+                        if (j < nseg) {
+#pragma unroll
+                            for (u32 u = 0; u < 8; u++) if (u < wd) {
+                                if (u < 4) n0 |= r8[u] << (8u * u); else n1 |= r8[u] << (8u * (u - 4u));
+                                if (r8[u] == 0xFFu) sb |= 1u << u;
+                            }
+                            if (sb) {
+                                u32 hk[8], fl_; hashes(j, hk, fl_);
+#pragma unroll
+                                for (u32 u = 0; u < 8; u++) if ((sb >> u) & 1u) ex[u] = __ldg(rec + 8 * (size_t)hk[u]);
+                            }
+                        }
+                        // (c) one-byte sizes of segment j+1
+                        if (j + 1 < nseg) issue(j + 1, r8, fr);
+                        // (d) CountSeeds of segment j-1
+                        if (j > 0) {
+                            if (quad) {
+                                u32 *csj = cs + (j - 1) * ncol;
+#pragma unroll
+                                for (u32 v = 0; v < 5; v++) if (v <= vmax) {                    // wd = 4 + vmax <= 8
+                                    const u32 e0 = fv[v], e1 = fv[v + 3], e2 = fv[v + 2], e3 = fv[v + 1];
+                                    u32 k = (e0 >> 31) ? 12u : 0u, total = (e0 & 0x7fffffffu) << k;
+                                    if (e1 >> 31) k = 12u; total += (e1 & 0x7fffffffu) << k;
+                                    if (e2 >> 31) k = 12u; total += (e2 & 0x7fffffffu) << k;
+                                    if (e3 >> 31) k = 12u; total += (e3 & 0x7fffffffu) << k;
+                                    csj[v] = total == 0u ? 9999999u : total;
+                                }
+                            } else count_seeds_row(cw, s_prof[j - 1], j - 1, s, I, vmax, cs + (j - 1) * ncol);
+                        }
+                        cap0 = n0; cap1 = n1; fa = fn; sa = sb;
                     }
                 } else for (u32 j = 0; j < nseg; j++) {
                     for (u32 d0 = 0; d0 < wd; d0 += 8) {

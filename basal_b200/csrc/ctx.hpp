@@ -10,7 +10,7 @@
 
 // One "lane" = a CUDA stream plus every device/pinned buffer one in-flight batch needs,
 // so that several host threads can overlap H2D / kernels / D2H on one GPU.
-#define BSL_NLANES 3
+#define BSL_NLANES 6
 struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[8] = {};

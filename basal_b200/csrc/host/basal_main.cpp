@@ -909,7 +909,7 @@ int main(int argc, char **argv) {
         fprintf(stderr, "\tquality cutoff: %d \tbase quality char: '%c' \tmax Ns: %u\n", O.qual_threshold, O.zero_qual, O.P.max_ns);
         fprintf(stderr, "\twildcard mapping approach \tseed size: %u \tindex interval: %u\n", O.P.seed_size, O.P.index_interval);
     }
-    const int nw = std::max<int>(std::max(O.procs, 1), (int)P.ctx.size() * 3);                 // three lanes per GPU context
+    const int nw = std::max<int>(std::max(O.procs, 1), (int)P.ctx.size() * 4);                 // at least four calls in flight per GPU context (six lanes each)
     if (O.verbose >= 1) fprintf(stderr, "[BASAL @%s] %s alignment(%zu GPU(s), %d host threads),\n", now_str(), pe ? "Pair-end" : "Single-end", P.ctx.size(), nw);
     check_input(O.a, pe ? "failed to open read file #1 (check -a option): " : "failed to open read file (check -a option): ");
     if (!P.fa.open(O.a, O.max_readlen) || P.fa.format < 0) { fprintf(stderr, "\t(format: unknown)\nUnknown input format.\n"); exit(1); }

@@ -292,8 +292,9 @@ def measure(capi, cfg, args, dist, rank, world, local, step_pairs, e2e_reps=3):
         host.append((a, b))
     n = host[0][0].n
     reads_per_step = n * (2 if cfg.paired else 1)
-    # one set of pinned result buffers per in-flight call (a context has three lanes = streams + device buffers)
-    N_INFLIGHT = int(os.environ.get("BENCH_INFLIGHT", "3"))
+    # one set of pinned result buffers per in-flight call (a context has six lanes = streams + device buffers; four callers measured
+    # best: 196 / 230 / 204 / 224 M reads/s with 3 / 4 / 5 / 6, profiles/README.md)
+    N_INFLIGHT = int(os.environ.get("BENCH_INFLIGHT", "4"))
     outs = [(capi.pinned_array(n * capi.HIT_DTYPE.itemsize).view(capi.HIT_DTYPE),
              capi.pinned_array(n * capi.HIT_DTYPE.itemsize).view(capi.HIT_DTYPE),
              capi.pinned_array(n * capi.PAIR_DTYPE.itemsize).view(capi.PAIR_DTYPE)) for _ in range(N_INFLIGHT)]

@@ -1,6 +1,11 @@
-bash tools/gpu_tests.sh r2v "matches_oracle or mixed" 0
+bash tools/gpu_tests.sh r2x "matches_oracle or mixed" 0
 export BENCH_SKIP_CPU=1
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r2v.json 2> gpurun_out/bench_r2v.err; echo "bench exit $?"; cut -c1-300 gpurun_out/bench_r2v.json
-export BENCH_CONFIG=4
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r2v_c4.csv python bench.py --steps 1 --warmup 1 > gpurun_out/ncu_launch_r2v_c4.log 2>&1; echo "ncu launches exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -f -k "regex:screen_bits|reduce_round" -s 12 -c 4 -o gpurun_out/prof_c4_r2v python bench.py --steps 1 --warmup 1 > gpurun_out/ncu_c4_r2v.log 2>&1; echo "ncu c4 $?"
+for k in 3 4 5 6; do
+  BENCH_INFLIGHT=$k timeout 600 python bench.py --steps 12 --warmup 3 > gpurun_out/bench_r2x_i$k.json 2> gpurun_out/bench_r2x_i$k.err; echo "inflight $k exit $?"
+  python - <<PY
+import json
+for l in open('gpurun_out/bench_r2x_i$k.json'):
+    if l.startswith('{'):
+        d=json.loads(l); print('inflight $k value', round(d['value']/1e6,1), 'e2e', round(d['e2e']['value']/1e6,1), [round(x/1e6,1) for x in d['e2e']['repetitions_reads_per_s']], 'pack', round(d['roofline']['ms_pack_per_step'],2))
+PY
+done
