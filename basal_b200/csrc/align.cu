@@ -217,7 +217,7 @@ __device__ __forceinline__ uint4 schedule_from_table(const u32 *cs, u32 *keys, u
     return make_uint4(sb[0], sb[1], sb[2], sb[3]);
 }
 
-__global__ void __launch_bounds__(PR_WARPS * 32, 6) prepare_reads(const __grid_constant__ KArgs A, u32 WQ, u32 WDM, u32 CSZ) {
+__global__ void __launch_bounds__(PR_WARPS * 32, 8) prepare_reads(const __grid_constant__ KArgs A, u32 WQ, u32 WDM, u32 CSZ) {
     extern __shared__ u32 psm[];
     __shared__ u16 s_prof[16][16];
     const DevTables *T = A.tab;
@@ -2335,7 +2335,6 @@ static int configure_kernels(bsl_ctx *ctx) {
     std::lock_guard<std::mutex> g(ctx->stats_mu);
     if (ctx->kernels_configured) return 0;
     CUDA_TRY(cudaFuncSetAttribute(prepare_reads, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(prepare_reads, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUDA_TRY(cudaFuncSetAttribute(prepare_deferred, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(screen_bits<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(screen_bits<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -2481,15 +2480,24 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
     {
         // prepare_reads keeps WQ + Wb + 1 + wd + nseg (ii + 1) words per read in shared memory (<= 200 KB per CTA for any -s / -I / length)
         const u32 WQ = 2 * Wb + 1;
-        const size_t smem_p = (size_t)PR_WARPS * 32 * ((WQ + Wb + 1 + pdims[0] + pdims[1]) | 1u) * 4;
+        // -I 4, -s a multiple of 4, at most 8 offsets per segment: the sizes of a segment never leave the registers (no cw[] in the row;
+        // 53 words = 8 CTAs per SM at 2x150 bp)
+        const u32 wdm = (P.index_interval == 4 && (P.seed_size & 3u) == 0 && pdims[0] <= 8) ? 0u : pdims[0];
+        const size_t smem_p = (size_t)PR_WARPS * 32 * ((WQ + Wb + 1 + wdm + pdims[1]) | 1u) * 4;
         if (smem_p > 200 * 1024) { set_error(ctx, "seed schedule does not fit the shared memory of prepare_reads"); return BSL_ELIMIT; }
+        if (ctx->prep_smem != smem_p) {
+            // room for 8 CTAs per SM (2x150 bp: all 228 KB; 100 bp: half of it, the rest stays L1 for the size gathers)
+            const size_t need = 8 * (smem_p + 1536), total = 228 * 1024;
+            CUDA_TRY(cudaFuncSetAttribute(prepare_reads, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::min<size_t>(100, (need * 100 + total - 1) / total)));
+            ctx->prep_smem = smem_p;
+        }
         const u32 groups = (n_slots + 31) / 32;
         if (carry) CUDA_TRY(cudaMemsetAsync(ln.d_st0, 0, (size_t)n_slots * 2, st));
-        prepare_reads<<<std::min<u32>((groups + PR_WARPS - 1) / PR_WARPS, (u32)sms * 16), PR_WARPS * 32, smem_p, st>>>(A, WQ, pdims[0], pdims[1]);
+        prepare_reads<<<std::min<u32>((groups + PR_WARPS - 1) / PR_WARPS, (u32)sms * 16), PR_WARPS * 32, smem_p, st>>>(A, WQ, wdm, pdims[1]);
         launches++;
         if (carry) {        // reads with an empty start-offset range: schedule from the state the earlier reads of the batch leave behind
-            const u32 wdm = P.index_interval + P.seed_size, csz = 16 * P.seed_size;
-            prepare_deferred<<<sms * 4, PD_WARPS * 32, (size_t)PD_WARPS * 32 * ((wdm + csz) | 1u) * 4, st>>>(A, wdm, csz);
+            const u32 wdd = P.index_interval + P.seed_size, csz = 16 * P.seed_size;
+            prepare_deferred<<<sms * 4, PD_WARPS * 32, (size_t)PD_WARPS * 32 * ((wdd + csz) | 1u) * 4, st>>>(A, wdd, csz);
             launches++;
         }
     }

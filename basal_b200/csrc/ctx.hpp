@@ -53,6 +53,7 @@ struct bsl_ctx {
     int sm_count = BSL_SM_COUNT;
     int occ_verify[4] = {0, 0, 0, 0};   // resident CTAs per SM of the verify_candidates variants
     int occ_bits = 0;                   // resident CTAs per SM of screen_bits (for occ_bits_wb words per read plane)
+    size_t prep_smem = 0;                    // dynamic shared memory of the last prepare_reads launch (its carveout hint follows it)
     u32 occ_bits_wb = 0;
     bool kernels_configured = false;    // opt-in shared-memory sizes set on this context's device
     int occ_screen = 0;                 // resident CTAs per SM of screen_candidates
