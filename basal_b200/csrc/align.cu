@@ -2486,9 +2486,13 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
         const size_t smem_p = (size_t)PR_WARPS * 32 * ((WQ + Wb + 1 + wdm + pdims[1]) | 1u) * 4;
         if (smem_p > 200 * 1024) { set_error(ctx, "seed schedule does not fit the shared memory of prepare_reads"); return BSL_ELIMIT; }
         if (ctx->prep_smem != smem_p) {
-            // room for 8 CTAs per SM (2x150 bp: all 228 KB; 100 bp: half of it, the rest stays L1 for the size gathers)
-            const size_t need = 8 * (smem_p + 1536), total = 228 * 1024;
-            CUDA_TRY(cudaFuncSetAttribute(prepare_reads, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::min<size_t>(100, (need * 100 + total - 1) / total)));
+            // The kernel wants L1 more than resident warps (its loads of the read bytes, of the size table and its stores all pass
+            // through it): ask for about 132 KB of shared memory — 8 CTAs per SM at 100 bp, 4 at 2x150 bp — and leave the rest of
+            // the 256 KB to L1. Measured at 2x150 bp: 1.88 ms with room for 8 or 7 CTAs (28 KB of L1), 1.26 ms for 6, 1.15 for 5,
+            // 1.13 for 4, 1.31 for 3 (profiles/README.md).
+            const size_t per_cta = smem_p + 1536, total = 228 * 1024;
+            const size_t ctas = std::min<size_t>(8, std::max<size_t>(3, (132 * 1024) / per_cta));
+            CUDA_TRY(cudaFuncSetAttribute(prepare_reads, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::min<size_t>(100, (ctas * per_cta * 100 + total - 1) / total)));
             ctx->prep_smem = smem_p;
         }
         const u32 groups = (n_slots + 31) / 32;
