@@ -1,24 +1,27 @@
 // align.cu — batched read mapping on the GPU (replaces SingleAlign/PairAlign::Do_Batch).
 //
 // Kernels (all sm_100a integer / LSU work, no tensor cores):
-//   prepare_reads2     a warp takes 32 reads: FilterReads, 2-bit planes and 1-bit streams of both chains, seed hashes,
-//                      bucket-size gathers and the seed schedule (ConvertBinaySeq + ReorderSeed); prepare_reads is the
-//                      warp-per-read fallback for schedules that do not fit its shared memory
+//   prepare_reads      a warp takes 32 reads: FilterReads, 2-bit planes and 1-bit streams of both chains, seed hashes,
+//                      bucket-size gathers and the seed schedule (ConvertBinaySeq + ReorderSeed); prepare_deferred finishes
+//                      the reads that inherit their start offset from earlier reads (SURVEY trap 3)
 //   build_lists        first active lists (SE reads / full pairs / lone mates)
 //   per search round r (= SnpAlign mode r of every still-active read, align.cpp:274-316):
-//     seed_lookup      thread per (read, chain): the I bucket look-ups of mode r; every non-empty bucket becomes an
-//                      "item" that owns a contiguous range of a flat candidate space; the bucket walks are copied
-//                      out to flat_loc in visiting order
-//     screen_bits      THE roofline kernel (single-conversion rules, -g 0): warp per 32 candidates, one 32-byte gather
-//                      per candidate from the one-bit forward plane (L2 resident), XOR/popcount lower bound of
-//                      CountMismatch; survivors are counted exactly on the 2-bit planes (drain_exact)
-//     screen_candidates  the same for multi-way / '-' rules, on the 2-bit planes
-//     verify_candidates  -g > 0: whole window of every candidate (CountMismatch + GapAlign's first test), 1 bit per candidate
-//     reduce_fast      thread per read with <= 4 marked candidates: AddHit replay from the mark records
-//     reduce_round     warp per read: replays marked candidates in discovery order with the reference's AddHit
-//                      semantics (dedup, -w feedback on the threshold, abort) and runs the single-gap search (GapAlign)
-//     pair_round       PE: SortHits4PE + GetPairs replay for level r (thread per pair; warp per pair on the
-//                      large-capacity path)
+//     seed_lookup      thread per (read, chain): the I look-ups of mode r (one 32-byte record per k-mer); every non-empty
+//                      bucket becomes an "item" that owns a contiguous range of a flat candidate space; the bucket walks
+//                      are copied out to flat_loc in visiting order
+//     screen_bits      THE roofline kernel (single-conversion and '-'-only rules, with or without -g): warp per 32
+//                      candidates, one 32-byte gather per candidate from the one-bit forward plane (L2 resident),
+//                      XOR/popcount lower bound of CountMismatch; survivors are counted exactly on the 2-bit planes
+//                      (drain_exact)
+//     screen_candidates  the same for multi-way rules without -g, on the 2-bit planes
+//     verify_candidates  multi-way rules with -g: whole window of every candidate (CountMismatch + GapAlign's first test)
+//     reduce_fast      thread per read with <= 4 marked candidates: AddHit replay from the mark records; lists the reads
+//                      it leaves to reduce_round
+//     reduce_round     warp per listed read: replays the marked candidates, 32 per trip, in discovery order with the
+//                      reference's AddHit semantics (dedup, -w feedback on the threshold, abort) and runs the single-gap
+//                      search (GapAlign)
+//     pair_round       PE: SortHits4PE + GetPairs replay for level r, thread per pair; pairs with long hit lists go to
+//                      pair_round_wide<256> / <2048> (warp per pair)
 //   finalize_reads     lowest non-empty level, -S tie-break, result records
 //
 // Discovery order inside a read is preserved exactly: the flat candidate index of a read's candidates grows in
@@ -2552,6 +2555,11 @@ static int align_range(bsl_ctx *ctx, Lane &ln, const bsl_batch *a, const bsl_bat
         if (G) oe = ctx->rule.single ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, screen_bits<true, true>, SB_WARPS * 32, smem_b) : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, screen_bits<false, true>, SB_WARPS * 32, smem_b);
         else oe = ctx->rule.single ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, screen_bits<true, false>, SB_WARPS * 32, smem_b) : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, screen_bits<false, false>, SB_WARPS * 32, smem_b);
         ctx->occ_bits = (oe == cudaSuccess && occ > 0) ? occ : 1; ctx->occ_bits_wb = Wb;
+        // shared memory for exactly the CTAs that fit, the rest of the SM's 256 KB stays L1 (with 28 KB of L1 the kernel takes 2.4 times as long)
+        const size_t need = (size_t)ctx->occ_bits * (smem_b + sizeof(uint4) * SB_WARPS * SC_QCAP + 1024), total = 228 * 1024;
+        const int pct = (int)std::min<size_t>(100, (need * 100 + total - 1) / total);
+        if (G) { if (ctx->rule.single) cudaFuncSetAttribute(screen_bits<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct); else cudaFuncSetAttribute(screen_bits<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct); }
+        else { if (ctx->rule.single) cudaFuncSetAttribute(screen_bits<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct); else cudaFuncSetAttribute(screen_bits<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct); }
     }
     const int grid_b = sms * ctx->occ_bits;
     auto launch_verify = [&](KArgs &K, u32 ci) {
