@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(PD_WARPS * 32) prepare_deferred(const __grid_c
     const DevTables *T = A.tab;
     for (u32 x = threadIdx.x; x < 256; x += blockDim.x) s_prof[x >> 4][x & 15u] = T->prof[x >> 4][x & 15u];
     __syncthreads();
-    const u32 I = A.I, s = A.s, Wb = A.Wb, W2 = 2 * Wb, shs = 64 - 2 * s, nfull = (1u << s) - 1u;
+    const u32 I = A.I, s = A.s, Wb = A.Wb, shs = 64 - 2 * s;
     const u32 RS = (WDM + CSZ) | 1u;
     u32 *cw = dsm + (size_t)threadIdx.x * RS, *cs = cw + WDM;
     const u32 n_def = A.ctr->defer_n;
@@ -823,7 +823,7 @@ __global__ void __launch_bounds__(VF_THREADS, NS == 3 ? 4 : 2) verify_candidates
     __shared__ uint4 s_mk[CHUNK];                         // marked candidates of the chunk: {flat index, g, snp | strand << 8 | chain << 9, slot}
     constexpr u32 NP = SINGLE ? 2 : 3;                    // streams copied from global memory: bases, N-mask, (convert-to mask)
     constexpr u32 NPL = NP + (GAP ? 1 : 0);               // + prefix mask
-    constexpr u32 PL_NM = 1, PL_CM = 2, PL_PM = NP;
+    constexpr u32 PL_CM = 2, PL_PM = NP;
     constexpr int NR = 8 * NS;                            // logical 32-bit words of the gathered sectors
     RoundCtr *rc = A.ctr->rc + ci;
     const unsigned long long al = min(rc->alloc, ~rc->limit_inv);
