@@ -409,6 +409,8 @@ def measure(capi, cfg, args, dist, rank, world, local, step_pairs, e2e_reps=3):
             src = hashlib.sha256(open(os.path.join(ROOT, "basal_b200", "csrc", "align.cu"), "rb").read()).hexdigest()
             # only a capture of the kernels as they are now counts (tools/ncu_traffic.py records the source hash)
             traffic = tj.get("dram_bytes_per_launch") if tj.get("kernel_source_sha256") == src else None
+            if traffic is None and rank == 0:
+                print("[bench] roofline.traffic: profiles/roofline_traffic.json was captured for another align.cu (tools/ncu_traffic.py re-captures it)", file=sys.stderr)
         except Exception:
             traffic = None
     out = {
