@@ -892,7 +892,7 @@ int main(int argc, char **argv) {
             cs.push_back(c);
         }
         rcs.assign(cs.size(), 0);
-        pool_thread = std::thread([&P, &O, n = cs.size()]() { P.make_pool((size_t)std::max<int>(std::max(O.procs, 1), (int)n * 3) + 2); });   // pinned staging (one set per worker) while the GPUs build their index
+        pool_thread = std::thread([&P, &O, n = cs.size()]() { P.make_pool((size_t)std::max<int>(std::max(O.procs, 1), (int)n * 4) + 2); });   // pinned staging (one set per worker) while the GPUs build their index
         for (size_t g = 0; g < cs.size(); g++) th.emplace_back([&, g]() { rcs[g] = bsl_index_build(cs[g], R.cat.data(), R.off.data(), R.len.data(), (u32)R.len.size()); });
         for (auto &t : th) t.join();
         for (size_t g = 0; g < cs.size(); g++) if (rcs[g] != 0) { fprintf(stderr, "index build failed on GPU %zu (%d): %s\n", g, rcs[g], bsl_last_error(cs[g])); exit(1); }
